@@ -1,0 +1,202 @@
+#!/usr/bin/env python
+"""Test infrastructure only -- NOT part of the product path.
+
+Generates tests/golden/*.npz by EXECUTING THE REFERENCE ITSELF (the py2 sources
+under /root/reference, made importable by oracle/_py2shim.py) on small seeded
+inputs.  These vectors pin oracle/ (the numpy restatement) and, through it, the
+CUDA path.  Run in the authoring container only (it needs /root/reference):
+
+    python oracle/make_golden.py
+
+The GPU box never runs this; it only reads the committed .npz fixtures.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import scipy.io.wavfile as wavfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+sys.path.insert(0, HERE)
+import _py2shim  # noqa: E402
+
+warnings.simplefilter("ignore")
+
+
+def synth_mix(seed, fs=8000, dur=0.6, nsrc=3, conv=False):
+    """Small stereo int16 mixture: AR(2)-coloured, gated noise sources."""
+    rng = np.random.default_rng(seed)
+    L = int(fs * dur)
+    mix = np.zeros((L, 2))
+    for j in range(nsrc):
+        e = rng.standard_normal(L)
+        s = np.zeros(L)
+        a1, a2 = 1.6 - 0.5 * j, -0.8 + 0.1 * j
+        for t in range(2, L):
+            s[t] = a1 * s[t - 1] + a2 * s[t - 2] + e[t]
+        gate = (np.sin(2 * np.pi * (1.5 + j) * np.arange(L) / fs + j) > -0.3)
+        s = s * gate / np.abs(s).max()
+        if conv:
+            for c in range(2):
+                h = rng.standard_normal(8) * np.exp(-np.arange(8) / 2.0)
+                mix[:, c] += np.convolve(s, h)[:L]
+        else:
+            th = (j + 1) * np.pi / (2.0 * (nsrc + 1))
+            mix[:, 0] += np.sin(th) * s
+            mix[:, 1] += np.cos(th) * s
+    mix += 0.003 * rng.standard_normal(mix.shape)
+    mix = 0.9 * mix / np.abs(mix).max()
+    return fs, np.int16(np.round(mix * 32767))
+
+
+def snapshot(model, prefix, out):
+    for j, sc in model.spat_comps.items():
+        out["%s_A%d" % (prefix, j)] = np.array(sc["params"])
+    for k, sp in model.spec_comps.items():
+        fac = sp["factor"][0]
+        out["%s_FB%d" % (prefix, k)] = np.array(fac["FB"])
+        out["%s_FW%d" % (prefix, k)] = np.array(fac["FW"])
+        out["%s_TW%d" % (prefix, k)] = np.array(fac["TW"])
+
+
+def run_fasst(ref, name, wav, conv, rank, iters, nbcomps=3, K=4, seed=0):
+    am = ref["audioModel"]
+    out = {}
+    np.random.seed(seed)
+    cls = am.MultiChanNMFConv if conv else am.MultiChanNMFInst_FASST
+    model = cls(audio=wav, nbComps=nbcomps, nbNMFComps=K, spatial_rank=rank,
+                wlen=256, hopsize=64, iter_num=iters, verbose=0,
+                ann_PSD_lim=[None, None])
+    if conv:
+        model.makeItConvolutive()
+    if name == "fasst_inst_r1":
+        out["Cx"] = model.Cx
+    out["ann0"] = np.array(model.noise["ann_PSD_lim"][0])
+    out["ann1"] = np.array(model.noise["ann_PSD_lim"][1])
+    snapshot(model, "init", out)
+    # one E-step on the initial parameters (audioModel.py:580-764)
+    model.noise["PSD"] = model.noise["ann_PSD_lim"][0]
+    scp, mm, rpi = model.retrieve_subsrc_params()
+    hRxx, hRxs, hRss, hWs, ll = model.compute_suff_stat(scp, mm)
+    out["e0_hat_Rxs"], out["e0_hat_Rss"] = hRxs, hRss
+    out["e0_hat_Ws"], out["e0_loglik"] = hWs, np.real(ll)
+    # full GEM (audioModel.py:330-382); keep the state after iteration 1 too
+    model.iter_num = 1
+    ll1 = model.estim_param_a_post_model()
+    snapshot(model, "it1", out)
+    out["ll_it1"] = np.real(ll1)
+    # restart from the same init for the full trajectory
+    np.random.seed(seed)
+    model = cls(audio=wav, nbComps=nbcomps, nbNMFComps=K, spatial_rank=rank,
+                wlen=256, hopsize=64, iter_num=iters, verbose=0,
+                ann_PSD_lim=[None, None])
+    if conv:
+        model.makeItConvolutive()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lls = model.estim_param_a_post_model()
+    out["logliks"] = np.real(lls)
+    snapshot(model, "final", out)
+    out["noise_PSD_final"] = np.array(model.noise["PSD"])
+    # separation (audioModel.py:1063-1236)
+    outdir = "/tmp/pyfasst_golden_out_%s" % name
+    os.makedirs(outdir, exist_ok=True)
+    model.separate_spat_comps(dir_results=outdir)
+    for n, f in enumerate(model.files["spat_comp"]):
+        fs, y = wavfile.read(f)
+        out["sep%d" % n] = y
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "logliks", out["logliks"])
+
+
+def run_stft(ref):
+    st = ref["stft"]
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(3001) * np.hanning(3001)
+    tf = st.STFT(linFTLen=256, atomHopFactor=0.25, fs=8000)
+    tf.computeTransform(x)
+    X = np.array(tf.transfo)
+    y = tf.invertTransform()
+    tf2 = st.STFT(linFTLen=2048, atomHopFactor=0.25, fs=44100)
+    x2 = rng.standard_normal(5000)
+    tf2.computeTransform(x2)
+    X2 = np.array(tf2.transfo)
+    y2 = tf2.invertTransform()
+    np.savez_compressed(os.path.join(GOLD, "stft.npz"), x=x, X=X, y=y,
+                        freqs=tf.freq_stamps, times=tf.time_stamps,
+                        x2=x2, X2=X2, y2=y2)
+    print("stft", X.shape, np.abs(y - x).max(), X2.shape)
+
+
+def run_inv(ref):
+    sst = ref["signalTools"]
+    rng = np.random.default_rng(11)
+    d = np.abs(rng.standard_normal((2, 6, 5))) + 0.1
+    o = 0.3 * (rng.standard_normal((6, 5)) + 1j * rng.standard_normal((6, 5)))
+    d[:, 0, 0] = 0.0  # exercises the determinant clamp (signalTools.py:186-188)
+    o[0, 0] = 0.0
+    d[:, 0, 1] = 1e-6
+    o[0, 1] = 1e-6
+    i_d, i_o, det = sst.inv_herm_mat_2d(d, o)
+    np.savez_compressed(os.path.join(GOLD, "inv2d.npz"), d=d, o=o, inv_d=i_d,
+                        inv_o=i_o, det=det)
+
+
+def run_simm(ref):
+    simm = ref["SIMM"]
+    rng = np.random.default_rng(3)
+    F, N, NF0, P, K, R = 65, 40, 24, 6, 3, 5
+    WF0 = np.abs(rng.standard_normal((F, NF0))) ** 2
+    WF0 /= WF0.max(axis=0)
+    WGAMMA = np.abs(rng.standard_normal((F, P)))
+    SXR = np.abs(rng.standard_normal((F, N))) ** 2 + 1e-3
+    SXL = np.abs(rng.standard_normal((F, N))) ** 2 + 1e-3
+    init = dict(HGAMMA0=np.abs(rng.standard_normal((P, K))),
+                HPHI0=np.abs(rng.standard_normal((K, N))),
+                HF00=np.abs(rng.standard_normal((NF0, N))),
+                WM0=np.abs(rng.standard_normal((F, R))),
+                HM0=np.abs(rng.standard_normal((R, N))))
+    out = dict(WF0=WF0, WGAMMA=WGAMMA, SXR=SXR, SXL=SXL, **init)
+    # mono SIMM needs R == 1 (SIMM.py:388 broadcasts sumWM[R] against HM[R,N])
+    init1 = dict(init)
+    init1["WM0"] = init["WM0"][:, :1]
+    init1["HM0"] = init["HM0"][:1]
+    res = simm.SIMM(0.5 * (SXR + SXL), WF0, WGAMMA, numberOfFilters=K,
+                    numberOfAccompanimentSpectralShapes=1,
+                    numberOfIterations=4, verbose=False, **init1)
+    for nm, a in zip(("HGAMMA", "HPHI", "HF0", "HM", "WM"), res):
+        out["mono_" + nm] = a
+    np.random.seed(5)  # Stereo_SIMM draws betaR from np.random (SIMM.py:581)
+    res = simm.Stereo_SIMM(SXR, SXL, WF0, WGAMMA, numberOfFilters=K,
+                           numberOfAccompanimentSpectralShapes=R,
+                           numberOfIterations=4, verbose=False,
+                           computeError=True, **init)
+    for nm, a in zip(("alphaR", "alphaL", "HGAMMA", "HPHI", "HF0", "betaR",
+                      "betaL", "HM", "WM", "recoError"), res):
+        out["st_" + nm] = np.asarray(a)
+    np.savez_compressed(os.path.join(GOLD, "simm.npz"), **out)
+    print("simm alphaR", out["st_alphaR"], "err", out["st_recoError"][:3])
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref = _py2shim.load()
+    fs, mix = synth_mix(1)
+    wav = os.path.join(GOLD, "mix_inst.wav")
+    wavfile.write(wav, fs, mix)
+    fs, mixc = synth_mix(2, conv=True)
+    wavc = os.path.join(GOLD, "mix_conv.wav")
+    wavfile.write(wavc, fs, mixc)
+    run_inv(ref)
+    run_stft(ref)
+    run_fasst(ref, "fasst_inst_r1", wav, conv=False, rank=1, iters=6)
+    run_fasst(ref, "fasst_inst_r2", wav, conv=False, rank=2, iters=6)
+    run_fasst(ref, "fasst_conv_r1", wavc, conv=True, rank=1, iters=6)
+    run_fasst(ref, "fasst_conv_r2", wavc, conv=True, rank=2, iters=6, nbcomps=2)
+    run_simm(ref)
+
+
+if __name__ == "__main__":
+    main()
