@@ -1,0 +1,186 @@
+/* pyfasst_b200 -- C ABI of the B200 (sm_100a) kernels behind pyfasst's FASST hot path.
+ *
+ * The reference (s-ben/pyfasst) is pure Python/NumPy and has no FFI layer; its
+ * operator boundary is the set of FASST methods listed below.  Each entry point
+ * here replaces the numerical body of one of them (reference file:line given
+ * per function, relative to /root/reference/pyfasst/).  The Python package
+ * `pyfasst_b200` keeps the reference's class / method names and binds these
+ * symbols with ctypes (pyfasst_b200/_lib.py); INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types cross the ABI.
+ *  - every pointer is a DEVICE pointer unless the parameter is documented "host".
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    all work is enqueued on it, nothing synchronises with the host.
+ *  - return value: PF_OK (0) or a negative PF_ERR_*; pf_last_error() gives the
+ *    message (thread local).  No exception crosses the ABI.
+ *  - `dtype` selects the storage/arithmetic type of the F x N planes and of the
+ *    NMF factors: PF_F32 (fast path) or PF_F64 (the reference's precision).
+ *    Mixing matrices, sufficient statistics, noise PSD and all reductions are
+ *    always float64 / complex128 (interleaved re,im doubles).
+ *  - planes are row-major [rows][ld] with frames contiguous; ld % 4 == 0 and
+ *    plane base pointers 16-byte aligned; padding frames (n >= N) are never read
+ *    as data and are kept at zero by the producers.
+ */
+#ifndef PYFASST_B200_H_
+#define PYFASST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 3
+
+#define PF_OK 0
+#define PF_ERR_ARG (-1)         /* invalid argument (ValueError on the Python side) */
+#define PF_ERR_CUDA (-2)        /* CUDA runtime / launch error */
+#define PF_ERR_UNSUPPORTED (-3) /* NotImplementedError on the Python side */
+
+#define PF_F32 0
+#define PF_F64 1
+
+/* bits of the device-side status word written by the solvers */
+#define PF_FLAG_SINGULAR 1 /* np.linalg.LinAlgError('Singular Matrix'), audioModel.py:858-861 */
+#define PF_FLAG_TW_RESTART 2 /* sum(TW) < eps: the reference re-draws TW, audioModel.py:2023-2025 */
+
+/* ---- library ---------------------------------------------------------------- */
+const char* pf_last_error(void);
+int pf_abi_version(void);
+/* kernels launched by this library since load (bench.py "gpu_launches") */
+unsigned long long pf_launch_count(void);
+/* Make `device` current for this library's CUDA runtime (call once per process/thread
+ * with the device the tensors live on). */
+int pf_set_device(int device);
+
+/* ---- K1: STFT front end  (tftransforms/stft.py:3-69, audioModel.py:250-328) --- */
+/* Framing + window + real FFT of `nch` channels in one launch.
+ * pcm     : double [nch][L] (already scaled, audioObject.py:124-127)
+ * window  : double [wlen] (host-built np.hanning etc.), nfft >= wlen, nfft = 2^k
+ * X       : dtype planes [2*nch][F][ld] = (re, im) per channel, F = nfft/2+1,
+ *           N = ceil(L/hop)+2 frames (stft.py:40)
+ * psd_sum : double [F], sum over channels and frames of |X|^2 (for the annealing
+ *           limits, audioModel.py:304-323); may be NULL
+ * The FFT itself always runs in float64. */
+int pf_stft(const double* pcm, int nch, int64_t L, const double* window, int wlen, int hop,
+            int nfft, void* X, int64_t N, int64_t ld, double* psd_sum, int dtype, void* stream);
+
+/* ---- K6: inverse STFT with overlap-add  (tftransforms/stft.py:71-131) --------- */
+/* Y       : dtype planes [2*nsig][F][ld]
+ * synth   : double [wlen] synthesis window; norm : double [(N-1)*hop+wlen]
+ *           = overlap-added synth*analysis (stft.py:117-129), host-built
+ * out     : double [nsig][Lout] ; sample t reads frames covering t + wlen/2
+ * pcm     : optional int16 [Lout][nsig] interleaved, = (int16)trunc(out*maxdata)
+ *           (audioModel.py:1227-1229) ; NULL to skip */
+int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld, const double* synth,
+             const double* norm, int wlen, int hop, int nfft, double* out, int64_t Lout,
+             int16_t* pcm, double maxdata, int dtype, void* stream);
+
+/* ---- K6: Wiener filter  (audioModel.py:1088-1236, :1327-1467) ----------------- */
+/* For every bin: Sigma = sum_j v_j R_j + s2 I, Y_g = (sum_{j in g} v_j R_j) Sigma^-1 x for
+ * `ngroups` output signals.  Y planes [ngroups][4][F][ld] (re0, im0, re1, im1).
+ * A: complex128 [R][2][F]; src_of_sub: host int[R]; group_of_src: host int[J], the output
+ * group of each spatial component (-1 = none).  workspace: >= F*(4J+J(J+1)/2)*8 bytes.
+ * noise_psd is the PSD of the LAST GEM iteration (audioModel.py:1385). */
+int pf_wiener_stereo(const void* X, const void* V, const void* A, const int* src_of_sub, int R,
+                     int J, const double* noise_psd, const int* group_of_src, int ngroups, int F,
+                     int64_t N, int64_t ld, void* Y, void* workspace, int64_t workspace_bytes,
+                     int dtype, void* stream);
+
+/* ---- K2: fused E-step  (audioModel.py:580-764, tools/signalTools.py:132-196) --- */
+/* Workspace planning: bytes needed by pf_estep_stereo for this shape. */
+int pf_estep_plan(int J, int64_t N, int dtype, int64_t* chunk, int* nsplit,
+                  int64_t* workspace_bytes, int F);
+/* X       : dtype planes [4][F][ld] (re0, im0, re1, im1): Cx = x x^H is rank one
+ *           (audioModel.py:293-302) so the kernel reads x instead of Cx
+ * V       : dtype planes [J][F][ld], power of each spatial component
+ *           (comp_spat_comp_power, audioModel.py:430-498)
+ * A       : complex128 [R][2][F] mixing vectors per sub-source (audioModel.py:562-576)
+ * src_of_sub : host int[R], spatial component of each sub-source
+ * noise_psd  : double [F]
+ * hatW    : dtype planes [J][F][ld]  = rank-mean of |Re diag| (audioModel.py:727-729,:408-414)
+ * hat_Rss : complex128 [F][R][R], hat_Rxs : complex128 [F][2][R]
+ * ll_f    : double [F], sum over frames of log(det Sigma * pi) + x^H Sigma^-1 x
+ *           (loglik = -sum(ll_f) / (F N), audioModel.py:660-664) */
+int pf_estep_stereo(const void* X, const void* V, const void* A, const int* src_of_sub, int R,
+                    int J, const double* noise_psd, int F, int64_t N, int64_t ld, void* hatW,
+                    void* hat_Rss, void* hat_Rxs, double* ll_f, void* workspace,
+                    int64_t workspace_bytes, int dtype, void* stream);
+
+/* ---- K3: spatial M-step  (audioModel.py:766-889) ------------------------------- */
+/* Instantaneous mixing: f-summed real statistics (audioModel.py:816-826).
+ * stats : double [I*n_upd + n_upd*n_upd]; under frequency sharding the caller
+ * all-reduces `stats` between the two calls. upd/oth: host int arrays. */
+int pf_mix_inst_stats(const void* hat_Rss, const void* hat_Rxs, const void* A, const int* upd,
+                      int n_upd, const int* oth, int n_oth, int R, int I, int F, double* stats,
+                      void* stream);
+/* Solve and broadcast over the local frequencies (audioModel.py:830-841).
+ * F_total = number of frequencies the statistics were summed over. */
+int pf_mix_inst_solve(const double* stats, double F_total, const int* upd, int n_upd, int I,
+                      int F, void* A, int* flags, void* stream);
+/* Convolutive mixing: A[:, :, f] = solve(hat_Rss[f]^T, hat_Rxs[f]^T) (audioModel.py:844-863) */
+int pf_mix_conv_solve(const void* hat_Rss, const void* hat_Rxs, int R, int I, int F, void* A,
+                      int* flags, void* stream);
+
+/* ---- K4: spectral M-step  (audioModel.py:430-498, :1469-1727) ------------------- */
+/* V[f,n] (+)= sum_k W[f,k] H[k,n];  W dtype [F][ldw], H dtype [K][ldh], V dtype [F][ldv] */
+int pf_spec_power(const void* W, int ldw, const void* H, int64_t ldh, void* V, int64_t ldv,
+                  int F, int K, int64_t N, int accumulate, int dtype, void* stream);
+/* C[m][n] = sum_k A[m][k] B[k][n] for the small factor products FB.FW (dtype, row-major) */
+int pf_small_matmul(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M,
+                    int K, int Nc, int dtype, void* stream);
+/* FB / FW update contractions over frames (audioModel.py:1521-1631):
+ *   num[f,k] = sum_n (hatW/P^2*O)[f,n] G[k,n],  den[f,k] = sum_n (O/P)[f,n] G[k,n]
+ * P, O are clamped at eps=1e-10 in the kernel.  Partial sums per frame split:
+ * num_partial/den_partial double [nsplit][F][K]. */
+int pf_nmf_fb_plan(int F, int K, int64_t N, int dtype, int64_t* chunk, int* nsplit);
+int pf_nmf_fb_contract(const void* hatW, const void* P, const void* O, int64_t ld, const void* G,
+                       int64_t ldg, int F, int K, int64_t N, double* num_partial,
+                       double* den_partial, int64_t chunk, int nsplit, int dtype, void* stream);
+/* TW update contractions over frequencies (audioModel.py:1634-1727), with the
+ * component's own power P' = max(W H, eps) formed on the fly from the updated W:
+ *   num[k,n] = sum_f W[f,k] (O hatW / P'^2)[f,n],  den[k,n] = sum_f W[f,k] (O / P')[f,n]
+ * Partial sums per frequency split: double [fsplit][K][ldo]. */
+int pf_nmf_tw_plan(int F, int K, int64_t N, int* fchunk, int* fsplit);
+int pf_nmf_tw_contract(const void* hatW, const void* O, int64_t ld, const void* W, int ldw,
+                       const void* H, int64_t ldh, int F, int K, int64_t N, double* num_partial,
+                       double* den_partial, int64_t ldo, int fchunk, int fsplit, int dtype,
+                       void* stream);
+/* out[i] = sum_s in[s][i] in a fixed order */
+int pf_sum_splits(const double* in, int nsplit, int64_t count, double* out, void* stream);
+/* theta[r][c] *= (num[r][c] / max(den[r][c], 1e-10))^omega (audioModel.py:1573,:1725) */
+int pf_mult_update(void* theta, int64_t ldt, const double* num, const double* den, int64_t ldnd,
+                   int rows, int64_t cols, double omega, int dtype, void* stream);
+
+/* ---- K5: renormalisation  (audioModel.py:1980-2040) ----------------------------- */
+int pf_spat_energy(const void* A, const int* src_of_sub, int R, int J, int I, int F,
+                   double* sums, void* stream);
+int pf_spat_scale(void* A, const int* src_of_sub, int R, int I, int F, const double* sums,
+                  const double* counts, void* stream);
+int pf_fb_scale_colmax(void* FB, int ldw, int F, int K, const double* sums, const double* counts,
+                       int j, double* colmax, int dtype, void* stream);
+int pf_fw_renorm(void* FW, int ldfw, int Kb, int Kw, const double* colmax, double* w, double* w2,
+                 int dtype, void* stream);
+int pf_scale_matrix(void* M, int64_t ldm, int rows, int64_t cols, const double* s, int by_row,
+                    int divide, double* total, int dtype, void* stream);
+
+/* totals[s] < eps  ->  *flags |= PF_FLAG_TW_RESTART ; totals are reset to zero */
+int pf_check_totals(double* totals, int count, double eps, int* flags, void* stream);
+
+/* ---- GEM loop glue  (audioModel.py:330-382) --------------------------------------- */
+/* noise[f] = ((sqrt_lim0[f]*(I-i) + sqrt_lim1[f]*i)/I)^2 with i read from *iter_dev
+ * (audioModel.py:368-373), so that a captured CUDA graph can be replayed. */
+int pf_noise_anneal(const double* sqrt_lim0, const double* sqrt_lim1, const int* iter_dev,
+                    int n_iter, int F, double* noise, void* stream);
+/* ll_sum[0] = sum_f ll_f[f]  (fixed order) */
+int pf_ll_reduce(const double* ll_f, int F, double* ll_sum, void* stream);
+/* logliks[*iter_dev] = -ll_sum[0] / bins ; if advance, ++*iter_dev */
+int pf_ll_store(const double* ll_sum, double bins, double* logliks, int* iter_dev, int advance,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYFASST_B200_H_ */

@@ -1,0 +1,303 @@
+"""ctypes binding of libpyfasst_b200.so (the C ABI declared in include/pyfasst_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or a call fails, an
+exception is raised.  `CudaKernels` is the object the GEM engine talks to; every
+method takes torch CUDA tensors (device memory + stream plumbing only) and
+enqueues hand-written sm_100a kernels on torch's current stream.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpyfasst_b200.so")
+
+PF_F32, PF_F64 = 0, 1
+PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2
+ABI_VERSION = 3
+
+c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+c_ip = ctypes.POINTER(ctypes.c_int)
+
+# name -> argument ctypes (return type is int unless listed in _RESTYPE)
+SIGNATURES = {
+    "pf_last_error": [],
+    "pf_abi_version": [],
+    "pf_launch_count": [],
+    "pf_set_device": [c_int],
+    "pf_stft": [c_vp, c_int, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_int,
+                c_vp],
+    "pf_istft": [c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64,
+                 c_vp, c_dbl, c_int, c_vp],
+    "pf_wiener_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_ip, c_int, c_int, c_i64,
+                         c_i64, c_vp, c_vp, c_i64, c_int, c_vp],
+    "pf_estep_plan": [c_int, c_i64, c_int, ctypes.POINTER(c_i64), c_ip, ctypes.POINTER(c_i64),
+                      c_int],
+    "pf_estep_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_int, c_i64, c_i64, c_vp,
+                        c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp],
+    "pf_mix_inst_stats": [c_vp, c_vp, c_vp, c_ip, c_int, c_ip, c_int, c_int, c_int, c_int, c_vp,
+                          c_vp],
+    "pf_mix_inst_solve": [c_vp, c_dbl, c_ip, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "pf_mix_conv_solve": [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "pf_spec_power": [c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int, c_int,
+                      c_vp],
+    "pf_small_matmul": [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
+    "pf_nmf_fb_plan": [c_int, c_int, c_i64, c_int, ctypes.POINTER(c_i64), c_ip],
+    "pf_nmf_fb_contract": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_vp, c_vp,
+                           c_i64, c_int, c_int, c_vp],
+    "pf_nmf_tw_plan": [c_int, c_int, c_i64, c_ip, c_ip],
+    "pf_nmf_tw_contract": [c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_i64, c_vp,
+                           c_vp, c_i64, c_int, c_int, c_int, c_vp],
+    "pf_sum_splits": [c_vp, c_int, c_i64, c_vp, c_vp],
+    "pf_mult_update": [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
+    "pf_spat_energy": [c_vp, c_ip, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "pf_spat_scale": [c_vp, c_ip, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "pf_fb_scale_colmax": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp],
+    "pf_fw_renorm": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
+    "pf_scale_matrix": [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_vp],
+    "pf_check_totals": [c_vp, c_int, c_dbl, c_vp, c_vp],
+    "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+    "pf_ll_reduce": [c_vp, c_int, c_vp, c_vp],
+    "pf_ll_store": [c_vp, c_dbl, c_vp, c_vp, c_int, c_vp],
+}
+_RESTYPE = {"pf_last_error": ctypes.c_char_p, "pf_launch_count": ctypes.c_ulonglong}
+
+_lib = None
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the shared library and declare every prototype.  Raises ImportError if
+    it has not been built (python -m pyfasst_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ImportError(
+            "pyfasst_b200: %s not found -- build it with `python -m pyfasst_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = args
+        fn.restype = _RESTYPE.get(name, c_int)
+    if lib.pf_abi_version() != ABI_VERSION:
+        raise ImportError("pyfasst_b200: ABI version %d, expected %d -- rebuild the library"
+                          % (lib.pf_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def _check(rc, lib):
+    if rc == 0:
+        return
+    msg = lib.pf_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -3:
+        raise NotImplementedError(msg)
+    raise KernelError(msg)
+
+
+def _iarr(values):
+    arr = (ctypes.c_int * max(len(values), 1))(*[int(v) for v in values])
+    return arr
+
+
+class CudaKernels(object):
+    """The kernels of the C ABI, called with torch CUDA tensors."""
+
+    name = "cuda"
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyfasst_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()
+                                   if device is None else device)
+        _check(self.lib.pf_set_device(self.device.index), self.lib)
+
+    # -- helpers ----------------------------------------------------------------
+    def _p(self, t):
+        if t is None:
+            return None
+        assert t.is_cuda and t.is_contiguous(), "kernel arguments must be contiguous CUDA tensors"
+        return t.data_ptr()
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def dtype_code(self, t):
+        if t.dtype == self.torch.float32:
+            return PF_F32
+        if t.dtype == self.torch.float64:
+            return PF_F64
+        raise ValueError("unsupported plane dtype %s" % t.dtype)
+
+    def launch_count(self):
+        return int(self.lib.pf_launch_count())
+
+    # -- K1 / K6 -------------------------------------------------------------------
+    def stft(self, pcm, window, hop, nfft, X, N, psd_sum):
+        nch, L = pcm.shape
+        F, ld = X.shape[1], X.shape[2]
+        assert X.shape[0] == 2 * nch and F == nfft // 2 + 1
+        _check(self.lib.pf_stft(self._p(pcm), nch, L, self._p(window), window.numel(), hop, nfft,
+                                self._p(X), N, ld, self._p(psd_sum), self.dtype_code(X),
+                                self._stream()), self.lib)
+
+    def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata):
+        nsig = Y.shape[0] // 2
+        F, ld = Y.shape[1], Y.shape[2]
+        assert out.shape[0] == nsig
+        _check(self.lib.pf_istft(self._p(Y), nsig, F, N, ld, self._p(synth), self._p(norm),
+                                 synth.numel(), hop, nfft, self._p(out), out.shape[1],
+                                 self._p(pcm), float(maxdata), self.dtype_code(Y),
+                                 self._stream()), self.lib)
+
+    def wiener_stereo(self, X, V, A, src_of_sub, noise, group_of_src, ngroups, N, Y, workspace):
+        J, F, ld = V.shape
+        R = A.shape[0]
+        _check(self.lib.pf_wiener_stereo(self._p(X), self._p(V), self._p(A), _iarr(src_of_sub), R,
+                                         J, self._p(noise), _iarr(group_of_src), ngroups, F, N,
+                                         ld, self._p(Y), self._p(workspace),
+                                         workspace.numel() * workspace.element_size(),
+                                         self.dtype_code(V), self._stream()), self.lib)
+
+    # -- K2 ---------------------------------------------------------------------------
+    def estep_workspace_bytes(self, J, F, N, dtype_code):
+        chunk, nsplit, nbytes = c_i64(), c_int(), c_i64()
+        _check(self.lib.pf_estep_plan(J, N, dtype_code, ctypes.byref(chunk), ctypes.byref(nsplit),
+                                      ctypes.byref(nbytes), F), self.lib)
+        return nbytes.value
+
+    def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace):
+        J, F, ld = V.shape
+        R = A.shape[0]
+        _check(self.lib.pf_estep_stereo(self._p(X), self._p(V), self._p(A), _iarr(src_of_sub), R,
+                                        J, self._p(noise), F, N, ld, self._p(hatW), self._p(Rss),
+                                        self._p(Rxs), self._p(ll_f), self._p(workspace),
+                                        workspace.numel() * workspace.element_size(),
+                                        self.dtype_code(V), self._stream()), self.lib)
+
+    # -- K3 ---------------------------------------------------------------------------
+    def mix_inst_stats(self, Rss, Rxs, A, upd, oth, stats):
+        R, I, F = A.shape
+        _check(self.lib.pf_mix_inst_stats(self._p(Rss), self._p(Rxs), self._p(A), _iarr(upd),
+                                          len(upd), _iarr(oth), len(oth), R, I, F,
+                                          self._p(stats), self._stream()), self.lib)
+
+    def mix_inst_solve(self, stats, F_total, upd, A, flags):
+        R, I, F = A.shape
+        _check(self.lib.pf_mix_inst_solve(self._p(stats), float(F_total), _iarr(upd), len(upd), I,
+                                          F, self._p(A), self._p(flags), self._stream()), self.lib)
+
+    def mix_conv_solve(self, Rss, Rxs, A, flags):
+        R, I, F = A.shape
+        _check(self.lib.pf_mix_conv_solve(self._p(Rss), self._p(Rxs), R, I, F, self._p(A),
+                                          self._p(flags), self._stream()), self.lib)
+
+    # -- K4 ---------------------------------------------------------------------------
+    def spec_power(self, W, H, V, N, accumulate):
+        F, K = W.shape
+        _check(self.lib.pf_spec_power(self._p(W), W.stride(0), self._p(H), H.stride(0),
+                                      self._p(V), V.stride(0), F, K, N, int(accumulate),
+                                      self.dtype_code(V), self._stream()), self.lib)
+
+    def small_matmul(self, A, B, C):
+        M, K = A.shape
+        Nc = B.shape[1]
+        _check(self.lib.pf_small_matmul(self._p(A), A.stride(0), self._p(B), B.stride(0),
+                                        self._p(C), C.stride(0), M, K, Nc, self.dtype_code(C),
+                                        self._stream()), self.lib)
+
+    def fb_plan(self, F, K, N, dtype_code):
+        chunk, nsplit = c_i64(), c_int()
+        _check(self.lib.pf_nmf_fb_plan(F, K, N, dtype_code, ctypes.byref(chunk),
+                                       ctypes.byref(nsplit)), self.lib)
+        return chunk.value, nsplit.value
+
+    def fb_contract(self, hatW, P, O, G, N, num_partial, den_partial, chunk, nsplit):
+        F, ld = hatW.shape
+        K = G.shape[0]
+        _check(self.lib.pf_nmf_fb_contract(self._p(hatW), self._p(P), self._p(O), ld, self._p(G),
+                                           G.stride(0), F, K, N, self._p(num_partial),
+                                           self._p(den_partial), chunk, nsplit,
+                                           self.dtype_code(hatW), self._stream()), self.lib)
+
+    def tw_plan(self, F, K, N):
+        fchunk, fsplit = c_int(), c_int()
+        _check(self.lib.pf_nmf_tw_plan(F, K, N, ctypes.byref(fchunk), ctypes.byref(fsplit)),
+               self.lib)
+        return fchunk.value, fsplit.value
+
+    def tw_contract(self, hatW, O, W, H, N, num_partial, den_partial, fchunk, fsplit):
+        F, ld = hatW.shape
+        K = W.shape[1]
+        _check(self.lib.pf_nmf_tw_contract(self._p(hatW), self._p(O), ld, self._p(W), W.stride(0),
+                                           self._p(H), H.stride(0), F, K, N,
+                                           self._p(num_partial), self._p(den_partial),
+                                           num_partial.shape[-1], fchunk, fsplit,
+                                           self.dtype_code(hatW), self._stream()), self.lib)
+
+    def sum_splits(self, parts, out):
+        nsplit = parts.shape[0]
+        _check(self.lib.pf_sum_splits(self._p(parts), nsplit, out.numel(), self._p(out),
+                                      self._stream()), self.lib)
+
+    def mult_update(self, theta, num, den, rows, cols, omega):
+        _check(self.lib.pf_mult_update(self._p(theta), theta.stride(0), self._p(num), self._p(den),
+                                       num.stride(0), rows, cols, float(omega),
+                                       self.dtype_code(theta), self._stream()), self.lib)
+
+    # -- K5 ---------------------------------------------------------------------------
+    def spat_energy(self, A, src_of_sub, J, sums):
+        R, I, F = A.shape
+        _check(self.lib.pf_spat_energy(self._p(A), _iarr(src_of_sub), R, J, I, F, self._p(sums),
+                                       self._stream()), self.lib)
+
+    def spat_scale(self, A, src_of_sub, sums, counts):
+        R, I, F = A.shape
+        _check(self.lib.pf_spat_scale(self._p(A), _iarr(src_of_sub), R, I, F, self._p(sums),
+                                      self._p(counts), self._stream()), self.lib)
+
+    def fb_scale_colmax(self, FB, sums, counts, j, colmax):
+        F, K = FB.shape
+        _check(self.lib.pf_fb_scale_colmax(self._p(FB), FB.stride(0), F, K, self._p(sums),
+                                           self._p(counts), j, self._p(colmax),
+                                           self.dtype_code(FB), self._stream()), self.lib)
+
+    def fw_renorm(self, FW, colmax, w, w2):
+        Kb, Kw = FW.shape
+        _check(self.lib.pf_fw_renorm(self._p(FW), FW.stride(0), Kb, Kw, self._p(colmax),
+                                     self._p(w), self._p(w2), self.dtype_code(FW),
+                                     self._stream()), self.lib)
+
+    def scale_matrix(self, M, rows, cols, s, by_row, divide, total=None):
+        _check(self.lib.pf_scale_matrix(self._p(M), M.stride(0), rows, cols, self._p(s),
+                                        int(by_row), int(divide), self._p(total),
+                                        self.dtype_code(M), self._stream()), self.lib)
+
+    def check_totals(self, totals, eps, flags):
+        _check(self.lib.pf_check_totals(self._p(totals), totals.numel(), float(eps),
+                                        self._p(flags), self._stream()), self.lib)
+
+    # -- glue ---------------------------------------------------------------------------
+    def noise_anneal(self, sqrt0, sqrt1, iter_dev, n_iter, noise):
+        _check(self.lib.pf_noise_anneal(self._p(sqrt0), self._p(sqrt1), self._p(iter_dev), n_iter,
+                                        noise.numel(), self._p(noise), self._stream()), self.lib)
+
+    def ll_reduce(self, ll_f, ll_sum):
+        _check(self.lib.pf_ll_reduce(self._p(ll_f), ll_f.numel(), self._p(ll_sum),
+                                     self._stream()), self.lib)
+
+    def ll_store(self, ll_sum, bins, logliks, iter_dev, advance):
+        _check(self.lib.pf_ll_store(self._p(ll_sum), float(bins), self._p(logliks),
+                                    self._p(iter_dev), int(advance), self._stream()), self.lib)

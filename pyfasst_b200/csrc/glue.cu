@@ -1,0 +1,120 @@
+// GEM-loop glue kernels: annealed noise PSD, log-likelihood bookkeeping, the small
+// factor products FB.FW.  Everything the loop of FASST.estim_param_a_post_model
+// (pyfasst/audioModel.py:330-382) does between the big kernels stays on the device so
+// that an iteration never synchronises with the host and can be captured in a CUDA
+// graph (the iteration index lives in device memory).
+#include "common.cuh"
+
+namespace pf {
+
+// noise[f] = ((sqrt(lim0)*(I-i) + sqrt(lim1)*i)/I)^2      (audioModel.py:368-373)
+__global__ void noise_anneal_kernel(const double* __restrict__ s0, const double* __restrict__ s1,
+                                    const int* __restrict__ iter_dev, int n_iter, int F,
+                                    double* __restrict__ noise) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const double i = (double)(*iter_dev);
+  const double I = (double)n_iter;
+  const double v = (s0[f] * (I - i) + s1[f] * i) / I;
+  noise[f] = v * v;
+}
+
+// single CTA, fixed-order tree: deterministic
+__global__ void ll_reduce_kernel(const double* __restrict__ ll_f, int F, double* __restrict__ out) {
+  __shared__ double s_red[32];
+  double acc = 0.0;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) acc += ll_f[f];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) d += s_red[w];
+    out[0] = d;
+  }
+}
+
+__global__ void ll_store_kernel(const double* __restrict__ ll_sum, double bins,
+                                double* __restrict__ logliks, int* __restrict__ iter_dev,
+                                int advance) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int i = *iter_dev;
+    logliks[i] = -ll_sum[0] / bins;  // audioModel.py:660-664 (mean over F*N)
+    if (advance) *iter_dev = i + 1;
+  }
+}
+
+template <typename T>
+__global__ void small_matmul_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B,
+                                    int ldb, T* __restrict__ C, int ldc, int M, int K, int Nc) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * Nc) return;
+  const int m = (int)(idx / Nc), n = (int)(idx % Nc);
+  // accumulate in double in index order, like a dot product of float64 rows
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * lda + k] * (double)B[(size_t)k * ldb + n];
+  C[(size_t)m * ldc + n] = (T)acc;
+}
+
+__global__ void check_totals_kernel(double* __restrict__ totals, int count, double eps,
+                                    int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (totals[i] < eps) atomicOr(flags, PF_FLAG_TW_RESTART);
+  totals[i] = 0.0;
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" int pf_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    set_error("pf_set_device(%d): %s", device, cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  return PF_OK;
+}
+
+extern "C" int pf_check_totals(double* totals, int count, double eps, int* flags, void* stream) {
+  PF_REQUIRE(count > 0, "pf_check_totals: count=%d", count);
+  check_totals_kernel<<<ceil_div(count, 64), 64, 0, as_stream(stream)>>>(totals, count, eps, flags);
+  return check_launch("check_totals_kernel");
+}
+
+extern "C" int pf_noise_anneal(const double* sqrt_lim0, const double* sqrt_lim1,
+                               const int* iter_dev, int n_iter, int F, double* noise,
+                               void* stream) {
+  PF_REQUIRE(F > 0 && n_iter > 0, "pf_noise_anneal: F=%d n_iter=%d", F, n_iter);
+  noise_anneal_kernel<<<ceil_div(F, 256), 256, 0, as_stream(stream)>>>(sqrt_lim0, sqrt_lim1,
+                                                                      iter_dev, n_iter, F, noise);
+  return check_launch("noise_anneal_kernel");
+}
+
+extern "C" int pf_ll_reduce(const double* ll_f, int F, double* ll_sum, void* stream) {
+  PF_REQUIRE(F > 0, "pf_ll_reduce: F=%d", F);
+  ll_reduce_kernel<<<1, 256, 0, as_stream(stream)>>>(ll_f, F, ll_sum);
+  return check_launch("ll_reduce_kernel");
+}
+
+extern "C" int pf_ll_store(const double* ll_sum, double bins, double* logliks, int* iter_dev,
+                           int advance, void* stream) {
+  PF_REQUIRE(bins > 0, "pf_ll_store: bins=%g", bins);
+  ll_store_kernel<<<1, 32, 0, as_stream(stream)>>>(ll_sum, bins, logliks, iter_dev, advance);
+  return check_launch("ll_store_kernel");
+}
+
+extern "C" int pf_small_matmul(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                               int M, int K, int Nc, int dtype, void* stream) {
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_small_matmul: bad dtype %d", dtype);
+  PF_REQUIRE(M > 0 && K > 0 && Nc > 0, "pf_small_matmul: empty problem");
+  const int grid = ceil_div((long)M * Nc, 256);
+  if (dtype == PF_F32)
+    small_matmul_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+        (const float*)A, lda, (const float*)B, ldb, (float*)C, ldc, M, K, Nc);
+  else
+    small_matmul_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
+        (const double*)A, lda, (const double*)B, ldb, (double*)C, ldc, M, K, Nc);
+  return check_launch("small_matmul_kernel");
+}

@@ -1,0 +1,383 @@
+// K1 / K6 -- STFT front end and inverse STFT with overlap-add, sm_100a.
+//
+// Replaces the frame loops of pyfasst/tftransforms/stft.py (stft :3-69, istft :71-131)
+// and the per-channel transform calls of FASST.comp_transf_Cx (audioModel.py:266-302) /
+// FASST.separate_comps (audioModel.py:1188-1217).
+//
+// Forward: one CTA transforms a tile of TN consecutive frames of one channel.  Each
+// frame is framed (half a window of implicit zeros in front, zero fill behind,
+// stft.py:40-63), windowed, packed as nfft/2 complex samples, transformed by an in-place
+// radix-2 FFT in shared memory (float64) and unpacked to the nfft/2+1 bins of the real
+// transform.  The bins of the TN frames are staged in shared memory and written out as
+// full 32-byte sectors of the frame-contiguous planes X[2*ch+{0,1}][F][ld].
+//
+// Inverse: one CTA produces TN*hop output samples of one signal.  It walks the frames
+// overlapping its segment in ascending order (the reference's accumulation order,
+// stft.py:112-121), loading them in sector-sized groups, inverts each with the same FFT
+// and adds the synthesis-windowed samples into a shared-memory segment: overlap-add as a
+// gather, deterministic, no atomics.  The segment is then divided by the overlap-added
+// window product (stft.py:117-129) and optionally truncated to int16
+// (audioModel.py:1227-1229).
+#include "common.cuh"
+
+namespace pf {
+
+constexpr int FFT_THREADS = 256;
+
+__device__ __forceinline__ double2 cmul_d(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// in-place radix-2 decimation-in-time FFT of M points held bit-reversed in buf;
+// tw[k] = exp(-2 pi i k / (2M)), k < M.  All threads of the CTA take part.
+__device__ __forceinline__ void fft_inplace(double2* buf, const double2* __restrict__ tw, int M) {
+  for (int half = 1; half < M; half <<= 1) {
+    const int tstep = M / half;
+    for (int b = threadIdx.x; b < M / 2; b += FFT_THREADS) {
+      const int grp = b / half, pos = b - grp * half;
+      const int i0 = grp * 2 * half + pos, i1 = i0 + half;
+      const double2 w = __ldg(tw + pos * tstep);
+      const double2 t = cmul_d(w, buf[i1]);
+      const double2 u = buf[i0];
+      buf[i1] = make_double2(u.x - t.x, u.y - t.y);
+      buf[i0] = make_double2(u.x + t.x, u.y + t.y);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+struct Sector {  // elements of T in one 32-byte DRAM sector
+  static constexpr int N = 32 / sizeof(T);
+};
+
+// ---- forward ------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(FFT_THREADS)
+stft_kernel(const double* __restrict__ pcm, long L, const double* __restrict__ window, int wlen,
+            int hop, int nfft, int log2m, const double2* __restrict__ tw, T* __restrict__ X,
+            int F, long N, long ld) {
+  constexpr int TN = Sector<T>::N;
+  constexpr int ROW = 2 * TN + 1;  // padded staging row: (re[TN], im[TN]) per bin
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = nfft / 2;
+  double2* buf = reinterpret_cast<double2*>(smem_raw);
+  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)M * sizeof(double2));
+  const int ch = blockIdx.y;
+  const long n0 = (long)blockIdx.x * TN;
+  const double* x = pcm + (size_t)ch * L;
+
+  for (int t = 0; t < TN; ++t) {
+    const long n = n0 + t;
+    if (n >= N) {  // uniform per CTA
+      for (int k = threadIdx.x; k < F; k += FFT_THREADS) {
+        stage[k * ROW + t] = (T)0;
+        stage[k * ROW + TN + t] = (T)0;
+      }
+      continue;
+    }
+    // frame n covers samples n*hop - wlen/2 + i, i < wlen (stft.py:47-63)
+    const long base = n * hop - wlen / 2;
+    for (int m = threadIdx.x; m < M; m += FFT_THREADS) {
+      double v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * m + e;
+        const long s = base + i;
+        v[e] = (i < wlen && s >= 0 && s < L) ? x[s] * __ldg(window + i) : 0.0;
+      }
+      buf[__brev((unsigned)m) >> (32 - log2m)] = make_double2(v[0], v[1]);
+    }
+    __syncthreads();
+    fft_inplace(buf, tw, M);
+    // unpack: X[k] = Xe + W^k Xo, Xe = (Z[k]+conj Z[M-k])/2, Xo = -i (Z[k]-conj Z[M-k])/2
+    for (int k = threadIdx.x; k <= M; k += FFT_THREADS) {
+      const double2 a = buf[k & (M - 1)];
+      const double2 bq = buf[(M - k) & (M - 1)];
+      const double2 b = make_double2(bq.x, -bq.y);
+      const double2 xe = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+      const double2 d = make_double2(0.5 * (a.x - b.x), 0.5 * (a.y - b.y));
+      const double2 xo = make_double2(d.y, -d.x);  // -i * d
+      const double2 w = (k < M) ? __ldg(tw + k) : make_double2(-1.0, 0.0);
+      const double2 r = cmul_d(w, xo);
+      stage[k * ROW + t] = (T)(xe.x + r.x);
+      stage[k * ROW + TN + t] = (T)(xe.y + r.y);
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // write the tile: per (bin, re/im) one 32-byte sector
+  const size_t plane = (size_t)F * ld;
+  for (int i = threadIdx.x; i < F * 2 * TN; i += FFT_THREADS) {
+    const int t = i % TN;
+    const int c = (i / TN) & 1;
+    const int k = i / (2 * TN);
+    const long n = n0 + t;
+    if (n < ld) X[(size_t)(2 * ch + c) * plane + (size_t)k * ld + n] = stage[k * ROW + c * TN + t];
+  }
+}
+
+// psd_sum[f] = sum over planes and frames of X^2 (audioModel.py:304-319), fixed order
+template <typename T>
+__global__ void psd_sum_kernel(const T* __restrict__ X, int nplanes, int F, long N, long ld,
+                               double* __restrict__ out) {
+  const int f = blockIdx.x;
+  double acc = 0.0;
+  for (int p = 0; p < nplanes; ++p) {
+    const T* row = X + ((size_t)p * F + f) * ld;
+    for (long n = threadIdx.x; n < N; n += blockDim.x) {
+      const double v = (double)row[n];
+      acc += v * v;
+    }
+  }
+  __shared__ double s_red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) d += s_red[w];
+    out[f] = d;
+  }
+}
+
+// ---- inverse --------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(FFT_THREADS)
+istft_kernel(const T* __restrict__ Y, int F, long N, long ld, const double* __restrict__ synth,
+             const double* __restrict__ norm, int wlen, int hop, int nfft, int log2m,
+             const double2* __restrict__ tw, int seg_frames, double* __restrict__ out, long Lout,
+             int16_t* __restrict__ pcm, int nsig, double maxdata) {
+  constexpr int SG = Sector<T>::N;
+  constexpr int ROW = 2 * SG + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = nfft / 2;
+  const int seg_len = seg_frames * hop;
+  double2* buf = reinterpret_cast<double2*>(smem_raw);
+  double* seg = reinterpret_cast<double*>(smem_raw + (size_t)M * sizeof(double2));
+  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)M * sizeof(double2) +
+                                  (size_t)seg_len * sizeof(double));
+  const int sig = blockIdx.y;
+  const long tau0 = (long)blockIdx.x * seg_len;  // padded time of the first sample
+  const long tau1 = tau0 + seg_len;
+  // frames n with n*hop < tau1 and n*hop + wlen > tau0
+  long n_lo = (tau0 - wlen >= 0) ? (tau0 - wlen) / hop + 1 : 0;
+  long n_hi = (tau1 - 1) / hop;
+  if (n_hi > N - 1) n_hi = N - 1;
+  for (int i = threadIdx.x; i < seg_len; i += FFT_THREADS) seg[i] = 0.0;
+  const size_t plane = (size_t)F * ld;
+  const T* Yre = Y + (size_t)(2 * sig) * plane;
+  const T* Yim = Yre + plane;
+  const double invM = 1.0 / (double)M;
+
+  for (long g0 = (n_lo / SG) * SG; g0 <= n_hi; g0 += SG) {
+    __syncthreads();
+    // stage the group's bins: one sector per (bin, re/im)
+    for (int i = threadIdx.x; i < F * 2 * SG; i += FFT_THREADS) {
+      const int t = i % SG;
+      const int c = (i / SG) & 1;
+      const int k = i / (2 * SG);
+      const long n = g0 + t;
+      T v = (T)0;
+      if (n < N) v = (c ? Yim : Yre)[(size_t)k * ld + n];
+      stage[k * ROW + c * SG + t] = v;
+    }
+    __syncthreads();
+    for (int t = 0; t < SG; ++t) {
+      const long n = g0 + t;
+      if (n < n_lo || n > n_hi) continue;  // uniform per CTA
+      // pack: Z[k] = Xe + i Xo, Xe = (X[k]+conj X[M-k])/2, Xo = conj(W^k) (X[k]-conj X[M-k])/2;
+      // the imaginary parts of X[0] and X[M] are ignored like numpy's irfft does
+      for (int k = threadIdx.x; k < M; k += FFT_THREADS) {
+        double2 a = make_double2((double)stage[k * ROW + t], (double)stage[k * ROW + SG + t]);
+        double2 b = make_double2((double)stage[(M - k) * ROW + t],
+                                 -(double)stage[(M - k) * ROW + SG + t]);
+        if (k == 0) { a.y = 0.0; b.y = 0.0; }
+        const double2 xe = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+        const double2 d = make_double2(0.5 * (a.x - b.x), 0.5 * (a.y - b.y));
+        const double2 wq = __ldg(tw + k);
+        const double2 xo = cmul_d(make_double2(wq.x, -wq.y), d);
+        // Z = xe + i xo ; store conj(Z) so the forward FFT yields conj(IFFT) * M
+        buf[__brev((unsigned)k) >> (32 - log2m)] = make_double2(xe.x - xo.y, -(xe.y + xo.x));
+      }
+      __syncthreads();
+      fft_inplace(buf, tw, M);
+      // x[2m] = Re z[m], x[2m+1] = Im z[m], z = conj(buf)/M ; overlap-add (stft.py:112-116)
+      const long fr0 = n * hop;
+      for (int m = threadIdx.x; m < M; m += FFT_THREADS) {
+        const double2 z = buf[m];
+        const double xs[2] = {z.x * invM, -z.y * invM};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = 2 * m + e;
+          const long tau = fr0 + i;
+          if (i < wlen && tau >= tau0 && tau < tau1) seg[tau - tau0] += __ldg(synth + i) * xs[e];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < seg_len; i += FFT_THREADS) {
+    const long tau = tau0 + i;
+    const long tout = tau - wlen / 2;  // the first half window is dropped (stft.py:123)
+    if (tout < 0 || tout >= Lout) continue;
+    const double v = seg[i] / __ldg(norm + tau);
+    out[(size_t)sig * Lout + tout] = v;
+    if (pcm != nullptr) pcm[(size_t)tout * nsig + sig] = (int16_t)(int)(v * maxdata);
+  }
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// twiddle table exp(-2 pi i k / nfft), k < nfft/2, cached per nfft on the device
+struct TwiddleCache {
+  int nfft = 0;
+  int device = -1;
+  double2* ptr = nullptr;
+};
+static TwiddleCache g_tw[4];
+
+static const double2* twiddles(int nfft, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& c : g_tw)
+    if (c.nfft == nfft && c.device == dev) return c.ptr;
+  TwiddleCache* slot = nullptr;
+  for (auto& c : g_tw)
+    if (c.ptr == nullptr) { slot = &c; break; }
+  if (slot == nullptr) {
+    slot = &g_tw[0];
+    cudaFree(slot->ptr);
+    slot->ptr = nullptr;
+  }
+  const int M = nfft / 2;
+  double2* host = (double2*)malloc(sizeof(double2) * M);
+  for (int k = 0; k < M; ++k) {
+    const double ang = -2.0 * 3.14159265358979323846 * (double)k / (double)nfft;
+    host[k] = make_double2(cos(ang), sin(ang));
+  }
+  if (cudaMalloc(&slot->ptr, sizeof(double2) * M) != cudaSuccess) {
+    free(host);
+    slot->ptr = nullptr;
+    return nullptr;
+  }
+  // synchronous copy: the table must be complete before host memory is released
+  cudaMemcpy(slot->ptr, host, sizeof(double2) * M, cudaMemcpyHostToDevice);
+  free(host);
+  slot->nfft = nfft;
+  slot->device = dev;
+  (void)st;
+  return slot->ptr;
+}
+
+template <typename T>
+static int launch_stft(const double* pcm, int nch, long L, const double* window, int wlen, int hop,
+                       int nfft, void* X, long N, long ld, double* psd_sum, cudaStream_t st) {
+  constexpr int TN = Sector<T>::N;
+  const int M = nfft / 2, F = M + 1;
+  const double2* tw = twiddles(nfft, st);
+  if (tw == nullptr) {
+    set_error("pf_stft: cannot allocate the twiddle table");
+    return PF_ERR_CUDA;
+  }
+  const size_t smem = (size_t)M * sizeof(double2) + (size_t)F * (2 * TN + 1) * sizeof(T);
+  cudaError_t e = cudaFuncSetAttribute(stft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) {
+    set_error("pf_stft: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  dim3 grid(ceil_div(N, TN), nch);
+  stft_kernel<T><<<grid, FFT_THREADS, smem, st>>>(pcm, L, window, wlen, hop, nfft, ilog2(M), tw,
+                                                 (T*)X, F, N, ld);
+  int rc = check_launch("stft_kernel");
+  if (rc) return rc;
+  if (psd_sum != nullptr) {
+    psd_sum_kernel<T><<<F, 256, 0, st>>>((const T*)X, 2 * nch, F, N, ld, psd_sum);
+    rc = check_launch("psd_sum_kernel");
+  }
+  return rc;
+}
+
+template <typename T>
+static int launch_istft(const void* Y, int nsig, int F, long N, long ld, const double* synth,
+                        const double* norm, int wlen, int hop, int nfft, double* out, long Lout,
+                        int16_t* pcm, double maxdata, cudaStream_t st) {
+  constexpr int SG = Sector<T>::N;
+  const int M = nfft / 2;
+  const double2* tw = twiddles(nfft, st);
+  if (tw == nullptr) {
+    set_error("pf_istft: cannot allocate the twiddle table");
+    return PF_ERR_CUDA;
+  }
+  // segment of ~16 frames: 16/(16 + wlen/hop - 1) of the inverse FFTs are not redundant
+  int seg_frames = 16;
+  const size_t fixed = (size_t)M * sizeof(double2) + (size_t)F * (2 * SG + 1) * sizeof(T);
+  while (seg_frames > 1 && fixed + (size_t)seg_frames * hop * sizeof(double) > 200 * 1024)
+    seg_frames /= 2;
+  const size_t smem = fixed + (size_t)seg_frames * hop * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(istft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) {
+    set_error("pf_istft: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  const long total = (N - 1) * hop + wlen;
+  dim3 grid(ceil_div(total, (long)seg_frames * hop), nsig);
+  istft_kernel<T><<<grid, FFT_THREADS, smem, st>>>((const T*)Y, F, N, ld, synth, norm, wlen, hop,
+                                                  nfft, ilog2(M), tw, seg_frames, out, Lout, pcm,
+                                                  nsig, maxdata);
+  return check_launch("istft_kernel");
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+static int check_fft_args(const char* who, int wlen, int hop, int nfft) {
+  PF_REQUIRE(nfft >= 16 && nfft <= 4096 && (nfft & (nfft - 1)) == 0,
+             "%s: nfft=%d must be a power of two in [16, 4096]", who, nfft);
+  PF_REQUIRE(wlen >= 2 && wlen <= nfft && wlen % 2 == 0, "%s: wlen=%d (nfft=%d)", who, wlen, nfft);
+  PF_REQUIRE(hop >= 1 && hop <= wlen, "%s: hop=%d (wlen=%d)", who, hop, wlen);
+  return PF_OK;
+}
+
+extern "C" int pf_stft(const double* pcm, int nch, int64_t L, const double* window, int wlen,
+                       int hop, int nfft, void* X, int64_t N, int64_t ld, double* psd_sum,
+                       int dtype, void* stream) {
+  int rc = check_fft_args("pf_stft", wlen, hop, nfft);
+  if (rc) return rc;
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_stft: bad dtype %d", dtype);
+  PF_REQUIRE(nch >= 1 && nch <= 16 && L > 0, "pf_stft: nch=%d L=%ld", nch, (long)L);
+  PF_REQUIRE(N == (L + hop - 1) / hop + 2, "pf_stft: N=%ld is not ceil(L/hop)+2 (stft.py:40)",
+             (long)N);
+  PF_REQUIRE(ld >= N && ld % 4 == 0, "pf_stft: ld=%ld must be >= N and a multiple of 4", (long)ld);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == PF_F32)
+    return launch_stft<float>(pcm, nch, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+  return launch_stft<double>(pcm, nch, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+}
+
+extern "C" int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld,
+                        const double* synth, const double* norm, int wlen, int hop, int nfft,
+                        double* out, int64_t Lout, int16_t* pcm, double maxdata, int dtype,
+                        void* stream) {
+  int rc = check_fft_args("pf_istft", wlen, hop, nfft);
+  if (rc) return rc;
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_istft: bad dtype %d", dtype);
+  PF_REQUIRE(F == nfft / 2 + 1, "pf_istft: F=%d != nfft/2+1", F);
+  PF_REQUIRE(nsig >= 1 && nsig <= 65535 && N >= 1 && Lout >= 1, "pf_istft: nsig=%d N=%ld", nsig,
+             (long)N);
+  PF_REQUIRE(ld >= N && ld % 4 == 0, "pf_istft: ld=%ld must be >= N and a multiple of 4", (long)ld);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == PF_F32)
+    return launch_istft<float>(Y, nsig, F, N, ld, synth, norm, wlen, hop, nfft, out, Lout, pcm,
+                               maxdata, st);
+  return launch_istft<double>(Y, nsig, F, N, ld, synth, norm, wlen, hop, nfft, out, Lout, pcm,
+                              maxdata, st);
+}

@@ -1,0 +1,458 @@
+"""Device-resident GEM engine: orchestrates the sm_100a kernels of one FASST model.
+
+This is the host side of the hot path: it mirrors the control flow of
+FASST.estim_param_a_post_model / GEM_iteration / update_spectral_components /
+renormalize_parameters (ref: pyfasst/audioModel.py:330-428, :1469-1727, :1980-2040)
+but every array lives in HBM and every numerical step is a kernel of the C ABI
+(include/pyfasst_b200.h).  One iteration enqueues ~40 kernels on the current
+stream and never synchronises with the host (the iteration counter, the annealed
+noise PSD and the log-likelihood trace live on the device), so the whole loop can
+be captured in a CUDA graph.
+
+Frequency sharding (one process per GPU): each rank owns the rows
+[f_lo, f_hi) of X, V, hat_W, FB, A and the noise PSD; TW (and FW) are replicated.
+The E-step, the FB update and the convolutive mixing update are local; per
+iteration the ranks all-reduce the TW numerators/denominators [S,2,K,N], the
+scalar log-likelihood, the instantaneous-mixing statistics, the spatial energies
+(SUM) and the FB column maxima (MAX) -- see `Comm`.
+
+Supported model structure (what MultiChanNMFInst_FASST / MultiChanNMFConv build,
+audioModel.py:2349-2393, :2488-2508): stereo; one spectral component per spatial
+component, one factor each with FB [F,Kb], FW [Kb,Kw] (fixed), TW [Kw,N] 'NMF'
+constrained, TB empty; FB / TW / mixing parameters individually 'free' or 'fixed';
+all spatial components instantaneous, or all convolutive and free (Q7).  Anything
+else raises NotImplementedError -- there is no CPU fallback.
+"""
+import numpy as np
+
+EPS = 1e-10  # ref: audioModel.py:61
+
+
+class Comm(object):
+    """Collectives of the frequency-sharded GEM loop over torch.distributed."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def allreduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def allreduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+
+    def allgather(self, t):
+        out = [t.new_empty(t.shape) for _ in range(self.world)]
+        self.dist.all_gather(out, t.contiguous(), group=self.group)
+        return out
+
+
+def shard_bounds(F, world):
+    """Contiguous frequency shards, sizes differing by at most one (1025 = 129 + 7*128)."""
+    base, extra = divmod(F, world)
+    lo = [r * base + min(r, extra) for r in range(world)]
+    return [(lo[r], lo[r] + base + (1 if r < extra else 0)) for r in range(world)]
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class GemEngine(object):
+    def __init__(self, kernels, F_total, N, dtype="float32", comm=None, f_range=None):
+        import torch
+        self.torch = torch
+        self.k = kernels
+        self.dev = kernels.device
+        self.tdtype = {"float32": torch.float32, "float64": torch.float64}[dtype]
+        self.F_total = int(F_total)
+        self.N = int(N)
+        self.ld = _round_up(self.N, 32)
+        self.comm = comm
+        if f_range is None:
+            if comm is not None and comm.world > 1:
+                f_range = shard_bounds(self.F_total, comm.world)[comm.rank]
+            else:
+                f_range = (0, self.F_total)
+        self.f_lo, self.f_hi = f_range
+        self.F = self.f_hi - self.f_lo
+        if self.F <= 0:
+            raise ValueError("empty frequency shard %r" % (f_range,))
+        self.X = None
+        self.J = 0
+        self.n_iter_done = 0
+
+    # ------------------------------------------------------------------ allocation
+    def _zeros(self, shape, dtype=None):
+        return self.torch.zeros(shape, dtype=dtype or self.tdtype, device=self.dev)
+
+    def _upload(self, arr, dtype=None):
+        """Host array -> new device tensor (always a copy, never an alias of `arr`)."""
+        t = self.torch.tensor(np.asarray(arr))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.dev).contiguous()
+
+    def _f64(self, arr):
+        return self._upload(np.asarray(arr, dtype=np.float64))
+
+    def _sharded(self):
+        return self.comm is not None and self.comm.world > 1
+
+    # ------------------------------------------------------------------ inputs
+    def set_X_planes(self, X):
+        """X: device planes [4, F_local, ld] (re0, im0, re1, im1) of dtype self.tdtype."""
+        assert tuple(X.shape) == (4, self.F, self.ld) and X.dtype == self.tdtype
+        self.X = X
+
+    def set_X_host(self, Xc):
+        """Xc: complex [2, F_total, N] host array (e.g. an STFT computed elsewhere)."""
+        Xc = np.asarray(Xc)[:, self.f_lo:self.f_hi]
+        planes = np.zeros([4, self.F, self.ld])
+        planes[0, :, :self.N], planes[1, :, :self.N] = Xc[0].real, Xc[0].imag
+        planes[2, :, :self.N], planes[3, :, :self.N] = Xc[1].real, Xc[1].imag
+        self.X = self._upload(planes, self.tdtype)
+
+    def set_noise(self, sim_ann_opt, lim0, lim1, psd):
+        """Mirrors the noise handling of estim_param_a_post_model (audioModel.py:355-373)."""
+        sl = slice(self.f_lo, self.f_hi)
+        self.sim_ann_opt = sim_ann_opt
+        self.anneal = sim_ann_opt in ("ann", "ann_ns_inj")
+        self.sqrt0 = self._f64(np.sqrt(np.asarray(lim0, dtype=np.float64)[sl]))
+        self.sqrt1 = self._f64(np.sqrt(np.asarray(lim1, dtype=np.float64)[sl]))
+        if sim_ann_opt == "ann":
+            psd0 = np.asarray(lim0, dtype=np.float64)
+        elif sim_ann_opt == "no_ann":
+            psd0 = np.asarray(lim1, dtype=np.float64)
+        else:
+            psd0 = np.asarray(psd, dtype=np.float64)
+        self.noise = self._f64(np.broadcast_to(psd0, (self.F_total,))[sl])
+
+    def set_model(self, spat_comps, spec_comps, nmfUpdateCoeff=1.0):
+        """Validates the structure and uploads the parameters (host dicts -> HBM)."""
+        torch = self.torch
+        J = len(spat_comps)
+        if sorted(spat_comps.keys()) != list(range(J)):
+            raise ValueError("spat_comps keys must be 0..J-1")
+        mix_types = [spat_comps[j]["mix_type"] for j in range(J)]
+        self.free_A = [spat_comps[j]["frdm_prior"] == "free" for j in range(J)]
+        if all(m == "inst" for m in mix_types):
+            self.mix_type = "inst"
+        elif all(m == "conv" for m in mix_types):
+            self.mix_type = "conv"
+            if any(self.free_A) and not all(self.free_A):
+                raise NotImplementedError(
+                    "convolutive mixing with fixed components: the reference solves with the "
+                    "full hat_Rss (audioModel.py:857) and cannot run this either")
+        else:
+            raise NotImplementedError("mixed instantaneous / convolutive spatial components")
+        # sub-source layout (retrieve_subsrc_params, audioModel.py:541-556)
+        self.ranks, self.src_of_sub = [], []
+        for j in range(J):
+            p = np.asarray(spat_comps[j]["params"])
+            r = p.shape[1] if mix_types[j] == "inst" else p.shape[0]
+            nc = p.shape[0] if mix_types[j] == "inst" else p.shape[1]
+            if nc != 2:
+                raise AttributeError("Nb channels %d not implemented yet" % nc)
+            start = len(self.src_of_sub)
+            self.ranks.append(list(range(start, start + r)))
+            self.src_of_sub.extend([j] * r)
+        R = len(self.src_of_sub)
+        A = np.zeros([R, 2, self.F], dtype=np.complex128)
+        for j in range(J):
+            p = np.asarray(spat_comps[j]["params"])
+            if mix_types[j] == "inst":
+                A[self.ranks[j]] = p.T[:, :, None]
+            else:
+                if p.shape[2] != self.F_total:
+                    raise ValueError("convolutive params must be [rank, 2, F]")
+                A[self.ranks[j]] = p[:, :, self.f_lo:self.f_hi]
+        self.J, self.R = J, R
+        self.A = self._upload(A)
+        # spectral components: one per spatial component, single NMF factor
+        S = len(spec_comps)
+        if sorted(spec_comps.keys()) != list(range(S)):
+            raise ValueError("spec_comps keys must be 0..S-1")
+        owner = [spec_comps[s]["spat_comp_ind"] for s in range(S)]
+        if sorted(owner) != list(range(J)):
+            raise NotImplementedError(
+                "the device GEM path needs exactly one spectral component per spatial component")
+        self.spec = []
+        for s in range(S):
+            facs = spec_comps[s]["factor"]
+            if len(facs) != 1:
+                raise NotImplementedError("multi-factor spectral components (source/filter "
+                                          "models) are not on the device path yet")
+            fac = facs[list(facs.keys())[0]]
+            if len(fac["TB"]):
+                raise NotImplementedError("time-blob factors (TB) are not on the device path yet")
+            if fac.get("TW_constr", "NMF") != "NMF":
+                raise NotImplementedError("discrete-state TW constraints (GMM/HMM)")
+            if fac["FW_frdm_prior"] == "free":
+                raise NotImplementedError("free FW update is not on the device path yet")
+            FB = np.asarray(fac["FB"], dtype=np.float64)
+            FW = np.asarray(fac["FW"], dtype=np.float64)
+            TW = np.asarray(fac["TW"], dtype=np.float64)
+            if FB.shape[0] != self.F_total or TW.shape[1] != self.N or \
+                    FW.shape != (FB.shape[1], TW.shape[0]):
+                raise ValueError("inconsistent factor shapes FB%s FW%s TW%s"
+                                 % (FB.shape, FW.shape, TW.shape))
+            Kb, Kw = FW.shape
+            TWp = np.zeros([Kw, self.ld])
+            TWp[:, :self.N] = TW
+            ent = {
+                "j": owner[s], "Kb": Kb, "Kw": Kw,
+                "FB_free": fac["FB_frdm_prior"] == "free",
+                "TW_free": fac["TW_frdm_prior"] == "free",
+                "FB": self._upload(FB[self.f_lo:self.f_hi], self.tdtype),
+                "FW": self._upload(FW, self.tdtype),
+                "TW": self._upload(TWp, self.tdtype),
+                "W": self._zeros([self.F, Kw]),
+                "G": self._zeros([Kb, self.ld]),
+            }
+            self.spec.append(ent)
+        self.omega = float(nmfUpdateCoeff)
+        self._alloc_work()
+
+    def _alloc_work(self):
+        torch, k = self.torch, self.k
+        F, ld, J, R, N = self.F, self.ld, self.J, self.R, self.N
+        f64, c128 = torch.float64, torch.complex128
+        self.V = self._zeros([J, F, ld])
+        self.hatW = self._zeros([J, F, ld])
+        self.Rss = self._zeros([F, R, R], c128)
+        self.Rxs = self._zeros([F, 2, R], c128)
+        self.ll_f = self._zeros([F], f64)
+        self.ll_sum = self._zeros([1], f64)
+        self.flags = self._zeros([1], torch.int32)
+        self.iter_dev = self._zeros([1], torch.int32)
+        code = k.dtype_code(self.V)
+        nbytes = k.estep_workspace_bytes(J, F, N, code)
+        self.ws = self._zeros([(nbytes + 7) // 8], f64)
+        self.stats = self._zeros([2 * R + R * R], f64)
+        self.sums = self._zeros([J], f64)
+        counts = np.array([len(self.ranks[j]) * 2 * self.F_total for j in range(J)], dtype=np.float64)
+        self.counts = self._f64(counts)
+        Kmax = max(max(e["Kb"], e["Kw"]) for e in self.spec)
+        S = len(self.spec)
+        self.colmax = self._zeros([S, Kmax], f64)
+        self.wcol = self._zeros([S, Kmax], f64)
+        self.w2 = self._zeros([S, Kmax], f64)
+        self.totals = self._zeros([S], f64)
+        # FB update partial sums (one buffer, reused per component)
+        self.fb_plan, fb_size = {}, 0
+        for e in self.spec:
+            chunk, nsplit = k.fb_plan(F, e["Kb"], N, code)
+            self.fb_plan[id(e)] = (chunk, nsplit)
+            fb_size = max(fb_size, nsplit * F * e["Kb"])
+        self.fb_part = self._zeros([2, fb_size], f64)
+        self.fb_nd = self._zeros([2, F * Kmax], f64)
+        # TW update partial sums; the reduced num/den of all components share one
+        # buffer so that a single all-reduce serves the whole iteration
+        self.tw_plan, tw_size = {}, 0
+        for e in self.spec:
+            fchunk, fsplit = k.tw_plan(F, e["Kw"], N)
+            self.tw_plan[id(e)] = (fchunk, fsplit)
+            tw_size = max(tw_size, fsplit * e["Kw"] * ld)
+        self.tw_part = self._zeros([2, tw_size], f64)
+        self.tw_nd = self._zeros([S, 2, Kmax, ld], f64)
+
+    # ------------------------------------------------------------------ pieces
+    def compute_powers(self, with_G=True):
+        """W = FB FW, V_j = W H (comp_spat_comp_power, audioModel.py:430-498), G = FW H."""
+        k = self.k
+        for e in self.spec:
+            k.small_matmul(e["FB"], e["FW"], e["W"])
+            k.spec_power(e["W"], e["TW"], self.V[e["j"]], self.N, False)
+            if with_G and e["FB_free"]:
+                k.spec_power(e["FW"], e["TW"], e["G"], self.N, False)
+
+    def estep(self):
+        """compute_suff_stat (audioModel.py:580-764) on the current parameters."""
+        self.k.estep_stereo(self.X, self.V, self.A, self.src_of_sub, self.noise, self.N,
+                            self.hatW, self.Rss, self.Rxs, self.ll_f, self.ws)
+
+    def update_mix(self):
+        """update_mix_matrix (audioModel.py:766-889)."""
+        k = self.k
+        if not any(self.free_A):
+            return
+        if self.mix_type == "inst":
+            upd = [r for j in range(self.J) if self.free_A[j] for r in self.ranks[j]]
+            oth = [r for j in range(self.J) if not self.free_A[j] for r in self.ranks[j]]
+            n = 2 * len(upd) + len(upd) ** 2
+            stats = self.stats[:n]
+            k.mix_inst_stats(self.Rss, self.Rxs, self.A, upd, oth, stats)
+            if self._sharded():
+                self.comm.allreduce_sum(stats)
+            k.mix_inst_solve(stats, self.F_total, upd, self.A, self.flags)
+        else:
+            k.mix_conv_solve(self.Rss, self.Rxs, self.A, self.flags)
+
+    def update_spectral(self):
+        """NMF branch of update_spectral_components (audioModel.py:1509-1727): for every
+        component FB (frames contracted, local rows) then TW (frequencies contracted,
+        all-reduced under sharding).  V_j still holds the pre-update power: it is both
+        `comp_spat_comp_power(spat_ind)` of the FB update (Q3) and the stale
+        `other_fact_power` (Q1/Q2)."""
+        k, N, F = self.k, self.N, self.F
+        any_tw = False
+        for s, e in enumerate(self.spec):
+            j = e["j"]
+            if e["FB_free"]:
+                chunk, nsplit = self.fb_plan[id(e)]
+                cnt = F * e["Kb"]
+                pn = self.fb_part[0, :nsplit * cnt].view(nsplit, F, e["Kb"])
+                pd = self.fb_part[1, :nsplit * cnt].view(nsplit, F, e["Kb"])
+                k.fb_contract(self.hatW[j], self.V[j], self.V[j], e["G"], N, pn, pd, chunk, nsplit)
+                num = self.fb_nd[0, :cnt].view(F, e["Kb"])
+                den = self.fb_nd[1, :cnt].view(F, e["Kb"])
+                k.sum_splits(pn, num)
+                k.sum_splits(pd, den)
+                k.mult_update(e["FB"], num, den, F, e["Kb"], self.omega)
+                k.small_matmul(e["FB"], e["FW"], e["W"])
+            if e["TW_free"]:
+                any_tw = True
+                fchunk, fsplit = self.tw_plan[id(e)]
+                cnt = e["Kw"] * self.ld
+                pn = self.tw_part[0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+                pd = self.tw_part[1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+                k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit)
+                k.sum_splits(pn, self.tw_nd[s, 0, :e["Kw"]])
+                k.sum_splits(pd, self.tw_nd[s, 1, :e["Kw"]])
+        if any_tw and self._sharded():
+            self.comm.allreduce_sum(self.tw_nd)
+        for s, e in enumerate(self.spec):
+            if e["TW_free"]:
+                k.mult_update(e["TW"], self.tw_nd[s, 0], self.tw_nd[s, 1], e["Kw"], N, self.omega)
+
+    def renormalize(self):
+        """renormalize_parameters (audioModel.py:1980-2040)."""
+        k = self.k
+        k.spat_energy(self.A, self.src_of_sub, self.J, self.sums)
+        if self._sharded():
+            self.comm.allreduce_sum(self.sums)
+        k.spat_scale(self.A, self.src_of_sub, self.sums, self.counts)
+        for s, e in enumerate(self.spec):
+            k.fb_scale_colmax(e["FB"], self.sums, self.counts, e["j"], self.colmax[s])
+        if self._sharded():
+            self.comm.allreduce_max(self.colmax)
+        for s, e in enumerate(self.spec):
+            k.fw_renorm(e["FW"], self.colmax[s], self.wcol[s], self.w2[s])
+            k.scale_matrix(e["FB"], self.F, e["Kb"], self.wcol[s], False, True)
+            k.scale_matrix(e["TW"], e["Kw"], self.N, self.w2[s], True, False, self.totals[s:s + 1])
+        k.check_totals(self.totals, EPS, self.flags)
+
+    def gem_iteration(self, n_iter_total, logliks):
+        """One GEM iteration (audioModel.py:364-376, :384-428), fully stream-ordered."""
+        k = self.k
+        if self.anneal:
+            k.noise_anneal(self.sqrt0, self.sqrt1, self.iter_dev, n_iter_total, self.noise)
+        self.compute_powers()
+        self.estep()
+        k.ll_reduce(self.ll_f, self.ll_sum)
+        if self._sharded():
+            self.comm.allreduce_sum(self.ll_sum)
+        k.ll_store(self.ll_sum, float(self.F_total) * self.N, logliks, self.iter_dev, True)
+        self.update_mix()
+        self.update_spectral()
+        self.renormalize()
+
+    # ------------------------------------------------------------------ drivers
+    def run(self, n_iter, use_graph=False):
+        """estim_param_a_post_model: n_iter GEM iterations; returns logliks (host)."""
+        torch = self.torch
+        logliks = torch.ones([max(n_iter, 1)], dtype=torch.float64, device=self.dev)
+        self.iter_dev.zero_()
+        self.flags.zero_()
+        self.totals.fill_(1.0)
+        if use_graph and n_iter > 1 and self.dev.type == "cuda":
+            self._run_graph(n_iter, logliks)
+        else:
+            for _ in range(n_iter):
+                self.gem_iteration(n_iter, logliks)
+        self.n_iter_done = n_iter
+        self.check_flags()
+        return logliks[:n_iter].cpu().numpy()
+
+    def _run_graph(self, n_iter, logliks):
+        torch = self.torch
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.gem_iteration(n_iter, logliks)  # warm-up iteration, also iteration 0
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.gem_iteration(n_iter, logliks)
+        for _ in range(n_iter - 1):
+            graph.replay()
+
+    def check_flags(self):
+        flags = int(self.flags.cpu().item())
+        if flags & 1:
+            raise np.linalg.LinAlgError("Singular Matrix")
+        if flags & 2:
+            import warnings
+            warnings.warn("sum(TW) fell below eps for a component: the reference would "
+                          "re-draw TW at random here (audioModel.py:2023-2025)")
+
+    def suff_stat(self):
+        """One E-step on the current parameters; returns host arrays shaped like the
+        reference's compute_suff_stat outputs (local frequency rows)."""
+        self.compute_powers(with_G=False)
+        self.estep()
+        self.k.ll_reduce(self.ll_f, self.ll_sum)
+        if self._sharded():
+            self.comm.allreduce_sum(self.ll_sum)
+        ll = -float(self.ll_sum.cpu().item()) / (float(self.F_total) * self.N)
+        hat_Rxs = self.Rxs.cpu().numpy()
+        hat_Rss = self.Rss.cpu().numpy()
+        hat_W = self.hatW[:, :, :self.N].to(self.torch.float64).cpu().numpy()
+        return hat_Rxs, hat_Rss, hat_W, ll
+
+    # ------------------------------------------------------------------ outputs
+    def _gather_f(self, t, axis):
+        """Host array of a frequency-sharded tensor, concatenated over ranks."""
+        if not self._sharded():
+            return t.cpu().numpy()
+        shards = shard_bounds(self.F_total, self.comm.world)
+        fmax = max(hi - lo for lo, hi in shards)
+        t = t.movedim(axis, 0)
+        pad = t.new_zeros((fmax,) + tuple(t.shape[1:]))
+        pad[:t.shape[0]] = t
+        parts = self.comm.allgather(pad)
+        full = self.torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, shards)], dim=0)
+        return full.movedim(0, axis).cpu().numpy()
+
+    def read_model(self, spat_comps, spec_comps):
+        """Writes the device parameters back into the user-visible dicts."""
+        A = self._gather_f(self.A, 2)
+        for j in range(self.J):
+            if self.mix_type == "inst":
+                # Q6: complex dtype after the update (audioModel.py:878-882)
+                spat_comps[j]["params"] = np.ascontiguousarray(A[self.ranks[j], :, 0].T)
+            else:
+                spat_comps[j]["params"] = np.ascontiguousarray(A[self.ranks[j]])
+        for s, e in enumerate(self.spec):
+            fac = spec_comps[s]["factor"]
+            fac = fac[list(fac.keys())[0]]
+            fac["FB"] = self._gather_f(e["FB"], 0).astype(np.float64)
+            fac["FW"] = e["FW"].cpu().numpy().astype(np.float64)
+            fac["TW"] = e["TW"][:, :self.N].cpu().numpy().astype(np.float64)
+
+    def noise_psd(self):
+        return self._gather_f(self.noise, 0)
+
+    def wiener(self, group_of_src, ngroups):
+        """Wiener-filtered STFTs Y[g] = Sigma_g Sigma_x^-1 x as planes [ngroups*4, F, ld]
+        (compute_sigma_comp_2d / compute_inv_sigma_mix_2d / compute_Wiener_gain_2d,
+        audioModel.py:1327-1467, with the last iteration's noise PSD, :1385)."""
+        self.compute_powers(with_G=False)
+        Y = self._zeros([ngroups * 4, self.F, self.ld])
+        self.k.wiener_stereo(self.X, self.V, self.A, self.src_of_sub, self.noise, group_of_src,
+                             ngroups, self.N, Y, self.ws)
+        return Y

@@ -1,0 +1,350 @@
+"""NumPy stand-ins for the kernels of the C ABI (TEST INFRASTRUCTURE ONLY).
+
+`FakeKernels` has the method surface of pyfasst_b200._lib.CudaKernels but works on
+torch CPU tensors with NumPy.  Each method is the *specification* of the CUDA kernel of
+the same name: the `-m gpu` tests compare every CUDA kernel with its stand-in, and the
+CPU tests run the GEM engine's orchestration (pyfasst_b200/engine.py) on the stand-ins
+and compare the result with the oracle / the reference's golden vectors -- so the host
+logic is verified without a GPU.  The product never imports this file: GemEngine is
+always constructed with CudaKernels outside tests/.
+
+Plane arithmetic is done in the dtype of the plane tensors (float32 or float64) and
+reductions in float64, like the kernels.
+"""
+import numpy as np
+import torch
+
+EPS = 1e-10
+
+
+def _np(t):
+    return t.numpy() if t is not None else None
+
+
+class FakeKernels(object):
+    name = "fake"
+
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.launches = 0
+
+    def dtype_code(self, t):
+        return {torch.float32: 0, torch.float64: 1}[t.dtype]
+
+    def launch_count(self):
+        return self.launches
+
+    # ---- K1 / K6 -------------------------------------------------------------------
+    def stft(self, pcm, window, hop, nfft, X, N, psd_sum):
+        self.launches += 1
+        x, w = _np(pcm), _np(window)
+        nch, L = x.shape
+        wlen = w.size
+        Xo = _np(X)
+        Xo[:] = 0
+        for c in range(nch):
+            buf = np.zeros((N - 1) * hop + wlen + nfft)
+            buf[wlen // 2: wlen // 2 + L] = x[c]
+            idx = hop * np.arange(N)[:, None] + np.arange(wlen)[None, :]
+            S = np.fft.rfft(w[None, :] * buf[idx], nfft, axis=1).T
+            Xo[2 * c, :, :N] = S.real
+            Xo[2 * c + 1, :, :N] = S.imag
+        if psd_sum is not None:
+            _np(psd_sum)[:] = (Xo[:, :, :N].astype(np.float64) ** 2).sum(axis=(0, 2))
+
+    def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata):
+        self.launches += 1
+        Yn, ws, nrm = _np(Y), _np(synth), _np(norm)
+        nsig = Yn.shape[0] // 2
+        wlen = ws.size
+        total = (N - 1) * hop + wlen
+        o = _np(out)
+        Lout = o.shape[1]
+        for s in range(nsig):
+            S = Yn[2 * s, :, :N].astype(np.float64) + 1j * Yn[2 * s + 1, :, :N].astype(np.float64)
+            frames = np.fft.irfft(S.T, nfft, axis=1)[:, :wlen] * ws[None, :]
+            data = np.zeros(total)
+            for n in range(N):
+                data[n * hop:n * hop + wlen] += frames[n]
+            data = (data / nrm)[wlen // 2:]
+            m = min(Lout, data.size)
+            o[s, :m] = data[:m]
+        if pcm is not None:
+            _np(pcm)[:] = np.int16(o.T * maxdata)
+
+    def _spat(self, A, src_of_sub, J):
+        """R_j = sum_r a_r a_r^H per frequency: [J, F] arrays r00, r11, r01."""
+        A = _np(A)
+        F = A.shape[2]
+        r00, r11 = np.zeros([J, F]), np.zeros([J, F])
+        r01 = np.zeros([J, F], dtype=complex)
+        for r, j in enumerate(src_of_sub):
+            r00[j] += np.abs(A[r, 0]) ** 2
+            r11[j] += np.abs(A[r, 1]) ** 2
+            r01[j] += A[r, 0] * np.conj(A[r, 1])
+        return r00, r11, r01
+
+    def _sigma_inv_y(self, X, V, A, src_of_sub, noise, N):
+        J = V.shape[0]
+        t = {torch.float32: np.float32, torch.float64: np.float64}[V.dtype]
+        r00, r11, r01 = self._spat(A, src_of_sub, J)
+        Xn, Vn = _np(X)[:, :, :N], _np(V)[:, :, :N]
+        s2 = _np(noise).astype(t)[:, None]
+        col = lambda a: a.astype(t)[:, None]
+        s00 = s2 + sum(Vn[j] * col(r00[j]) for j in range(J))
+        s11 = s2 + sum(Vn[j] * col(r11[j]) for j in range(J))
+        s01r = sum(Vn[j] * col(r01[j].real) for j in range(J))
+        s01i = sum(Vn[j] * col(r01[j].imag) for j in range(J))
+        det = s2 * (s00 + (s11 - s2))
+        for j in range(J):
+            for k in range(j, J):
+                if j == k:
+                    d = r00[j] * r11[j] - np.abs(r01[j]) ** 2
+                else:
+                    d = r00[j] * r11[k] + r11[j] * r00[k] - 2 * np.real(r01[j] * np.conj(r01[k]))
+                det = det + Vn[j] * Vn[k] * col(np.maximum(d, 0.0))
+        det = np.maximum(det, t(EPS))
+        idet = t(1) / det
+        i00, i11, i01r, i01i = s11 * idet, s00 * idet, -s01r * idet, -s01i * idet
+        x0r, x0i, x1r, x1i = Xn
+        y0r = i00 * x0r + i01r * x1r - i01i * x1i
+        y0i = i00 * x0i + i01r * x1i + i01i * x1r
+        y1r = i01r * x0r + i01i * x0i + i11 * x1r
+        y1i = i01r * x0i - i01i * x0r + i11 * x1i
+        return (r00, r11, r01), det, (i00, i11, i01r, i01i), (y0r, y0i, y1r, y1i), col
+
+    def wiener_stereo(self, X, V, A, src_of_sub, noise, group_of_src, ngroups, N, Y, workspace):
+        self.launches += 2
+        J = V.shape[0]
+        (r00, r11, r01), det, inv, (y0r, y0i, y1r, y1i), col = self._sigma_inv_y(
+            X, V, A, src_of_sub, noise, N)
+        Vn, Yn = _np(V)[:, :, :N], _np(Y)
+        Yn[:] = 0
+        for g in range(ngroups):
+            g00 = sum(Vn[j] * col(r00[j]) for j in range(J) if group_of_src[j] == g)
+            g11 = sum(Vn[j] * col(r11[j]) for j in range(J) if group_of_src[j] == g)
+            g01r = sum(Vn[j] * col(r01[j].real) for j in range(J) if group_of_src[j] == g)
+            g01i = sum(Vn[j] * col(r01[j].imag) for j in range(J) if group_of_src[j] == g)
+            Yn[4 * g + 0, :, :N] = g00 * y0r + g01r * y1r - g01i * y1i
+            Yn[4 * g + 1, :, :N] = g00 * y0i + g01r * y1i + g01i * y1r
+            Yn[4 * g + 2, :, :N] = g01r * y0r + g01i * y0i + g11 * y1r
+            Yn[4 * g + 3, :, :N] = g01r * y0i - g01i * y0r + g11 * y1i
+
+    # ---- K2 ---------------------------------------------------------------------------
+    def estep_workspace_bytes(self, J, F, N, dtype_code):
+        return 64
+
+    def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace):
+        self.launches += 3
+        J, F, ld = V.shape
+        R = A.shape[0]
+        t = {torch.float32: np.float32, torch.float64: np.float64}[V.dtype]
+        (r00, r11, r01), det, (i00, i11, i01r, i01i), (y0r, y0i, y1r, y1i), col = \
+            self._sigma_inv_y(X, V, A, src_of_sub, noise, N)
+        Xn, Vn = _np(X)[:, :, :N], _np(V)[:, :, :N]
+        x0r, x0i, x1r, x1i = Xn
+        quad = x0r * y0r + x0i * y0i + x1r * y1r + x1i * y1i
+        _np(ll_f)[:] = (np.log(det) + t(np.log(np.pi)) + quad).astype(np.float64).sum(1)
+        m00 = y0r * y0r + y0i * y0i - i00
+        m11 = y1r * y1r + y1i * y1i - i11
+        m01r = y0r * y1r + y0i * y1i - i01r
+        m01i = y0i * y1r - y0r * y1i - i01i
+        count = np.bincount(src_of_sub, minlength=J)
+        hw = _np(hatW)
+        hw[:] = 0
+        for j in range(J):
+            q = (col(r00[j]) * m00 + col(r11[j]) * m11
+                 + t(2) * (col(r01[j].real) * m01r + col(r01[j].imag) * m01i))
+            hw[j, :, :N] = np.abs(Vn[j] + Vn[j] * Vn[j] * (q * t(1.0 / count[j])))
+        f64 = np.float64
+        S = np.zeros([J, J, F, 2, 2], dtype=complex)
+        for j in range(J):
+            for k in range(j, J):
+                p = Vn[j] * Vn[k]
+                S[j, k, :, 0, 0] = (p * m00).astype(f64).sum(1)
+                S[j, k, :, 1, 1] = (p * m11).astype(f64).sum(1)
+                S[j, k, :, 0, 1] = (p * m01r).astype(f64).sum(1) + 1j * (p * m01i).astype(f64).sum(1)
+                S[j, k, :, 1, 0] = np.conj(S[j, k, :, 0, 1])
+                S[k, j] = S[j, k]
+        x = [x0r + 1j * x0i, x1r + 1j * x1i]
+        y = [y0r + 1j * y0i, y1r + 1j * y1i]
+        T = np.zeros([J, F, 2, 2], dtype=complex)
+        for j in range(J):
+            for c in range(2):
+                for c2 in range(2):
+                    T[j, :, c, c2] = (Vn[j] * x[c] * np.conj(y[c2])).astype(complex).sum(1)
+        sv = Vn.astype(f64).sum(2)
+        Af = np.transpose(_np(A), (2, 1, 0))  # [F, 2, R]
+        hRss, hRxs = _np(Rss), _np(Rxs)
+        for r1 in range(R):
+            j1 = src_of_sub[r1]
+            for r2 in range(R):
+                hRss[:, r1, r2] = np.einsum("fi,fij,fj->f", np.conj(Af[:, :, r1]),
+                                            S[j1, src_of_sub[r2]], Af[:, :, r2]) / N
+            hRss[:, r1, r1] = np.real(hRss[:, r1, r1]) + sv[j1] / N
+            hRxs[:, :, r1] = np.einsum("fij,fj->fi", T[j1], Af[:, :, r1]) / N
+        hRss[:] = 0.5 * (hRss + np.conj(np.transpose(hRss, (0, 2, 1))))
+
+    # ---- K3 ---------------------------------------------------------------------------
+    def mix_inst_stats(self, Rss, Rxs, A, upd, oth, stats):
+        self.launches += 1
+        hRss, hRxs, An = _np(Rss), _np(Rxs), _np(A)
+        F = An.shape[2]
+        rxs = hRxs[:, :, upd].copy()
+        if len(oth):
+            for f in range(F):
+                rxs[f] -= np.dot(An[oth, :, f].T, hRss[f][np.ix_(oth, upd)])
+        rxs = np.real(rxs.sum(0))  # [2, Ku]
+        rss = np.real(hRss[:, np.vstack(upd), upd].sum(0))  # [Ku, Ku]
+        _np(stats)[:] = np.concatenate([rxs.ravel(), rss.ravel()])
+
+    def mix_inst_solve(self, stats, F_total, upd, A, flags):
+        self.launches += 1
+        st = _np(stats)
+        Ku = len(upd)
+        rxs = st[:2 * Ku].reshape(2, Ku) / F_total
+        rss = st[2 * Ku:].reshape(Ku, Ku) / F_total
+        try:
+            sol = np.linalg.solve(rss.T, rxs.T)
+        except np.linalg.LinAlgError:
+            _np(flags)[0] |= 1
+            return
+        _np(A)[upd] = sol[:, :, None]
+
+    def mix_conv_solve(self, Rss, Rxs, A, flags):
+        self.launches += 1
+        hRss, hRxs, An = _np(Rss), _np(Rxs), _np(A)
+        for f in range(An.shape[2]):
+            try:
+                An[:, :, f] = np.linalg.solve(hRss[f].T, hRxs[f].T)
+            except np.linalg.LinAlgError:
+                _np(flags)[0] |= 1
+
+    # ---- K4 ---------------------------------------------------------------------------
+    def spec_power(self, W, H, V, N, accumulate):
+        self.launches += 1
+        out = np.dot(_np(W), _np(H)[:, :N])
+        Vn = _np(V)
+        if accumulate:
+            Vn[:, :N] += out
+        else:
+            Vn[:, :N] = out
+        Vn[:, N:] = 0
+
+    def small_matmul(self, A, B, C):
+        self.launches += 1
+        _np(C)[:] = np.dot(_np(A).astype(np.float64), _np(B).astype(np.float64))
+
+    def fb_plan(self, F, K, N, dtype_code):
+        return N, 1
+
+    def fb_contract(self, hatW, P, O, G, N, num_partial, den_partial, chunk, nsplit):
+        self.launches += 1
+        t = _np(hatW).dtype.type
+        hw, p, o = _np(hatW)[:, :N], _np(P)[:, :N], _np(O)[:, :N]
+        g = _np(G)[:, :N]
+        p, o = np.maximum(p, t(EPS)), np.maximum(o, t(EPS))
+        e2 = o / p
+        e1 = hw / p / p * o
+        _np(num_partial)[:] = 0
+        _np(den_partial)[:] = 0
+        _np(num_partial)[0] = np.dot(e1.astype(np.float64), g.T.astype(np.float64))
+        _np(den_partial)[0] = np.dot(e2.astype(np.float64), g.T.astype(np.float64))
+
+    def tw_plan(self, F, K, N):
+        return F, 1
+
+    def tw_contract(self, hatW, O, W, H, N, num_partial, den_partial, fchunk, fsplit):
+        self.launches += 1
+        t = _np(hatW).dtype.type
+        hw, o = _np(hatW)[:, :N], np.maximum(_np(O)[:, :N], t(EPS))
+        Wn, Hn = _np(W), _np(H)[:, :N]
+        p = np.maximum(np.dot(Wn, Hn), t(EPS))
+        e2 = o / p
+        e1 = o * (hw / p / p)
+        _np(num_partial)[:] = 0
+        _np(den_partial)[:] = 0
+        _np(num_partial)[0, :, :N] = np.dot(Wn.T.astype(np.float64), e1.astype(np.float64))
+        _np(den_partial)[0, :, :N] = np.dot(Wn.T.astype(np.float64), e2.astype(np.float64))
+
+    def sum_splits(self, parts, out):
+        self.launches += 1
+        p = _np(parts)
+        _np(out).reshape(-1)[:] = p.reshape(p.shape[0], -1).sum(0)
+
+    def mult_update(self, theta, num, den, rows, cols, omega):
+        self.launches += 1
+        th = _np(theta)
+        ratio = _np(num)[:rows, :cols] / np.maximum(_np(den)[:rows, :cols], EPS)
+        th[:rows, :cols] = th[:rows, :cols].astype(np.float64) * ratio ** omega
+
+    # ---- K5 ---------------------------------------------------------------------------
+    def spat_energy(self, A, src_of_sub, J, sums):
+        self.launches += 1
+        An = _np(A)
+        s = np.zeros(J)
+        for r, j in enumerate(src_of_sub):
+            s[j] += (np.abs(An[r]) ** 2).sum()
+        _np(sums)[:] = s
+
+    def spat_scale(self, A, src_of_sub, sums, counts):
+        self.launches += 1
+        An = _np(A)
+        e = _np(sums) / _np(counts)
+        for r, j in enumerate(src_of_sub):
+            An[r] /= np.sqrt(e[j])
+
+    def fb_scale_colmax(self, FB, sums, counts, j, colmax):
+        self.launches += 1
+        fb = _np(FB)
+        g = _np(sums)[j] / _np(counts)[j]
+        fb[:] = fb.astype(np.float64) * g
+        _np(colmax)[:fb.shape[1]] = fb.astype(np.float64).max(axis=0)
+
+    def fw_renorm(self, FW, colmax, w, w2):
+        self.launches += 1
+        fw = _np(FW)
+        Kb, Kw = fw.shape
+        wv = _np(colmax)[:Kb].copy()
+        wv[wv == 0] = 1.0
+        _np(w)[:Kb] = wv
+        fw[:] = fw.astype(np.float64) * wv[:, None]
+        w2v = fw.astype(np.float64).mean(axis=0)
+        w2v[w2v == 0] = 1.0
+        _np(w2)[:Kw] = w2v
+        fw[:] = fw.astype(np.float64) / w2v
+
+    def scale_matrix(self, M, rows, cols, s, by_row, divide, total=None):
+        self.launches += 1
+        m = _np(M)
+        sv = _np(s)
+        sc = sv[:rows, None] if by_row else sv[None, :cols]
+        v = m[:rows, :cols].astype(np.float64)
+        v = v / sc if divide else v * sc
+        m[:rows, :cols] = v
+        if total is not None:
+            _np(total)[0] += m[:rows, :cols].astype(np.float64).sum()
+
+    def check_totals(self, totals, eps, flags):
+        self.launches += 1
+        tt = _np(totals)
+        if (tt < eps).any():
+            _np(flags)[0] |= 2
+        tt[:] = 0
+
+    # ---- glue ---------------------------------------------------------------------------
+    def noise_anneal(self, sqrt0, sqrt1, iter_dev, n_iter, noise):
+        self.launches += 1
+        i = float(_np(iter_dev)[0])
+        _np(noise)[:] = ((_np(sqrt0) * (n_iter - i) + _np(sqrt1) * i) / n_iter) ** 2
+
+    def ll_reduce(self, ll_f, ll_sum):
+        self.launches += 1
+        _np(ll_sum)[0] = _np(ll_f).sum()
+
+    def ll_store(self, ll_sum, bins, logliks, iter_dev, advance):
+        self.launches += 1
+        i = int(_np(iter_dev)[0])
+        _np(logliks)[i] = -_np(ll_sum)[0] / bins
+        if advance:
+            _np(iter_dev)[0] = i + 1
