@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- GEM throughput of the FASST hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one GEM iteration (E-step + spatial / spectral M-step + renormalisation,
+ref pyfasst/audioModel.py:384-428) over the whole synthetic mixture.  Workload at N=1 =
+BASELINE.json configs[1]: synthetic 10-min stereo 44.1 kHz mixture, STFT 2048 / hop 512
+(F=1025, N=51682, 52.97 M TF bins), MultiChanNMFInst_FASST with 4 sources x K=32 NMF
+components, full-rank (rank 2) spatial model.  N>1: the same mixture, sharded by
+frequency bin (one process per GPU, NCCL), i.e. strong scaling.
+
+Printed JSON (one line, rank 0):
+  value     TF-bins*iterations/s with X and the parameters resident in HBM (CUDA events)
+  e2e       the same metric through the public API with host buffers:
+            MultiChanNMFInst_FASST.comp_transf_Cx() (PCM host->device + STFT) +
+            estim_param_a_post_model() (parameters host->device, K iterations,
+            parameters + log-likelihoods device->host), wall clock around synchronised calls
+  roofline  fused E-step kernel: algorithmic bytes 4*(I^2+2J) per bin / its CUDA-event time
+  cpu_baseline  the oracle (NumPy restatement of the reference, float64) on a bounded crop
+`--impl reference` times that oracle instead (the reference is Python 2 and cannot run
+here) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 44100
+WLEN, HOP = 2048, 512
+NSRC, NNMF, RANK = 4, 32, 2
+METRIC = "gem_tf_bins_iters_per_s"
+UNIT = "TF-bins*iters/s"
+
+
+# --------------------------------------------------------------------------- workload
+def synth_mix(duration_s, seed=1234, fs=FS, nsrc=NSRC):
+    """Stereo int16 mixture: AR(2)-coloured Gaussian sources with random on/off
+    envelopes, instantaneous mixing, white noise at -40 dB."""
+    import scipy.signal as sps
+    rng = np.random.default_rng(seed)
+    L = int(round(duration_s * fs))
+    mix = np.zeros((L, 2))
+    for j in range(nsrc):
+        r, th = 0.97 - 0.02 * j, np.pi * (0.05 + 0.11 * j)
+        s = sps.lfilter([1.0], [1.0, -2 * r * np.cos(th), r * r], rng.standard_normal(L))
+        # random on/off envelope, segments of 0.1 - 1 s
+        nseg = int(duration_s / 0.1) + 2
+        lens = rng.integers(int(0.1 * fs), int(1.0 * fs), nseg)
+        state = rng.random(nseg) < 0.6
+        env = np.repeat(state, lens)[:L].astype(np.float64)
+        if env.size < L:
+            env = np.pad(env, (0, L - env.size))
+        s = s * env / (np.abs(s).max() + 1e-12)
+        ang = (j + 1) * np.pi / (2.0 * (nsrc + 1))
+        mix[:, 0] += np.sin(ang) * s
+        mix[:, 1] += np.cos(ang) * s
+    mix += 10 ** (-40 / 20.0) * np.abs(mix).max() * rng.standard_normal(mix.shape)
+    mix = 0.9 * mix / np.abs(mix).max()
+    return np.int16(np.round(mix * 32767))
+
+
+def write_wav(path, pcm):
+    import scipy.io.wavfile as wavfile
+    wavfile.write(path, FS, pcm)
+
+
+def n_frames(L):
+    return int(np.ceil(L / float(HOP)) + 2)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def oracle_model(pcm, iters):
+    from oracle import fasst_oracle as fo
+    maxdata = np.maximum(1.1 * np.abs(pcm).max(), 1e-10)
+    np.random.seed(0)
+    return fo.OracleFASST((FS, pcm / maxdata, maxdata), nbComps=NSRC, nbNMFComps=NNMF,
+                          spatial_rank=RANK, wlen=WLEN, hopsize=HOP, iter_num=iters)
+
+
+def cpu_gem_rate(crop_s, iters, warm=0):
+    """TF-bins*iters/s of the oracle (reference algorithm, NumPy float64) on a crop."""
+    pcm = synth_mix(crop_s)
+    m = oracle_model(pcm, iters + warm)
+    bins = m.nbFreqsSigRepr * m.nbFramesSigRepr
+    for _ in range(warm):
+        m.GEM_iteration()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        m.GEM_iteration()
+    dt = time.perf_counter() - t0
+    return bins * iters / dt, bins, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    crop_s = args.cpu_crop_s
+    rate, bins, dt = cpu_gem_rate(crop_s, args.steps, args.warmup)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, note="CPU arm: the oracle (NumPy restatement of the "
+                                  "reference's GEM_iteration, float64) on a %.1f s crop of "
+                                  "the same synthetic mixture (%d TF bins per step); the "
+                                  "reference itself is Python 2 and cannot be run" %
+                                  (crop_s, bins)),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d GEM iterations on a %.1f s crop (%d bins), NumPy "
+                                   "float64, BLAS threads = %d" % (args.steps, crop_s, bins, cores)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, note=None):
+    L = int(round(args.duration_s * FS))
+    cfg = {"workload": "configs[1]: synthetic %.0f-s stereo 44.1 kHz mix, "
+                       "MultiChanNMFInst_FASST %d sources x K=%d, spatial rank %d, "
+                       "STFT %d/hop %d" % (args.duration_s, NSRC, NNMF, RANK, WLEN, HOP),
+           "F": WLEN // 2 + 1, "N": n_frames(L), "tf_bins": (WLEN // 2 + 1) * n_frames(L),
+           "sources": NSRC, "nmf_comps": NNMF, "spatial_rank": RANK,
+           "sharding": "frequency bins over %d GPU(s)" % args.gpus,
+           "l2": "inputs larger than L2 (X + V + hat_W planes >> 126 MB), no flush needed"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import pyfasst_b200.audioModel as am
+    from pyfasst_b200.engine import Comm
+
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = Comm()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pcm = synth_mix(args.duration_s)
+    tmp = tempfile.mkdtemp(prefix="pyfasst_bench_")
+    wav = os.path.join(tmp, "mix_rank%d.wav" % rank)
+    write_wav(wav, pcm)
+    L = pcm.shape[0]
+    F, N = WLEN // 2 + 1, n_frames(L)
+    bins = F * N
+    dtype = "float32" if args.dtype == "f32" else "float64"
+
+    def make_model(iters):
+        np.random.seed(0)
+        return am.MultiChanNMFInst_FASST(audio=wav, nbComps=NSRC, nbNMFComps=NNMF,
+                                         spatial_rank=RANK, wlen=WLEN, hopsize=HOP,
+                                         iter_num=iters, ann_PSD_lim=[None, None],
+                                         compute_dtype=dtype, comm=comm)
+
+    # ---- device-resident throughput (`value`) and per-phase / E-step kernel times -------
+    model = make_model(args.steps + args.warmup)
+    kern = model._k()
+    eng = model._engine()
+    total_iters = args.steps + args.warmup
+    logliks = torch.ones(total_iters, dtype=torch.float64, device=eng.dev)
+    eng.iter_dev.zero_()
+    eng.flags.zero_()
+    eng.totals.fill_(1.0)
+    for _ in range(args.warmup):
+        eng.gem_iteration(total_iters, logliks)
+    events = []
+
+    def mark(label):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        events.append((label, ev))
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = kern.launch_count()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        eng.gem_iteration(total_iters, logliks, mark)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = kern.launch_count() - launches0
+    ms = t_start.elapsed_time(t_end)
+    eng.check_flags()
+    phases = {}
+    for (l0, e0), (l1, e1) in zip(events[:-1], events[1:]):
+        if l1 != "begin":
+            phases[l1] = phases.get(l1, 0.0) + e0.elapsed_time(e1)
+    phases = {k: v / args.steps for k, v in phases.items()}
+    ms_t = torch.tensor([ms], dtype=torch.float64, device=eng.dev)
+    est = torch.tensor([phases["estep"]], dtype=torch.float64, device=eng.dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    estep_ms = float(est.item())
+    value = bins * args.steps / (ms * 1e-3)
+    final_ll = logliks.cpu().numpy()
+    del eng, model
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the public API with host buffers (`e2e`) ---------------------
+    def api_run(iters):
+        m = make_model(iters)  # constructor = reference behaviour (reads the WAV, STFT, init)
+        barrier()
+        t0 = time.perf_counter()
+        m.comp_transf_Cx()     # PCM host->device + STFT kernels (timed again on purpose)
+        ll = m.estim_param_a_post_model()  # params H2D, GEM iterations, params + LL D2H
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        npar = sum(np.asarray(sc["params"]).nbytes for sc in m.spat_comps.values()) + \
+            sum(f["FB"].nbytes + f["FW"].nbytes + f["TW"].nbytes
+                for sp in m.spec_comps.values() for f in sp["factor"].values())
+        return t1 - t0, npar, ll
+
+    api_run(max(1, args.warmup))
+    dt, npar, ll_api = api_run(args.steps)
+    dt_t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+    dt = float(dt_t.item())
+    h2d = (pcm.size * 8 + npar) / float(args.steps)
+    d2h = (npar + 8 * args.steps) / float(args.steps)
+    e2e = {"value": bins * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "wall_s": dt,
+           "what": "comp_transf_Cx() + estim_param_a_post_model() with iter_num=steps, host "
+                   "numpy in / out"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused E-step) -----------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    sz = 4 if args.dtype == "f32" else 8
+    bytes_per_bin = sz * (4 + 2 * NSRC)  # I^2 reals of x (=Cx, rank one) + V_j + hat_W_j
+    local_bins = bins / float(world)
+    achieved = bytes_per_bin * local_bins / (estep_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "estep_stereo_kernel", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "bytes_per_bin": bytes_per_bin, "ms_per_launch": estep_ms,
+                "traffic": args.traffic}
+
+    # ---- CPU baseline: the oracle on a bounded crop -----------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cbins, cdt = cpu_gem_rate(args.cpu_crop_s, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "1 GEM iteration of the oracle (NumPy float64 restatement of the "
+                         "reference) on a %.1f s crop (%d bins, %.1f s)" %
+                         (args.cpu_crop_s, cbins, cdt)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "phases_ms": phases, "loglik_last": float(final_ll[total_iters - 1]),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--duration-s", type=float, default=600.0)
+    ap.add_argument("--cpu-crop-s", type=float, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per E-step launch from the committed ncu capture")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        if args.cpu_crop_s is None:
+            args.cpu_crop_s = 4.0
+        run_reference(args, rank)
+        return
+    if args.cpu_crop_s is None:
+        args.cpu_crop_s = 20.0
+    if world != args.gpus:
+        sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE\n"
+                         % (args.gpus, world))
+        args.gpus = world
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,413 @@
+"""FASST audio source separation models on B200 (drop-in for pyfasst/audioModel.py).
+
+Same class names, constructor arguments, public methods and user-visible state as the
+reference (`FASST` audioModel.py:66-2294, `MultiChanNMFInst_FASST` :2296-2420,
+`MultiChanNMFConv` :2422-2508): `spat_comps`, `spec_comps` and `noise` stay plain
+NumPy-holding dicts that the user may read and edit between calls
+(doc/source/description.rst:125-197).  Every numerical method packs that state into HBM,
+runs the sm_100a kernels through the C ABI (GemEngine, pyfasst_b200/engine.py) and
+writes the result back -- there is no NumPy implementation of the maths in here and no
+CPU fallback: without the CUDA library / a GPU the methods raise.
+
+Extra keyword arguments (not in the reference):
+    compute_dtype : 'float32' (default, fast path) or 'float64' (the reference's precision)
+    kernels       : kernel provider (default: the CUDA kernels)
+    comm          : pyfasst_b200.engine.Comm for frequency sharding over several GPUs
+    use_cuda_graph: replay the GEM iteration as a CUDA graph
+"""
+import os
+import warnings
+
+import numpy as np
+
+from . import audioObject as ao
+from .engine import GemEngine
+from .tftransforms.tft import tftransforms
+from .tftransforms import stft as _stft
+
+eps = 1e-10  # ref: audioModel.py:61
+
+
+class FASST(object):
+    """Flexible Audio Source Separation Toolbox model (ref: audioModel.py:66-2294)."""
+
+    implemented_transf = ['stft']
+
+    def __init__(self, audio, transf='stft', wlen=2048, hopsize=512, iter_num=50,
+                 sim_ann_opt='ann', ann_PSD_lim=[None, None], verbose=0, nmfUpdateCoeff=1.,
+                 tffmin=25, tffmax=18000, tfWinFunc=None, tfbpo=48, lambdaCorr=0.,
+                 compute_dtype='float32', kernels=None, comm=None, use_cuda_graph=False):
+        self.verbose = verbose
+        self.nmfUpdateCoeff = nmfUpdateCoeff
+        if isinstance(audio, ao.AudioObject):
+            self.audioObject = audio
+        elif isinstance(audio, str):
+            self.audioObject = ao.AudioObject(filename=audio)
+        else:
+            raise AttributeError("The provided audio parameter is not a supported format.")
+        self.sig_repr_params = {
+            'transf': transf.lower(),
+            'wlen': ao.nextpow2(wlen),   # ref: audioModel.py:192-193
+            'fsize': ao.nextpow2(wlen),
+            'hopsize': hopsize,
+            'tffmin': tffmin, 'tffmax': tffmax, 'tfbpo': tfbpo, 'tfWinFunc': tfWinFunc,
+        }
+        self.sig_repr_params['hopfactor'] = 1. * hopsize / self.sig_repr_params['wlen']
+        if self.sig_repr_params['transf'] not in self.implemented_transf \
+                or self.sig_repr_params['transf'] not in tftransforms:
+            raise NotImplementedError(self.sig_repr_params['transf'] + " not yet implemented.")
+        if lambdaCorr != 0:
+            raise NotImplementedError("lambdaCorr > 0 (correlation penalty, audioModel.py:"
+                                      "1534-1552) is not on the device path yet")
+        if compute_dtype not in ('float32', 'float64'):
+            raise ValueError("compute_dtype must be 'float32' or 'float64'")
+        self.compute_dtype = compute_dtype
+        self._kernels = kernels
+        self._comm = comm
+        self._use_cuda_graph = use_cuda_graph
+        # NB the reference does not forward tfWinFunc: the window is always Hann
+        # (audioModel.py:206-214 / stft.py:361)
+        self.tft = tftransforms[self.sig_repr_params['transf']](
+            fmin=tffmin, fmax=tffmax, bins=tfbpo, fs=self.audioObject.samplerate, perfRast=1,
+            linFTLen=self.sig_repr_params['fsize'],
+            atomHopFactor=self.sig_repr_params['hopfactor'], kernels=kernels)
+        self.demixParams = {
+            'tffmin': tffmin, 'tffmax': tffmax, 'tfbpo': tfbpo,
+            'tfrepresentation': transf.lower(), 'wlen': self.sig_repr_params['wlen'],
+            'hopsize': self.sig_repr_params['wlen'] // 2, 'neighbors': 20, 'winFunc': tfWinFunc}
+        self.noise = {
+            'PSD': np.zeros(self.sig_repr_params['fsize'] // 2 + 1),
+            'sim_ann_opt': sim_ann_opt,
+            'ann_PSD_lim': ann_PSD_lim,
+        }
+        self.spat_comps = {}
+        self.spec_comps = {}
+        self.iter_num = iter_num
+        self.lambdaCorr = lambdaCorr
+        self._X = None
+        self._Cx = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _k(self):
+        if self._kernels is None:
+            self._kernels = _stft.default_kernels()
+        return self._kernels
+
+    def _engine(self, psd_mode=None):
+        """A GEM engine loaded with the current user-visible state (H9: the dicts are
+        the source of truth at every public-method entry)."""
+        if self._X is None:
+            self.comp_transf_Cx()
+        eng = GemEngine(self._k(), self.nbFreqsSigRepr, self.nbFramesSigRepr,
+                        dtype=self.compute_dtype, comm=self._comm)
+        eng.set_X_planes(self._X)
+        lim = self.noise['ann_PSD_lim']
+        opt = self.noise['sim_ann_opt'] if psd_mode is None else psd_mode
+        eng.set_noise(opt, lim[0], lim[1], self.noise['PSD'])
+        eng.set_model(self.spat_comps, self.spec_comps, self.nmfUpdateCoeff)
+        return eng
+
+    # ------------------------------------------------------------------ K1
+    def comp_transf_Cx(self):
+        """Signal representation: STFT of every channel on the device, noise-annealing
+        limits from the mixture PSD (ref: audioModel.py:250-328).  `Cx` (rank one,
+        Cx[n1,n2] = X[n1] conj(X[n2]), :293-302) is not stored: the kernels read X; the
+        `Cx` attribute is built on demand."""
+        import torch
+        if self.sig_repr_params['transf'] not in self.implemented_transf:
+            raise ValueError(self.sig_repr_params['transf'] + " not implemented - yet?")
+        k = self._k()
+        data = np.asarray(self.audioObject.data, dtype=np.float64)
+        if data.ndim == 1:
+            data = data[:, None]
+        nc = data.shape[1]
+        if nc != 2:
+            raise AttributeError("Nb channels " + str(nc) + " not implemented yet")
+        pcm = torch.tensor(np.ascontiguousarray(data.T)).to(k.device)
+        F = self.sig_repr_params['fsize'] // 2 + 1
+        psd = torch.zeros(F, dtype=torch.float64, device=k.device)
+        X, N = _stft.stft_planes(k, pcm, self.tft.window, self.sig_repr_params['hopsize'],
+                                 self.sig_repr_params['fsize'], self.compute_dtype, psd)
+        self.nbFreqsSigRepr, self.nbFramesSigRepr = F, N
+        self._Cx = None
+        del self.audioObject.data  # like the reference (:288): re-read at separation
+        if self._comm is not None and self._comm.world > 1:
+            from .engine import shard_bounds
+            lo, hi = shard_bounds(F, self._comm.world)[self._comm.rank]
+            X = X[:, lo:hi].contiguous()
+        self._X = X
+        lim = self.noise['ann_PSD_lim']
+        if lim[0] is None or lim[1] is None:
+            mix_psd = psd.cpu().numpy() / (N * nc)  # mean over frames, then over channels
+            if lim[0] is None:
+                lim[0] = mix_psd / 100.
+            if lim[1] is None:
+                lim[1] = mix_psd / 10000.
+        if self.noise['sim_ann_opt'] in ('ann'):  # substring test, as in the reference (:324)
+            self.noise['PSD'] = lim[0]
+
+    @property
+    def Cx(self):
+        """Upper triangle of the empirical covariance, [3, F, N] complex128 (host copy)."""
+        if self._Cx is None:
+            if self._X is None:
+                self.comp_transf_Cx()
+            if self._comm is not None and self._comm.world > 1:
+                raise NotImplementedError("Cx is not gathered under frequency sharding")
+            X = self._X[:, :, :self.nbFramesSigRepr].cpu().numpy().astype(np.float64)
+            x0, x1 = X[0] + 1j * X[1], X[2] + 1j * X[3]
+            self._Cx = np.array([x0 * np.conj(x0), x0 * np.conj(x1), x1 * np.conj(x1)])
+        return self._Cx
+
+    # ------------------------------------------------------------------ GEM
+    def estim_param_a_post_model(self):
+        """Runs `iter_num` GEM iterations on the device; returns the log-likelihoods
+        (ref: audioModel.py:330-382)."""
+        opt = self.noise['sim_ann_opt']
+        if opt not in ('ann', 'no_ann', 'ann_ns_inj'):
+            warnings.warn("To add noise to the signal, provide the sim_ann_opt from any of "
+                          "'ann', 'no_ann' or 'ann_ns_inj' ")
+        eng = self._engine()
+        logliks = eng.run(self.iter_num, use_graph=self._use_cuda_graph)
+        eng.read_model(self.spat_comps, self.spec_comps)
+        self.noise['PSD'] = eng.noise_psd()
+        self._last_engine_stats = {'launches': self._k().launch_count()}
+        return logliks
+
+    def GEM_iteration(self):
+        """One GEM iteration with the current noise PSD (ref: audioModel.py:384-428)."""
+        eng = self._engine(psd_mode='fixed')
+        ll = eng.run(1)
+        eng.read_model(self.spat_comps, self.spec_comps)
+        return float(ll[0])
+
+    def comp_spat_comp_power(self, spat_comp_ind, spec_comp_ind=[], factor_ind=[]):
+        """V = power of one spatial component [F, N] (ref: audioModel.py:430-498)."""
+        if len(factor_ind) or (len(spec_comp_ind) and any(
+                self.spec_comps[s]['spat_comp_ind'] != spat_comp_ind for s in spec_comp_ind)):
+            raise NotImplementedError("factor / foreign spectral-component selection")
+        eng = self._engine(psd_mode='fixed')
+        eng.compute_powers(with_G=False)
+        V = eng._gather_f(eng.V[spat_comp_ind], 0)
+        return V[:, :self.nbFramesSigRepr].astype(np.float64)
+
+    def retrieve_subsrc_params(self):
+        """(spat_comp_powers [Rtot,F,N], mix_matrix [Rtot,2,F], rank_part_ind)
+        (ref: audioModel.py:514-578)."""
+        eng = self._engine(psd_mode='fixed')
+        eng.compute_powers(with_G=False)
+        V = eng._gather_f(eng.V, 1)[:, :, :self.nbFramesSigRepr].astype(np.float64)
+        A = eng._gather_f(eng.A, 2)
+        rank_part_ind = {j: np.array(r) for j, r in enumerate(eng.ranks)}
+        powers = np.zeros([eng.R, self.nbFreqsSigRepr, self.nbFramesSigRepr])
+        for j, idx in rank_part_ind.items():
+            powers[idx] = V[j][None]
+        return powers, A, rank_part_ind
+
+    def compute_suff_stat(self, spat_comp_powers, mix_matrix):
+        """E-step sufficient statistics for given sub-source powers and mixing vectors
+        (ref: audioModel.py:580-764).  Returns (hat_Rxx, hat_Rxs, hat_Rss, hat_Ws,
+        loglik) with the reference's shapes; every sub-source is treated as its own
+        rank-one component so that hat_Ws is per sub-source."""
+        import torch
+        if self._X is None:
+            self.comp_transf_Cx()
+        if self._comm is not None and self._comm.world > 1:
+            raise NotImplementedError("compute_suff_stat under frequency sharding: use "
+                                      "estim_param_a_post_model")
+        k = self._k()
+        powers = np.asarray(spat_comp_powers)
+        mix = np.asarray(mix_matrix)
+        R, F, N = powers.shape
+        if mix.shape[1] != 2:
+            raise ValueError("Nb channels not supported:" + str(mix.shape[1]))
+        eng = GemEngine(k, F, N, dtype=self.compute_dtype)
+        eng.set_X_planes(self._X)
+        eng.set_noise('fixed', self.noise['PSD'], self.noise['PSD'], self.noise['PSD'])
+        Vp = np.zeros([R, F, eng.ld])
+        Vp[:, :, :N] = powers
+        V = eng._upload(Vp, eng.tdtype)
+        A = eng._upload(mix.astype(np.complex128))
+        src = list(range(R))
+        hatW = eng._zeros([R, F, eng.ld])
+        Rss = eng._zeros([F, R, R], torch.complex128)
+        Rxs = eng._zeros([F, 2, R], torch.complex128)
+        ll_f = eng._zeros([F], torch.float64)
+        ws = eng._zeros([(k.estep_workspace_bytes(R, F, N, k.dtype_code(V)) + 7) // 8],
+                        torch.float64)
+        k.estep_stereo(eng.X, V, A, src, eng.noise, N, hatW, Rss, Rxs, ll_f, ws)
+        loglik = -float(ll_f.sum().cpu().item()) / (F * N)
+        hat_Rxx = np.mean(self.Cx, axis=-1)
+        return (hat_Rxx, Rxs.cpu().numpy(), Rss.cpu().numpy(),
+                hatW[:, :, :N].cpu().numpy().astype(np.float64), loglik)
+
+    def renormalize_parameters(self):
+        """Energy normalisation across A, FB, FW, TW (ref: audioModel.py:1980-2040)."""
+        eng = self._engine(psd_mode='fixed')
+        eng.flags.zero_()
+        eng.totals.fill_(1.0)
+        eng.renormalize()
+        eng.check_flags()
+        eng.read_model(self.spat_comps, self.spec_comps)
+
+    # ------------------------------------------------------------------ K6
+    def separate_spat_comps(self, dir_results=None, suffix=None):
+        """One separated (stereo) signal per spatial component (ref: audioModel.py:1063-1086)."""
+        spec_comp_ind = {}
+        for spat_ind in range(len(self.spat_comps)):
+            spec_comp_ind[spat_ind] = []
+        for spec_ind, spec_comp in self.spec_comps.items():
+            spec_comp_ind[spec_comp['spat_comp_ind']].append(spec_ind)
+        self.separate_comps(dir_results=dir_results, spec_comp_ind=spec_comp_ind, suffix=suffix)
+
+    def separate_comps(self, dir_results=None, spec_comp_ind=None, suffix=None):
+        """Wiener separation of groups of spectral components, inverse STFT and WAV output
+        (ref: audioModel.py:1088-1236).  File names: <dir>/<root>_<n>-<nbSources>[_suffix].wav"""
+        pcm = self.separate_comps_pcm(spec_comp_ind)
+        if dir_results is None:
+            dir_results = '/'.join(self.audioObject.filename.split('/')[:-1])
+        if not hasattr(self, "files"):
+            self.files = {}
+        self.files['spat_comp'] = []
+        nbSources = pcm.shape[0]
+        fileroot = self.audioObject.filename.split('/')[-1][:-4]
+        for n in range(nbSources):
+            _suffix = ''
+            if suffix is not None and n in suffix:
+                _suffix = '_' + suffix[n]
+            name = dir_results + '/' + fileroot + '_' + str(n) + '-' + str(nbSources) + \
+                _suffix + '.wav'
+            self.files['spat_comp'].append(name)
+            out = ao.AudioObject(filename=name, mode='w')
+            out._data = pcm[n]
+            out._maxdata = 1
+            out._encoding = 'pcm16'
+            out.samplerate = self.audioObject.samplerate
+            out._write()
+
+    def separate_comps_pcm(self, spec_comp_ind=None):
+        """int16 [nbSources, L, 2]: the separated signals of `separate_comps` before they are
+        written (device: Wiener filter K6 + inverse STFT with overlap-add)."""
+        import torch
+        if self.audioObject.channels != 2:
+            raise NotImplementedError()
+        if spec_comp_ind is None:
+            spec_comp_ind = {s: [s] for s in range(len(self.spec_comps))}
+        nbSources = len(spec_comp_ind)
+        eng = self._engine(psd_mode='fixed')
+        # group of each spatial component (one spectral component per spatial component)
+        group_of_src = [-1] * eng.J
+        for n in range(nbSources):
+            for s in spec_comp_ind[n]:
+                j = self.spec_comps[s]['spat_comp_ind']
+                if group_of_src[j] not in (-1, n):
+                    raise NotImplementedError("a spatial component in two output groups")
+                group_of_src[j] = n
+        Y = eng.wiener(group_of_src, nbSources)
+        if eng._sharded():
+            Y = torch.tensor(eng._gather_f(Y, 1)).to(eng.dev)
+        L = self.audioObject.nframes
+        maxdata = float(self.audioObject._maxdata)
+        hop, nfft = self.sig_repr_params['hopsize'], self.sig_repr_params['fsize']
+        _, pcm = _stft.istft_planes(self._k(), Y, self.nbFramesSigRepr, self.tft.synthWindow,
+                                    self.tft.window, hop, nfft, length=L, maxdata=maxdata)
+        # pcm: [L, 2*nbSources] with signal index = 2*source + channel
+        return np.ascontiguousarray(
+            pcm.cpu().numpy().reshape(L, nbSources, 2).transpose(1, 0, 2))
+
+
+class MultiChanNMFInst_FASST(FASST):
+    """Multichannel NMF, instantaneous mixing (ref: audioModel.py:2296-2420)."""
+
+    def __init__(self, audio, nbComps=3, nbNMFComps=4, spatial_rank=2, **kwargs):
+        super(MultiChanNMFInst_FASST, self).__init__(audio=audio, **kwargs)
+        self.comp_transf_Cx()
+        self.nbComps = nbComps
+        self.nbNMFComps = nbNMFComps
+        self.rank = np.atleast_1d(spatial_rank)
+        if self.rank.size < self.nbComps:
+            self.rank = [self.rank[0], ] * self.nbComps
+        self._initialize_structures()
+
+    def _initialize_structures(self):
+        """Random initial parameters with the reference's np.random call order
+        (ref: audioModel.py:2349-2393), then renormalisation on the device."""
+        nc = self.audioObject.channels
+        self.spat_comps = {}
+        self.spec_comps = {}
+        for j in range(self.nbComps):
+            params = np.random.randn(nc, self.rank[j])
+            if nc == 2:  # sources spread evenly over the stereo field
+                ang = (j + 1) * np.pi / (2. * (self.nbComps + 1))
+                params = np.array([np.sin(ang) + np.random.randn(self.rank[j]) * np.sqrt(0.01),
+                                   np.cos(ang) + np.random.randn(self.rank[j]) * np.sqrt(0.01)])
+            self.spat_comps[j] = {'time_dep': 'indep', 'mix_type': 'inst',
+                                  'frdm_prior': 'free', 'params': params}
+            factor = {
+                'FB': 0.75 * np.abs(np.random.randn(self.nbFreqsSigRepr, self.nbNMFComps)) + 0.25,
+                'FW': np.eye(self.nbNMFComps),
+                'TW': 0.75 * np.abs(np.random.randn(self.nbNMFComps, self.nbFramesSigRepr)) + 0.25,
+                'TB': [],
+                'FB_frdm_prior': 'free', 'FW_frdm_prior': 'fixed',
+                'TW_frdm_prior': 'free', 'TB_frdm_prior': [],
+                'TW_constr': 'NMF',
+            }
+            self.spec_comps[j] = {'spat_comp_ind': j, 'factor': {0: factor}}
+        self.renormalize_parameters()
+
+    def setSpecCompFB(self, compNb, FB, FB_frdm_prior='fixed'):
+        """Sets the frequency basis of one spectral component (ref: audioModel.py:2395-2420)."""
+        speccomp = self.spec_comps[compNb]['factor'][0]
+        if self.nbFreqsSigRepr != FB.shape[0]:
+            raise AttributeError("Size of provided FB is not consistent with inner attributes")
+        speccomp['FB'] = np.copy(FB)
+        ncomp = FB.shape[1]
+        speccomp['FW'] = np.eye(ncomp)
+        speccomp['TW'] = 0.75 * np.abs(np.random.randn(ncomp, self.nbFramesSigRepr)) + 0.25
+        speccomp['FB_frdm_prior'] = FB_frdm_prior
+
+
+class MultiChanNMFConv(MultiChanNMFInst_FASST):
+    """Multichannel NMF, convolutive mixing (ref: audioModel.py:2422-2508)."""
+
+    def __init__(self, audio, nbComps=3, nbNMFComps=4, spatial_rank=2, **kwargs):
+        super(MultiChanNMFConv, self).__init__(audio=audio, nbComps=nbComps,
+                                               nbNMFComps=nbNMFComps,
+                                               spatial_rank=spatial_rank, **kwargs)
+
+    def makeItConvolutive(self):
+        """Instantaneous -> convolutive: the mixing vector is copied to every frequency
+        (ref: audioModel.py:2488-2508)."""
+        nc = self.audioObject.channels
+        for nspat, (spat_ind, spat_comp) in enumerate(self.spat_comps.items()):
+            if spat_comp['mix_type'] != 'inst':
+                warnings.warn("Spatial component %d " % spat_ind +
+                              "already not instantaneous, skipping...")
+                continue
+            spat_comp['mix_type'] = 'conv'
+            inst = np.asarray(spat_comp['params'])
+            spat_comp['params'] = np.zeros([self.rank[nspat], nc, self.nbFreqsSigRepr],
+                                           dtype=complex)
+            spat_comp['params'][:] = inst.T[:, :, None]
+
+    def initializeConvParams(self, initMethod='rand'):
+        """Random convolutive mixing parameters (ref: audioModel.py:2224-2294, 'rand'
+        branch).  The DEMIX initialisation ('demix', the reference's default) is out of
+        scope of the accelerated path."""
+        nc = self.audioObject.channels
+        if 'rand' not in initMethod:
+            if initMethod == 'demix':
+                raise NotImplementedError("DEMIX initialisation is not part of this package")
+            raise ValueError("Init method not implemented.")
+        for spat_ind, spat_comp in self.spat_comps.items():
+            if spat_comp['mix_type'] != 'inst':
+                warnings.warn("Spatial component %d " % spat_ind +
+                              "already not instantaneous, overwriting...")
+            spat_comp['mix_type'] = 'conv'
+        A = (np.random.randn(len(self.spat_comps), self.nbFreqsSigRepr, nc)
+             + 1j * np.random.randn(len(self.spat_comps), self.nbFreqsSigRepr, nc))
+        for nspat, (spat_ind, spat_comp) in enumerate(self.spat_comps.items()):
+            spat_comp['params'] = np.zeros([self.rank[nspat], nc, self.nbFreqsSigRepr],
+                                           dtype=complex)
+            for r in range(self.rank[nspat]):
+                spat_comp['params'][r] = A[spat_ind].T

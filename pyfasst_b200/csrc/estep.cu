@@ -447,8 +447,12 @@ extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
                                int F, int64_t N, int64_t ld, void* hatW, void* hat_Rss,
                                void* hat_Rxs, double* ll_f, void* workspace,
                                int64_t workspace_bytes, int dtype, void* stream) {
-  PF_REQUIRE(J >= 1 && J <= MAXJ, "pf_estep_stereo: J=%d out of range (1..%d)", J, MAXJ);
-  PF_REQUIRE(R >= J && R <= MAXR, "pf_estep_stereo: R=%d out of range (J..%d)", R, MAXR);
+  if (J > MAXJ || R > MAXR) {
+    set_error("pf_estep_stereo: J=%d spatial components / R=%d sub-sources not supported "
+              "(max %d / %d)", J, R, MAXJ, MAXR);
+    return PF_ERR_UNSUPPORTED;
+  }
+  PF_REQUIRE(J >= 1 && R >= J, "pf_estep_stereo: J=%d R=%d", J, R);
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_estep_stereo: bad dtype %d", dtype);
   PF_REQUIRE(ld >= N && ld % 4 == 0, "pf_estep_stereo: ld=%ld must be >= N and a multiple of 4",
              (long)ld);

@@ -346,20 +346,29 @@ class GemEngine(object):
             k.scale_matrix(e["TW"], e["Kw"], self.N, self.w2[s], True, False, self.totals[s:s + 1])
         k.check_totals(self.totals, EPS, self.flags)
 
-    def gem_iteration(self, n_iter_total, logliks):
-        """One GEM iteration (audioModel.py:364-376, :384-428), fully stream-ordered."""
+    def gem_iteration(self, n_iter_total, logliks, mark=None):
+        """One GEM iteration (audioModel.py:364-376, :384-428), fully stream-ordered.
+        `mark(label)` (optional) is called between the phases -- bench.py records CUDA
+        events there."""
         k = self.k
+        mark = mark or (lambda label: None)
+        mark("begin")
         if self.anneal:
             k.noise_anneal(self.sqrt0, self.sqrt1, self.iter_dev, n_iter_total, self.noise)
         self.compute_powers()
+        mark("powers")
         self.estep()
+        mark("estep")
         k.ll_reduce(self.ll_f, self.ll_sum)
         if self._sharded():
             self.comm.allreduce_sum(self.ll_sum)
         k.ll_store(self.ll_sum, float(self.F_total) * self.N, logliks, self.iter_dev, True)
         self.update_mix()
+        mark("mix")
         self.update_spectral()
+        mark("spectral")
         self.renormalize()
+        mark("renorm")
 
     # ------------------------------------------------------------------ drivers
     def run(self, n_iter, use_graph=False):
