@@ -81,55 +81,60 @@ def n_frames(L):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    """SM clock and throttle reasons DURING the timed region, polled through NVML
+    (nvidia-ml-py) every ~5 ms from a thread; nvidia-smi is the fallback."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+               "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.error = None
+
+    def _loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA index through the UUID-free
+            # common case (CUDA_VISIBLE_DEVICES unset or a prefix of the device list)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.005)
+        except Exception as exc:  # noqa: BLE001 -- reported in the JSON line
+            self.error = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(self.NAMES, parts[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(smax)) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+               "sm_max_mhz": self.sm_max, "samples": len(self.samples),
+               "reasons": sorted(self.reasons), "how": "NVML polled every 5 ms during the "
+                                                       "timed region"}
+        if self.error:
+            out["error"] = self.error
+        return out
 
 
 # --------------------------------------------------------------------------- CPU arm

@@ -181,11 +181,14 @@ class CudaKernels(object):
     def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace):
         J, F, ld = V.shape
         R = A.shape[0]
+        code = self.dtype_code(V)
+        if code == PF_F32 and os.environ.get("PYFASST_ESTEP_FLOAT_ALGEBRA") == "1":
+            code = 2  # measurement only: float32 per-bin algebra (inaccurate at high SNR)
         _check(self.lib.pf_estep_stereo(self._p(X), self._p(V), self._p(A), _iarr(src_of_sub), R,
                                         J, self._p(noise), F, N, ld, self._p(hatW), self._p(Rss),
                                         self._p(Rxs), self._p(ll_f), self._p(workspace),
                                         workspace.numel() * workspace.element_size(),
-                                        self.dtype_code(V), self._stream()), self.lib)
+                                        code, self._stream()), self.lib)
 
     # -- K3 ---------------------------------------------------------------------------
     def mix_inst_stats(self, Rss, Rxs, A, upd, oth, stats):

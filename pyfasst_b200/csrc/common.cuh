@@ -90,6 +90,27 @@ __device__ __forceinline__ T warp_max(T v) {
   return v;
 }
 
+// ---- cp.async (LDGSTS): global -> shared without staging registers -------------
+// 16-byte copy, L2 only (.cg); src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src),
+               "r"(src_bytes));
+}
+// 4- or 8-byte copy (.ca), for small strided tiles
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src,
+                                               int src_bytes) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(dst), "l"(gmem_src),
+               "n"(BYTES), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING));
+}
+
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace pf

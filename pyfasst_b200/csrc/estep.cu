@@ -29,6 +29,7 @@ namespace pf {
 constexpr int ESTEP_THREADS = 128;
 constexpr int MAXJ = 6;
 constexpr int MAXR = 16;
+constexpr int PF_F32_FASTMATH = 2;  // float storage AND float per-bin algebra (experiments)
 
 __host__ __device__ constexpr int npairs(int J) { return J * (J + 1) / 2; }
 // accumulators per frequency: S (4 per pair), T (8 per source), sv (J), ll (1)
@@ -43,9 +44,9 @@ struct SubMap {
 
 // ---- per-frequency coefficients from the mixing matrix ----------------------
 // A: complex128 [R][2][F] (mix_matrix of retrieve_subsrc_params, audioModel.py:562-576)
-template <typename T>
+// coef[f] = { R_j (4 reals per source), D_jk (mixed discriminants, one per source pair) }
 __global__ void spat_coef_kernel(const double2* __restrict__ A, SubMap map, int R, int J,
-                                 int F, T* __restrict__ coef) {
+                                 int F, double* __restrict__ coef) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   double Rj[MAXJ][4];
@@ -59,9 +60,9 @@ __global__ void spat_coef_kernel(const double2* __restrict__ A, SubMap map, int 
     Rj[j][2] += a0.x * a1.x + a0.y * a1.y;  // Re a0 conj(a1)
     Rj[j][3] += a0.y * a1.x - a0.x * a1.y;  // Im a0 conj(a1)
   }
-  T* c = coef + (size_t)f * ncoef(J);
+  double* c = coef + (size_t)f * ncoef(J);
   for (int j = 0; j < J; ++j)
-    for (int e = 0; e < 4; ++e) c[4 * j + e] = (T)Rj[j][e];
+    for (int e = 0; e < 4; ++e) c[4 * j + e] = Rj[j][e];
   int p = 4 * J;
   for (int j = 0; j < J; ++j)
     for (int k = j; k < J; ++k) {
@@ -71,38 +72,97 @@ __global__ void spat_coef_kernel(const double2* __restrict__ A, SubMap map, int 
       else
         d = Rj[j][0] * Rj[k][1] + Rj[j][1] * Rj[k][0] -
             2.0 * (Rj[j][2] * Rj[k][2] + Rj[j][3] * Rj[k][3]);
-      c[p++] = (T)fmax(d, 0.0);  // mixed discriminants of PSD matrices are >= 0
+      c[p++] = fmax(d, 0.0);  // mixed discriminants of PSD matrices are >= 0
     }
 }
 
+// 1/x: for double, a float reciprocal refined by two Newton steps (4 DFMA) instead of
+// the ~20-instruction IEEE division; relative error < 1e-14.
+__device__ __forceinline__ float fast_rcp(float x) { return 1.0f / x; }
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r = (double)(1.0f / (float)x);
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  return r;
+}
+
+// Per-bin algebra shared by the E-step and the Wiener filter.
+// Sigma = s2 I + sum_j v_j R_j ; returns Sigma^-1 (i00, i11, i01) in the compute type C and
+// det Sigma / the pair products v_j v_k in the type D.  The determinant is expanded into
+// non-negative terms (no s00*s11 - |s01|^2 cancellation), so it is safe in float32; only the
+// entries of Sigma (which the adjugate later cancels against x) need the type C.  A common
+// relative error of 1/det scales Sigma^-1 and y together and is harmless.
+template <typename C, typename D, int J>
+__device__ __forceinline__ void sigma_inverse(const C (&vj)[J], const D (&vd)[J],
+                                              const C* __restrict__ coef,
+                                              const D* __restrict__ dcoef, C s2,
+                                              D (&pr)[J * (J + 1) / 2], D& det, C& i00, C& i11,
+                                              C& i01r, C& i01i) {
+  C s00 = s2, s11 = s2, s01r = (C)0, s01i = (C)0;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    s00 += vj[j] * coef[4 * j + 0];
+    s11 += vj[j] * coef[4 * j + 1];
+    s01r += vj[j] * coef[4 * j + 2];
+    s01i += vj[j] * coef[4 * j + 3];
+  }
+  const D d2 = (D)s2;
+  det = d2 * ((D)s00 + ((D)s11 - d2));
+  int p = 0;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int k = j; k < J; ++k) {
+      pr[p] = vd[j] * vd[k];
+      det += pr[p] * dcoef[p];
+      ++p;
+    }
+  det = pf_max(det, (D)1e-10);  // Q5 clamp (det >= 0 here, so sign(det+eps) = +1)
+  const C idet = (C)fast_rcp(det);
+  i00 = s11 * idet;
+  i11 = s00 * idet;
+  i01r = -s01r * idet;
+  i01i = -s01i * idet;
+}
+
 // ---- the fused per-bin kernel -------------------------------------------------
-template <typename T, int J>
+// T: storage type of the planes; C: type of the per-bin algebra.  With T = float the
+// algebra still runs in double: Sigma^-1 has entries ~ 1/noise, and the posterior power
+// a^H (y y^H - Sigma^-1) a cancels them down by the condition number of Sigma, which in
+// float32 costs eps*cond(Sigma) ~ 1e-2 at 50-60 dB bins.  The per-frequency moment sums
+// are accumulated in T (their rounding is random and averages out over frames).
+template <typename T, typename C, int J>
 __global__ void __launch_bounds__(ESTEP_THREADS)
 estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
-                    const T* __restrict__ coef, const double* __restrict__ noise,
+                    const double* __restrict__ coef, const double* __restrict__ noise,
                     SubMap map, T* __restrict__ hatW, double* __restrict__ partial, int F,
                     long N, long ld, long chunk, int nsplit) {
   constexpr int VEC = VecOf<T>::N;
   constexpr int NP = npairs(J);
   constexpr int NA = nacc(J);
   constexpr int NC = ncoef(J);
-  constexpr T kEps = (T)1e-10;          // audioModel.py:61 / signalTools eps
-  constexpr T kLogPi = (T)1.1447298858494002;  // log(pi): Q4, log(det*pi)
+  constexpr float kLogPi = 1.1447298858494002f;  // log(pi): Q4, log(det*pi)
 
   const int f = blockIdx.y;
   const int split = blockIdx.x;
-  __shared__ T s_coef[NC];
+  __shared__ C s_coef[NC];
+  __shared__ T s_dcoef[NP];  // the mixed discriminants in the storage type (determinant)
   __shared__ double s_red[ESTEP_THREADS / 32][NA];
-  if (threadIdx.x < NC) s_coef[threadIdx.x] = coef[(size_t)f * NC + threadIdx.x];
+  if (threadIdx.x < NC) {
+    const double c = coef[(size_t)f * NC + threadIdx.x];
+    s_coef[threadIdx.x] = (C)c;
+    if (threadIdx.x >= 4 * J) s_dcoef[threadIdx.x - 4 * J] = (T)c;
+  }
   __syncthreads();
-  const T s2 = (T)noise[f];
+  const C s2 = (C)noise[f];
   T invrank[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) invrank[j] = (T)map.invrank[j];
 
-  T acc[NA];
+  T acc[NA - 1];
 #pragma unroll
-  for (int i = 0; i < NA; ++i) acc[i] = (T)0;
+  for (int i = 0; i < NA - 1; ++i) acc[i] = (T)0;
+  double acc_ll = 0.0;
 
   const long plane = (long)F * ld;
   const long row = (long)f * ld;
@@ -126,78 +186,64 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         for (int j = 0; j < J; ++j) w[j][e] = (T)0;
         continue;
       }
-      // Sigma_x = sum_j v_j R_j + s2 I   (audioModel.py:613-652)
-      T s00 = s2, s11 = s2, s01r = (T)0, s01i = (T)0;
+      // Sigma_x = sum_j v_j R_j + s2 I and its inverse (audioModel.py:613-654)
+      C vj[J], i00, i11, i01r, i01i;
+      T vt[J], pr[NP], det;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const T vj = v[j][e];
-        s00 += vj * s_coef[4 * j + 0];
-        s11 += vj * s_coef[4 * j + 1];
-        s01r += vj * s_coef[4 * j + 2];
-        s01i += vj * s_coef[4 * j + 3];
+        vt[j] = v[j][e];
+        vj[j] = (C)vt[j];
       }
-      // det Sigma as a sum of non-negative terms (no s00*s11-|s01|^2 cancellation)
-      T pr[NP];
-      T det = s2 * (s00 + (s11 - s2));
-      {
-        int p = 0;
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-#pragma unroll
-          for (int k = j; k < J; ++k) {
-            pr[p] = v[j][e] * v[k][e];
-            det += pr[p] * s_coef[4 * J + p];
-            ++p;
-          }
-      }
-      det = pf_max(det, kEps);  // Q5 clamp (det >= 0 here, so sign(det+eps) = +1)
-      const T idet = pf_rcp(det);
-      const T i00 = s11 * idet, i11 = s00 * idet;
-      const T i01r = -s01r * idet, i01i = -s01i * idet;
+      sigma_inverse<C, T, J>(vj, vt, s_coef, s_dcoef, s2, pr, det, i00, i11, i01r, i01i);
       // y = Sigma^-1 x
-      const T a0r = x0r[e], a0i = x0i[e], a1r = x1r[e], a1i = x1i[e];
-      const T y0r = i00 * a0r + i01r * a1r - i01i * a1i;
-      const T y0i = i00 * a0i + i01r * a1i + i01i * a1r;
-      const T y1r = i01r * a0r + i01i * a0i + i11 * a1r;
-      const T y1i = i01r * a0i - i01i * a0r + i11 * a1i;
-      // log-likelihood integrand (audioModel.py:660-664)
-      const T quad = a0r * y0r + a0i * y0i + a1r * y1r + a1i * y1i;
-      acc[NA - 1] += pf_log(det) + kLogPi + quad;
+      const C a0r = (C)x0r[e], a0i = (C)x0i[e], a1r = (C)x1r[e], a1i = (C)x1i[e];
+      const C y0r = i00 * a0r + i01r * a1r - i01i * a1i;
+      const C y0i = i00 * a0i + i01r * a1i + i01i * a1r;
+      const C y1r = i01r * a0r + i01i * a0i + i11 * a1r;
+      const C y1i = i01r * a0i - i01i * a0r + i11 * a1i;
+      const T z0r = (T)y0r, z0i = (T)y0i, z1r = (T)y1r, z1i = (T)y1i;
+      const T b0r = x0r[e], b0i = x0i[e], b1r = x1r[e], b1i = x1i[e];
+      // log-likelihood integrand log(det*pi) + x^H Sigma^-1 x (audioModel.py:660-664)
+      const T quad = b0r * z0r + b0i * z0i + b1r * z1r + b1i * z1i;
+      if (sizeof(T) == 8)
+        acc_ll += log((double)det) + 1.1447298858494002 + (double)quad;
+      else
+        acc_ll += (double)(logf((float)det) + kLogPi + (float)quad);
       // M = y y^H - Sigma^-1
-      const T m00 = y0r * y0r + y0i * y0i - i00;
-      const T m11 = y1r * y1r + y1i * y1i - i11;
-      const T m01r = y0r * y1r + y0i * y1i - i01r;
-      const T m01i = y0i * y1r - y0r * y1i - i01i;
-      // posterior source power (audioModel.py:727-729, :408-414)
+      const C m00 = y0r * y0r + y0i * y0i - i00;
+      const C m11 = y1r * y1r + y1i * y1i - i11;
+      const C m01r = y0r * y1r + y0i * y1i - i01r;
+      const C m01i = y0i * y1r - y0r * y1i - i01i;
+      // posterior source power (audioModel.py:727-729, :408-414): tr(M R_j) cancels the
+      // ~1/noise entries of M, so it is formed in C; the rest is safe in T
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const T q = s_coef[4 * j + 0] * m00 + s_coef[4 * j + 1] * m11 +
-                    (T)2 * (s_coef[4 * j + 2] * m01r + s_coef[4 * j + 3] * m01i);
-        const T vj = v[j][e];
-        w[j][e] = pf_abs(vj + vj * vj * (q * invrank[j]));
+        const T q = (T)(s_coef[4 * j + 0] * m00 + s_coef[4 * j + 1] * m11 +
+                        (C)2 * (s_coef[4 * j + 2] * m01r + s_coef[4 * j + 3] * m01i));
+        w[j][e] = pf_abs(vt[j] + vt[j] * vt[j] * (q * invrank[j]));
       }
-      // S_jk += v_j v_k M
+      // S_jk += v_j v_k M   (accumulated in T)
+      const T t00 = (T)m00, t11 = (T)m11, t01r = (T)m01r, t01i = (T)m01i;
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        acc[4 * p + 0] += pr[p] * m00;
-        acc[4 * p + 1] += pr[p] * m11;
-        acc[4 * p + 2] += pr[p] * m01r;
-        acc[4 * p + 3] += pr[p] * m01i;
+        acc[4 * p + 0] += pr[p] * t00;
+        acc[4 * p + 1] += pr[p] * t11;
+        acc[4 * p + 2] += pr[p] * t01r;
+        acc[4 * p + 3] += pr[p] * t01i;
       }
       // U = x y^H ; T_j += v_j U ; sv_j += v_j
-      const T u00r = a0r * y0r + a0i * y0i, u00i = a0i * y0r - a0r * y0i;
-      const T u01r = a0r * y1r + a0i * y1i, u01i = a0i * y1r - a0r * y1i;
-      const T u10r = a1r * y0r + a1i * y0i, u10i = a1i * y0r - a1r * y0i;
-      const T u11r = a1r * y1r + a1i * y1i, u11i = a1i * y1r - a1r * y1i;
+      const T u00r = b0r * z0r + b0i * z0i, u00i = b0i * z0r - b0r * z0i;
+      const T u01r = b0r * z1r + b0i * z1i, u01i = b0i * z1r - b0r * z1i;
+      const T u10r = b1r * z0r + b1i * z0i, u10i = b1i * z0r - b1r * z0i;
+      const T u11r = b1r * z1r + b1i * z1i, u11i = b1i * z1r - b1r * z1i;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const T vj = v[j][e];
         T* t = acc + 4 * NP + 8 * j;
-        t[0] += vj * u00r; t[1] += vj * u00i;
-        t[2] += vj * u01r; t[3] += vj * u01i;
-        t[4] += vj * u10r; t[5] += vj * u10i;
-        t[6] += vj * u11r; t[7] += vj * u11i;
-        acc[4 * NP + 8 * J + j] += vj;
+        t[0] += vt[j] * u00r; t[1] += vt[j] * u00i;
+        t[2] += vt[j] * u01r; t[3] += vt[j] * u01i;
+        t[4] += vt[j] * u10r; t[5] += vt[j] * u10i;
+        t[6] += vt[j] * u11r; t[7] += vt[j] * u11i;
+        acc[4 * NP + 8 * J + j] += vt[j];
       }
     }
 #pragma unroll
@@ -206,10 +252,15 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 
   // fixed-order block reduction in double (H8: deterministic, no float atomics)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (lanes are summed in the storage type: one 32-bit shuffle per step instead of two)
 #pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    double d = warp_sum((double)acc[i]);
-    if (lane == 0) s_red[warp][i] = d;
+  for (int i = 0; i < NA - 1; ++i) {
+    const T d = warp_sum(acc[i]);
+    if (lane == 0) s_red[warp][i] = (double)d;
+  }
+  {
+    double d = warp_sum(acc_ll);
+    if (lane == 0) s_red[warp][NA - 1] = d;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NA; i += ESTEP_THREADS) {
@@ -286,19 +337,24 @@ struct GroupMap {
   int group_of_src[MAXJ];  // output group of each spatial component, -1 = not written
 };
 
-template <typename T, int J>
+template <typename T, typename C, int J>
 __global__ void __launch_bounds__(256)
-wiener_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V, const T* __restrict__ coef,
-                     const double* __restrict__ noise, GroupMap gm, int ngroups,
-                     T* __restrict__ Y, int F, long N, long ld) {
+wiener_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
+                     const double* __restrict__ coef, const double* __restrict__ noise,
+                     GroupMap gm, int ngroups, T* __restrict__ Y, int F, long N, long ld) {
   constexpr int VEC = VecOf<T>::N;
   constexpr int NC = ncoef(J);
-  constexpr T kEps = (T)1e-10;
+  constexpr int NP = npairs(J);
   const int f = blockIdx.y;
-  __shared__ T s_coef[NC];
-  if (threadIdx.x < NC) s_coef[threadIdx.x] = coef[(size_t)f * NC + threadIdx.x];
+  __shared__ C s_coef[NC];
+  __shared__ T s_dcoef[NP];
+  if (threadIdx.x < NC) {
+    const double c = coef[(size_t)f * NC + threadIdx.x];
+    s_coef[threadIdx.x] = (C)c;
+    if (threadIdx.x >= 4 * J) s_dcoef[threadIdx.x - 4 * J] = (T)c;
+  }
   __syncthreads();
-  const T s2 = (T)noise[f];
+  const C s2 = (C)noise[f];
   const long plane = (long)F * ld;
   const long row = (long)f * ld;
   const long n0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
@@ -310,50 +366,43 @@ wiener_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V, const T* 
   load_vec<T>(X + 3 * plane + row + n0, x1i);
 #pragma unroll
   for (int j = 0; j < J; ++j) load_vec<T>(V + j * plane + row + n0, v[j]);
-  T y0r[VEC], y0i[VEC], y1r[VEC], y1i[VEC];
+  C y0r[VEC], y0i[VEC], y1r[VEC], y1i[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    T s00 = s2, s11 = s2, s01r = (T)0, s01i = (T)0;
+    C vj[J], i00, i11, i01r, i01i;
+    T vt[J], pr[NP], det;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      s00 += v[j][e] * s_coef[4 * j + 0];
-      s11 += v[j][e] * s_coef[4 * j + 1];
-      s01r += v[j][e] * s_coef[4 * j + 2];
-      s01i += v[j][e] * s_coef[4 * j + 3];
+      vt[j] = v[j][e];
+      vj[j] = (C)vt[j];
     }
-    T det = s2 * (s00 + (s11 - s2));
-    int p = 0;
-#pragma unroll
-    for (int j = 0; j < J; ++j)
-#pragma unroll
-      for (int k = j; k < J; ++k) det += v[j][e] * v[k][e] * s_coef[4 * J + (p++)];
-    det = pf_max(det, kEps);
-    const T idet = pf_rcp(det);
-    const T i00 = s11 * idet, i11 = s00 * idet, i01r = -s01r * idet, i01i = -s01i * idet;
-    y0r[e] = i00 * x0r[e] + i01r * x1r[e] - i01i * x1i[e];
-    y0i[e] = i00 * x0i[e] + i01r * x1i[e] + i01i * x1r[e];
-    y1r[e] = i01r * x0r[e] + i01i * x0i[e] + i11 * x1r[e];
-    y1i[e] = i01r * x0i[e] - i01i * x0r[e] + i11 * x1i[e];
+    sigma_inverse<C, T, J>(vj, vt, s_coef, s_dcoef, s2, pr, det, i00, i11, i01r, i01i);
+    const C a0r = (C)x0r[e], a0i = (C)x0i[e], a1r = (C)x1r[e], a1i = (C)x1i[e];
+    y0r[e] = i00 * a0r + i01r * a1r - i01i * a1i;
+    y0i[e] = i00 * a0i + i01r * a1i + i01i * a1r;
+    y1r[e] = i01r * a0r + i01i * a0i + i11 * a1r;
+    y1i[e] = i01r * a0i - i01i * a0r + i11 * a1i;
   }
   for (int g = 0; g < ngroups; ++g) {
     T o0r[VEC], o0i[VEC], o1r[VEC], o1i[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       // Sigma_g = sum_{j in g} v_j R_j
-      T g00 = (T)0, g11 = (T)0, g01r = (T)0, g01i = (T)0;
+      C g00 = (C)0, g11 = (C)0, g01r = (C)0, g01i = (C)0;
 #pragma unroll
       for (int j = 0; j < J; ++j)
         if (gm.group_of_src[j] == g) {
-          g00 += v[j][e] * s_coef[4 * j + 0];
-          g11 += v[j][e] * s_coef[4 * j + 1];
-          g01r += v[j][e] * s_coef[4 * j + 2];
-          g01i += v[j][e] * s_coef[4 * j + 3];
+          const C vv = (C)v[j][e];
+          g00 += vv * s_coef[4 * j + 0];
+          g11 += vv * s_coef[4 * j + 1];
+          g01r += vv * s_coef[4 * j + 2];
+          g01i += vv * s_coef[4 * j + 3];
         }
       // out = Sigma_g y
-      o0r[e] = g00 * y0r[e] + g01r * y1r[e] - g01i * y1i[e];
-      o0i[e] = g00 * y0i[e] + g01r * y1i[e] + g01i * y1r[e];
-      o1r[e] = g01r * y0r[e] + g01i * y0i[e] + g11 * y1r[e];
-      o1i[e] = g01r * y0i[e] - g01i * y0r[e] + g11 * y1i[e];
+      o0r[e] = (T)(g00 * y0r[e] + g01r * y1r[e] - g01i * y1i[e]);
+      o0i[e] = (T)(g00 * y0i[e] + g01r * y1i[e] + g01i * y1r[e]);
+      o1r[e] = (T)(g01r * y0r[e] + g01i * y0i[e] + g11 * y1r[e]);
+      o1i[e] = (T)(g01r * y0i[e] - g01i * y0r[e] + g11 * y1i[e]);
       if (n0 + e >= N) o0r[e] = o0i[e] = o1r[e] = o1i[e] = (T)0;
     }
     T* out = Y + (size_t)g * 4 * plane + row + n0;
@@ -364,55 +413,54 @@ wiener_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V, const T* 
   }
 }
 
-template <typename T, int J>
-static int launch_wiener(const void* X, const void* V, const void* coef, const double* noise,
+template <typename T, typename C, int J>
+static int launch_wiener(const void* X, const void* V, const double* coef, const double* noise,
                          const GroupMap& gm, int ngroups, void* Y, int F, long N, long ld,
                          cudaStream_t st) {
   constexpr int VEC = VecOf<T>::N;
   dim3 grid(ceil_div(N, 256L * VEC), F);
-  wiener_stereo_kernel<T, J><<<grid, 256, 0, st>>>((const T*)X, (const T*)V, (const T*)coef, noise,
-                                                  gm, ngroups, (T*)Y, F, N, ld);
+  wiener_stereo_kernel<T, C, J><<<grid, 256, 0, st>>>((const T*)X, (const T*)V, coef, noise, gm,
+                                                     ngroups, (T*)Y, F, N, ld);
   return check_launch("wiener_stereo_kernel");
 }
 
-template <typename T>
-static int dispatch_wiener(int J, const void* X, const void* V, const void* coef,
+template <typename T, typename C>
+static int dispatch_wiener(int J, const void* X, const void* V, const double* coef,
                            const double* noise, const GroupMap& gm, int ngroups, void* Y, int F,
                            long N, long ld, cudaStream_t st) {
   switch (J) {
-    case 1: return launch_wiener<T, 1>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
-    case 2: return launch_wiener<T, 2>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
-    case 3: return launch_wiener<T, 3>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
-    case 4: return launch_wiener<T, 4>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
-    case 5: return launch_wiener<T, 5>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
-    case 6: return launch_wiener<T, 6>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
+    case 1: return launch_wiener<T, C, 1>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
+    case 2: return launch_wiener<T, C, 2>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
+    case 3: return launch_wiener<T, C, 3>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
+    case 4: return launch_wiener<T, C, 4>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
+    case 5: return launch_wiener<T, C, 5>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
+    case 6: return launch_wiener<T, C, 6>(X, V, coef, noise, gm, ngroups, Y, F, N, ld, st);
   }
   set_error("pf_wiener_stereo: J=%d spatial components not supported (1..%d)", J, MAXJ);
   return PF_ERR_UNSUPPORTED;
 }
 
-template <typename T, int J>
-static int launch_estep(const void* X, const void* V, const void* coef, const double* noise,
+template <typename T, typename C, int J>
+static int launch_estep(const void* X, const void* V, const double* coef, const double* noise,
                         const SubMap& map, void* hatW, double* partial, int F, long N,
                         long ld, long chunk, int nsplit, cudaStream_t st) {
   dim3 grid(nsplit, F);
-  estep_stereo_kernel<T, J><<<grid, ESTEP_THREADS, 0, st>>>(
-      (const T*)X, (const T*)V, (const T*)coef, noise, map, (T*)hatW, partial, F, N, ld, chunk,
-      nsplit);
+  estep_stereo_kernel<T, C, J><<<grid, ESTEP_THREADS, 0, st>>>(
+      (const T*)X, (const T*)V, coef, noise, map, (T*)hatW, partial, F, N, ld, chunk, nsplit);
   return check_launch("estep_stereo_kernel");
 }
 
-template <typename T>
-static int dispatch_estep(int J, const void* X, const void* V, const void* coef,
+template <typename T, typename C>
+static int dispatch_estep(int J, const void* X, const void* V, const double* coef,
                           const double* noise, const SubMap& map, void* hatW, double* partial,
                           int F, long N, long ld, long chunk, int nsplit, cudaStream_t st) {
   switch (J) {
-    case 1: return launch_estep<T, 1>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
-    case 2: return launch_estep<T, 2>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
-    case 3: return launch_estep<T, 3>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
-    case 4: return launch_estep<T, 4>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
-    case 5: return launch_estep<T, 5>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
-    case 6: return launch_estep<T, 6>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
+    case 1: return launch_estep<T, C, 1>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
+    case 2: return launch_estep<T, C, 2>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
+    case 3: return launch_estep<T, C, 3>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
+    case 4: return launch_estep<T, C, 4>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
+    case 5: return launch_estep<T, C, 5>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
+    case 6: return launch_estep<T, C, 6>(X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st);
   }
   set_error("pf_estep_stereo: J=%d spatial components not supported (1..%d)", J, MAXJ);
   return PF_ERR_UNSUPPORTED;
@@ -427,10 +475,10 @@ extern "C" int pf_estep_plan(int J, int64_t N, int dtype, int64_t* chunk, int* n
   PF_REQUIRE(J >= 1 && J <= MAXJ, "pf_estep_plan: J=%d out of range", J);
   const long vec = dtype == PF_F64 ? 2 : 4;
   const long pass = ESTEP_THREADS * vec;
-  // aim for ~16 passes per CTA so the end-of-CTA reduction is amortised, while
+  // aim for ~32 passes per CTA so the end-of-CTA reduction is amortised, while
   // keeping at least ~4 CTAs per SM in flight on a 148-SM part
   long passes = (N + pass - 1) / pass;
-  long per_cta = 16;
+  long per_cta = 32;
   long want_ctas = 148L * 8;
   while (per_cta > 1 && (long)F * ((passes + per_cta - 1) / per_cta) < want_ctas) per_cta /= 2;
   long c = per_cta * pass;
@@ -453,7 +501,8 @@ extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
     return PF_ERR_UNSUPPORTED;
   }
   PF_REQUIRE(J >= 1 && R >= J, "pf_estep_stereo: J=%d R=%d", J, R);
-  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_estep_stereo: bad dtype %d", dtype);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64 || dtype == PF_F32_FASTMATH,
+             "pf_estep_stereo: bad dtype %d", dtype);
   PF_REQUIRE(ld >= N && ld % 4 == 0, "pf_estep_stereo: ld=%ld must be >= N and a multiple of 4",
              (long)ld);
   PF_REQUIRE(F > 0 && N > 0, "pf_estep_stereo: empty problem F=%d N=%ld", F, (long)N);
@@ -476,21 +525,21 @@ extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
              (long)workspace_bytes, (long)need);
   cudaStream_t st = as_stream(stream);
   double* partial = (double*)workspace;
-  void* coef = (void*)(partial + (size_t)F * nsplit * nacc(J));
-  int rc;
-  if (dtype == PF_F32) {
-    spat_coef_kernel<float><<<ceil_div(F, 128), 128, 0, st>>>((const double2*)A, map, R, J, F,
-                                                             (float*)coef);
-    if ((rc = check_launch("spat_coef_kernel"))) return rc;
-    rc = dispatch_estep<float>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, chunk,
-                               nsplit, st);
-  } else {
-    spat_coef_kernel<double><<<ceil_div(F, 128), 128, 0, st>>>((const double2*)A, map, R, J, F,
-                                                              (double*)coef);
-    if ((rc = check_launch("spat_coef_kernel"))) return rc;
-    rc = dispatch_estep<double>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, chunk,
-                                nsplit, st);
-  }
+  double* coef = partial + (size_t)F * nsplit * nacc(J);
+  spat_coef_kernel<<<ceil_div(F, 128), 128, 0, st>>>((const double2*)A, map, R, J, F, coef);
+  int rc = check_launch("spat_coef_kernel");
+  if (rc) return rc;
+  // the per-bin algebra always runs in float64 (see estep_stereo_kernel); PF_F32_FASTMATH
+  // (float algebra) exists only to measure what that costs
+  if (dtype == PF_F32)
+    rc = dispatch_estep<float, double>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld,
+                                       chunk, nsplit, st);
+  else if (dtype == PF_F32_FASTMATH)
+    rc = dispatch_estep<float, float>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld,
+                                      chunk, nsplit, st);
+  else
+    rc = dispatch_estep<double, double>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld,
+                                        chunk, nsplit, st);
   if (rc) return rc;
   estep_finalize_kernel<<<F, 64, 0, st>>>(partial, (const double2*)A, map, R, J, F, N, nsplit,
                                           (double2*)hat_Rss, (double2*)hat_Rxs, ll_f);
@@ -525,15 +574,11 @@ extern "C" int pf_wiener_stereo(const void* X, const void* V, const void* A,
     gm.group_of_src[j] = group_of_src[j];
   }
   cudaStream_t st = as_stream(stream);
-  int rc;
-  if (dtype == PF_F32) {
-    spat_coef_kernel<float><<<ceil_div(F, 128), 128, 0, st>>>((const double2*)A, map, R, J, F,
-                                                             (float*)workspace);
-    if ((rc = check_launch("spat_coef_kernel"))) return rc;
-    return dispatch_wiener<float>(J, X, V, workspace, noise_psd, gm, ngroups, Y, F, N, ld, st);
-  }
-  spat_coef_kernel<double><<<ceil_div(F, 128), 128, 0, st>>>((const double2*)A, map, R, J, F,
-                                                            (double*)workspace);
-  if ((rc = check_launch("spat_coef_kernel"))) return rc;
-  return dispatch_wiener<double>(J, X, V, workspace, noise_psd, gm, ngroups, Y, F, N, ld, st);
+  double* coef = (double*)workspace;
+  spat_coef_kernel<<<ceil_div(F, 128), 128, 0, st>>>((const double2*)A, map, R, J, F, coef);
+  int rc = check_launch("spat_coef_kernel");
+  if (rc) return rc;
+  if (dtype == PF_F32)
+    return dispatch_wiener<float, double>(J, X, V, coef, noise_psd, gm, ngroups, Y, F, N, ld, st);
+  return dispatch_wiener<double, double>(J, X, V, coef, noise_psd, gm, ngroups, Y, F, N, ld, st);
 }

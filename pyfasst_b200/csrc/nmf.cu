@@ -200,68 +200,277 @@ fb_contract_kernel(const T* __restrict__ hatW, const T* __restrict__ Pp, const T
   }
 }
 
-// ============================ TW update: contract over frequencies ==============
-constexpr int TW_THREADS = 128;
-constexpr int TW_FT = 64;  // rows of W staged per step
 
+// ---- FB update, fast path: P and O are the same plane (one spectral component per
+// spatial component, single factor -- what MultiChanNMFInst_FASST / MultiChanNMFConv build).
+// Then O/P = 1 exactly, so den[f,k] = sum_n G[k,n] for every f (a row sum of G, computed by
+// g_rowsum_kernel) and only num[f,k] = sum_n (hatW/P)[f,n] G[k,n] has to be contracted.
+// A CTA owns FB_ROWS rows and a run of frames; the hatW / P / G tiles of a step (128 frames)
+// are brought to shared memory by cp.async through a 3-stage ring; a warp owns FR rows, a
+// lane 4 (2) frames of the tile, and accumulates FR x KC partial sums that are reduced across
+// the lanes once at the end.
+constexpr int FBF_THREADS = 256;
+constexpr int FBF_FR = 4;
+constexpr int FBF_ROWS = (FBF_THREADS / 32) * FBF_FR;  // 32 rows per CTA
+constexpr int FBF_STAGES = 3;
+
+template <typename T, int KC>
+struct FbfStage {
+  static constexpr int NT = 32 * VecOf<T>::N;
+  T g[KC][NT];
+  T hw[FBF_ROWS][NT];
+  T p[FBF_ROWS][NT];
+};
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(FBF_THREADS, 1)
+fb_contract_same_kernel(const T* __restrict__ hatW, const T* __restrict__ Pp, long ld,
+                        const T* __restrict__ G, long ldg, int k0, int K, int F, long N,
+                        long chunk, int nsplit, double* __restrict__ num) {
+  constexpr int VEC = VecOf<T>::N;
+  constexpr int NT = 32 * VEC;
+  constexpr int VPR = NT / VEC;  // 16-byte vectors per tile row (= 32)
+  constexpr T kEps = (T)1e-10;
+  extern __shared__ __align__(16) unsigned char fbf_smem[];
+  FbfStage<T, KC>* stages = reinterpret_cast<FbfStage<T, KC>*>(fbf_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fblk = blockIdx.y * FBF_ROWS;
+  const int split = blockIdx.x;
+  const long begin = (long)split * chunk;
+  long end = begin + chunk;
+  if (end > N) end = N;
+  const int nsteps = (int)((end - begin + NT - 1) / NT);
+
+  auto issue = [&](int step) {
+    FbfStage<T, KC>& st = stages[step % FBF_STAGES];
+    const long nb = begin + (long)step * NT;
+    for (int i = threadIdx.x; i < KC * VPR; i += FBF_THREADS) {
+      const int k = i / VPR, c = i % VPR;
+      const long n = nb + (long)c * VEC;
+      const bool ok = (k0 + k < K) && (n + VEC <= ldg);
+      cp_async16(&st.g[k][c * VEC], ok ? (const void*)(G + (long)(k0 + k) * ldg + n) : (const void*)G,
+                 ok ? 16 : 0);
+    }
+    for (int i = threadIdx.x; i < FBF_ROWS * VPR; i += FBF_THREADS) {
+      const int r = i / VPR, c = i % VPR;
+      const long n = nb + (long)c * VEC;
+      const int f = fblk + r;
+      const bool ok = (f < F) && (n + VEC <= ld);
+      const long off = ok ? (long)f * ld + n : 0;
+      cp_async16(&st.hw[r][c * VEC], hatW + off, ok ? 16 : 0);
+      cp_async16(&st.p[r][c * VEC], Pp + off, ok ? 16 : 0);
+    }
+  };
+
+  T an[FBF_FR][KC];
+#pragma unroll
+  for (int r = 0; r < FBF_FR; ++r)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) an[r][k] = (T)0;
+
+#pragma unroll
+  for (int s = 0; s < FBF_STAGES - 1; ++s) {
+    if (s < nsteps) issue(s);
+    cp_async_commit();
+  }
+  for (int s = 0; s < nsteps; ++s) {
+    if (s + FBF_STAGES - 1 < nsteps) issue(s + FBF_STAGES - 1);
+    cp_async_commit();
+    cp_async_wait<FBF_STAGES - 1>();  // stage s has landed
+    __syncthreads();
+    const FbfStage<T, KC>& st = stages[s % FBF_STAGES];
+    T e1[FBF_FR][VEC];
+#pragma unroll
+    for (int r = 0; r < FBF_FR; ++r) {
+      T hw[VEC], p[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        hw[e] = st.hw[warp * FBF_FR + r][lane * VEC + e];
+        p[e] = st.p[warp * FBF_FR + r][lane * VEC + e];
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        e1[r][e] = hw[e] * pf_rcp(pf_max(p[e], kEps));  // hatW / P^2 * O with O == P
+    }
+    // k in groups of 4: the group's G vectors are loaded, then 64 FMAs; the empty asm keeps
+    // the compiler from hoisting all KC shared-memory loads (and their registers) up front
+#pragma unroll
+    for (int kg = 0; kg < KC; kg += 4) {
+      T g[4][VEC];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) g[kk][e] = st.g[kg + kk][lane * VEC + e];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int r = 0; r < FBF_FR; ++r)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) an[r][kg + kk] += e1[r][e] * g[kk][e];
+      asm volatile("" ::: "memory");
+    }
+    __syncthreads();  // the ring slot of stage s is refilled by the next issue()
+  }
+  if (sizeof(T) == 4) {
+    // lanes hold partial sums over their frames.  1280 shuffles per thread would cost as much
+    // as ~10 steps of the main loop, so the FR*KC values are transposed through the (now idle)
+    // ring instead: lane l then adds the 32 partials of values l, l+32, ... in double.
+    constexpr int NV = FBF_FR * KC;
+    T* red = reinterpret_cast<T*>(fbf_smem) + (size_t)warp * NV * 33;
+#pragma unroll
+    for (int r = 0; r < FBF_FR; ++r)
+#pragma unroll
+      for (int k = 0; k < KC; ++k) red[(r * KC + k) * 33 + lane] = an[r][k];
+    __syncwarp();
+    for (int v = lane; v < NV; v += 32) {
+      double d = 0.0;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) d += (double)red[v * 33 + l];
+      const int r = v / KC, k = v % KC;
+      const int f = fblk + warp * FBF_FR + r;
+      if (f < F && k0 + k < K) num[((size_t)split * F + f) * K + k0 + k] = d;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < FBF_FR; ++r) {
+      const int f = fblk + warp * FBF_FR + r;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const double sn = warp_sum((double)an[r][k]);
+        if (lane == 0 && f < F && k0 + k < K) num[((size_t)split * F + f) * K + k0 + k] = sn;
+      }
+    }
+  }
+}
+
+// den[split][f][k] = sum over the split's frames of G[k][n], broadcast over f
+template <typename T>
+__global__ void g_rowsum_kernel(const T* __restrict__ G, long ldg, int K, int F, long N,
+                                long chunk, double* __restrict__ den) {
+  const int split = blockIdx.x, k = blockIdx.y;
+  const long begin = (long)split * chunk;
+  long end = begin + chunk;
+  if (end > N) end = N;
+  double acc = 0.0;
+  for (long n = begin + threadIdx.x; n < end; n += blockDim.x) acc += (double)G[(long)k * ldg + n];
+  __shared__ double s_red[32];
+  __shared__ double s_tot;
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) d += s_red[w];
+    s_tot = d;
+  }
+  __syncthreads();
+  const double tot = s_tot;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) den[((size_t)split * F + f) * K + k] = tot;
+}
+
+// ============================ TW update: contract over frequencies ==============
+constexpr int TW_THREADS = 128;  // one frame per thread
+constexpr int TW_RT = 16;        // rows of a pipeline stage
+constexpr int TW_STAGES = 3;
+
+template <typename T, int KC>
+struct TwStage {
+  T hw[TW_RT][TW_THREADS];
+  T o[TW_RT][TW_THREADS];
+  T w[TW_RT][KC];
+};
+
+// A CTA owns 128 frames and the frequency rows [fb, fe); the hatW / O / W tiles of 16 rows
+// come in through a 3-stage cp.async ring.  Thread n keeps H[:, n] and the 2 x KC partial sums
+// of frame n in registers and walks the rows: P' = max(W H, eps) (own power with the updated
+// W, audioModel.py:1639-1645), then num += W e1, den += W e2.
 template <typename T, int KC>
 __global__ void __launch_bounds__(TW_THREADS)
 tw_contract_kernel(const T* __restrict__ hatW, const T* __restrict__ Op, long ld,
                    const T* __restrict__ W, int ldw, const T* __restrict__ H, long ldh, int K,
                    int F, long N, int fchunk, int fsplit, double* __restrict__ num,
                    double* __restrict__ den, long ldo) {
+  constexpr int VEC = VecOf<T>::N;
+  constexpr int VPR = TW_THREADS / VEC;  // 16-byte vectors per tile row
   constexpr T kEps = (T)1e-10;
-  __shared__ __align__(16) T s_w[TW_FT][KC];
-  const long n = (long)blockIdx.x * TW_THREADS + threadIdx.x;
+  extern __shared__ __align__(16) unsigned char tw_smem[];
+  TwStage<T, KC>* stages = reinterpret_cast<TwStage<T, KC>*>(tw_smem);
+  const long nb = (long)blockIdx.x * TW_THREADS;
+  const long n = nb + threadIdx.x;
   const int split = blockIdx.y;
   const int fb = split * fchunk;
   int fe = fb + fchunk;
   if (fe > F) fe = F;
+  const int nsteps = (fe - fb + TW_RT - 1) / TW_RT;
   const bool live = n < N;
+
+  auto issue = [&](int step) {
+    TwStage<T, KC>& st = stages[step % TW_STAGES];
+    const int f0 = fb + step * TW_RT;
+    for (int i = threadIdx.x; i < TW_RT * VPR; i += TW_THREADS) {
+      const int r = i / VPR, c = i % VPR;
+      const long nn = nb + (long)c * VEC;
+      const int f = f0 + r;
+      const bool ok = (f < fe) && (nn + VEC <= ld);
+      const long off = ok ? (long)f * ld + nn : 0;
+      cp_async16(&st.hw[r][c * VEC], hatW + off, ok ? 16 : 0);
+      cp_async16(&st.o[r][c * VEC], Op + off, ok ? 16 : 0);
+    }
+    for (int i = threadIdx.x; i < TW_RT * KC; i += TW_THREADS) {
+      const int r = i / KC, k = i % KC;
+      const int f = f0 + r;
+      const bool ok = (f < fe) && (k < K);
+      cp_async_small<sizeof(T)>(&st.w[r][k], W + (ok ? (long)f * ldw + k : 0),
+                                ok ? (int)sizeof(T) : 0);
+    }
+  };
+
   T h[KC], an[KC], ad[KC];
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
     h[k] = (live && k < K) ? H[(long)k * ldh + n] : (T)0;
     an[k] = ad[k] = (T)0;
   }
-  for (int ft = fb; ft < fe; ft += TW_FT) {
+#pragma unroll
+  for (int s = 0; s < TW_STAGES - 1; ++s) {
+    if (s < nsteps) issue(s);
+    cp_async_commit();
+  }
+  for (int s = 0; s < nsteps; ++s) {
+    if (s + TW_STAGES - 1 < nsteps) issue(s + TW_STAGES - 1);
+    cp_async_commit();
+    cp_async_wait<TW_STAGES - 1>();
     __syncthreads();
-    for (int i = threadIdx.x; i < TW_FT * KC; i += TW_THREADS) {
-      const int r = i / KC, k = i % KC;
-      const int f = ft + r;
-      s_w[r][k] = (f < fe && k < K) ? W[(long)f * ldw + k] : (T)0;
-    }
-    __syncthreads();
-    const int rows = (fe - ft < TW_FT) ? (fe - ft) : TW_FT;
-    if (!live) continue;
+    const TwStage<T, KC>& st = stages[s % TW_STAGES];
+    const int rows = min(TW_RT, fe - (fb + s * TW_RT));
     for (int r = 0; r < rows; ++r) {
-      const long idx = (long)(ft + r) * ld + n;
-      const T hw = __ldg(hatW + idx);
-      const T o = pf_max(__ldg(Op + idx), kEps);
+      const T hw = st.hw[r][threadIdx.x];
+      const T o = pf_max(st.o[r][threadIdx.x], kEps);
       T w[KC];
       T p = (T)0;
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
-        w[k] = s_w[r][k];
+        w[k] = st.w[r][k];
         p += w[k] * h[k];
       }
-      p = pf_max(p, kEps);                 // own power with the updated W (:1639-1645)
+      p = pf_max(p, kEps);
       const T rp = pf_rcp(p);
-      const T e2 = o * rp;                 // other / P            (:1694-1701)
-      const T e1 = o * (hw * rp * rp);     // other * hat_W / P^2  (:1714-1720)
+      const T e2 = o * rp;               // other / P'            (:1694-1701)
+      const T e1 = o * (hw * rp * rp);   // other * hat_W / P'^2  (:1714-1720)
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
         an[k] += w[k] * e1;
         ad[k] += w[k] * e2;
       }
     }
+    __syncthreads();
   }
-  if (!live) return;
+  if (n >= ldo) return;
 #pragma unroll
   for (int k = 0; k < KC; ++k)
     if (k < K) {
-      num[((size_t)split * K + k) * ldo + n] = (double)an[k];
-      den[((size_t)split * K + k) * ldo + n] = (double)ad[k];
+      num[((size_t)split * K + k) * ldo + n] = live ? (double)an[k] : 0.0;
+      den[((size_t)split * K + k) * ldo + n] = live ? (double)ad[k] : 0.0;
     }
 }
 
@@ -325,10 +534,57 @@ static int launch_tw(const void* hatW, const void* O, long ld, const void* W, in
                      const void* H, long ldh, int K, int F, long N, int fchunk, int fsplit,
                      double* num, double* den, long ldo, cudaStream_t st) {
   dim3 grid(ceil_div(N, TW_THREADS), fsplit);
-  tw_contract_kernel<T, KC><<<grid, TW_THREADS, 0, st>>>((const T*)hatW, (const T*)O, ld,
-                                                         (const T*)W, ldw, (const T*)H, ldh, K, F,
-                                                         N, fchunk, fsplit, num, den, ldo);
+  const size_t smem = sizeof(TwStage<T, KC>) * TW_STAGES;
+  cudaError_t e = cudaFuncSetAttribute(tw_contract_kernel<T, KC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("tw_contract_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  tw_contract_kernel<T, KC><<<grid, TW_THREADS, smem, st>>>(
+      (const T*)hatW, (const T*)O, ld, (const T*)W, ldw, (const T*)H, ldh, K, F, N, fchunk,
+      fsplit, num, den, ldo);
   return check_launch("tw_contract_kernel");
+}
+
+template <typename T, int KC>
+static int launch_fb_same(const void* hatW, const void* P, long ld, const void* G, long ldg,
+                          int k0, int K, int F, long N, long chunk, int nsplit, double* num,
+                          cudaStream_t st) {
+  dim3 grid(nsplit, ceil_div(F, FBF_ROWS));
+  const size_t smem = sizeof(FbfStage<T, KC>) * FBF_STAGES;
+  cudaError_t e = cudaFuncSetAttribute(fb_contract_same_kernel<T, KC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("fb_contract_same_kernel: %zu bytes of shared memory: %s", smem,
+              cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  fb_contract_same_kernel<T, KC><<<grid, FBF_THREADS, smem, st>>>(
+      (const T*)hatW, (const T*)P, ld, (const T*)G, ldg, k0, K, F, N, chunk, nsplit, num);
+  return check_launch("fb_contract_same_kernel");
+}
+
+template <typename T>
+static int dispatch_fb_same(const void* hatW, const void* P, long ld, const void* G, long ldg,
+                            int K, int F, long N, long chunk, int nsplit, double* num, double* den,
+                            cudaStream_t st) {
+  int rc = PF_OK;
+  for (int k0 = 0; k0 < K && rc == PF_OK; k0 += 32) {
+    const int kc = K - k0;
+    if (kc <= 4)
+      rc = launch_fb_same<T, 4>(hatW, P, ld, G, ldg, k0, K, F, N, chunk, nsplit, num, st);
+    else if (kc <= 8)
+      rc = launch_fb_same<T, 8>(hatW, P, ld, G, ldg, k0, K, F, N, chunk, nsplit, num, st);
+    else if (kc <= 16)
+      rc = launch_fb_same<T, 16>(hatW, P, ld, G, ldg, k0, K, F, N, chunk, nsplit, num, st);
+    else
+      rc = launch_fb_same<T, 32>(hatW, P, ld, G, ldg, k0, K, F, N, chunk, nsplit, num, st);
+  }
+  if (rc) return rc;
+  dim3 grid(nsplit, K);
+  g_rowsum_kernel<T><<<grid, 256, 0, st>>>((const T*)G, ldg, K, F, N, chunk, den);
+  return check_launch("g_rowsum_kernel");
 }
 
 template <typename T>
@@ -369,20 +625,17 @@ extern "C" int pf_spec_power(const void* W, int ldw, const void* H, int64_t ldh,
 }
 
 extern "C" int pf_nmf_fb_plan(int F, int K, int64_t N, int dtype, int64_t* chunk, int* nsplit) {
+  // ~32 steps of one tile (128 / 64 frames) per CTA: many CTAs of equal, moderate length
+  // balance over the 148 SMs without a tail, and the end-of-CTA reduction stays amortised
   const long vec = dtype == PF_F64 ? 2 : 4;
   const long nt = 32 * vec;
-  const int kc = K >= 17 ? 32 : (K > 8 ? 16 : (K > 4 ? 8 : 4));
-  const int fr = kc == 4 ? 8 : (kc == 8 ? 4 : 2);
-  const int ft = (FB_THREADS / 32) * fr;
-  const long fblocks = (F + ft - 1) / ft;
   long steps = (N + nt - 1) / nt;
-  // enough CTAs for ~4 per SM, at least 8 steps each
-  long ns = (148L * 4 + fblocks - 1) / fblocks;
-  if (ns > steps / 8) ns = steps / 8;
-  if (ns < 1) ns = 1;
-  long per = (steps + ns - 1) / ns;
+  long per = 32;
+  const long fblocks = (F + FBF_ROWS - 1) / FBF_ROWS;
+  while (per > 4 && fblocks * ((steps + per - 1) / per) < 148L * 2) per /= 2;
   *chunk = per * nt;
   *nsplit = (int)((N + *chunk - 1) / *chunk);
+  (void)K;
   return PF_OK;
 }
 
@@ -393,7 +646,16 @@ extern "C" int pf_nmf_fb_contract(const void* hatW, const void* P, const void* O
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_nmf_fb_contract: bad dtype %d", dtype);
   PF_REQUIRE(ld % 4 == 0 && ldg % 4 == 0, "pf_nmf_fb_contract: ld/ldg must be multiples of 4");
   PF_REQUIRE(chunk > 0 && (int64_t)nsplit * chunk >= N, "pf_nmf_fb_contract: bad split plan");
+  const long nt = 32 * (dtype == PF_F64 ? 2 : 4);
+  PF_REQUIRE(chunk % nt == 0, "pf_nmf_fb_contract: chunk must be a multiple of %ld frames", nt);
   cudaStream_t st = as_stream(stream);
+  if (P == O) {  // one plane: O/P == 1, see fb_contract_same_kernel
+    if (dtype == PF_F32)
+      return dispatch_fb_same<float>(hatW, P, ld, G, ldg, K, F, N, chunk, nsplit, num_partial,
+                                     den_partial, st);
+    return dispatch_fb_same<double>(hatW, P, ld, G, ldg, K, F, N, chunk, nsplit, num_partial,
+                                    den_partial, st);
+  }
   if (dtype == PF_F32)
     return dispatch_fb<float>(hatW, P, O, ld, G, ldg, K, F, N, chunk, nsplit, num_partial,
                               den_partial, st);
@@ -402,14 +664,19 @@ extern "C" int pf_nmf_fb_contract(const void* hatW, const void* P, const void* O
 }
 
 extern "C" int pf_nmf_tw_plan(int F, int K, int64_t N, int* fchunk, int* fsplit) {
+  // a CTA covers 128 frames; split the frequency axis until ~3 CTAs per SM are in flight,
+  // keeping at least two pipeline stages of rows per CTA
   const long nblocks = (N + TW_THREADS - 1) / TW_THREADS;
-  long fs = (148L * 8 + nblocks - 1) / nblocks;
-  if (fs > (F + 63) / 64) fs = (F + 63) / 64;
+  long fs = (148L * 3 + nblocks / 2) / nblocks;
+  const long max_fs = (F + 2 * TW_RT - 1) / (2 * TW_RT);
+  if (fs > max_fs) fs = max_fs;
+  if (fs > 64) fs = 64;
   if (fs < 1) fs = 1;
   int fc = (int)((F + fs - 1) / fs);
-  fc = ((fc + TW_FT - 1) / TW_FT) * TW_FT;
+  fc = ((fc + TW_RT - 1) / TW_RT) * TW_RT;
   *fchunk = fc;
   *fsplit = (F + fc - 1) / fc;
+  (void)K;
   return PF_OK;
 }
 

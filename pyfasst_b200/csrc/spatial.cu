@@ -265,7 +265,8 @@ __global__ void fw_renorm_kernel(T* __restrict__ FW, int ldfw, int Kb, int Kw,
   }
 }
 
-// M[r][c] *= (by_row ? s[r] : s[c]) or /= ; optional sum of the result (TW restart test)
+// M[r][c] *= (by_row ? s[r] : s[c]) or /= ; optional sum of the result (TW restart test,
+// audioModel.py:2023): one atomic per CTA after a block reduction
 template <typename T>
 __global__ void scale_matrix_kernel(T* __restrict__ M, long ldm, int rows, long cols,
                                     const double* __restrict__ s, int by_row, int divide,
@@ -280,8 +281,15 @@ __global__ void scale_matrix_kernel(T* __restrict__ M, long ldm, int rows, long 
     M[(size_t)r * ldm + c] = (T)v;
   }
   if (total != nullptr) {
+    __shared__ double s_red[32];
     v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(total, v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double d = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) d += s_red[w];
+      if (d != 0.0) atomicAdd(total, d);
+    }
   }
 }
 

@@ -85,10 +85,12 @@ class FakeKernels(object):
         return r00, r11, r01
 
     def _sigma_inv_y(self, X, V, A, src_of_sub, noise, N):
+        """Per-bin algebra in float64 whatever the storage type (like the kernels, which
+        keep Sigma^-1 and y in double: see estep_stereo_kernel)."""
         J = V.shape[0]
-        t = {torch.float32: np.float32, torch.float64: np.float64}[V.dtype]
+        t = np.float64
         r00, r11, r01 = self._spat(A, src_of_sub, J)
-        Xn, Vn = _np(X)[:, :, :N], _np(V)[:, :, :N]
+        Xn, Vn = _np(X)[:, :, :N].astype(t), _np(V)[:, :, :N].astype(t)
         s2 = _np(noise).astype(t)[:, None]
         col = lambda a: a.astype(t)[:, None]
         s00 = s2 + sum(Vn[j] * col(r00[j]) for j in range(J))
@@ -118,7 +120,7 @@ class FakeKernels(object):
         J = V.shape[0]
         (r00, r11, r01), det, inv, (y0r, y0i, y1r, y1i), col = self._sigma_inv_y(
             X, V, A, src_of_sub, noise, N)
-        Vn, Yn = _np(V)[:, :, :N], _np(Y)
+        Vn, Yn = _np(V)[:, :, :N].astype(np.float64), _np(Y)
         Yn[:] = 0
         for g in range(ngroups):
             g00 = sum(Vn[j] * col(r00[j]) for j in range(J) if group_of_src[j] == g)
@@ -138,13 +140,13 @@ class FakeKernels(object):
         self.launches += 3
         J, F, ld = V.shape
         R = A.shape[0]
-        t = {torch.float32: np.float32, torch.float64: np.float64}[V.dtype]
+        t = np.float64
         (r00, r11, r01), det, (i00, i11, i01r, i01i), (y0r, y0i, y1r, y1i), col = \
             self._sigma_inv_y(X, V, A, src_of_sub, noise, N)
-        Xn, Vn = _np(X)[:, :, :N], _np(V)[:, :, :N]
+        Xn, Vn = _np(X)[:, :, :N].astype(t), _np(V)[:, :, :N].astype(t)
         x0r, x0i, x1r, x1i = Xn
         quad = x0r * y0r + x0i * y0i + x1r * y1r + x1i * y1i
-        _np(ll_f)[:] = (np.log(det) + t(np.log(np.pi)) + quad).astype(np.float64).sum(1)
+        _np(ll_f)[:] = (np.log(det) + np.log(np.pi) + quad).sum(1)
         m00 = y0r * y0r + y0i * y0i - i00
         m11 = y1r * y1r + y1i * y1i - i11
         m01r = y0r * y1r + y0i * y1i - i01r
