@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 3
+#define PF_ABI_VERSION 4
 
 #define PF_OK 0
 #define PF_ERR_ARG (-1)         /* invalid argument (ValueError on the Python side) */
@@ -57,15 +57,23 @@ int pf_set_device(int device);
 
 /* ---- K1: STFT front end  (tftransforms/stft.py:3-69, audioModel.py:250-328) --- */
 /* Framing + window + real FFT of `nch` channels in one launch.
- * pcm     : double [nch][L] (already scaled, audioObject.py:124-127)
+ * pcm     : the samples in the layout the host has them in (pcm_format):
+ *           PF_PCM_F64_PLANAR double [nch][L]; PF_PCM_I16 / PF_PCM_I32 / PF_PCM_F32
+ *           interleaved [L][nch] as read from a WAV file.  Every sample is divided by
+ *           pcm_div in float64 first (the reference's data / (1.1*max), audioObject.py:124-127)
  * window  : double [wlen] (host-built np.hanning etc.), nfft >= wlen, nfft = 2^k
  * X       : dtype planes [2*nch][F][ld] = (re, im) per channel, F = nfft/2+1,
  *           N = ceil(L/hop)+2 frames (stft.py:40)
  * psd_sum : double [F], sum over channels and frames of |X|^2 (for the annealing
  *           limits, audioModel.py:304-323); may be NULL
  * The FFT itself always runs in float64. */
-int pf_stft(const double* pcm, int nch, int64_t L, const double* window, int wlen, int hop,
-            int nfft, void* X, int64_t N, int64_t ld, double* psd_sum, int dtype, void* stream);
+#define PF_PCM_F64_PLANAR 0
+#define PF_PCM_I16 1
+#define PF_PCM_I32 2
+#define PF_PCM_F32 3
+int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch, int64_t L,
+            const double* window, int wlen, int hop, int nfft, void* X, int64_t N, int64_t ld,
+            double* psd_sum, int dtype, void* stream);
 
 /* ---- K6: inverse STFT with overlap-add  (tftransforms/stft.py:71-131) --------- */
 /* Y       : dtype planes [2*nsig][F][ld]

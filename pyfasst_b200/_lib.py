@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpyfasst_b200.so")
 
 PF_F32, PF_F64 = 0, 1
 PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 c_ip = ctypes.POINTER(ctypes.c_int)
@@ -26,8 +26,8 @@ SIGNATURES = {
     "pf_abi_version": [],
     "pf_launch_count": [],
     "pf_set_device": [c_int],
-    "pf_stft": [c_vp, c_int, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_int,
-                c_vp],
+    "pf_stft": [c_vp, c_int, c_dbl, c_int, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64,
+                c_vp, c_int, c_vp],
     "pf_istft": [c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64,
                  c_vp, c_dbl, c_int, c_vp],
     "pf_wiener_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_ip, c_int, c_int, c_i64,
@@ -145,13 +145,19 @@ class CudaKernels(object):
         return int(self.lib.pf_launch_count())
 
     # -- K1 / K6 -------------------------------------------------------------------
-    def stft(self, pcm, window, hop, nfft, X, N, psd_sum):
-        nch, L = pcm.shape
+    def stft(self, pcm, window, hop, nfft, X, N, psd_sum, pcm_div=1.0):
+        """pcm: float64 [nch, L] (planar) or int16 / int32 / float32 [L, nch] (interleaved)."""
+        torch = self.torch
+        if pcm.dtype == torch.float64:
+            fmt, (nch, L) = 0, pcm.shape
+        else:
+            fmt = {torch.int16: 1, torch.int32: 2, torch.float32: 3}[pcm.dtype]
+            L, nch = pcm.shape
         F, ld = X.shape[1], X.shape[2]
         assert X.shape[0] == 2 * nch and F == nfft // 2 + 1
-        _check(self.lib.pf_stft(self._p(pcm), nch, L, self._p(window), window.numel(), hop, nfft,
-                                self._p(X), N, ld, self._p(psd_sum), self.dtype_code(X),
-                                self._stream()), self.lib)
+        _check(self.lib.pf_stft(self._p(pcm), fmt, float(pcm_div), nch, L, self._p(window),
+                                window.numel(), hop, nfft, self._p(X), N, ld, self._p(psd_sum),
+                                self.dtype_code(X), self._stream()), self.lib)
 
     def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata):
         nsig = Y.shape[0] // 2

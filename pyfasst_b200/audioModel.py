@@ -117,20 +117,37 @@ class FASST(object):
         if self.sig_repr_params['transf'] not in self.implemented_transf:
             raise ValueError(self.sig_repr_params['transf'] + " not implemented - yet?")
         k = self._k()
-        data = np.asarray(self.audioObject.data, dtype=np.float64)
-        if data.ndim == 1:
-            data = data[:, None]
-        nc = data.shape[1]
+        aobj = self.audioObject
+        if hasattr(aobj, '_data'):
+            # the user already holds the scaled float64 samples (e.g. set through `.data`)
+            data = np.asarray(aobj._data, dtype=np.float64)
+            if data.ndim == 1:
+                data = data[:, None]
+            nc = data.shape[1]
+            pcm, div = torch.tensor(np.ascontiguousarray(data.T)).to(k.device), 1.0
+        else:
+            # ship the samples as stored (int16: 4x fewer bytes than float64) and let the
+            # STFT kernel apply the reference's scaling data / (1.1 max|data|)
+            if not hasattr(aobj, '_raw'):
+                aobj._read_raw()
+            raw = aobj._raw if hasattr(aobj._raw, "numpy") else torch.from_numpy(
+                np.ascontiguousarray(aobj._raw))
+            if raw.dim() == 1:
+                raw = raw[:, None]
+            nc = raw.shape[1]
+            if raw.dtype not in (torch.int16, torch.int32, torch.float32):
+                raw = raw.to(torch.float64).t().contiguous()  # planar float64 path
+            pcm, div = raw.to(k.device, non_blocking=True), float(aobj._maxdata)
         if nc != 2:
             raise AttributeError("Nb channels " + str(nc) + " not implemented yet")
-        pcm = torch.tensor(np.ascontiguousarray(data.T)).to(k.device)
         F = self.sig_repr_params['fsize'] // 2 + 1
         psd = torch.zeros(F, dtype=torch.float64, device=k.device)
         X, N = _stft.stft_planes(k, pcm, self.tft.window, self.sig_repr_params['hopsize'],
-                                 self.sig_repr_params['fsize'], self.compute_dtype, psd)
+                                 self.sig_repr_params['fsize'], self.compute_dtype, psd,
+                                 pcm_div=div)
         self.nbFreqsSigRepr, self.nbFramesSigRepr = F, N
         self._Cx = None
-        del self.audioObject.data  # like the reference (:288): re-read at separation
+        del self.audioObject.data  # like the reference (:288); `_raw`, if any, is kept
         if self._comm is not None and self._comm.world > 1:
             from .engine import shard_bounds
             lo, hi = shard_bounds(F, self._comm.world)[self._comm.rank]

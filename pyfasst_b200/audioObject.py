@@ -41,17 +41,44 @@ class AudioObject(object):
         self.filename = filename
         self.mode = mode
 
-    def _read(self):
+    def _read_raw(self):
+        """Reads the file WITHOUT building the scaled float64 copy: `_raw` keeps the samples
+        as stored ([nframes, channels] or [nframes]); `_maxdata` as in `_read`.  The STFT
+        kernel scales on the device (pf_stft: pcm / pcm_div), so the hot path never touches
+        a 4x larger float64 array on the host."""
         if 'r' not in self.mode:
             raise ValueError("Not in read mode.")
-        self._samplerate, self._data, self._encoding = wavread(self.filename)
-        if len(self._data.shape) == 2:
-            self._nframes, self._channels = self._data.shape
+        self._samplerate, raw, self._encoding = wavread(self.filename)
+        self._set_raw(raw)
+
+    def _set_raw(self, raw):
+        """Adopt an in-memory PCM array (numpy or a pinned torch tensor), [nframes, channels]."""
+        self._raw = raw
+        shape = tuple(raw.shape)
+        if len(shape) == 2:
+            self._nframes, self._channels = shape
         else:
-            self._nframes = self._data.size
-            self._channels = 1
-        self._maxdata = np.maximum(1.1 * np.abs(self._data).max(), 1e-10)
-        self._data = self._data / self._maxdata
+            self._nframes, self._channels = int(np.prod(shape)), 1
+        arr = raw.numpy() if hasattr(raw, "numpy") else np.asarray(raw)
+        if not hasattr(self, "_encoding"):
+            self._encoding = arr.dtype
+        # 1.1 * max|x| without the abs() temporary (ref: audioObject.py:124-126)
+        peak = 0.0
+        if arr.size:
+            lo, hi = arr.min(), arr.max()
+            if np.issubdtype(arr.dtype, np.signedinteger) and lo == np.iinfo(arr.dtype).min:
+                # np.abs() of the most negative integer wraps to itself in the reference
+                rest = arr[arr > lo]
+                lo = rest.min() if rest.size else 0
+            peak = max(abs(float(lo)), abs(float(hi)))
+        self._maxdata = np.maximum(1.1 * peak, 1e-10)
+
+    def _read(self):
+        """ref: audioObject.py:112-127"""
+        if not hasattr(self, '_raw'):
+            self._read_raw()
+        raw = self._raw.numpy() if hasattr(self._raw, "numpy") else np.asarray(self._raw)
+        self._data = raw / self._maxdata
 
     def _write(self):
         if 'w' not in self.mode:

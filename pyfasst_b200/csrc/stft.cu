@@ -52,11 +52,22 @@ struct Sector {  // elements of T in one 32-byte DRAM sector
 };
 
 // ---- forward ------------------------------------------------------------------------
-template <typename T>
+// sample (channel ch, time s) of the input in its host layout, as the scaled float64 the
+// reference works on (audioObject.py:124-127: data / maxdata)
+template <int FMT>
+__device__ __forceinline__ double pcm_sample(const void* __restrict__ pcm, int nch, long L, int ch,
+                                             long s, double div) {
+  if (FMT == PF_PCM_F64_PLANAR) return reinterpret_cast<const double*>(pcm)[(size_t)ch * L + s] / div;
+  if (FMT == PF_PCM_I16) return (double)reinterpret_cast<const int16_t*>(pcm)[(size_t)s * nch + ch] / div;
+  if (FMT == PF_PCM_I32) return (double)reinterpret_cast<const int32_t*>(pcm)[(size_t)s * nch + ch] / div;
+  return (double)reinterpret_cast<const float*>(pcm)[(size_t)s * nch + ch] / div;
+}
+
+template <typename T, int FMT>
 __global__ void __launch_bounds__(FFT_THREADS)
-stft_kernel(const double* __restrict__ pcm, long L, const double* __restrict__ window, int wlen,
-            int hop, int nfft, int log2m, const double2* __restrict__ tw, T* __restrict__ X,
-            int F, long N, long ld) {
+stft_kernel(const void* __restrict__ pcm, int nch, double div, long L,
+            const double* __restrict__ window, int wlen, int hop, int nfft, int log2m,
+            const double2* __restrict__ tw, T* __restrict__ X, int F, long N, long ld) {
   constexpr int TN = Sector<T>::N;
   constexpr int ROW = 2 * TN + 1;  // padded staging row: (re[TN], im[TN]) per bin
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -65,7 +76,6 @@ stft_kernel(const double* __restrict__ pcm, long L, const double* __restrict__ w
   T* stage = reinterpret_cast<T*>(smem_raw + (size_t)M * sizeof(double2));
   const int ch = blockIdx.y;
   const long n0 = (long)blockIdx.x * TN;
-  const double* x = pcm + (size_t)ch * L;
 
   for (int t = 0; t < TN; ++t) {
     const long n = n0 + t;
@@ -84,7 +94,9 @@ stft_kernel(const double* __restrict__ pcm, long L, const double* __restrict__ w
       for (int e = 0; e < 2; ++e) {
         const int i = 2 * m + e;
         const long s = base + i;
-        v[e] = (i < wlen && s >= 0 && s < L) ? x[s] * __ldg(window + i) : 0.0;
+        v[e] = (i < wlen && s >= 0 && s < L)
+                   ? pcm_sample<FMT>(pcm, nch, L, ch, s, div) * __ldg(window + i)
+                   : 0.0;
       }
       buf[__brev((unsigned)m) >> (32 - log2m)] = make_double2(v[0], v[1]);
     }
@@ -275,9 +287,10 @@ static const double2* twiddles(int nfft, cudaStream_t st) {
   return slot->ptr;
 }
 
-template <typename T>
-static int launch_stft(const double* pcm, int nch, long L, const double* window, int wlen, int hop,
-                       int nfft, void* X, long N, long ld, double* psd_sum, cudaStream_t st) {
+template <typename T, int FMT>
+static int launch_stft(const void* pcm, int nch, double div, long L, const double* window, int wlen,
+                       int hop, int nfft, void* X, long N, long ld, double* psd_sum,
+                       cudaStream_t st) {
   constexpr int TN = Sector<T>::N;
   const int M = nfft / 2, F = M + 1;
   const double2* tw = twiddles(nfft, st);
@@ -286,15 +299,15 @@ static int launch_stft(const double* pcm, int nch, long L, const double* window,
     return PF_ERR_CUDA;
   }
   const size_t smem = (size_t)M * sizeof(double2) + (size_t)F * (2 * TN + 1) * sizeof(T);
-  cudaError_t e = cudaFuncSetAttribute(stft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(stft_kernel<T, FMT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("pf_stft: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return PF_ERR_CUDA;
   }
   dim3 grid(ceil_div(N, TN), nch);
-  stft_kernel<T><<<grid, FFT_THREADS, smem, st>>>(pcm, L, window, wlen, hop, nfft, ilog2(M), tw,
-                                                 (T*)X, F, N, ld);
+  stft_kernel<T, FMT><<<grid, FFT_THREADS, smem, st>>>(pcm, nch, div, L, window, wlen, hop, nfft,
+                                                      ilog2(M), tw, (T*)X, F, N, ld);
   int rc = check_launch("stft_kernel");
   if (rc) return rc;
   if (psd_sum != nullptr) {
@@ -302,6 +315,24 @@ static int launch_stft(const double* pcm, int nch, long L, const double* window,
     rc = check_launch("psd_sum_kernel");
   }
   return rc;
+}
+
+template <typename T>
+static int dispatch_stft(int fmt, const void* pcm, int nch, double div, long L,
+                         const double* window, int wlen, int hop, int nfft, void* X, long N,
+                         long ld, double* psd_sum, cudaStream_t st) {
+  switch (fmt) {
+    case PF_PCM_F64_PLANAR:
+      return launch_stft<T, PF_PCM_F64_PLANAR>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+    case PF_PCM_I16:
+      return launch_stft<T, PF_PCM_I16>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+    case PF_PCM_I32:
+      return launch_stft<T, PF_PCM_I32>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+    case PF_PCM_F32:
+      return launch_stft<T, PF_PCM_F32>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+  }
+  set_error("pf_stft: unknown PCM format %d", fmt);
+  return PF_ERR_ARG;
 }
 
 template <typename T>
@@ -347,20 +378,23 @@ static int check_fft_args(const char* who, int wlen, int hop, int nfft) {
   return PF_OK;
 }
 
-extern "C" int pf_stft(const double* pcm, int nch, int64_t L, const double* window, int wlen,
-                       int hop, int nfft, void* X, int64_t N, int64_t ld, double* psd_sum,
-                       int dtype, void* stream) {
+extern "C" int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch, int64_t L,
+                       const double* window, int wlen, int hop, int nfft, void* X, int64_t N,
+                       int64_t ld, double* psd_sum, int dtype, void* stream) {
   int rc = check_fft_args("pf_stft", wlen, hop, nfft);
   if (rc) return rc;
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_stft: bad dtype %d", dtype);
   PF_REQUIRE(nch >= 1 && nch <= 16 && L > 0, "pf_stft: nch=%d L=%ld", nch, (long)L);
+  PF_REQUIRE(pcm_div != 0.0, "pf_stft: pcm_div must not be zero");
   PF_REQUIRE(N == (L + hop - 1) / hop + 2, "pf_stft: N=%ld is not ceil(L/hop)+2 (stft.py:40)",
              (long)N);
   PF_REQUIRE(ld >= N && ld % 4 == 0, "pf_stft: ld=%ld must be >= N and a multiple of 4", (long)ld);
   cudaStream_t st = as_stream(stream);
   if (dtype == PF_F32)
-    return launch_stft<float>(pcm, nch, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
-  return launch_stft<double>(pcm, nch, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+    return dispatch_stft<float>(pcm_format, pcm, nch, pcm_div, L, window, wlen, hop, nfft, X, N,
+                                ld, psd_sum, st);
+  return dispatch_stft<double>(pcm_format, pcm, nch, pcm_div, L, window, wlen, hop, nfft, X, N, ld,
+                               psd_sum, st);
 }
 
 extern "C" int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld,

@@ -43,16 +43,22 @@ def overlap_norm(window, analysisWindow, hopsize, nframes):
     return norm
 
 
-def stft_planes(kernels, pcm, window, hopsize, nfft, dtype="float64", psd_sum=None):
-    """pcm: device float64 [nch, L].  Returns (X planes [2*nch, F, ld] of `dtype`, N)."""
+def stft_planes(kernels, pcm, window, hopsize, nfft, dtype="float64", psd_sum=None,
+                pcm_div=1.0):
+    """pcm: device float64 [nch, L] (planar) or int16 / int32 / float32 [L, nch] as read
+    from a WAV file; every sample is divided by `pcm_div` on the device.
+    Returns (X planes [2*nch, F, ld] of `dtype`, N)."""
     import torch
-    nch, L = pcm.shape
+    if pcm.dtype == torch.float64:
+        nch, L = pcm.shape
+    else:
+        L, nch = pcm.shape
     N = number_of_frames(L, hopsize)
     ld = (N + 31) // 32 * 32
     F = nfft // 2 + 1
     X = torch.zeros([2 * nch, F, ld], dtype=_tdtype(torch, dtype), device=pcm.device)
     win = torch.tensor(np.asarray(window, dtype=np.float64)).to(pcm.device)
-    kernels.stft(pcm, win, int(hopsize), int(nfft), X, N, psd_sum)
+    kernels.stft(pcm, win, int(hopsize), int(nfft), X, N, psd_sum, pcm_div)
     return X, N
 
 

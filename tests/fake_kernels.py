@@ -35,9 +35,12 @@ class FakeKernels(object):
         return self.launches
 
     # ---- K1 / K6 -------------------------------------------------------------------
-    def stft(self, pcm, window, hop, nfft, X, N, psd_sum):
+    def stft(self, pcm, window, hop, nfft, X, N, psd_sum, pcm_div=1.0):
         self.launches += 1
         x, w = _np(pcm), _np(window)
+        if x.dtype != np.float64:
+            x = x.T  # interleaved [L, nch] -> planar
+        x = x.astype(np.float64) / pcm_div
         nch, L = x.shape
         wlen = w.size
         Xo = _np(X)
