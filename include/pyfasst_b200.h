@@ -177,6 +177,12 @@ int pf_scale_matrix(void* M, int64_t ldm, int rows, int64_t cols, const double* 
 /* totals[s] < eps  ->  *flags |= PF_FLAG_TW_RESTART ; totals are reset to zero */
 int pf_check_totals(double* totals, int count, double eps, int* flags, void* stream);
 
+/* ---- tcgen05 self-test (pins the descriptor / layout conventions of csrc/tc.cuh) ------ */
+/* D[128][N] = A B^T in tf32 (split3: 3xTF32, fp32-class accuracy).  A: a_mn ? [K][128] :
+ * [128][K]; B: b_mn ? [K][N] : [N][K]; float32 device buffers; N, K multiples of 32. */
+int pf_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn,
+                   int split3, void* stream);
+
 /* ---- GEM loop glue  (audioModel.py:330-382) --------------------------------------- */
 /* noise[f] = ((sqrt_lim0[f]*(I-i) + sqrt_lim1[f]*i)/I)^2 with i read from *iter_dev
  * (audioModel.py:368-373), so that a captured CUDA graph can be replayed. */

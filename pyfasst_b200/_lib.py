@@ -57,6 +57,7 @@ SIGNATURES = {
     "pf_fw_renorm": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "pf_scale_matrix": [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     "pf_check_totals": [c_vp, c_int, c_dbl, c_vp, c_vp],
+    "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_ll_reduce": [c_vp, c_int, c_vp, c_vp],
     "pf_ll_store": [c_vp, c_dbl, c_vp, c_vp, c_int, c_vp],
