@@ -20,6 +20,8 @@
 // P = max(power of all spectral comps of the spatial comp, eps) (Q3),
 // O = max(other-factor power, eps) which for single-factor models is the component's
 // own power before the update (Q1/Q2).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pf {
@@ -603,6 +605,18 @@ static int dispatch_tw(const void* hatW, const void* O, long ld, const void* W, 
 
 using namespace pf;
 
+// tcgen05 versions (nmf_tc.cu), float32 planes only
+int pf_fb_contract_tc(const float* hatW, const float* P, long ld, const float* G, long ldg, int K,
+                      int F, long N, long chunk, int nsplit, double* num, cudaStream_t st);
+static bool use_tensor_cores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PYFASST_NO_TENSOR_CORES");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" int pf_spec_power(const void* W, int ldw, const void* H, int64_t ldh, void* V,
                              int64_t ldv, int F, int K, int64_t N, int accumulate, int dtype,
                              void* stream) {
@@ -625,11 +639,22 @@ extern "C" int pf_spec_power(const void* W, int ldw, const void* H, int64_t ldh,
 }
 
 extern "C" int pf_nmf_fb_plan(int F, int K, int64_t N, int dtype, int64_t* chunk, int* nsplit) {
-  // ~32 steps of one tile (128 / 64 frames) per CTA: many CTAs of equal, moderate length
-  // balance over the 148 SMs without a tail, and the end-of-CTA reduction stays amortised
   const long vec = dtype == PF_F64 ? 2 : 4;
   const long nt = 32 * vec;
   long steps = (N + nt - 1) / nt;
+  if (dtype == PF_F32 && use_tensor_cores()) {
+    // tcgen05 kernel: CTAs of 128 rows, two resident per SM -> ~2 x 148 CTAs of equal length
+    const long fblocks = (F + 127) / 128;
+    long ns = (2 * 148L + fblocks - 1) / fblocks;
+    if (ns > steps) ns = steps;
+    if (ns < 1) ns = 1;
+    const long per = (steps + ns - 1) / ns;
+    *chunk = per * nt;
+    *nsplit = (int)((N + *chunk - 1) / *chunk);
+    return PF_OK;
+  }
+  // CUDA-core kernel: ~32 steps of one tile (128 / 64 frames) per CTA: many CTAs of equal,
+  // moderate length balance over the 148 SMs without a tail
   long per = 32;
   const long fblocks = (F + FBF_ROWS - 1) / FBF_ROWS;
   while (per > 4 && fblocks * ((steps + per - 1) / per) < 148L * 2) per /= 2;
@@ -650,6 +675,15 @@ extern "C" int pf_nmf_fb_contract(const void* hatW, const void* P, const void* O
   PF_REQUIRE(chunk % nt == 0, "pf_nmf_fb_contract: chunk must be a multiple of %ld frames", nt);
   cudaStream_t st = as_stream(stream);
   if (P == O) {  // one plane: O/P == 1, see fb_contract_same_kernel
+    if (dtype == PF_F32 && use_tensor_cores()) {
+      int rc = pf_fb_contract_tc((const float*)hatW, (const float*)P, ld, (const float*)G, ldg, K,
+                                 F, N, chunk, nsplit, num_partial, st);
+      if (rc) return rc;
+      dim3 grid(nsplit, K);
+      g_rowsum_kernel<float><<<grid, 256, 0, st>>>((const float*)G, ldg, K, F, N, chunk,
+                                                   den_partial);
+      return check_launch("g_rowsum_kernel");
+    }
     if (dtype == PF_F32)
       return dispatch_fb_same<float>(hatW, P, ld, G, ldg, K, F, N, chunk, nsplit, num_partial,
                                      den_partial, st);

@@ -8,9 +8,12 @@
 //   K-major  [rows][32 k]  : byte(r, k) = (r/8)*1024 + (r%8)*128 + (((k/4) ^ (r%8)) * 16) + (k%4)*4
 //                            one MMA (K = 8) reads 32 bytes of each row: descriptor start
 //                            address advanced by 32 bytes per K step; SBO = 1024 (8-row groups)
-//   MN-major [8 k][mn]     : byte(k, m) = (m/32)*LBO + k*128 + ((((m%32)/4) ^ k) * 16) + (m%4)*4
-//                            one MMA reads one such 8-row group (K = 8); LBO = distance between
-//                            32-element groups along MN, SBO = distance between 8-row K groups
+//   MN-major [k][mn]       : tf32 operands that are contiguous along M / N must use the
+//                            SWIZZLE_128B_BASE32B layout (32-byte swizzle granules, 4-row atoms):
+//                            byte(k, m) = (m/32)*LBO + (k/4)*SBO + (k%4)*128
+//                                         + ((((m%32)/8) ^ (k%4)) * 32) + (m%8)*4
+//                            LBO = distance between 32-element groups along MN, SBO = distance
+//                            between 4-row groups along K; one MMA (K = 8) reads two K groups
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,16 +26,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- descriptors ---------------------------------------------------------------------
-// 64-bit shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version field = 1
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
-                                                    uint32_t sbo_bytes) {
+// 64-bit shared-memory matrix descriptor (Blackwell version field = 1).
+// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major tf32 tiles)
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // version
-  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr) {
+  return smem_desc(saddr, 16, 1024, LAYOUT_SW128);
+}
+__device__ __forceinline__ uint64_t smem_desc_mnmajor(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return smem_desc(saddr, lbo, sbo, LAYOUT_SW128_BASE32B);
 }
 
 // 32-bit instruction descriptor: D = F32, A = B = TF32, dense, M x N, operand majors
@@ -45,9 +56,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, 
 __device__ __forceinline__ uint32_t kmajor_off(int r, int k) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4);
 }
-// byte offset of element (k row in [0,8), m) in an MN-major SW128 tile; group stride lbo
-__device__ __forceinline__ uint32_t mnmajor_off(int k, int m, uint32_t lbo) {
-  return (uint32_t)((m >> 5) * lbo + k * 128 + (((((m & 31) >> 2) ^ k) & 7) << 4) + (m & 3) * 4);
+// byte offset of element (k, m) in an MN-major SW128_BASE32B tile
+__device__ __forceinline__ uint32_t mnmajor_off(int k, int m, uint32_t lbo, uint32_t sbo) {
+  return (uint32_t)((m >> 5) * lbo + (k >> 2) * sbo + (k & 3) * 128 +
+                    (((((m & 31) >> 3) ^ (k & 3)) & 3) << 5) + (m & 7) * 4);
 }
 
 // ---- TMEM ------------------------------------------------------------------------------

@@ -23,7 +23,8 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
   unsigned char* a_lo = a_hi + a_bytes;
   unsigned char* b_hi = a_lo + a_bytes;
   unsigned char* b_lo = b_hi + b_bytes;
-  const uint32_t lbo = 1024, sbo_a = 4 * 1024, sbo_b = (uint32_t)(N / 32) * 1024;
+  // MN-major tiles of a 32-row K chunk: per 32-wide MN group all 32 k rows are stacked
+  const uint32_t lbo = 32 * 128, sbo = 512;
 
   uint32_t ncols = 32;
   while ((int)ncols < N) ncols <<= 1;
@@ -48,8 +49,7 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
       float hi, lo;
       tc::split_tf32(x, hi, lo);
       if (!split3) hi = x;
-      const uint32_t off = a_mn ? (uint32_t)(k >> 3) * sbo_a + tc::mnmajor_off(k & 7, r, lbo)
-                                : tc::kmajor_off(r, k);
+      const uint32_t off = a_mn ? tc::mnmajor_off(k, r, lbo, sbo) : tc::kmajor_off(r, k);
       *reinterpret_cast<float*>(a_hi + off) = hi;
       *reinterpret_cast<float*>(a_lo + off) = lo;
     }
@@ -61,8 +61,7 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
       float hi, lo;
       tc::split_tf32(x, hi, lo);
       if (!split3) hi = x;
-      const uint32_t off = b_mn ? (uint32_t)(k >> 3) * sbo_b + tc::mnmajor_off(k & 7, n, lbo)
-                                : tc::kmajor_off(n, k);
+      const uint32_t off = b_mn ? tc::mnmajor_off(k, n, lbo, sbo) : tc::kmajor_off(n, k);
       *reinterpret_cast<float*>(b_hi + off) = hi;
       *reinterpret_cast<float*>(b_lo + off) = lo;
     }
@@ -71,11 +70,15 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     if (tid == 0) {
       tc::fence_after_thread_sync();
       for (int j = 0; j < 4; ++j) {
-        const uint32_t ao = a_mn ? j * sbo_a : j * 32, bo = b_mn ? j * sbo_b : j * 32;
-        const uint64_t dah = tc::smem_desc_sw128(tc::smem_u32(a_hi) + ao, a_mn ? lbo : 16, a_mn ? sbo_a : 1024);
-        const uint64_t dal = tc::smem_desc_sw128(tc::smem_u32(a_lo) + ao, a_mn ? lbo : 16, a_mn ? sbo_a : 1024);
-        const uint64_t dbh = tc::smem_desc_sw128(tc::smem_u32(b_hi) + bo, b_mn ? lbo : 16, b_mn ? sbo_b : 1024);
-        const uint64_t dbl = tc::smem_desc_sw128(tc::smem_u32(b_lo) + bo, b_mn ? lbo : 16, b_mn ? sbo_b : 1024);
+        // K step j: 32 bytes further along a K-major row, 8 rows (1024 bytes) further down an
+        // MN-major column
+        const uint32_t ao = a_mn ? j * 1024 : j * 32, bo = b_mn ? j * 1024 : j * 32;
+        const uint32_t pah = tc::smem_u32(a_hi) + ao, pal = tc::smem_u32(a_lo) + ao;
+        const uint32_t pbh = tc::smem_u32(b_hi) + bo, pbl = tc::smem_u32(b_lo) + bo;
+        const uint64_t dah = a_mn ? tc::smem_desc_mnmajor(pah, lbo, sbo) : tc::smem_desc_kmajor(pah);
+        const uint64_t dal = a_mn ? tc::smem_desc_mnmajor(pal, lbo, sbo) : tc::smem_desc_kmajor(pal);
+        const uint64_t dbh = b_mn ? tc::smem_desc_mnmajor(pbh, lbo, sbo) : tc::smem_desc_kmajor(pbh);
+        const uint64_t dbl = b_mn ? tc::smem_desc_mnmajor(pbl, lbo, sbo) : tc::smem_desc_kmajor(pbl);
         tc::mma_tf32(tmem, dah, dbh, idesc, (k0 > 0 || j > 0) ? 1u : 0u);
         if (split3) {
           tc::mma_tf32(tmem, dah, dbl, idesc, 1u);
