@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 4
+#define PF_ABI_VERSION 5
 
 #define PF_OK 0
 #define PF_ERR_ARG (-1)         /* invalid argument (ValueError on the Python side) */
@@ -151,11 +151,15 @@ int pf_nmf_fb_contract(const void* hatW, const void* P, const void* O, int64_t l
  * component's own power P' = max(W H, eps) formed on the fly from the updated W:
  *   num[k,n] = sum_f W[f,k] (O hatW / P'^2)[f,n],  den[k,n] = sum_f W[f,k] (O / P')[f,n]
  * Partial sums per frequency split: double [fsplit][K][ldo]. */
-int pf_nmf_tw_plan(int F, int K, int64_t N, int* fchunk, int* fsplit);
+int pf_nmf_tw_plan(int F, int K, int64_t N, int dtype, int* fchunk, int* fsplit);
+/* scratch_plane: optional dtype [F][ld] work plane.  With it, float32 planes and K <= 32 the
+ * contractions run on the tensor cores (tcgen05 kind::tf32, 3xTF32 split): P' = W H is written
+ * to the scratch plane by one kernel and contracted by a second; without it (or for float64)
+ * P' is formed on the fly on the CUDA cores. */
 int pf_nmf_tw_contract(const void* hatW, const void* O, int64_t ld, const void* W, int ldw,
                        const void* H, int64_t ldh, int F, int K, int64_t N, double* num_partial,
-                       double* den_partial, int64_t ldo, int fchunk, int fsplit, int dtype,
-                       void* stream);
+                       double* den_partial, int64_t ldo, int fchunk, int fsplit,
+                       void* scratch_plane, int dtype, void* stream);
 /* out[i] = sum_s in[s][i] in a fixed order */
 int pf_sum_splits(const double* in, int nsplit, int64_t count, double* out, void* stream);
 /* theta[r][c] *= (num[r][c] / max(den[r][c], 1e-10))^omega (audioModel.py:1573,:1725) */

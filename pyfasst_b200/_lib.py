@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpyfasst_b200.so")
 
 PF_F32, PF_F64 = 0, 1
 PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 c_ip = ctypes.POINTER(ctypes.c_int)
@@ -46,9 +46,9 @@ SIGNATURES = {
     "pf_nmf_fb_plan": [c_int, c_int, c_i64, c_int, ctypes.POINTER(c_i64), c_ip],
     "pf_nmf_fb_contract": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_vp, c_vp,
                            c_i64, c_int, c_int, c_vp],
-    "pf_nmf_tw_plan": [c_int, c_int, c_i64, c_ip, c_ip],
+    "pf_nmf_tw_plan": [c_int, c_int, c_i64, c_int, c_ip, c_ip],
     "pf_nmf_tw_contract": [c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_i64, c_vp,
-                           c_vp, c_i64, c_int, c_int, c_int, c_vp],
+                           c_vp, c_i64, c_int, c_int, c_vp, c_int, c_vp],
     "pf_sum_splits": [c_vp, c_int, c_i64, c_vp, c_vp],
     "pf_mult_update": [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
     "pf_spat_energy": [c_vp, c_ip, c_int, c_int, c_int, c_int, c_vp, c_vp],
@@ -242,20 +242,22 @@ class CudaKernels(object):
                                            self._p(den_partial), chunk, nsplit,
                                            self.dtype_code(hatW), self._stream()), self.lib)
 
-    def tw_plan(self, F, K, N):
+    def tw_plan(self, F, K, N, dtype_code):
         fchunk, fsplit = c_int(), c_int()
-        _check(self.lib.pf_nmf_tw_plan(F, K, N, ctypes.byref(fchunk), ctypes.byref(fsplit)),
-               self.lib)
+        _check(self.lib.pf_nmf_tw_plan(F, K, N, dtype_code, ctypes.byref(fchunk),
+                                       ctypes.byref(fsplit)), self.lib)
         return fchunk.value, fsplit.value
 
-    def tw_contract(self, hatW, O, W, H, N, num_partial, den_partial, fchunk, fsplit):
+    def tw_contract(self, hatW, O, W, H, N, num_partial, den_partial, fchunk, fsplit,
+                    scratch=None):
         F, ld = hatW.shape
         K = W.shape[1]
         _check(self.lib.pf_nmf_tw_contract(self._p(hatW), self._p(O), ld, self._p(W), W.stride(0),
                                            self._p(H), H.stride(0), F, K, N,
                                            self._p(num_partial), self._p(den_partial),
                                            num_partial.shape[-1], fchunk, fsplit,
-                                           self.dtype_code(hatW), self._stream()), self.lib)
+                                           self._p(scratch), self.dtype_code(hatW),
+                                           self._stream()), self.lib)
 
     def sum_splits(self, parts, out):
         nsplit = parts.shape[0]

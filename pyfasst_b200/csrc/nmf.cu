@@ -608,6 +608,11 @@ using namespace pf;
 // tcgen05 versions (nmf_tc.cu), float32 planes only
 int pf_fb_contract_tc(const float* hatW, const float* P, long ld, const float* G, long ldg, int K,
                       int F, long N, long chunk, int nsplit, double* num, cudaStream_t st);
+int pf_spec_power_tc(const float* W, int ldw, const float* H, long ldh, float* V, long ldv, int F,
+                     int K, long N, cudaStream_t st);
+int pf_tw_contract_tc(const float* hatW, const float* O, const float* Pn, long ld, const float* W,
+                      int ldw, int K, int F, long N, int fchunk, int fsplit, double* num,
+                      double* den, long ldo, cudaStream_t st);
 static bool use_tensor_cores() {
   static int v = -1;
   if (v < 0) {
@@ -625,6 +630,10 @@ extern "C" int pf_spec_power(const void* W, int ldw, const void* H, int64_t ldh,
   PF_REQUIRE(ldv % 4 == 0 && ldh % 4 == 0 && ldv >= N, "pf_spec_power: ldv/ldh must be multiples of 4");
   cudaStream_t st = as_stream(stream);
   const int FT = (SP_THREADS / 32) * SP_FR;
+  // large float32 products go to the tensor cores (3xTF32); the CUDA-core kernel serves
+  // float64, accumulation into V, K > 32 and the small factor products
+  if (dtype == PF_F32 && !accumulate && K <= 32 && F >= 64 && N >= 1024 && use_tensor_cores())
+    return pf_spec_power_tc((const float*)W, ldw, (const float*)H, ldh, (float*)V, ldv, F, K, N, st);
   if (dtype == PF_F32) {
     dim3 grid(ceil_div(ldv, 32 * 4), ceil_div(F, FT));
     spec_power_kernel<float><<<grid, SP_THREADS, 0, st>>>((const float*)W, ldw, (const float*)H,
@@ -697,10 +706,27 @@ extern "C" int pf_nmf_fb_contract(const void* hatW, const void* P, const void* O
                              den_partial, st);
 }
 
-extern "C" int pf_nmf_tw_plan(int F, int K, int64_t N, int* fchunk, int* fsplit) {
-  // a CTA covers 128 frames; split the frequency axis until ~3 CTAs per SM are in flight,
-  // keeping at least two pipeline stages of rows per CTA
-  const long nblocks = (N + TW_THREADS - 1) / TW_THREADS;
+extern "C" int pf_nmf_tw_plan(int F, int K, int64_t N, int dtype, int* fchunk, int* fsplit) {
+  const long nblocks = (N + TW_THREADS - 1) / TW_THREADS;  // both kernels: 128 frames per CTA
+  if (dtype == PF_F32 && K <= 32 && use_tensor_cores()) {
+    // tcgen05 kernel: two CTAs per SM; pick the frequency split (1..4) that fills whole
+    // waves of 2 x 148 CTAs best (every split costs a K x N partial-sum plane)
+    long best = 1;
+    double best_eff = 0.0;
+    for (long fs = 1; fs <= 4; ++fs) {
+      if (fs > 1 && (F + fs - 1) / fs < 4 * 16) break;
+      const long ctas = nblocks * fs, slots = 2 * 148;
+      const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = fs; }
+    }
+    int fc = (int)((F + best - 1) / best);
+    fc = ((fc + 15) / 16) * 16;
+    *fchunk = fc;
+    *fsplit = (F + fc - 1) / fc;
+    return PF_OK;
+  }
+  // CUDA-core kernel: split the frequency axis until ~3 CTAs per SM are in flight, keeping
+  // at least two pipeline stages of rows per CTA
   long fs = (148L * 3 + nblocks / 2) / nblocks;
   const long max_fs = (F + 2 * TW_RT - 1) / (2 * TW_RT);
   if (fs > max_fs) fs = max_fs;
@@ -710,17 +736,27 @@ extern "C" int pf_nmf_tw_plan(int F, int K, int64_t N, int* fchunk, int* fsplit)
   fc = ((fc + TW_RT - 1) / TW_RT) * TW_RT;
   *fchunk = fc;
   *fsplit = (F + fc - 1) / fc;
-  (void)K;
   return PF_OK;
 }
 
 extern "C" int pf_nmf_tw_contract(const void* hatW, const void* O, int64_t ld, const void* W,
                                   int ldw, const void* H, int64_t ldh, int F, int K, int64_t N,
                                   double* num_partial, double* den_partial, int64_t ldo,
-                                  int fchunk, int fsplit, int dtype, void* stream) {
+                                  int fchunk, int fsplit, void* scratch_plane, int dtype,
+                                  void* stream) {
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_nmf_tw_contract: bad dtype %d", dtype);
   PF_REQUIRE(fchunk > 0 && (int64_t)fsplit * fchunk >= F, "pf_nmf_tw_contract: bad split plan");
   cudaStream_t st = as_stream(stream);
+  if (dtype == PF_F32 && K <= 32 && scratch_plane != nullptr && F >= 64 && N >= 1024 &&
+      fchunk % 16 == 0 && use_tensor_cores()) {
+    // tensor-core path: P' = W' H into the scratch plane, then the two contractions
+    int rc = pf_spec_power_tc((const float*)W, ldw, (const float*)H, ldh, (float*)scratch_plane,
+                              ld, F, K, N, st);
+    if (rc) return rc;
+    return pf_tw_contract_tc((const float*)hatW, (const float*)O, (const float*)scratch_plane, ld,
+                             (const float*)W, ldw, K, F, N, fchunk, fsplit, num_partial,
+                             den_partial, ldo, st);
+  }
   if (dtype == PF_F32)
     return dispatch_tw<float>(hatW, O, ld, W, ldw, H, ldh, K, F, N, fchunk, fsplit, num_partial,
                               den_partial, ldo, st);

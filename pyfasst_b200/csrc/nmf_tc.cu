@@ -181,6 +181,328 @@ fb_contract_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ 
   if (warp == 0) tc::tmem_dealloc(tmem, 32);
 }
 
+// ============================ V = W H ====================================================
+// D[128 f][256 n] = W[128 f][32 k] H[32 k][256 n]: A = W is K-major (k contiguous), B = H is
+// MN-major (frames contiguous).  A CTA keeps its W block (hi / lo) in shared memory and walks
+// frame tiles; the B tiles and the TMEM accumulators are double buffered so that the MMAs of
+// tile t overlap the write-out of tile t-1.
+constexpr int SPT_THREADS = 256;
+constexpr int SPT_NT = 256;  // frames per tile (= UMMA N)
+constexpr uint32_t SPT_LBO = 32 * 128, SPT_SBO = 512;
+
+struct SptSmem {
+  unsigned char a_hi[128 * 32 * 4];
+  unsigned char a_lo[128 * 32 * 4];
+  unsigned char b_hi[2][32 * SPT_NT * 4];
+  unsigned char b_lo[2][32 * SPT_NT * 4];
+  float tr[SPT_THREADS / 32][32 * 36];  // per-warp transpose tiles of the write-out
+};
+
+__global__ void __launch_bounds__(SPT_THREADS, 1)
+spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restrict__ H, long ldh,
+                     float* __restrict__ V, long ldv, int F, int K, long N, int tiles_per_cta) {
+  extern __shared__ __align__(1024) unsigned char spt_smem[];
+  __shared__ uint64_t mbar[2];
+  __shared__ uint32_t tmem_base;
+  unsigned char* base = spt_smem + ((1024 - (tc::smem_u32(spt_smem) & 1023)) & 1023);
+  SptSmem& sm = *reinterpret_cast<SptSmem*>(base);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fblk = blockIdx.y * 128;
+  const long ntiles = (ldv + SPT_NT - 1) / SPT_NT;
+  const long t_begin = (long)blockIdx.x * tiles_per_cta;
+  long t_end = t_begin + tiles_per_cta;
+  if (t_end > ntiles) t_end = ntiles;
+  const int nt = (int)(t_end - t_begin);
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 512);
+  if (tid == 0) {
+    tc::mbar_init(&mbar[0], 1);
+    tc::mbar_init(&mbar[1], 1);
+    tc::fence_mbar_init();
+  }
+  // W block: 128 rows x 32 k, zero padded (k >= K, f >= F)
+  for (int i = tid; i < 128 * 32; i += SPT_THREADS) {
+    const int r = i >> 5, k = i & 31;
+    const int f = fblk + r;
+    const float x = (f < F && k < K) ? W[(long)f * ldw + k] : 0.f;
+    float hi, lo;
+    tc::split_tf32(x, hi, lo);
+    const uint32_t off = tc::kmajor_off(r, k);
+    *reinterpret_cast<float*>(sm.a_hi + off) = hi;
+    *reinterpret_cast<float*>(sm.a_lo + off) = lo;
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = tc::idesc_tf32(128, SPT_NT, 0, 1);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // thread -> float4 (k, n4) of the 32 x 256 H tile: 8 per thread
+  float4 h_n[8];
+  auto fetch = [&](long tile) {
+    const long nb = tile * SPT_NT;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = tid + q * SPT_THREADS;  // 0 .. 2047
+      const int k = i >> 6, c = i & 63;
+      const long n = nb + c * 4;
+      h_n[q] = (k < K && n + 4 <= ldh) ? ldg4(H + (long)k * ldh + n) : zero4;
+    }
+  };
+  // write-out of one accumulator: a warp reads 32 rows x 32 columns from TMEM (thread = row),
+  // transposes them through a padded shared-memory tile and stores 4 rows x 128 contiguous
+  // bytes per instruction (full 128-byte lines instead of 32 half-used sectors)
+  float* tr = reinterpret_cast<float*>(sm.tr[warp]);
+  auto write_out = [&](int b, long tile) {
+    // warps 0-3: columns [0,128); warps 4-7: columns [128,256) of accumulator b
+    const int wq = warp & 3, half = warp >> 2;
+    const long nb = tile * SPT_NT + half * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * SPT_NT + half * 128 + c0), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(tr + lane * 36 + i) =
+            make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                        __uint_as_float(v[i + 3]));
+      __syncwarp();
+      const long n = nb + c0 + (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const int f = fblk + wq * 32 + r;
+        const float4 x = *reinterpret_cast<const float4*>(tr + r * 36 + (lane & 7) * 4);
+        if (f < F && n + 4 <= ldv) *reinterpret_cast<float4*>(V + (long)f * ldv + n) = x;
+      }
+      __syncwarp();
+    }
+  };
+
+  if (nt > 0) fetch(t_begin);
+  for (int t = 0; t < nt; ++t) {
+    const int b = t & 1;
+    // B tile t -> smem slot b (free: the MMAs of tile t-2 were waited for in the epilogue of t-2)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = tid + q * SPT_THREADS;
+      const int k = i >> 6, c = i & 63;
+      st_split4(sm.b_hi[b], sm.b_lo[b], tc::mnmajor_off(k, c * 4, SPT_LBO, SPT_SBO), h_n[q]);
+    }
+    if (t + 1 < nt) fetch(t_begin + t + 1);
+    tc::fence_proxy_async();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+      const uint32_t ah = tc::smem_u32(sm.a_hi), al = tc::smem_u32(sm.a_lo);
+      const uint32_t bh = tc::smem_u32(sm.b_hi[b]), bl = tc::smem_u32(sm.b_lo[b]);
+      const uint32_t d = tmem + (uint32_t)(b * SPT_NT);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t dah = tc::smem_desc_kmajor(ah + j * 32), dal = tc::smem_desc_kmajor(al + j * 32);
+        const uint64_t dbh = tc::smem_desc_mnmajor(bh + j * 1024, SPT_LBO, SPT_SBO);
+        const uint64_t dbl = tc::smem_desc_mnmajor(bl + j * 1024, SPT_LBO, SPT_SBO);
+        tc::mma_tf32(d, dah, dbh, idesc, j > 0 ? 1u : 0u);
+        tc::mma_tf32(d, dah, dbl, idesc, 1u);
+        tc::mma_tf32(d, dal, dbh, idesc, 1u);
+      }
+      tc::mma_commit(&mbar[b]);
+    }
+    if (t > 0) {  // write tile t-1 while the tensor core works on tile t
+      tc::mbar_wait(&mbar[b ^ 1], (uint32_t)(((t - 1) >> 1) & 1));
+      tc::fence_after_thread_sync();
+      write_out(b ^ 1, t_begin + t - 1);
+    }
+  }
+  if (nt > 0) {
+    const int b = (nt - 1) & 1;
+    tc::mbar_wait(&mbar[b], (uint32_t)(((nt - 1) >> 1) & 1));
+    tc::fence_after_thread_sync();
+    write_out(b, t_begin + nt - 1);
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ============================ TW update ==================================================
+// num^T[128 n][32 k] += E1^T[128 n][16 f] W[16 f][32 k] (and den with E2) per step of 16
+// frequency rows: both operands are MN-major (A: frames contiguous, B: components contiguous).
+// P' = max(W' H, eps) -- the component's power with the updated W (audioModel.py:1639-1645) --
+// is read from a plane produced by spec_power_tc_kernel just before.
+constexpr int TWT_THREADS = 256;
+constexpr int TWT_FR = 16;   // frequency rows per step (two K = 8 MMAs)
+constexpr int TWT_NT = 128;  // frames per CTA (= UMMA M)
+constexpr uint32_t TWT_LBO = TWT_FR * 128, TWT_SBO = 512;
+
+struct TwtStage {
+  unsigned char a1_hi[TWT_FR * TWT_NT * 4];
+  unsigned char a1_lo[TWT_FR * TWT_NT * 4];
+  unsigned char a2_hi[TWT_FR * TWT_NT * 4];
+  unsigned char a2_lo[TWT_FR * TWT_NT * 4];
+  unsigned char b_hi[TWT_FR * 32 * 4];
+  unsigned char b_lo[TWT_FR * 32 * 4];
+};
+
+__global__ void __launch_bounds__(TWT_THREADS, 2)
+tw_contract_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ Op,
+                      const float* __restrict__ Pn, long ld, const float* __restrict__ W, int ldw,
+                      int K, int F, long N, int fchunk, int fsplit, double* __restrict__ num,
+                      double* __restrict__ den, long ldo) {
+  extern __shared__ __align__(1024) unsigned char twt_smem[];
+  __shared__ uint64_t mbar_free[2];
+  __shared__ uint64_t mbar_done;
+  __shared__ uint32_t tmem_base;
+  unsigned char* base = twt_smem + ((1024 - (tc::smem_u32(twt_smem) & 1023)) & 1023);
+  TwtStage* stages = reinterpret_cast<TwtStage*>(base);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long nb = (long)blockIdx.x * TWT_NT;
+  const int split = blockIdx.y;
+  const int fb = split * fchunk;
+  int fe = fb + fchunk;
+  if (fe > F) fe = F;
+  const int nsteps = (fe - fb + TWT_FR - 1) / TWT_FR;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
+  if (tid == 0) {
+    tc::mbar_init(&mbar_free[0], 1);
+    tc::mbar_init(&mbar_free[1], 1);
+    tc::mbar_init(&mbar_done, 1);
+    tc::fence_mbar_init();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = tc::idesc_tf32(128, 32, 1, 1);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // thread -> float4 (f, n4) of the 16 x 128 plane tiles: 2 per plane and step
+  int prow[2], pcol[2];
+  uint32_t poff[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = tid + q * TWT_THREADS;  // 0 .. 511
+    prow[q] = i >> 5;
+    pcol[q] = (i & 31) * 4;
+    poff[q] = tc::mnmajor_off(prow[q], pcol[q], TWT_LBO, TWT_SBO);
+  }
+  // W tile 16 x 32: threads 0..127 hold 4 consecutive k of one row
+  const int wrow = tid >> 3, wk = (tid & 7) * 4;
+  const uint32_t woff = tc::mnmajor_off(wrow, wk, TWT_LBO, TWT_SBO);
+
+  float4 hw_n[2], o_n[2], p_n[2], w_n;
+  auto fetch = [&](int step) {
+    const int f0 = fb + step * TWT_FR;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int f = f0 + prow[q];
+      const long n = nb + pcol[q];
+      const bool ok = (f < fe) && (n + 4 <= ld);
+      const long off = (long)f * ld + n;
+      hw_n[q] = ok ? ldg4(hatW + off) : zero4;
+      o_n[q] = ok ? ldg4(Op + off) : zero4;
+      p_n[q] = ok ? ldg4(Pn + off) : zero4;
+    }
+    w_n = zero4;
+    if (tid < 128) {
+      const int f = f0 + wrow;
+      if (f < fe) {
+        const float* wr = W + (long)f * ldw;
+        w_n.x = (wk + 0 < K) ? __ldg(wr + wk + 0) : 0.f;
+        w_n.y = (wk + 1 < K) ? __ldg(wr + wk + 1) : 0.f;
+        w_n.z = (wk + 2 < K) ? __ldg(wr + wk + 2) : 0.f;
+        w_n.w = (wk + 3 < K) ? __ldg(wr + wk + 3) : 0.f;
+      }
+    }
+  };
+  auto e12 = [&](float hw, float o, float p, float& e1, float& e2) {
+    // rows beyond the shard (all-zero loads) contribute nothing: W is zero there as well
+    const float oc = fmaxf(o, kEpsF);
+    const float rp = fast_rcpf(fmaxf(p, kEpsF));
+    e2 = oc * rp;               // other / P'            (audioModel.py:1694-1701)
+    e1 = oc * (hw * rp * rp);   // other * hat_W / P'^2  (audioModel.py:1714-1720)
+  };
+
+  if (nsteps > 0) fetch(0);
+  for (int s = 0; s < nsteps; ++s) {
+    const int b = s & 1;
+    float4 hw[2], o[2], p[2];
+    const float4 w = w_n;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { hw[q] = hw_n[q]; o[q] = o_n[q]; p[q] = p_n[q]; }
+    if (s + 1 < nsteps) fetch(s + 1);
+    if (s >= 2) tc::mbar_wait(&mbar_free[b], (uint32_t)(((s >> 1) - 1) & 1));
+    TwtStage& st = stages[b];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 e1, e2;
+      e12(hw[q].x, o[q].x, p[q].x, e1.x, e2.x);
+      e12(hw[q].y, o[q].y, p[q].y, e1.y, e2.y);
+      e12(hw[q].z, o[q].z, p[q].z, e1.z, e2.z);
+      e12(hw[q].w, o[q].w, p[q].w, e1.w, e2.w);
+      st_split4(st.a1_hi, st.a1_lo, poff[q], e1);
+      st_split4(st.a2_hi, st.a2_lo, poff[q], e2);
+    }
+    if (tid < 128) st_split4(st.b_hi, st.b_lo, woff, w);
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+      const uint32_t a1h = tc::smem_u32(st.a1_hi), a1l = tc::smem_u32(st.a1_lo);
+      const uint32_t a2h = tc::smem_u32(st.a2_hi), a2l = tc::smem_u32(st.a2_lo);
+      const uint32_t bh = tc::smem_u32(st.b_hi), bl = tc::smem_u32(st.b_lo);
+#pragma unroll
+      for (int j = 0; j < TWT_FR / 8; ++j) {
+        const uint64_t dbh = tc::smem_desc_mnmajor(bh + j * 1024, TWT_LBO, TWT_SBO);
+        const uint64_t dbl = tc::smem_desc_mnmajor(bl + j * 1024, TWT_LBO, TWT_SBO);
+        const uint64_t d1h = tc::smem_desc_mnmajor(a1h + j * 1024, TWT_LBO, TWT_SBO);
+        const uint64_t d1l = tc::smem_desc_mnmajor(a1l + j * 1024, TWT_LBO, TWT_SBO);
+        const uint64_t d2h = tc::smem_desc_mnmajor(a2h + j * 1024, TWT_LBO, TWT_SBO);
+        const uint64_t d2l = tc::smem_desc_mnmajor(a2l + j * 1024, TWT_LBO, TWT_SBO);
+        const uint32_t acc = (s > 0 || j > 0) ? 1u : 0u;
+        tc::mma_tf32(tmem, d1h, dbh, idesc, acc);
+        tc::mma_tf32(tmem, d1h, dbl, idesc, 1u);
+        tc::mma_tf32(tmem, d1l, dbh, idesc, 1u);
+        tc::mma_tf32(tmem + 32, d2h, dbh, idesc, acc);
+        tc::mma_tf32(tmem + 32, d2h, dbl, idesc, 1u);
+        tc::mma_tf32(tmem + 32, d2l, dbh, idesc, 1u);
+      }
+      tc::mma_commit(&mbar_free[b]);
+      if (s == nsteps - 1) tc::mma_commit(&mbar_done);
+    }
+  }
+  if (nsteps > 0) tc::mbar_wait(&mbar_done, 0);
+  tc::fence_after_thread_sync();
+  if (warp < 4) {
+    const long n = nb + warp * 32 + lane;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      uint32_t v[32];
+      if (nsteps > 0) {
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(which * 32), v);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      double* out = which ? den : num;
+      if (n < ldo) {
+        const bool live = n < N;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k < K) out[((size_t)split * K + k) * ldo + n] = live ? (double)__uint_as_float(v[k]) : 0.0;
+      }
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
 }  // namespace pf
 
 using namespace pf;
@@ -203,4 +525,43 @@ int pf_fb_contract_tc(const float* hatW, const float* P, long ld, const float* G
     if (rc) return rc;
   }
   return PF_OK;
+}
+
+// V = W H for float32 planes, K <= 32 (called from pf_spec_power)
+int pf_spec_power_tc(const float* W, int ldw, const float* H, long ldh, float* V, long ldv, int F,
+                     int K, long N, cudaStream_t st) {
+  const size_t smem = sizeof(SptSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(spec_power_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("spec_power_tc_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  const long ntiles = (ldv + SPT_NT - 1) / SPT_NT;
+  const int fblocks = ceil_div(F, 128);
+  // one CTA per SM (it owns all 512 TMEM columns): split the frame tiles over ~148 CTAs
+  long splits = 148 / fblocks;  // never more CTAs than SMs: a second wave would double the time
+  if (splits > ntiles) splits = ntiles;
+  if (splits < 1) splits = 1;
+  const int per = (int)((ntiles + splits - 1) / splits);
+  dim3 grid(ceil_div(ntiles, per), fblocks);
+  spec_power_tc_kernel<<<grid, SPT_THREADS, smem, st>>>(W, ldw, H, ldh, V, ldv, F, K, N, per);
+  return check_launch("spec_power_tc_kernel");
+}
+
+// TW update contractions for float32 planes, K <= 32; Pn = W' H (from pf_spec_power_tc)
+int pf_tw_contract_tc(const float* hatW, const float* O, const float* Pn, long ld, const float* W,
+                      int ldw, int K, int F, long N, int fchunk, int fsplit, double* num,
+                      double* den, long ldo, cudaStream_t st) {
+  const size_t smem = 2 * sizeof(TwtStage) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tw_contract_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("tw_contract_tc_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  dim3 grid(ceil_div(N, TWT_NT), fsplit);
+  tw_contract_tc_kernel<<<grid, TWT_THREADS, smem, st>>>(hatW, O, Pn, ld, W, ldw, K, F, N, fchunk,
+                                                       fsplit, num, den, ldo);
+  return check_launch("tw_contract_tc_kernel");
 }

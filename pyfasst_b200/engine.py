@@ -254,10 +254,12 @@ class GemEngine(object):
         # buffer so that a single all-reduce serves the whole iteration
         self.tw_plan, tw_size = {}, 0
         for e in self.spec:
-            fchunk, fsplit = k.tw_plan(F, e["Kw"], N)
+            fchunk, fsplit = k.tw_plan(F, e["Kw"], N, code)
             self.tw_plan[id(e)] = (fchunk, fsplit)
             tw_size = max(tw_size, fsplit * e["Kw"] * ld)
         self.tw_part = self._zeros([2, tw_size], f64)
+        # work plane for P' = W'H of the tensor-core TW path (float32 planes only)
+        self.scratch = self._zeros([F, ld]) if self.tdtype == torch.float32 else None
         self.tw_nd = self._zeros([S, 2, Kmax, ld], f64)
 
     # ------------------------------------------------------------------ pieces
@@ -320,7 +322,8 @@ class GemEngine(object):
                 cnt = e["Kw"] * self.ld
                 pn = self.tw_part[0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
                 pd = self.tw_part[1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
-                k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit)
+                k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit,
+                              self.scratch)
                 k.sum_splits(pn, self.tw_nd[s, 0, :e["Kw"]])
                 k.sum_splits(pd, self.tw_nd[s, 1, :e["Kw"]])
         if any_tw and self._sharded():

@@ -256,10 +256,11 @@ class FakeKernels(object):
         _np(num_partial)[0] = np.dot(e1.astype(np.float64), g.T.astype(np.float64))
         _np(den_partial)[0] = np.dot(e2.astype(np.float64), g.T.astype(np.float64))
 
-    def tw_plan(self, F, K, N):
+    def tw_plan(self, F, K, N, dtype_code):
         return F, 1
 
-    def tw_contract(self, hatW, O, W, H, N, num_partial, den_partial, fchunk, fsplit):
+    def tw_contract(self, hatW, O, W, H, N, num_partial, den_partial, fchunk, fsplit,
+                    scratch=None):
         self.launches += 1
         t = _np(hatW).dtype.type
         hw, o = _np(hatW)[:, :N], np.maximum(_np(O)[:, :N], t(EPS))

@@ -127,7 +127,8 @@ def test_wiener_stereo(ck, fk, dt):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("F,K,N", [(7, 3, 50), (130, 4, 1001), (65, 32, 700), (40, 40, 333)])
+@pytest.mark.parametrize("F,K,N", [(7, 3, 50), (130, 4, 1001), (65, 32, 700), (40, 40, 333),
+                                   (300, 32, 2500), (129, 5, 1025), (64, 17, 4000)])
 def test_spec_power(ck, fk, dt, F, K, N):
     rng = np.random.default_rng(K)
     ld = (N + 31) // 32 * 32
@@ -158,7 +159,7 @@ def test_small_matmul(ck, fk, dt):
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("F,K,N", [(9, 4, 300), (130, 4, 5000), (33, 32, 2100), (20, 7, 130),
-                                   (18, 16, 600)])
+                                   (18, 16, 600), (300, 32, 2500), (257, 20, 1100)])
 def test_fb_contract(ck, fk, dt, F, K, N):
     rng = np.random.default_rng(N)
     ld = (N + 31) // 32 * 32
@@ -186,8 +187,12 @@ def test_fb_contract(ck, fk, dt, F, K, N):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("F,K,N", [(9, 4, 300), (130, 4, 5000), (257, 32, 700), (70, 7, 130)])
-def test_tw_contract(ck, fk, dt, F, K, N):
+@pytest.mark.parametrize("scratch", [False, True])
+@pytest.mark.parametrize("F,K,N", [(9, 4, 300), (130, 4, 5000), (257, 32, 700), (70, 7, 130),
+                                   (300, 32, 2500), (129, 20, 1100)])
+def test_tw_contract(ck, fk, dt, F, K, N, scratch):
+    """With a scratch plane, float32 planes and a large enough problem the tensor-core
+    (tcgen05, 3xTF32) path runs; the CUDA-core path otherwise."""
     rng = np.random.default_rng(N + 1)
     ld = (N + 31) // 32 * 32
     hatW = rnd(rng, (F, N), dt, positive=True, pad_to=ld)
@@ -196,17 +201,19 @@ def test_tw_contract(ck, fk, dt, F, K, N):
     H = rnd(rng, (K, N), dt, positive=True, pad_to=ld)
     res = []
     for k, dev in ((fk, "cpu"), (ck, "cuda")):
-        fchunk, fsplit = k.tw_plan(F, K, N)
+        fchunk, fsplit = k.tw_plan(F, K, N, k.dtype_code(hatW))
         pn = torch.zeros((fsplit, K, ld), dtype=torch.float64, device=dev)
         pd = torch.zeros((fsplit, K, ld), dtype=torch.float64, device=dev)
-        k.tw_contract(hatW.to(dev), O.to(dev), W.to(dev), H.to(dev), N, pn, pd, fchunk, fsplit)
+        sc = torch.zeros((F, ld), dtype=dt, device=dev) if scratch else None
+        k.tw_contract(hatW.to(dev), O.to(dev), W.to(dev), H.to(dev), N, pn, pd, fchunk, fsplit, sc)
         num = torch.zeros((K, ld), dtype=torch.float64, device=dev)
         den = torch.zeros((K, ld), dtype=torch.float64, device=dev)
         k.sum_splits(pn, num)
         k.sum_splits(pd, den)
-        res.append((num.cpu().numpy()[:, :N], den.cpu().numpy()[:, :N]))
-    assert rel(res[1][0], res[0][0]) < tol(dt)
-    assert rel(res[1][1], res[0][1]) < tol(dt)
+        res.append((num.cpu().numpy(), den.cpu().numpy()))
+    assert rel(res[1][0][:, :N], res[0][0][:, :N]) < tol(dt)
+    assert rel(res[1][1][:, :N], res[0][1][:, :N]) < tol(dt)
+    assert (res[1][0][:, N:] == 0).all() and (res[1][1][:, N:] == 0).all()
 
 
 @pytest.mark.parametrize("dt", DTYPES)
