@@ -7,8 +7,9 @@ A "step" is one GEM iteration (E-step + spatial / spectral M-step + renormalisat
 ref pyfasst/audioModel.py:384-428) over the whole synthetic mixture.  Workload at N=1 =
 BASELINE.json configs[1]: synthetic 10-min stereo 44.1 kHz mixture, STFT 2048 / hop 512
 (F=1025, N=51682, 52.97 M TF bins), MultiChanNMFInst_FASST with 4 sources x K=32 NMF
-components, full-rank (rank 2) spatial model.  N>1: the same mixture, sharded by
-frequency bin (one process per GPU, NCCL), i.e. strong scaling.
+components, full-rank (rank 2) spatial model.  N>1: WEAK scaling -- one mixture of N x 10
+minutes (80 min at N=8, the size class of BASELINE configs[3]) whose frames are sharded over
+the GPUs (one process per GPU, NCCL all-reduce of the per-frequency statistics).
 
 Printed JSON (one line, rank 0):
   value     TF-bins*iterations/s with X and the parameters resident in HBM (CUDA events)
@@ -169,7 +170,7 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, note="CPU arm: the oracle (NumPy restatement of the "
                                   "reference's GEM_iteration, float64) on a %.1f s crop of "
@@ -186,13 +187,15 @@ def run_reference(args, rank):
 
 
 def workload_config(args, note=None):
-    L = int(round(args.duration_s * FS))
-    cfg = {"workload": "configs[1]: synthetic %.0f-s stereo 44.1 kHz mix, "
-                       "MultiChanNMFInst_FASST %d sources x K=%d, spatial rank %d, "
-                       "STFT %d/hop %d" % (args.duration_s, NSRC, NNMF, RANK, WLEN, HOP),
+    L = int(round(args.duration_s * FS)) * args.gpus
+    cfg = {"workload": "configs[1]: synthetic %.0f-s stereo 44.1 kHz mix per GPU (x%d GPUs = %.0f s, "
+                       "weak scaling), MultiChanNMFInst_FASST %d sources x K=%d, spatial rank %d, "
+                       "STFT %d/hop %d" % (args.duration_s, args.gpus, args.duration_s * args.gpus,
+                                           NSRC, NNMF, RANK, WLEN, HOP),
            "F": WLEN // 2 + 1, "N": n_frames(L), "tf_bins": (WLEN // 2 + 1) * n_frames(L),
            "sources": NSRC, "nmf_comps": NNMF, "spatial_rank": RANK,
-           "sharding": "frequency bins over %d GPU(s)" % args.gpus,
+           "sharding": "frames over %d GPU(s); all-reduce of the per-frequency E-step statistics "
+                       "and of the FB numerators/denominators (NCCL)" % args.gpus,
            "l2": "inputs larger than L2 (X + V + hat_W planes >> 126 MB), no flush needed"}
     if note:
         cfg["note"] = note
@@ -218,21 +221,29 @@ def run_ours(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    pcm = synth_mix(args.duration_s)
-    tmp = tempfile.mkdtemp(prefix="pyfasst_bench_")
-    wav = os.path.join(tmp, "mix_rank%d.wav" % rank)
-    write_wav(wav, pcm)
+    # N = 1: the 10-min mixture of configs[1].  N > 1: weak scaling -- the mixture is N such
+    # blocks back to back (one per GPU) and its frames are sharded over the ranks.
+    block = synth_mix(args.duration_s)
+    pcm = block if world == 1 else np.ascontiguousarray(np.tile(block, (world, 1)))
     L = pcm.shape[0]
     F, N = WLEN // 2 + 1, n_frames(L)
     bins = F * N
     dtype = "float32" if args.dtype == "f32" else "float64"
+    import pyfasst_b200.audioObject as ao
 
-    def make_model(iters):
+    def make_audio(raw):
+        a = ao.AudioObject("synthetic_mix.wav")
+        a._samplerate = FS
+        a._set_raw(raw, compute_max=(world == 1))
+        return a
+
+    def make_model(iters, raw=None):
         np.random.seed(0)
-        return am.MultiChanNMFInst_FASST(audio=wav, nbComps=NSRC, nbNMFComps=NNMF,
-                                         spatial_rank=RANK, wlen=WLEN, hopsize=HOP,
-                                         iter_num=iters, ann_PSD_lim=[None, None],
-                                         compute_dtype=dtype, comm=comm)
+        return am.MultiChanNMFInst_FASST(audio=make_audio(pcm if raw is None else raw),
+                                         nbComps=NSRC, nbNMFComps=NNMF, spatial_rank=RANK,
+                                         wlen=WLEN, hopsize=HOP, iter_num=iters,
+                                         ann_PSD_lim=[None, None], compute_dtype=dtype,
+                                         comm=comm, shard="time")
 
     # ---- device-resident throughput (`value`) and per-phase / E-step kernel times -------
     model = make_model(args.steps + args.warmup)
@@ -292,7 +303,7 @@ def run_ours(args, rank, world):
         stages = {}
         barrier()
         t0 = time.perf_counter()
-        m.audioObject._set_raw(pinned)  # host PCM -> AudioObject (1.1*max scaling factor)
+        m.audioObject._set_raw(pinned, compute_max=(world == 1))  # host PCM -> AudioObject
         m.comp_transf_Cx()     # PCM host->device + STFT kernels (+ annealing limits D2H)
         torch.cuda.synchronize()
         stages["comp_transf_Cx_s"] = time.perf_counter() - t0
@@ -333,7 +344,7 @@ def run_ours(args, rank, world):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     sz = 4 if args.dtype == "f32" else 8
     bytes_per_bin = sz * (4 + 2 * NSRC)  # I^2 reals of x (=Cx, rank one) + V_j + hat_W_j
-    local_bins = bins / float(world)
+    local_bins = bins / float(world)  # frames are split evenly over the ranks
     achieved = bytes_per_bin * local_bins / (estep_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "estep_stereo_kernel", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -353,7 +364,7 @@ def run_ours(args, rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(args), "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "phases_ms": phases, "loglik_last": float(final_ll[total_iters - 1]),

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 5
+#define PF_ABI_VERSION 7
 
 #define PF_OK 0
 #define PF_ERR_ARG (-1)         /* invalid argument (ValueError on the Python side) */
@@ -71,9 +71,12 @@ int pf_set_device(int device);
 #define PF_PCM_I16 1
 #define PF_PCM_I32 2
 #define PF_PCM_F32 3
-int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch, int64_t L,
-            const double* window, int wlen, int hop, int nfft, void* X, int64_t N, int64_t ld,
-            double* psd_sum, int dtype, void* stream);
+/* Frame sharding: `pcm` may be a window [sample0, sample0 + L) of a longer signal of
+ * L_total samples, and X then holds the frames [frame0, frame0 + N) of that signal
+ * (whole signal: sample0 = 0, L = L_total, frame0 = 0, N = ceil(L/hop)+2). */
+int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch, int64_t L, int64_t sample0,
+            int64_t L_total, const double* window, int wlen, int hop, int nfft, void* X,
+            int64_t frame0, int64_t N, int64_t ld, double* psd_sum, int dtype, void* stream);
 
 /* ---- K6: inverse STFT with overlap-add  (tftransforms/stft.py:71-131) --------- */
 /* Y       : dtype planes [2*nsig][F][ld]
@@ -111,11 +114,13 @@ int pf_estep_plan(int J, int64_t N, int dtype, int64_t* chunk, int* nsplit,
  * hatW    : dtype planes [J][F][ld]  = rank-mean of |Re diag| (audioModel.py:727-729,:408-414)
  * hat_Rss : complex128 [F][R][R], hat_Rxs : complex128 [F][2][R]
  * ll_f    : double [F], sum over frames of log(det Sigma * pi) + x^H Sigma^-1 x
- *           (loglik = -sum(ll_f) / (F N), audioModel.py:660-664) */
+ *           (loglik = -sum(ll_f) / (F N), audioModel.py:660-664)
+ * N_norm  : number of frames the means hat_Rss / hat_Rxs are taken over (0 = N); when the
+ *           frames of a mixture are sharded over GPUs, pass the total and sum the results */
 int pf_estep_stereo(const void* X, const void* V, const void* A, const int* src_of_sub, int R,
                     int J, const double* noise_psd, int F, int64_t N, int64_t ld, void* hatW,
                     void* hat_Rss, void* hat_Rxs, double* ll_f, void* workspace,
-                    int64_t workspace_bytes, int dtype, void* stream);
+                    int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream);
 
 /* ---- K3: spatial M-step  (audioModel.py:766-889) ------------------------------- */
 /* Instantaneous mixing: f-summed real statistics (audioModel.py:816-826).
@@ -165,6 +170,13 @@ int pf_sum_splits(const double* in, int nsplit, int64_t count, double* out, void
 /* theta[r][c] *= (num[r][c] / max(den[r][c], 1e-10))^omega (audioModel.py:1573,:1725) */
 int pf_mult_update(void* theta, int64_t ldt, const double* num, const double* den, int64_t ldnd,
                    int rows, int64_t cols, double omega, int dtype, void* stream);
+
+/* the same with the split partial sums reduced on the fly: num/den_partial[s] is a
+ * [rows][ldnd] matrix at offset s * split_stride (doubles) */
+int pf_mult_update_splits(void* theta, int64_t ldt, const double* num_partial,
+                          const double* den_partial, int nsplit, int64_t split_stride,
+                          int64_t ldnd, int rows, int64_t cols, double omega, int dtype,
+                          void* stream);
 
 /* ---- K5: renormalisation  (audioModel.py:1980-2040) ----------------------------- */
 int pf_spat_energy(const void* A, const int* src_of_sub, int R, int J, int I, int F,

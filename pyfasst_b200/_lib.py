@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpyfasst_b200.so")
 
 PF_F32, PF_F64 = 0, 1
 PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 7
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 c_ip = ctypes.POINTER(ctypes.c_int)
@@ -26,8 +26,8 @@ SIGNATURES = {
     "pf_abi_version": [],
     "pf_launch_count": [],
     "pf_set_device": [c_int],
-    "pf_stft": [c_vp, c_int, c_dbl, c_int, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64,
-                c_vp, c_int, c_vp],
+    "pf_stft": [c_vp, c_int, c_dbl, c_int, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp,
+                c_i64, c_i64, c_i64, c_vp, c_int, c_vp],
     "pf_istft": [c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64,
                  c_vp, c_dbl, c_int, c_vp],
     "pf_wiener_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_ip, c_int, c_int, c_i64,
@@ -35,7 +35,7 @@ SIGNATURES = {
     "pf_estep_plan": [c_int, c_i64, c_int, ctypes.POINTER(c_i64), c_ip, ctypes.POINTER(c_i64),
                       c_int],
     "pf_estep_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_int, c_i64, c_i64, c_vp,
-                        c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp],
+                        c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
     "pf_mix_inst_stats": [c_vp, c_vp, c_vp, c_ip, c_int, c_ip, c_int, c_int, c_int, c_int, c_vp,
                           c_vp],
     "pf_mix_inst_solve": [c_vp, c_dbl, c_ip, c_int, c_int, c_int, c_vp, c_vp, c_vp],
@@ -51,6 +51,8 @@ SIGNATURES = {
                            c_vp, c_i64, c_int, c_int, c_vp, c_int, c_vp],
     "pf_sum_splits": [c_vp, c_int, c_i64, c_vp, c_vp],
     "pf_mult_update": [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
+    "pf_mult_update_splits": [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_i64, c_dbl,
+                              c_int, c_vp],
     "pf_spat_energy": [c_vp, c_ip, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "pf_spat_scale": [c_vp, c_ip, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "pf_fb_scale_colmax": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp],
@@ -146,8 +148,11 @@ class CudaKernels(object):
         return int(self.lib.pf_launch_count())
 
     # -- K1 / K6 -------------------------------------------------------------------
-    def stft(self, pcm, window, hop, nfft, X, N, psd_sum, pcm_div=1.0):
-        """pcm: float64 [nch, L] (planar) or int16 / int32 / float32 [L, nch] (interleaved)."""
+    def stft(self, pcm, window, hop, nfft, X, N, psd_sum, pcm_div=1.0, sample0=0, L_total=None,
+             frame0=0):
+        """pcm: float64 [nch, L] (planar) or int16 / int32 / float32 [L, nch] (interleaved);
+        a window [sample0, sample0+L) of a signal of L_total samples.  X receives the frames
+        [frame0, frame0+N)."""
         torch = self.torch
         if pcm.dtype == torch.float64:
             fmt, (nch, L) = 0, pcm.shape
@@ -156,9 +161,10 @@ class CudaKernels(object):
             L, nch = pcm.shape
         F, ld = X.shape[1], X.shape[2]
         assert X.shape[0] == 2 * nch and F == nfft // 2 + 1
-        _check(self.lib.pf_stft(self._p(pcm), fmt, float(pcm_div), nch, L, self._p(window),
-                                window.numel(), hop, nfft, self._p(X), N, ld, self._p(psd_sum),
-                                self.dtype_code(X), self._stream()), self.lib)
+        _check(self.lib.pf_stft(self._p(pcm), fmt, float(pcm_div), nch, L, sample0,
+                                L if L_total is None else L_total, self._p(window),
+                                window.numel(), hop, nfft, self._p(X), frame0, N, ld,
+                                self._p(psd_sum), self.dtype_code(X), self._stream()), self.lib)
 
     def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata):
         nsig = Y.shape[0] // 2
@@ -185,7 +191,8 @@ class CudaKernels(object):
                                       ctypes.byref(nbytes), F), self.lib)
         return nbytes.value
 
-    def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace):
+    def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace,
+                     N_norm=0):
         J, F, ld = V.shape
         R = A.shape[0]
         code = self.dtype_code(V)
@@ -195,7 +202,7 @@ class CudaKernels(object):
                                         J, self._p(noise), F, N, ld, self._p(hatW), self._p(Rss),
                                         self._p(Rxs), self._p(ll_f), self._p(workspace),
                                         workspace.numel() * workspace.element_size(),
-                                        code, self._stream()), self.lib)
+                                        int(N_norm), code, self._stream()), self.lib)
 
     # -- K3 ---------------------------------------------------------------------------
     def mix_inst_stats(self, Rss, Rxs, A, upd, oth, stats):
@@ -268,6 +275,15 @@ class CudaKernels(object):
         _check(self.lib.pf_mult_update(self._p(theta), theta.stride(0), self._p(num), self._p(den),
                                        num.stride(0), rows, cols, float(omega),
                                        self.dtype_code(theta), self._stream()), self.lib)
+
+    def mult_update_splits(self, theta, num_partial, den_partial, rows, cols, omega):
+        """num/den_partial: [nsplit, rows_alloc, ld] split partial sums."""
+        nsplit = num_partial.shape[0]
+        _check(self.lib.pf_mult_update_splits(self._p(theta), theta.stride(0),
+                                              self._p(num_partial), self._p(den_partial), nsplit,
+                                              num_partial.stride(0), num_partial.stride(1), rows,
+                                              cols, float(omega), self.dtype_code(theta),
+                                              self._stream()), self.lib)
 
     # -- K5 ---------------------------------------------------------------------------
     def spat_energy(self, A, src_of_sub, J, sums):

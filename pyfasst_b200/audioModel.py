@@ -12,7 +12,9 @@ CPU fallback: without the CUDA library / a GPU the methods raise.
 Extra keyword arguments (not in the reference):
     compute_dtype : 'float32' (default, fast path) or 'float64' (the reference's precision)
     kernels       : kernel provider (default: the CUDA kernels)
-    comm          : pyfasst_b200.engine.Comm for frequency sharding over several GPUs
+    comm          : pyfasst_b200.engine.Comm to shard one mixture over several GPUs
+    shard         : 'time' (frames, default: a few MB of collectives per iteration) or 'freq'
+                    (frequency bins; the TW numerators/denominators are all-reduced)
     use_cuda_graph: replay the GEM iteration as a CUDA graph
 """
 import os
@@ -36,7 +38,8 @@ class FASST(object):
     def __init__(self, audio, transf='stft', wlen=2048, hopsize=512, iter_num=50,
                  sim_ann_opt='ann', ann_PSD_lim=[None, None], verbose=0, nmfUpdateCoeff=1.,
                  tffmin=25, tffmax=18000, tfWinFunc=None, tfbpo=48, lambdaCorr=0.,
-                 compute_dtype='float32', kernels=None, comm=None, use_cuda_graph=False):
+                 compute_dtype='float32', kernels=None, comm=None, use_cuda_graph=False,
+                 shard='time'):
         self.verbose = verbose
         self.nmfUpdateCoeff = nmfUpdateCoeff
         if isinstance(audio, ao.AudioObject):
@@ -64,6 +67,7 @@ class FASST(object):
         self.compute_dtype = compute_dtype
         self._kernels = kernels
         self._comm = comm
+        self._shard = shard
         self._use_cuda_graph = use_cuda_graph
         # NB the reference does not forward tfWinFunc: the window is always Hann
         # (audioModel.py:206-214 / stft.py:361)
@@ -99,7 +103,7 @@ class FASST(object):
         if self._X is None:
             self.comp_transf_Cx()
         eng = GemEngine(self._k(), self.nbFreqsSigRepr, self.nbFramesSigRepr,
-                        dtype=self.compute_dtype, comm=self._comm)
+                        dtype=self.compute_dtype, comm=self._comm, shard=self._shard)
         eng.set_X_planes(self._X)
         lim = self.noise['ann_PSD_lim']
         opt = self.noise['sim_ann_opt'] if psd_mode is None else psd_mode
@@ -118,13 +122,27 @@ class FASST(object):
             raise ValueError(self.sig_repr_params['transf'] + " not implemented - yet?")
         k = self._k()
         aobj = self.audioObject
+        hop, nfft = self.sig_repr_params['hopsize'], self.sig_repr_params['fsize']
+        wlen = self.tft.window.size
+        if not hasattr(aobj, '_data') and not hasattr(aobj, '_raw'):
+            aobj._read_raw()
+        L = np.asarray(aobj._data).shape[0] if hasattr(aobj, '_data') else aobj._nframes
+        N = _stft.number_of_frames(L, hop)
+        multi = self._comm is not None and self._comm.world > 1
+        frames, s_lo, s_hi = None, 0, L
+        if multi and self._shard == 'time':
+            # this rank transforms its own frames only and ships only the samples they cover
+            from .engine import shard_bounds
+            frames = shard_bounds(N, self._comm.world)[self._comm.rank]
+            s_lo = min(max(0, frames[0] * hop - wlen // 2), L - 1)
+            s_hi = max(min(L, (frames[1] - 1) * hop + wlen - wlen // 2), s_lo + 1)
         if hasattr(aobj, '_data'):
             # the user already holds the scaled float64 samples (e.g. set through `.data`)
             data = np.asarray(aobj._data, dtype=np.float64)
             if data.ndim == 1:
                 data = data[:, None]
             nc = data.shape[1]
-            pcm, div = torch.tensor(np.ascontiguousarray(data.T)).to(k.device), 1.0
+            pcm, div = torch.tensor(np.ascontiguousarray(data[s_lo:s_hi].T)).to(k.device), 1.0
         else:
             # ship the samples as stored (int16: 4x fewer bytes than float64) and let the
             # STFT kernel apply the reference's scaling data / (1.1 max|data|)
@@ -135,20 +153,28 @@ class FASST(object):
             if raw.dim() == 1:
                 raw = raw[:, None]
             nc = raw.shape[1]
+            if not hasattr(aobj, '_maxdata'):
+                # sharded scan of the scaling factor 1.1 max|x| (audioObject.py:124-126)
+                peak = torch.tensor([aobj._peak(s_lo, s_hi)], dtype=torch.float64, device=k.device)
+                if multi:
+                    self._comm.allreduce_max(peak)
+                aobj._maxdata = np.maximum(1.1 * float(peak.item()), 1e-10)
+            raw = raw[s_lo:s_hi]
             if raw.dtype not in (torch.int16, torch.int32, torch.float32):
                 raw = raw.to(torch.float64).t().contiguous()  # planar float64 path
             pcm, div = raw.to(k.device, non_blocking=True), float(aobj._maxdata)
         if nc != 2:
             raise AttributeError("Nb channels " + str(nc) + " not implemented yet")
-        F = self.sig_repr_params['fsize'] // 2 + 1
+        F = nfft // 2 + 1
         psd = torch.zeros(F, dtype=torch.float64, device=k.device)
-        X, N = _stft.stft_planes(k, pcm, self.tft.window, self.sig_repr_params['hopsize'],
-                                 self.sig_repr_params['fsize'], self.compute_dtype, psd,
-                                 pcm_div=div)
+        X, _ = _stft.stft_planes(k, pcm, self.tft.window, hop, nfft, self.compute_dtype, psd,
+                                 pcm_div=div, frames=frames, sample0=s_lo, L_total=L)
         self.nbFreqsSigRepr, self.nbFramesSigRepr = F, N
         self._Cx = None
         del self.audioObject.data  # like the reference (:288); `_raw`, if any, is kept
-        if self._comm is not None and self._comm.world > 1:
+        if multi and self._shard == 'time':
+            self._comm.allreduce_sum(psd)
+        elif multi:
             from .engine import shard_bounds
             lo, hi = shard_bounds(F, self._comm.world)[self._comm.rank]
             X = X[:, lo:hi].contiguous()
@@ -322,7 +348,15 @@ class FASST(object):
                 group_of_src[j] = n
         Y = eng.wiener(group_of_src, nbSources)
         if eng._sharded():
-            Y = torch.tensor(eng._gather_f(Y, 1)).to(eng.dev)
+            # the inverse STFT needs every frequency of every frame: gather the shards (every
+            # rank then inverts the whole signal; separation is a one-off, not the GEM loop)
+            if eng.shard == 'freq':
+                Yh = eng._gather_f(Y, 1)
+            else:
+                Yn = eng._gather_n(Y[:, :, :eng.N].contiguous(), 2)
+                Yh = np.zeros(Yn.shape[:2] + ((Yn.shape[2] + 31) // 32 * 32,), dtype=Yn.dtype)
+                Yh[:, :, :Yn.shape[2]] = Yn
+            Y = torch.tensor(Yh).to(eng.dev)
         L = self.audioObject.nframes
         maxdata = float(self.audioObject._maxdata)
         hop, nfft = self.sig_repr_params['hopsize'], self.sig_repr_params['fsize']

@@ -51,8 +51,10 @@ class AudioObject(object):
         self._samplerate, raw, self._encoding = wavread(self.filename)
         self._set_raw(raw)
 
-    def _set_raw(self, raw):
-        """Adopt an in-memory PCM array (numpy or a pinned torch tensor), [nframes, channels]."""
+    def _set_raw(self, raw, compute_max=True):
+        """Adopt an in-memory PCM array (numpy or a pinned torch tensor), [nframes, channels].
+        With compute_max=False the scaling factor `_maxdata` is left to the consumer (a sharded
+        model scans only its own samples and all-reduces the maximum)."""
         self._raw = raw
         shape = tuple(raw.shape)
         if len(shape) == 2:
@@ -62,22 +64,33 @@ class AudioObject(object):
         arr = raw.numpy() if hasattr(raw, "numpy") else np.asarray(raw)
         if not hasattr(self, "_encoding"):
             self._encoding = arr.dtype
-        # 1.1 * max|x| without the abs() temporary (ref: audioObject.py:124-126)
+        if hasattr(self, "_maxdata"):
+            del self._maxdata
+        if compute_max:
+            self._maxdata = np.maximum(1.1 * self._peak(0, self._nframes), 1e-10)
+
+    def _peak(self, lo, hi):
+        """max|x| over the samples [lo, hi) of `_raw`, as np.abs(data).max() gives it
+        (ref: audioObject.py:124-126), without the abs() temporary."""
+        arr = self._raw.numpy() if hasattr(self._raw, "numpy") else np.asarray(self._raw)
+        arr = arr[lo:hi]
         peak = 0.0
         if arr.size:
-            lo, hi = arr.min(), arr.max()
-            if np.issubdtype(arr.dtype, np.signedinteger) and lo == np.iinfo(arr.dtype).min:
+            vmin, vmax = arr.min(), arr.max()
+            if np.issubdtype(arr.dtype, np.signedinteger) and vmin == np.iinfo(arr.dtype).min:
                 # np.abs() of the most negative integer wraps to itself in the reference
-                rest = arr[arr > lo]
-                lo = rest.min() if rest.size else 0
-            peak = max(abs(float(lo)), abs(float(hi)))
-        self._maxdata = np.maximum(1.1 * peak, 1e-10)
+                rest = arr[arr > vmin]
+                vmin = rest.min() if rest.size else 0
+            peak = max(abs(float(vmin)), abs(float(vmax)))
+        return peak
 
     def _read(self):
         """ref: audioObject.py:112-127"""
         if not hasattr(self, '_raw'):
             self._read_raw()
         raw = self._raw.numpy() if hasattr(self._raw, "numpy") else np.asarray(self._raw)
+        if not hasattr(self, '_maxdata'):
+            self._maxdata = np.maximum(1.1 * self._peak(0, self._nframes), 1e-10)
         self._data = raw / self._maxdata
 
     def _write(self):
@@ -111,7 +124,7 @@ class AudioObject(object):
 
     def _get_samplerate(self):
         if not hasattr(self, '_samplerate') and 'r' in self.mode:
-            self._read()
+            self._read_raw()  # metadata only: the float64 copy is built when `.data` is read
         return self._samplerate
 
     def _set_samplerate(self, samplerate):
@@ -125,11 +138,11 @@ class AudioObject(object):
     @property
     def channels(self):
         if not hasattr(self, '_channels'):
-            self._read()
+            self._read_raw()
         return self._channels
 
     @property
     def nframes(self):
         if not hasattr(self, '_nframes'):
-            self._read()
+            self._read_raw()
         return self._nframes

@@ -86,6 +86,17 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
+// float -> double without the (quarter-rate, XU pipe) F2F conversion: re-bias the exponent with
+// integer ops.  Exact for normal numbers; zero and denormals map to |x| < 1.2e-38, which is
+// far below every eps clamp of this path.  The E-step is limited by the XU pipe otherwise
+// (profiles/r01: 23 conversions per bin).
+__device__ __forceinline__ double widen(float x) {
+  const unsigned f = __float_as_uint(x);
+  const unsigned hi = (((f & 0x7fffffffu) >> 3) + 0x38000000u) | (f & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(f << 29));
+}
+__device__ __forceinline__ double widen(double x) { return x; }
+
 // Per-bin algebra shared by the E-step and the Wiener filter.
 // Sigma = s2 I + sum_j v_j R_j ; returns Sigma^-1 (i00, i11, i01) in the compute type C and
 // det Sigma / the pair products v_j v_k in the type D.  The determinant is expanded into
@@ -170,14 +181,30 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   long end = begin + chunk;
   if (end > N) end = N;
 
-  for (long n0 = begin + (long)threadIdx.x * VEC; n0 < end; n0 += (long)ESTEP_THREADS * VEC) {
-    T x0r[VEC], x0i[VEC], x1r[VEC], x1i[VEC], v[J][VEC], w[J][VEC];
-    load_vec<T>(X + 0 * plane + row + n0, x0r);
-    load_vec<T>(X + 1 * plane + row + n0, x0i);
-    load_vec<T>(X + 2 * plane + row + n0, x1r);
-    load_vec<T>(X + 3 * plane + row + n0, x1i);
+  // the loads of pass i+1 are issued before the arithmetic of pass i (register double
+  // buffering): with only two CTAs resident per SM the ~1 us HBM latency is otherwise exposed
+  constexpr bool kPrefetch = sizeof(T) == 4;
+  T nx[4][VEC], nv[J][VEC];
+  auto issue_loads = [&](long n) {
+    load_vec<T>(X + 0 * plane + row + n, nx[0]);
+    load_vec<T>(X + 1 * plane + row + n, nx[1]);
+    load_vec<T>(X + 2 * plane + row + n, nx[2]);
+    load_vec<T>(X + 3 * plane + row + n, nx[3]);
 #pragma unroll
-    for (int j = 0; j < J; ++j) load_vec<T>(V + j * plane + row + n0, v[j]);
+    for (int j = 0; j < J; ++j) load_vec<T>(V + j * plane + row + n, nv[j]);
+  };
+  const long stride = (long)ESTEP_THREADS * VEC;
+  if (kPrefetch && begin + (long)threadIdx.x * VEC < end) issue_loads(begin + (long)threadIdx.x * VEC);
+  for (long n0 = begin + (long)threadIdx.x * VEC; n0 < end; n0 += stride) {
+    T x0r[VEC], x0i[VEC], x1r[VEC], x1i[VEC], v[J][VEC], w[J][VEC];
+    if (!kPrefetch) issue_loads(n0);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      x0r[e] = nx[0][e]; x0i[e] = nx[1][e]; x1r[e] = nx[2][e]; x1i[e] = nx[3][e];
+#pragma unroll
+      for (int j = 0; j < J; ++j) v[j][e] = nv[j][e];
+    }
+    if (kPrefetch && n0 + stride < end) issue_loads(n0 + stride);
 
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
@@ -192,11 +219,12 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         vt[j] = v[j][e];
-        vj[j] = (C)vt[j];
+        vj[j] = (C)widen(vt[j]);
       }
       sigma_inverse<C, T, J>(vj, vt, s_coef, s_dcoef, s2, pr, det, i00, i11, i01r, i01i);
       // y = Sigma^-1 x
-      const C a0r = (C)x0r[e], a0i = (C)x0i[e], a1r = (C)x1r[e], a1i = (C)x1i[e];
+      const C a0r = (C)widen(x0r[e]), a0i = (C)widen(x0i[e]);
+      const C a1r = (C)widen(x1r[e]), a1i = (C)widen(x1i[e]);
       const C y0r = i00 * a0r + i01r * a1r - i01i * a1i;
       const C y0i = i00 * a0i + i01r * a1i + i01i * a1r;
       const C y1r = i01r * a0r + i01i * a0i + i11 * a1r;
@@ -208,7 +236,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
       if (sizeof(T) == 8)
         acc_ll += log((double)det) + 1.1447298858494002 + (double)quad;
       else
-        acc_ll += (double)(logf((float)det) + kLogPi + (float)quad);
+        acc_ll += (double)(__logf((float)det) + kLogPi + (float)quad);
       // M = y y^H - Sigma^-1
       const C m00 = y0r * y0r + y0i * y0i - i00;
       const C m11 = y1r * y1r + y1i * y1i - i11;
@@ -494,7 +522,7 @@ extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
                                const int* src_of_sub, int R, int J, const double* noise_psd,
                                int F, int64_t N, int64_t ld, void* hatW, void* hat_Rss,
                                void* hat_Rxs, double* ll_f, void* workspace,
-                               int64_t workspace_bytes, int dtype, void* stream) {
+                               int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream) {
   if (J > MAXJ || R > MAXR) {
     set_error("pf_estep_stereo: J=%d spatial components / R=%d sub-sources not supported "
               "(max %d / %d)", J, R, MAXJ, MAXR);
@@ -541,7 +569,10 @@ extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
     rc = dispatch_estep<double, double>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld,
                                         chunk, nsplit, st);
   if (rc) return rc;
-  estep_finalize_kernel<<<F, 64, 0, st>>>(partial, (const double2*)A, map, R, J, F, N, nsplit,
+  // hat_Rss / hat_Rxs are means over N_norm frames: the local N, or the length of the whole
+  // mixture when the frames are sharded over several GPUs (the partial means are then summed)
+  estep_finalize_kernel<<<F, 64, 0, st>>>(partial, (const double2*)A, map, R, J, F,
+                                          N_norm > 0 ? N_norm : N, nsplit,
                                           (double2*)hat_Rss, (double2*)hat_Rxs, ll_f);
   return check_launch("estep_finalize_kernel");
 }

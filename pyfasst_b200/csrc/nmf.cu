@@ -500,6 +500,27 @@ __global__ void mult_update_kernel(T* __restrict__ theta, long ldt, const double
   theta[(size_t)r * ldt + c] = (T)((double)theta[(size_t)r * ldt + c] * g);
 }
 
+// theta *= (sum_s num[s] / max(sum_s den[s], eps))^omega with the split partial sums reduced
+// on the fly in a fixed order (one launch instead of two sum_splits + mult_update)
+template <typename T>
+__global__ void mult_update_splits_kernel(T* __restrict__ theta, long ldt,
+                                          const double* __restrict__ num,
+                                          const double* __restrict__ den, int nsplit,
+                                          long split_stride, long ldnd, int rows, long cols,
+                                          double omega) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= cols || r >= rows) return;
+  double sn = 0.0, sd = 0.0;
+  for (int s = 0; s < nsplit; ++s) {
+    sn += num[(size_t)s * split_stride + (size_t)r * ldnd + c];
+    sd += den[(size_t)s * split_stride + (size_t)r * ldnd + c];
+  }
+  const double ratio = sn / fmax(sd, 1e-10);
+  const double g = (omega == 1.0) ? ratio : pow(ratio, omega);
+  theta[(size_t)r * ldt + c] = (T)((double)theta[(size_t)r * ldt + c] * g);
+}
+
 template <typename T, int KC, int FR>
 static int launch_fb(const void* hatW, const void* P, const void* O, long ld, const void* G,
                      long ldg, int k0, int K, int F, long N, long chunk, int nsplit, double* num,
@@ -784,4 +805,21 @@ extern "C" int pf_mult_update(void* theta, int64_t ldt, const double* num, const
     mult_update_kernel<double><<<grid, 256, 0, as_stream(stream)>>>((double*)theta, ldt, num, den,
                                                                    ldnd, rows, cols, omega);
   return check_launch("mult_update_kernel");
+}
+
+extern "C" int pf_mult_update_splits(void* theta, int64_t ldt, const double* num_partial,
+                                     const double* den_partial, int nsplit, int64_t split_stride,
+                                     int64_t ldnd, int rows, int64_t cols, double omega, int dtype,
+                                     void* stream) {
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_mult_update_splits: bad dtype %d", dtype);
+  PF_REQUIRE(rows > 0 && cols > 0 && nsplit >= 1, "pf_mult_update_splits: empty");
+  dim3 grid(ceil_div(cols, 128), rows);
+  if (dtype == PF_F32)
+    mult_update_splits_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(
+        (float*)theta, ldt, num_partial, den_partial, nsplit, split_stride, ldnd, rows, cols, omega);
+  else
+    mult_update_splits_kernel<double><<<grid, 128, 0, as_stream(stream)>>>(
+        (double*)theta, ldt, num_partial, den_partial, nsplit, split_stride, ldnd, rows, cols,
+        omega);
+  return check_launch("mult_update_splits_kernel");
 }

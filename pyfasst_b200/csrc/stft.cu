@@ -65,8 +65,8 @@ __device__ __forceinline__ double pcm_sample(const void* __restrict__ pcm, int n
 
 template <typename T, int FMT>
 __global__ void __launch_bounds__(FFT_THREADS)
-stft_kernel(const void* __restrict__ pcm, int nch, double div, long L,
-            const double* __restrict__ window, int wlen, int hop, int nfft, int log2m,
+stft_kernel(const void* __restrict__ pcm, int nch, double div, long L, long sample0, long Ltot,
+            long frame0, const double* __restrict__ window, int wlen, int hop, int nfft, int log2m,
             const double2* __restrict__ tw, T* __restrict__ X, int F, long N, long ld) {
   constexpr int TN = Sector<T>::N;
   constexpr int ROW = 2 * TN + 1;  // padded staging row: (re[TN], im[TN]) per bin
@@ -87,15 +87,16 @@ stft_kernel(const void* __restrict__ pcm, int nch, double div, long L,
       continue;
     }
     // frame n covers samples n*hop - wlen/2 + i, i < wlen (stft.py:47-63)
-    const long base = n * hop - wlen / 2;
+    const long base = (frame0 + n) * hop - wlen / 2;  // global sample index of the frame start
     for (int m = threadIdx.x; m < M; m += FFT_THREADS) {
       double v[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int i = 2 * m + e;
         const long s = base + i;
-        v[e] = (i < wlen && s >= 0 && s < L)
-                   ? pcm_sample<FMT>(pcm, nch, L, ch, s, div) * __ldg(window + i)
+        const long sl = s - sample0;  // index into the window of samples we were given
+        v[e] = (i < wlen && s >= 0 && s < Ltot && sl >= 0 && sl < L)
+                   ? pcm_sample<FMT>(pcm, nch, L, ch, sl, div) * __ldg(window + i)
                    : 0.0;
       }
       buf[__brev((unsigned)m) >> (32 - log2m)] = make_double2(v[0], v[1]);
@@ -288,9 +289,9 @@ static const double2* twiddles(int nfft, cudaStream_t st) {
 }
 
 template <typename T, int FMT>
-static int launch_stft(const void* pcm, int nch, double div, long L, const double* window, int wlen,
-                       int hop, int nfft, void* X, long N, long ld, double* psd_sum,
-                       cudaStream_t st) {
+static int launch_stft(const void* pcm, int nch, double div, long L, long sample0, long Ltot,
+                       long frame0, const double* window, int wlen, int hop, int nfft, void* X,
+                       long N, long ld, double* psd_sum, cudaStream_t st) {
   constexpr int TN = Sector<T>::N;
   const int M = nfft / 2, F = M + 1;
   const double2* tw = twiddles(nfft, st);
@@ -306,8 +307,9 @@ static int launch_stft(const void* pcm, int nch, double div, long L, const doubl
     return PF_ERR_CUDA;
   }
   dim3 grid(ceil_div(N, TN), nch);
-  stft_kernel<T, FMT><<<grid, FFT_THREADS, smem, st>>>(pcm, nch, div, L, window, wlen, hop, nfft,
-                                                      ilog2(M), tw, (T*)X, F, N, ld);
+  stft_kernel<T, FMT><<<grid, FFT_THREADS, smem, st>>>(pcm, nch, div, L, sample0, Ltot, frame0,
+                                                      window, wlen, hop, nfft, ilog2(M), tw,
+                                                      (T*)X, F, N, ld);
   int rc = check_launch("stft_kernel");
   if (rc) return rc;
   if (psd_sum != nullptr) {
@@ -318,19 +320,20 @@ static int launch_stft(const void* pcm, int nch, double div, long L, const doubl
 }
 
 template <typename T>
-static int dispatch_stft(int fmt, const void* pcm, int nch, double div, long L,
-                         const double* window, int wlen, int hop, int nfft, void* X, long N,
-                         long ld, double* psd_sum, cudaStream_t st) {
+static int dispatch_stft(int fmt, const void* pcm, int nch, double div, long L, long sample0,
+                         long Ltot, long frame0, const double* window, int wlen, int hop, int nfft,
+                         void* X, long N, long ld, double* psd_sum, cudaStream_t st) {
+#define PF_STFT_CASE(F_)                                                                       \
+  case F_:                                                                                     \
+    return launch_stft<T, F_>(pcm, nch, div, L, sample0, Ltot, frame0, window, wlen, hop, nfft, \
+                              X, N, ld, psd_sum, st);
   switch (fmt) {
-    case PF_PCM_F64_PLANAR:
-      return launch_stft<T, PF_PCM_F64_PLANAR>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
-    case PF_PCM_I16:
-      return launch_stft<T, PF_PCM_I16>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
-    case PF_PCM_I32:
-      return launch_stft<T, PF_PCM_I32>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
-    case PF_PCM_F32:
-      return launch_stft<T, PF_PCM_F32>(pcm, nch, div, L, window, wlen, hop, nfft, X, N, ld, psd_sum, st);
+    PF_STFT_CASE(PF_PCM_F64_PLANAR)
+    PF_STFT_CASE(PF_PCM_I16)
+    PF_STFT_CASE(PF_PCM_I32)
+    PF_STFT_CASE(PF_PCM_F32)
   }
+#undef PF_STFT_CASE
   set_error("pf_stft: unknown PCM format %d", fmt);
   return PF_ERR_ARG;
 }
@@ -379,22 +382,27 @@ static int check_fft_args(const char* who, int wlen, int hop, int nfft) {
 }
 
 extern "C" int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch, int64_t L,
-                       const double* window, int wlen, int hop, int nfft, void* X, int64_t N,
-                       int64_t ld, double* psd_sum, int dtype, void* stream) {
+                       int64_t sample0, int64_t L_total, const double* window, int wlen, int hop,
+                       int nfft, void* X, int64_t frame0, int64_t N, int64_t ld, double* psd_sum,
+                       int dtype, void* stream) {
   int rc = check_fft_args("pf_stft", wlen, hop, nfft);
   if (rc) return rc;
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_stft: bad dtype %d", dtype);
   PF_REQUIRE(nch >= 1 && nch <= 16 && L > 0, "pf_stft: nch=%d L=%ld", nch, (long)L);
   PF_REQUIRE(pcm_div != 0.0, "pf_stft: pcm_div must not be zero");
-  PF_REQUIRE(N == (L + hop - 1) / hop + 2, "pf_stft: N=%ld is not ceil(L/hop)+2 (stft.py:40)",
-             (long)N);
+  PF_REQUIRE(sample0 >= 0 && sample0 + L <= L_total, "pf_stft: samples [%ld, %ld) outside [0, %ld)",
+             (long)sample0, (long)(sample0 + L), (long)L_total);
+  const int64_t n_total = (L_total + hop - 1) / hop + 2;  // stft.py:40
+  PF_REQUIRE(frame0 >= 0 && N >= 1 && frame0 + N <= n_total,
+             "pf_stft: frames [%ld, %ld) outside [0, ceil(L/hop)+2 = %ld)", (long)frame0,
+             (long)(frame0 + N), (long)n_total);
   PF_REQUIRE(ld >= N && ld % 4 == 0, "pf_stft: ld=%ld must be >= N and a multiple of 4", (long)ld);
   cudaStream_t st = as_stream(stream);
   if (dtype == PF_F32)
-    return dispatch_stft<float>(pcm_format, pcm, nch, pcm_div, L, window, wlen, hop, nfft, X, N,
-                                ld, psd_sum, st);
-  return dispatch_stft<double>(pcm_format, pcm, nch, pcm_div, L, window, wlen, hop, nfft, X, N, ld,
-                               psd_sum, st);
+    return dispatch_stft<float>(pcm_format, pcm, nch, pcm_div, L, sample0, L_total, frame0, window,
+                                wlen, hop, nfft, X, N, ld, psd_sum, st);
+  return dispatch_stft<double>(pcm_format, pcm, nch, pcm_div, L, sample0, L_total, frame0, window,
+                               wlen, hop, nfft, X, N, ld, psd_sum, st);
 }
 
 extern "C" int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld,

@@ -9,12 +9,18 @@ stream and never synchronises with the host (the iteration counter, the annealed
 noise PSD and the log-likelihood trace live on the device), so the whole loop can
 be captured in a CUDA graph.
 
-Frequency sharding (one process per GPU): each rank owns the rows
-[f_lo, f_hi) of X, V, hat_W, FB, A and the noise PSD; TW (and FW) are replicated.
-The E-step, the FB update and the convolutive mixing update are local; per
-iteration the ranks all-reduce the TW numerators/denominators [S,2,K,N], the
-scalar log-likelihood, the instantaneous-mixing statistics, the spatial energies
-(SUM) and the FB column maxima (MAX) -- see `Comm`.
+Multi-GPU (one process per GPU, `Comm` over torch.distributed), two sharding modes:
+
+* shard='freq' (what BASELINE.json prescribes): each rank owns the rows [f_lo, f_hi) of X, V,
+  hat_W, FB, A and the noise PSD; TW (and FW) are replicated.  The E-step, the FB update and
+  the convolutive mixing update are local; per iteration the ranks all-reduce the TW
+  numerators/denominators [S,2,K,N] (SUM), the scalar log-likelihood, the instantaneous-mixing
+  statistics, the spatial energies (SUM) and the FB column maxima (MAX).
+* shard='time': each rank owns the frames [n_lo, n_hi) of X, V, hat_W and TW; FB, FW, A and the
+  noise PSD are replicated.  The TW update is local; per iteration the ranks all-reduce the
+  per-frequency E-step statistics (hat_Rss, hat_Rxs, log-likelihood: O(F R^2)) and the FB
+  numerators/denominators [S,2,F,K] -- a few MB whatever the length of the mixture, where the
+  frequency mode moves O(K N) per iteration.  This is the mode bench.py scales with.
 
 Supported model structure (what MultiChanNMFInst_FASST / MultiChanNMFConv build,
 audioModel.py:2349-2393, :2488-2508): stereo; one spectral component per spatial
@@ -62,25 +68,33 @@ def _round_up(n, m):
 
 
 class GemEngine(object):
-    def __init__(self, kernels, F_total, N, dtype="float32", comm=None, f_range=None):
+    def __init__(self, kernels, F_total, N, dtype="float32", comm=None, f_range=None,
+                 shard="freq", n_range=None):
         import torch
         self.torch = torch
         self.k = kernels
         self.dev = kernels.device
         self.tdtype = {"float32": torch.float32, "float64": torch.float64}[dtype]
         self.F_total = int(F_total)
-        self.N = int(N)
-        self.ld = _round_up(self.N, 32)
+        self.N_total = int(N)
         self.comm = comm
+        if shard not in ("freq", "time"):
+            raise ValueError("shard must be 'freq' or 'time'")
+        self.shard = shard
+        multi = comm is not None and comm.world > 1
         if f_range is None:
-            if comm is not None and comm.world > 1:
-                f_range = shard_bounds(self.F_total, comm.world)[comm.rank]
-            else:
-                f_range = (0, self.F_total)
+            f_range = shard_bounds(self.F_total, comm.world)[comm.rank] \
+                if (multi and shard == "freq") else (0, self.F_total)
+        if n_range is None:
+            n_range = shard_bounds(self.N_total, comm.world)[comm.rank] \
+                if (multi and shard == "time") else (0, self.N_total)
         self.f_lo, self.f_hi = f_range
+        self.n_lo, self.n_hi = n_range
         self.F = self.f_hi - self.f_lo
-        if self.F <= 0:
-            raise ValueError("empty frequency shard %r" % (f_range,))
+        self.N = self.n_hi - self.n_lo   # local frames
+        self.ld = _round_up(self.N, 32)
+        if self.F <= 0 or self.N <= 0:
+            raise ValueError("empty shard f=%r n=%r" % (f_range, n_range))
         self.X = None
         self.J = 0
         self.n_iter_done = 0
@@ -102,6 +116,12 @@ class GemEngine(object):
     def _sharded(self):
         return self.comm is not None and self.comm.world > 1
 
+    def _fshard(self):
+        return self._sharded() and self.shard == "freq"
+
+    def _tshard(self):
+        return self._sharded() and self.shard == "time"
+
     # ------------------------------------------------------------------ inputs
     def set_X_planes(self, X):
         """X: device planes [4, F_local, ld] (re0, im0, re1, im1) of dtype self.tdtype."""
@@ -109,8 +129,8 @@ class GemEngine(object):
         self.X = X
 
     def set_X_host(self, Xc):
-        """Xc: complex [2, F_total, N] host array (e.g. an STFT computed elsewhere)."""
-        Xc = np.asarray(Xc)[:, self.f_lo:self.f_hi]
+        """Xc: complex [2, F_total, N_total] host array (e.g. an STFT computed elsewhere)."""
+        Xc = np.asarray(Xc)[:, self.f_lo:self.f_hi, self.n_lo:self.n_hi]
         planes = np.zeros([4, self.F, self.ld])
         planes[0, :, :self.N], planes[1, :, :self.N] = Xc[0].real, Xc[0].imag
         planes[2, :, :self.N], planes[3, :, :self.N] = Xc[1].real, Xc[1].imag
@@ -196,13 +216,13 @@ class GemEngine(object):
             FB = np.asarray(fac["FB"], dtype=np.float64)
             FW = np.asarray(fac["FW"], dtype=np.float64)
             TW = np.asarray(fac["TW"], dtype=np.float64)
-            if FB.shape[0] != self.F_total or TW.shape[1] != self.N or \
+            if FB.shape[0] != self.F_total or TW.shape[1] != self.N_total or \
                     FW.shape != (FB.shape[1], TW.shape[0]):
                 raise ValueError("inconsistent factor shapes FB%s FW%s TW%s"
                                  % (FB.shape, FW.shape, TW.shape))
             Kb, Kw = FW.shape
             TWp = np.zeros([Kw, self.ld])
-            TWp[:, :self.N] = TW
+            TWp[:, :self.N] = TW[:, self.n_lo:self.n_hi]
             ent = {
                 "j": owner[s], "Kb": Kb, "Kw": Kw,
                 "FB_free": fac["FB_frdm_prior"] == "free",
@@ -223,9 +243,13 @@ class GemEngine(object):
         f64, c128 = torch.float64, torch.complex128
         self.V = self._zeros([J, F, ld])
         self.hatW = self._zeros([J, F, ld])
-        self.Rss = self._zeros([F, R, R], c128)
-        self.Rxs = self._zeros([F, 2, R], c128)
-        self.ll_f = self._zeros([F], f64)
+        # hat_Rss, hat_Rxs and the per-frequency log-likelihood sums share one buffer so that
+        # the time-sharded mode reduces them with a single all-reduce
+        self.estat = self._zeros([F * (2 * R * R + 4 * R + 1)], f64)
+        o1, o2 = 2 * F * R * R, 2 * F * R * R + 4 * F * R
+        self.Rss = torch.view_as_complex(self.estat[:o1].view(F, R, R, 2))
+        self.Rxs = torch.view_as_complex(self.estat[o1:o2].view(F, 2, R, 2))
+        self.ll_f = self.estat[o2:]
         self.ll_sum = self._zeros([1], f64)
         self.flags = self._zeros([1], torch.int32)
         self.iter_dev = self._zeros([1], torch.int32)
@@ -249,7 +273,7 @@ class GemEngine(object):
             self.fb_plan[id(e)] = (chunk, nsplit)
             fb_size = max(fb_size, nsplit * F * e["Kb"])
         self.fb_part = self._zeros([2, fb_size], f64)
-        self.fb_nd = self._zeros([2, F * Kmax], f64)
+        self.fb_nd = self._zeros([S, 2, F * Kmax], f64)
         # TW update partial sums; the reduced num/den of all components share one
         # buffer so that a single all-reduce serves the whole iteration
         self.tw_plan, tw_size = {}, 0
@@ -275,7 +299,9 @@ class GemEngine(object):
     def estep(self):
         """compute_suff_stat (audioModel.py:580-764) on the current parameters."""
         self.k.estep_stereo(self.X, self.V, self.A, self.src_of_sub, self.noise, self.N,
-                            self.hatW, self.Rss, self.Rxs, self.ll_f, self.ws)
+                            self.hatW, self.Rss, self.Rxs, self.ll_f, self.ws, self.N_total)
+        if self._tshard():  # means over all frames: sum the ranks' partial statistics
+            self.comm.allreduce_sum(self.estat)
 
     def update_mix(self):
         """update_mix_matrix (audioModel.py:766-889)."""
@@ -288,7 +314,7 @@ class GemEngine(object):
             n = 2 * len(upd) + len(upd) ** 2
             stats = self.stats[:n]
             k.mix_inst_stats(self.Rss, self.Rxs, self.A, upd, oth, stats)
-            if self._sharded():
+            if self._fshard():
                 self.comm.allreduce_sum(stats)
             k.mix_inst_solve(stats, self.F_total, upd, self.A, self.flags)
         else:
@@ -301,52 +327,75 @@ class GemEngine(object):
         `comp_spat_comp_power(spat_ind)` of the FB update (Q3) and the stale
         `other_fact_power` (Q1/Q2)."""
         k, N, F = self.k, self.N, self.F
+        # FB: contraction over the (local) frames.  Different components are independent given
+        # hat_W and V, so under time sharding all FB sums are reduced with one all-reduce.
+        any_fb = False
+        for s, e in enumerate(self.spec):
+            if not e["FB_free"]:
+                continue
+            any_fb = True
+            j = e["j"]
+            chunk, nsplit = self.fb_plan[id(e)]
+            cnt = F * e["Kb"]
+            pn = self.fb_part[0, :nsplit * cnt].view(nsplit, F, e["Kb"])
+            pd = self.fb_part[1, :nsplit * cnt].view(nsplit, F, e["Kb"])
+            k.fb_contract(self.hatW[j], self.V[j], self.V[j], e["G"], N, pn, pd, chunk, nsplit)
+            if self._tshard():
+                k.sum_splits(pn, self.fb_nd[s, 0, :cnt])
+                k.sum_splits(pd, self.fb_nd[s, 1, :cnt])
+            else:
+                k.mult_update_splits(e["FB"], pn, pd, F, e["Kb"], self.omega)
+                k.small_matmul(e["FB"], e["FW"], e["W"])
+        if any_fb and self._tshard():
+            self.comm.allreduce_sum(self.fb_nd)
+            for s, e in enumerate(self.spec):
+                if e["FB_free"]:
+                    cnt = F * e["Kb"]
+                    k.mult_update(e["FB"], self.fb_nd[s, 0, :cnt].view(F, e["Kb"]),
+                                  self.fb_nd[s, 1, :cnt].view(F, e["Kb"]), F, e["Kb"], self.omega)
+                    k.small_matmul(e["FB"], e["FW"], e["W"])
+        # TW: contraction over the (local) frequencies with the updated W
         any_tw = False
         for s, e in enumerate(self.spec):
+            if not e["TW_free"]:
+                continue
+            any_tw = True
             j = e["j"]
-            if e["FB_free"]:
-                chunk, nsplit = self.fb_plan[id(e)]
-                cnt = F * e["Kb"]
-                pn = self.fb_part[0, :nsplit * cnt].view(nsplit, F, e["Kb"])
-                pd = self.fb_part[1, :nsplit * cnt].view(nsplit, F, e["Kb"])
-                k.fb_contract(self.hatW[j], self.V[j], self.V[j], e["G"], N, pn, pd, chunk, nsplit)
-                num = self.fb_nd[0, :cnt].view(F, e["Kb"])
-                den = self.fb_nd[1, :cnt].view(F, e["Kb"])
-                k.sum_splits(pn, num)
-                k.sum_splits(pd, den)
-                k.mult_update(e["FB"], num, den, F, e["Kb"], self.omega)
-                k.small_matmul(e["FB"], e["FW"], e["W"])
-            if e["TW_free"]:
-                any_tw = True
-                fchunk, fsplit = self.tw_plan[id(e)]
-                cnt = e["Kw"] * self.ld
-                pn = self.tw_part[0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
-                pd = self.tw_part[1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
-                k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit,
-                              self.scratch)
+            fchunk, fsplit = self.tw_plan[id(e)]
+            cnt = e["Kw"] * self.ld
+            pn = self.tw_part[0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+            pd = self.tw_part[1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+            k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit,
+                          self.scratch)
+            if self._fshard():
                 k.sum_splits(pn, self.tw_nd[s, 0, :e["Kw"]])
                 k.sum_splits(pd, self.tw_nd[s, 1, :e["Kw"]])
-        if any_tw and self._sharded():
+            else:  # reduce the frequency splits inside the update kernel
+                k.mult_update_splits(e["TW"], pn, pd, e["Kw"], N, self.omega)
+        if any_tw and self._fshard():
             self.comm.allreduce_sum(self.tw_nd)
-        for s, e in enumerate(self.spec):
-            if e["TW_free"]:
-                k.mult_update(e["TW"], self.tw_nd[s, 0], self.tw_nd[s, 1], e["Kw"], N, self.omega)
+            for s, e in enumerate(self.spec):
+                if e["TW_free"]:
+                    k.mult_update(e["TW"], self.tw_nd[s, 0], self.tw_nd[s, 1], e["Kw"], N,
+                                  self.omega)
 
     def renormalize(self):
         """renormalize_parameters (audioModel.py:1980-2040)."""
         k = self.k
         k.spat_energy(self.A, self.src_of_sub, self.J, self.sums)
-        if self._sharded():
+        if self._fshard():
             self.comm.allreduce_sum(self.sums)
         k.spat_scale(self.A, self.src_of_sub, self.sums, self.counts)
         for s, e in enumerate(self.spec):
             k.fb_scale_colmax(e["FB"], self.sums, self.counts, e["j"], self.colmax[s])
-        if self._sharded():
+        if self._fshard():
             self.comm.allreduce_max(self.colmax)
         for s, e in enumerate(self.spec):
             k.fw_renorm(e["FW"], self.colmax[s], self.wcol[s], self.w2[s])
             k.scale_matrix(e["FB"], self.F, e["Kb"], self.wcol[s], False, True)
             k.scale_matrix(e["TW"], e["Kw"], self.N, self.w2[s], True, False, self.totals[s:s + 1])
+        if self._tshard():
+            self.comm.allreduce_sum(self.totals)
         k.check_totals(self.totals, EPS, self.flags)
 
     def gem_iteration(self, n_iter_total, logliks, mark=None):
@@ -363,9 +412,9 @@ class GemEngine(object):
         self.estep()
         mark("estep")
         k.ll_reduce(self.ll_f, self.ll_sum)
-        if self._sharded():
+        if self._fshard():
             self.comm.allreduce_sum(self.ll_sum)
-        k.ll_store(self.ll_sum, float(self.F_total) * self.N, logliks, self.iter_dev, True)
+        k.ll_store(self.ll_sum, float(self.F_total) * self.N_total, logliks, self.iter_dev, True)
         self.update_mix()
         mark("mix")
         self.update_spectral()
@@ -418,27 +467,35 @@ class GemEngine(object):
         self.compute_powers(with_G=False)
         self.estep()
         self.k.ll_reduce(self.ll_f, self.ll_sum)
-        if self._sharded():
+        if self._fshard():
             self.comm.allreduce_sum(self.ll_sum)
-        ll = -float(self.ll_sum.cpu().item()) / (float(self.F_total) * self.N)
+        ll = -float(self.ll_sum.cpu().item()) / (float(self.F_total) * self.N_total)
         hat_Rxs = self.Rxs.cpu().numpy()
         hat_Rss = self.Rss.cpu().numpy()
-        hat_W = self.hatW[:, :, :self.N].to(self.torch.float64).cpu().numpy()
+        hat_W = self._gather_n(self.hatW[:, :, :self.N].to(self.torch.float64), 2)
         return hat_Rxs, hat_Rss, hat_W, ll
 
     # ------------------------------------------------------------------ outputs
-    def _gather_f(self, t, axis):
-        """Host array of a frequency-sharded tensor, concatenated over ranks."""
-        if not self._sharded():
+    def _gather(self, t, axis, total, which):
+        """Host array of a tensor sharded along `axis` (`which` = 'freq' or 'time'),
+        concatenated over the ranks; replicated tensors are read locally."""
+        if not self._sharded() or self.shard != which:
             return t.cpu().numpy()
-        shards = shard_bounds(self.F_total, self.comm.world)
-        fmax = max(hi - lo for lo, hi in shards)
+        shards = shard_bounds(total, self.comm.world)
+        smax = max(hi - lo for lo, hi in shards)
         t = t.movedim(axis, 0)
-        pad = t.new_zeros((fmax,) + tuple(t.shape[1:]))
+        pad = t.new_zeros((smax,) + tuple(t.shape[1:]))
         pad[:t.shape[0]] = t
         parts = self.comm.allgather(pad)
         full = self.torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, shards)], dim=0)
         return full.movedim(0, axis).cpu().numpy()
+
+    def _gather_f(self, t, axis):
+        return self._gather(t, axis, self.F_total, "freq")
+
+    def _gather_n(self, t, axis):
+        """`t` holds the local frames (without padding) along `axis`."""
+        return self._gather(t, axis, self.N_total, "time")
 
     def read_model(self, spat_comps, spec_comps):
         """Writes the device parameters back into the user-visible dicts."""
@@ -454,7 +511,7 @@ class GemEngine(object):
             fac = fac[list(fac.keys())[0]]
             fac["FB"] = self._gather_f(e["FB"], 0).astype(np.float64)
             fac["FW"] = e["FW"].cpu().numpy().astype(np.float64)
-            fac["TW"] = e["TW"][:, :self.N].cpu().numpy().astype(np.float64)
+            fac["TW"] = self._gather_n(e["TW"][:, :self.N], 1).astype(np.float64)
 
     def noise_psd(self):
         return self._gather_f(self.noise, 0)

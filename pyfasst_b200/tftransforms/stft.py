@@ -44,21 +44,25 @@ def overlap_norm(window, analysisWindow, hopsize, nframes):
 
 
 def stft_planes(kernels, pcm, window, hopsize, nfft, dtype="float64", psd_sum=None,
-                pcm_div=1.0):
+                pcm_div=1.0, frames=None, sample0=0, L_total=None):
     """pcm: device float64 [nch, L] (planar) or int16 / int32 / float32 [L, nch] as read
-    from a WAV file; every sample is divided by `pcm_div` on the device.
-    Returns (X planes [2*nch, F, ld] of `dtype`, N)."""
+    from a WAV file; every sample is divided by `pcm_div` on the device.  `pcm` may be the
+    window [sample0, sample0+L) of a signal of L_total samples and `frames` = (n_lo, n_hi)
+    the range of frames to compute (frame sharding).
+    Returns (X planes [2*nch, F, ld] of `dtype`, number of frames computed)."""
     import torch
     if pcm.dtype == torch.float64:
         nch, L = pcm.shape
     else:
         L, nch = pcm.shape
-    N = number_of_frames(L, hopsize)
+    L_total = L if L_total is None else L_total
+    n_lo, n_hi = (0, number_of_frames(L_total, hopsize)) if frames is None else frames
+    N = n_hi - n_lo
     ld = (N + 31) // 32 * 32
     F = nfft // 2 + 1
     X = torch.zeros([2 * nch, F, ld], dtype=_tdtype(torch, dtype), device=pcm.device)
     win = torch.tensor(np.asarray(window, dtype=np.float64)).to(pcm.device)
-    kernels.stft(pcm, win, int(hopsize), int(nfft), X, N, psd_sum, pcm_div)
+    kernels.stft(pcm, win, int(hopsize), int(nfft), X, N, psd_sum, pcm_div, sample0, L_total, n_lo)
     return X, N
 
 

@@ -35,20 +35,23 @@ class FakeKernels(object):
         return self.launches
 
     # ---- K1 / K6 -------------------------------------------------------------------
-    def stft(self, pcm, window, hop, nfft, X, N, psd_sum, pcm_div=1.0):
+    def stft(self, pcm, window, hop, nfft, X, N, psd_sum, pcm_div=1.0, sample0=0, L_total=None,
+             frame0=0):
         self.launches += 1
         x, w = _np(pcm), _np(window)
         if x.dtype != np.float64:
             x = x.T  # interleaved [L, nch] -> planar
         x = x.astype(np.float64) / pcm_div
         nch, L = x.shape
+        L_total = L if L_total is None else L_total
         wlen = w.size
         Xo = _np(X)
         Xo[:] = 0
+        ntot = int(np.ceil(L_total / float(hop)) + 2)
         for c in range(nch):
-            buf = np.zeros((N - 1) * hop + wlen + nfft)
-            buf[wlen // 2: wlen // 2 + L] = x[c]
-            idx = hop * np.arange(N)[:, None] + np.arange(wlen)[None, :]
+            buf = np.zeros((ntot - 1) * hop + wlen + nfft)
+            buf[wlen // 2 + sample0: wlen // 2 + sample0 + L] = x[c]
+            idx = hop * (frame0 + np.arange(N))[:, None] + np.arange(wlen)[None, :]
             S = np.fft.rfft(w[None, :] * buf[idx], nfft, axis=1).T
             Xo[2 * c, :, :N] = S.real
             Xo[2 * c + 1, :, :N] = S.imag
@@ -139,8 +142,10 @@ class FakeKernels(object):
     def estep_workspace_bytes(self, J, F, N, dtype_code):
         return 64
 
-    def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace):
+    def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace,
+                     N_norm=0):
         self.launches += 3
+        Nn = N_norm if N_norm > 0 else N
         J, F, ld = V.shape
         R = A.shape[0]
         t = np.float64
@@ -185,9 +190,9 @@ class FakeKernels(object):
             j1 = src_of_sub[r1]
             for r2 in range(R):
                 hRss[:, r1, r2] = np.einsum("fi,fij,fj->f", np.conj(Af[:, :, r1]),
-                                            S[j1, src_of_sub[r2]], Af[:, :, r2]) / N
-            hRss[:, r1, r1] = np.real(hRss[:, r1, r1]) + sv[j1] / N
-            hRxs[:, :, r1] = np.einsum("fij,fj->fi", T[j1], Af[:, :, r1]) / N
+                                            S[j1, src_of_sub[r2]], Af[:, :, r2]) / Nn
+            hRss[:, r1, r1] = np.real(hRss[:, r1, r1]) + sv[j1] / Nn
+            hRxs[:, :, r1] = np.einsum("fij,fj->fi", T[j1], Af[:, :, r1]) / Nn
         hRss[:] = 0.5 * (hRss + np.conj(np.transpose(hRss, (0, 2, 1))))
 
     # ---- K3 ---------------------------------------------------------------------------
@@ -283,6 +288,13 @@ class FakeKernels(object):
         th = _np(theta)
         ratio = _np(num)[:rows, :cols] / np.maximum(_np(den)[:rows, :cols], EPS)
         th[:rows, :cols] = th[:rows, :cols].astype(np.float64) * ratio ** omega
+
+    def mult_update_splits(self, theta, num_partial, den_partial, rows, cols, omega):
+        self.launches += 1
+        th = _np(theta)
+        num = _np(num_partial).sum(0)[:rows, :cols]
+        den = _np(den_partial).sum(0)[:rows, :cols]
+        th[:rows, :cols] = th[:rows, :cols].astype(np.float64) * (num / np.maximum(den, EPS)) ** omega
 
     # ---- K5 ---------------------------------------------------------------------------
     def spat_energy(self, A, src_of_sub, J, sums):
