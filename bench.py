@@ -311,6 +311,8 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         stages["estim_param_a_post_model_s"] = t1 - t0 - stages["comp_transf_Cx_s"]
+        for key in ("pack_s", "gem_s", "unpack_s"):
+            stages["estim." + key] = m._last_engine_stats[key]
         npar = sum(np.asarray(sc["params"]).nbytes for sc in m.spat_comps.values()) + \
             sum(f["FB"].nbytes + f["FW"].nbytes + f["TW"].nbytes
                 for sp in m.spec_comps.values() for f in sp["factor"].values())

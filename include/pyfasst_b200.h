@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 7
+#define PF_ABI_VERSION 8
 
 #define PF_OK 0
 #define PF_ERR_ARG (-1)         /* invalid argument (ValueError on the Python side) */
@@ -192,6 +192,14 @@ int pf_scale_matrix(void* M, int64_t ldm, int rows, int64_t cols, const double* 
 
 /* totals[s] < eps  ->  *flags |= PF_FLAG_TW_RESTART ; totals are reset to zero */
 int pf_check_totals(double* totals, int count, double eps, int* flags, void* stream);
+
+/* ---- dense float32 GEMM on the tensor cores (SIMM: every np.dot of SIMM.py:303-393, :613-941) */
+/* C[M x N] = op(A) op(B), row-major float32, tcgen05 kind::tf32 with the 3xTF32 split
+ * (float32-class accuracy).  transA: A is given as A^T, i.e. stored [K][M]; transB: B is given
+ * as B^T, i.e. stored [N][K].  Leading dimensions multiples of 4, pointers 16-byte aligned;
+ * K % 4 == 0 (zero padded) whenever an operand is contiguous along K. */
+int pf_gemm_tf32x3(const float* A, int64_t lda, int transA, const float* B, int64_t ldb,
+                   int transB, float* C, int64_t ldc, int M, int N, int K, void* stream);
 
 /* ---- tcgen05 self-test (pins the descriptor / layout conventions of csrc/tc.cuh) ------ */
 /* D[128][N] = A B^T in tf32 (split3: 3xTF32, fp32-class accuracy).  A: a_mn ? [K][128] :

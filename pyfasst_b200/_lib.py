@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpyfasst_b200.so")
 
 PF_F32, PF_F64 = 0, 1
 PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 c_ip = ctypes.POINTER(ctypes.c_int)
@@ -59,6 +59,8 @@ SIGNATURES = {
     "pf_fw_renorm": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "pf_scale_matrix": [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     "pf_check_totals": [c_vp, c_int, c_dbl, c_vp, c_vp],
+    "pf_gemm_tf32x3": [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int,
+                       c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_ll_reduce": [c_vp, c_int, c_vp, c_vp],
@@ -284,6 +286,12 @@ class CudaKernels(object):
                                               num_partial.stride(0), num_partial.stride(1), rows,
                                               cols, float(omega), self.dtype_code(theta),
                                               self._stream()), self.lib)
+
+    def gemm(self, A, B, C, M, N, K, transA=False, transB=False):
+        """C[M,N] = op(A) op(B) on the tensor cores (float32, 3xTF32); see pf_gemm_tf32x3."""
+        _check(self.lib.pf_gemm_tf32x3(self._p(A), A.stride(0), int(transA), self._p(B),
+                                       B.stride(0), int(transB), self._p(C), C.stride(0), M, N, K,
+                                       self._stream()), self.lib)
 
     # -- K5 ---------------------------------------------------------------------------
     def spat_energy(self, A, src_of_sub, J, sums):

@@ -210,11 +210,18 @@ class FASST(object):
         if opt not in ('ann', 'no_ann', 'ann_ns_inj'):
             warnings.warn("To add noise to the signal, provide the sim_ann_opt from any of "
                           "'ann', 'no_ann' or 'ann_ns_inj' ")
+        import time
+        t0 = time.perf_counter()
         eng = self._engine()
+        t1 = time.perf_counter()
         logliks = eng.run(self.iter_num, use_graph=self._use_cuda_graph)
+        t2 = time.perf_counter()
         eng.read_model(self.spat_comps, self.spec_comps)
         self.noise['PSD'] = eng.noise_psd()
-        self._last_engine_stats = {'launches': self._k().launch_count()}
+        t3 = time.perf_counter()
+        # host-side wall times of the three stages (pack to HBM, GEM loop, unpack to NumPy)
+        self._last_engine_stats = {'launches': self._k().launch_count(), 'pack_s': t1 - t0,
+                                   'gem_s': t2 - t1, 'unpack_s': t3 - t2}
         return logliks
 
     def GEM_iteration(self):

@@ -104,11 +104,19 @@ class GemEngine(object):
         return self.torch.zeros(shape, dtype=dtype or self.tdtype, device=self.dev)
 
     def _upload(self, arr, dtype=None):
-        """Host array -> new device tensor (always a copy, never an alias of `arr`)."""
-        t = self.torch.tensor(np.asarray(arr))
+        """Host array -> new device tensor (always a copy, never an alias of `arr`).  On a GPU
+        the dtype conversion runs on the device (the host side of a multi-rank job is often
+        limited to one thread per process)."""
+        a = np.ascontiguousarray(arr)
+        if self.dev.type == "cuda":
+            t = self.torch.from_numpy(a).to(self.dev)  # H2D copies: never aliases `arr`
+            if dtype is not None and t.dtype != dtype:
+                t = t.to(dtype)
+            return t.contiguous()
+        t = self.torch.tensor(a)
         if dtype is not None:
             t = t.to(dtype)
-        return t.to(self.dev).contiguous()
+        return t.contiguous()
 
     def _f64(self, arr):
         return self._upload(np.asarray(arr, dtype=np.float64))
@@ -221,15 +229,15 @@ class GemEngine(object):
                 raise ValueError("inconsistent factor shapes FB%s FW%s TW%s"
                                  % (FB.shape, FW.shape, TW.shape))
             Kb, Kw = FW.shape
-            TWp = np.zeros([Kw, self.ld])
-            TWp[:, :self.N] = TW[:, self.n_lo:self.n_hi]
+            TWd = self._zeros([Kw, self.ld])
+            TWd[:, :self.N] = self._upload(TW[:, self.n_lo:self.n_hi], self.tdtype)
             ent = {
                 "j": owner[s], "Kb": Kb, "Kw": Kw,
                 "FB_free": fac["FB_frdm_prior"] == "free",
                 "TW_free": fac["TW_frdm_prior"] == "free",
                 "FB": self._upload(FB[self.f_lo:self.f_hi], self.tdtype),
                 "FW": self._upload(FW, self.tdtype),
-                "TW": self._upload(TWp, self.tdtype),
+                "TW": TWd,
                 "W": self._zeros([self.F, Kw]),
                 "G": self._zeros([Kb, self.ld]),
             }
@@ -509,9 +517,10 @@ class GemEngine(object):
         for s, e in enumerate(self.spec):
             fac = spec_comps[s]["factor"]
             fac = fac[list(fac.keys())[0]]
-            fac["FB"] = self._gather_f(e["FB"], 0).astype(np.float64)
-            fac["FW"] = e["FW"].cpu().numpy().astype(np.float64)
-            fac["TW"] = self._gather_n(e["TW"][:, :self.N], 1).astype(np.float64)
+            f64 = self.torch.float64
+            fac["FB"] = self._gather_f(e["FB"].to(f64), 0)
+            fac["FW"] = e["FW"].to(f64).cpu().numpy()
+            fac["TW"] = self._gather_n(e["TW"][:, :self.N].to(f64), 1)
 
     def noise_psd(self):
         return self._gather_f(self.noise, 0)

@@ -376,4 +376,4 @@ def test_library_errors(ck):
         a = torch.zeros((7, 2, 2), dtype=torch.complex128, device="cuda")
         _lib._check(lib.pf_estep_stereo(x.data_ptr(), v.data_ptr(), a.data_ptr(),
                                         _lib._iarr(range(7)), 7, 7, None, 2, 32, 32, None, None,
-                                        None, None, None, 0, 0, None), lib)
+                                        None, None, None, 0, 0, 0, None), lib)
