@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 8
+#define PF_ABI_VERSION 9
 
 #define PF_OK 0
 #define PF_ERR_ARG (-1)         /* invalid argument (ValueError on the Python side) */
@@ -200,6 +200,68 @@ int pf_check_totals(double* totals, int count, double eps, int* flags, void* str
  * K % 4 == 0 (zero padded) whenever an operand is contiguous along K. */
 int pf_gemm_tf32x3(const float* A, int64_t lda, int transA, const float* B, int64_t ldb,
                    int transB, float* C, int64_t ldc, int M, int N, int K, void* stream);
+
+/* The same product with the contraction split over CTAs (few output tiles, long K: the
+ * contractions over the frame axis of SIMM.py:354-362, :376-381, :829-843, :909-916).  The partial
+ * products go to `workspace` (pf_gemm_splitk_plan gives its size) and are summed in a fixed
+ * order.  ldc must equal N rounded up to 4; the padding columns of C are written as zero. */
+int pf_gemm_splitk_plan(int M, int N, int K, int* ksplit, int64_t* workspace_bytes);
+int pf_gemm_tf32x3_splitk(const float* A, int64_t lda, int transA, const float* B, int64_t ldb,
+                          int transB, float* C, int64_t ldc, int M, int N, int K, float* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+/* ---- K7 / K8: SIMM and Stereo_SIMM  (SeparateLeadStereo/SIMM/SIMM.py:46-395, :397-943) -----------
+ * float32 planes, frames contiguous, ldn = N rounded up to 4; nch = 1 (SIMM) or 2 (Stereo_SIMM):
+ *   SF0, SPHI [F][ldn];  SX, hat, SM [F][nch ldn] (channel c in columns [c ldn, c ldn + N));
+ *   work planes [F][2 nch ldn].  a2 = alpha^2 (float[nch], device; 1 for the mono model),
+ *   b2 = beta^2 (float[nch][ldr], device).  Model: hat_c = a2_c SF0 SPHI + (WM b2_c) HM.
+ * Producers write zero into the padding columns of the work planes. */
+/* out = (num | den): c_c = a2_c other/max(hat_c,eps), num = sum_c c_c SX_c/max(hat_c,eps),
+ * den = sum_c c_c   (SIMM.py:304-305, :319-320, :352-353; :622-640, :685-700, :776-790) */
+int pf_simm_lead_terms(const float* other, const float* hat, const float* SX, const float* a2,
+                       float* out, int nch, int F, int64_t N, int64_t ldn, void* stream);
+/* out = (T_0 .. T_{nch-1} | I_0 .. I_{nch-1}), T = SX/hat^2, I = 1/hat; sq_clamp selects the
+ * stereo clamping max(hat^2, eps) (SIMM.py:741-750) against the mono one (:335-337) */
+int pf_simm_acc_terms(const float* hat, const float* SX, float* out, int nch, int sq_clamp, int F,
+                      int64_t N, int64_t ldn, void* stream);
+/* hat_c = max(a2_c SF0 SPHI + SM_c, eps)   (SIMM.py:313; :655-664) */
+int pf_simm_hat(const float* SM, const float* SF0, const float* SPHI, const float* a2, float* hat,
+                int nch, int F, int64_t N, int64_t ldn, void* stream);
+int64_t pf_simm_reduce_workspace_bytes(void);
+/* out[0] = sum_c IS(SX_c | hat_c)   (ISDistortion, SIMM.py:35-44), float64, fixed order */
+int pf_simm_is_divergence(const float* SX, const float* hat, int nch, int F, int64_t N,
+                          int64_t ldn, double* workspace, double* out, void* stream);
+/* alpha update of Stereo_SIMM (SIMM.py:869-896): alpha double[2] and a2 float[2] on the device */
+int pf_simm_alpha_update(const float* SX, const float* hat, const float* SF0, const float* SPHI,
+                         int F, int64_t N, int64_t ldn, double omega, double* workspace,
+                         double* alpha, float* a2, void* stream);
+/* theta[r][n] *= (num/max(den,eps))^omega, num = sum_c w[c][r] C[r][c ldn + n],
+ * den = sum_c w[c][r] C[r][(nch+c) ldn + n] (w = NULL: 1), then max(theta, floor_value) if > 0
+ * (SIMM.py:308-310, :321-323, :338-343; :641-650, :701-708, :752-763) */
+int pf_simm_update_rows(float* theta, int64_t ldt, const float* C, int64_t ldc, int nch,
+                        int64_t ldn, const float* w, int wld, double omega, double floor_value,
+                        int rows, int64_t N, void* stream);
+/* HPHI[k][:] *= rowscale[k] (if not NULL); s[n] = sum_k HPHI[k][n]; HPHI[:,n] /= s[n] where s>0
+ * (SIMM.py:324-326, :361-365) */
+int pf_simm_hphi_normalise(float* HPHI, int64_t ldn, int K, const float* rowscale, int64_t N,
+                           float* s_out, void* stream);
+/* P[r][n] *= s[n] (s has ld entries) / P[r][n] *= s[r] */
+int pf_simm_scale_columns(float* P, int64_t ld, int rows, int64_t N, const float* s, void* stream);
+int pf_simm_scale_rows(float* P, int64_t ld, int rows, int64_t N, const float* s, void* stream);
+/* HGAMMA update and column normalisation from tn/td = (num | den) HPHI^T  (SIMM.py:354-362) */
+int pf_simm_hgamma_update(float* HGAMMA, int ldhg, const float* WGAMMA, int ldwg, const float* tn,
+                          const float* td, int ldt, int F, int P, int K, double omega,
+                          float* s_out, void* stream);
+/* WM update and column normalisation from D = [2 nch][F][ldr] (T_c HM^T, I_c HM^T); the
+ * denominator is clamped in the mono model only  (SIMM.py:376-388; :829-866) */
+int pf_simm_wm_update(float* WM, int ldr, int R, const float* D, int nch, const float* b2,
+                      int clamp_den, double omega, int F, float* s_out, void* stream);
+/* beta update of Stereo_SIMM from D = [4][F][ldr]  (SIMM.py:909-941); beta double[2][ldr] */
+int pf_simm_beta_update(const float* WM, int ldr, int R, const float* D, int F, double omega,
+                        double* beta, float* b2, void* stream);
+/* WMs[c][f][r] = WM[f][r] b2[c][r] (b2 = NULL: 1), zero in the padding columns r >= R */
+int pf_simm_wm_scaled(const float* WM, int ldr, int R, const float* b2, int nch, int F, float* WMs,
+                      void* stream);
 
 /* ---- tcgen05 self-test (pins the descriptor / layout conventions of csrc/tc.cuh) ------ */
 /* D[128][N] = A B^T in tf32 (split3: 3xTF32, fp32-class accuracy).  A: a_mn ? [K][128] :

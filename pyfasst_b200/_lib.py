@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpyfasst_b200.so")
 
 PF_F32, PF_F64 = 0, 1
 PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 c_ip = ctypes.POINTER(ctypes.c_int)
@@ -61,12 +61,33 @@ SIGNATURES = {
     "pf_check_totals": [c_vp, c_int, c_dbl, c_vp, c_vp],
     "pf_gemm_tf32x3": [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int,
                        c_vp],
+    "pf_gemm_splitk_plan": [c_int, c_int, c_int, c_ip, ctypes.POINTER(c_i64)],
+    "pf_gemm_tf32x3_splitk": [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int,
+                              c_int, c_vp, c_i64, c_vp],
+    "pf_simm_lead_terms": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp],
+    "pf_simm_acc_terms": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_vp],
+    "pf_simm_hat": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp],
+    "pf_simm_reduce_workspace_bytes": [],
+    "pf_simm_is_divergence": [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_vp],
+    "pf_simm_alpha_update": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_dbl, c_vp, c_vp, c_vp,
+                             c_vp],
+    "pf_simm_update_rows": [c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_dbl, c_dbl,
+                            c_int, c_i64, c_vp],
+    "pf_simm_hphi_normalise": [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp],
+    "pf_simm_scale_columns": [c_vp, c_i64, c_int, c_i64, c_vp, c_vp],
+    "pf_simm_scale_rows": [c_vp, c_i64, c_int, c_i64, c_vp, c_vp],
+    "pf_simm_hgamma_update": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                              c_dbl, c_vp, c_vp],
+    "pf_simm_wm_update": [c_vp, c_int, c_int, c_vp, c_int, c_vp, c_int, c_dbl, c_int, c_vp, c_vp],
+    "pf_simm_beta_update": [c_vp, c_int, c_int, c_vp, c_int, c_dbl, c_vp, c_vp, c_vp],
+    "pf_simm_wm_scaled": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_ll_reduce": [c_vp, c_int, c_vp, c_vp],
     "pf_ll_store": [c_vp, c_dbl, c_vp, c_vp, c_int, c_vp],
 }
-_RESTYPE = {"pf_last_error": ctypes.c_char_p, "pf_launch_count": ctypes.c_ulonglong}
+_RESTYPE = {"pf_last_error": ctypes.c_char_p, "pf_launch_count": ctypes.c_ulonglong,
+            "pf_simm_reduce_workspace_bytes": ctypes.c_int64}
 
 _lib = None
 
@@ -292,6 +313,97 @@ class CudaKernels(object):
         _check(self.lib.pf_gemm_tf32x3(self._p(A), A.stride(0), int(transA), self._p(B),
                                        B.stride(0), int(transB), self._p(C), C.stride(0), M, N, K,
                                        self._stream()), self.lib)
+
+    def gemm_splitk_workspace_bytes(self, M, N, K):
+        ks, nbytes = c_int(), c_i64()
+        _check(self.lib.pf_gemm_splitk_plan(M, N, K, ctypes.byref(ks), ctypes.byref(nbytes)),
+               self.lib)
+        return nbytes.value
+
+    def gemm_splitk(self, A, B, C, M, N, K, workspace, transA=False, transB=False):
+        """The same product with the contraction split over CTAs (long K, few output tiles)."""
+        _check(self.lib.pf_gemm_tf32x3_splitk(self._p(A), A.stride(0), int(transA), self._p(B),
+                                              B.stride(0), int(transB), self._p(C), C.stride(0),
+                                              M, N, K, self._p(workspace),
+                                              workspace.numel() * workspace.element_size(),
+                                              self._stream()), self.lib)
+
+    # -- K7 / K8: SIMM (float32; arguments may be row-major VIEWS with unit column stride) --
+    def _pv(self, t):
+        if t is None:
+            return None
+        assert t.is_cuda and t.dtype in (self.torch.float32, self.torch.float64)
+        assert t.dim() == 1 or t.stride(-1) == 1, "rows must be contiguous"
+        return t.data_ptr()
+
+    def _call(self, name, *args):
+        _check(getattr(self.lib, name)(*args, self._stream()), self.lib)
+
+    def gemm_view(self, A, B, C, M, N, K, transA=False, transB=False, workspace=None):
+        """C = op(A) op(B) on row-major views; split-K when a workspace is given."""
+        if workspace is None:
+            self._call("pf_gemm_tf32x3", self._pv(A), A.stride(0), int(transA), self._pv(B),
+                       B.stride(0), int(transB), self._pv(C), C.stride(0), M, N, K)
+        else:
+            self._call("pf_gemm_tf32x3_splitk", self._pv(A), A.stride(0), int(transA),
+                       self._pv(B), B.stride(0), int(transB), self._pv(C), C.stride(0), M, N, K,
+                       self._pv(workspace), workspace.numel() * workspace.element_size())
+
+    def simm_reduce_workspace_bytes(self):
+        return int(self.lib.pf_simm_reduce_workspace_bytes())
+
+    def simm_lead_terms(self, other, hat, SX, a2, out, nch, F, N, ldn):
+        self._call("pf_simm_lead_terms", self._pv(other), self._pv(hat), self._pv(SX),
+                   self._pv(a2), self._pv(out), nch, F, N, ldn)
+
+    def simm_acc_terms(self, hat, SX, out, nch, sq_clamp, F, N, ldn):
+        self._call("pf_simm_acc_terms", self._pv(hat), self._pv(SX), self._pv(out), nch,
+                   int(sq_clamp), F, N, ldn)
+
+    def simm_hat(self, SM, SF0, SPHI, a2, hat, nch, F, N, ldn):
+        self._call("pf_simm_hat", self._pv(SM), self._pv(SF0), self._pv(SPHI), self._pv(a2),
+                   self._pv(hat), nch, F, N, ldn)
+
+    def simm_is_divergence(self, SX, hat, nch, F, N, ldn, workspace, out):
+        self._call("pf_simm_is_divergence", self._pv(SX), self._pv(hat), nch, F, N, ldn,
+                   self._pv(workspace), self._pv(out))
+
+    def simm_alpha_update(self, SX, hat, SF0, SPHI, F, N, ldn, omega, workspace, alpha, a2):
+        self._call("pf_simm_alpha_update", self._pv(SX), self._pv(hat), self._pv(SF0),
+                   self._pv(SPHI), F, N, ldn, float(omega), self._pv(workspace), self._pv(alpha),
+                   self._pv(a2))
+
+    def simm_update_rows(self, theta, C, nch, ldn, w, omega, floor_value, rows, N):
+        self._call("pf_simm_update_rows", self._pv(theta), theta.stride(0), self._pv(C),
+                   C.stride(0), nch, ldn, self._pv(w), 0 if w is None else w.stride(0),
+                   float(omega), float(floor_value), rows, N)
+
+    def simm_hphi_normalise(self, HPHI, K, rowscale, N, s_out):
+        self._call("pf_simm_hphi_normalise", self._pv(HPHI), HPHI.stride(0), K,
+                   self._pv(rowscale), N, self._pv(s_out))
+
+    def simm_scale_columns(self, P, rows, N, s):
+        self._call("pf_simm_scale_columns", self._pv(P), P.stride(0), rows, N, self._pv(s))
+
+    def simm_scale_rows(self, P, rows, N, s):
+        self._call("pf_simm_scale_rows", self._pv(P), P.stride(0), rows, N, self._pv(s))
+
+    def simm_hgamma_update(self, HGAMMA, WGAMMA, tn, td, F, P, K, omega, s_out):
+        self._call("pf_simm_hgamma_update", self._pv(HGAMMA), HGAMMA.stride(0), self._pv(WGAMMA),
+                   WGAMMA.stride(0), self._pv(tn), self._pv(td), tn.stride(0), F, P, K,
+                   float(omega), self._pv(s_out))
+
+    def simm_wm_update(self, WM, R, D, nch, b2, clamp_den, omega, F, s_out):
+        self._call("pf_simm_wm_update", self._pv(WM), WM.stride(0), R, self._pv(D), nch,
+                   self._pv(b2), int(clamp_den), float(omega), F, self._pv(s_out))
+
+    def simm_beta_update(self, WM, R, D, F, omega, beta, b2):
+        self._call("pf_simm_beta_update", self._pv(WM), WM.stride(0), R, self._pv(D), F,
+                   float(omega), self._pv(beta), self._pv(b2))
+
+    def simm_wm_scaled(self, WM, R, b2, nch, F, WMs):
+        self._call("pf_simm_wm_scaled", self._pv(WM), WM.stride(0), R, self._pv(b2), nch, F,
+                   self._pv(WMs))
 
     # -- K5 ---------------------------------------------------------------------------
     def spat_energy(self, A, src_of_sub, J, sums):

@@ -105,7 +105,7 @@ static_assert(sizeof(GtStage<64>) >= (GT_THREADS / 32) * 32 * 36 * sizeof(float)
 template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb,
-                   float* __restrict__ C, long ldc, int M, int N, int K) {
+                   float* __restrict__ C, long ldc, int M, int N, int K, int kper, long cstride) {
   extern __shared__ __align__(1024) unsigned char gt_smem[];
   __shared__ uint64_t mbar_free[2];
   __shared__ uint64_t mbar_done;
@@ -114,7 +114,11 @@ gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restric
   GtSmem<BN>& sm = *reinterpret_cast<GtSmem<BN>*>(base);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long m0 = (long)blockIdx.y * GT_BM, n0 = (long)blockIdx.x * BN;
-  const int nchunks = (K + GT_BK - 1) / GT_BK;
+  // split K: CTA z contracts k in [kbeg, kend) into the partial product C + z * cstride
+  const long kbeg = (long)blockIdx.z * kper;
+  const long kend = kbeg + kper < (long)K ? kbeg + kper : (long)K;
+  C += (long)blockIdx.z * cstride;
+  const int nchunks = kend > kbeg ? (int)((kend - kbeg + GT_BK - 1) / GT_BK) : 0;
   constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
 
   if (warp == 0) tc::tmem_alloc(&tmem_base, TCOLS);
@@ -132,8 +136,8 @@ gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restric
 
   OperandTile<GT_BM, !TA> ta;  // A is K-major unless its transpose is what is stored
   OperandTile<BN, TB> tb;      // B is K-major when B^T ([N][K]) is what is stored
-  ta.fetch(A, lda, m0, M, 0, K, tid);
-  tb.fetch(B, ldb, n0, N, 0, K, tid);
+  ta.fetch(A, lda, m0, M, kbeg, kend, tid);
+  tb.fetch(B, ldb, n0, N, kbeg, kend, tid);
   for (int s = 0; s < nchunks; ++s) {
     const int b = s & 1;
     GtStage<BN>& st = sm.stage[b];
@@ -141,8 +145,8 @@ gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restric
     ta.store(st.a_hi, st.a_lo, tid);
     tb.store(st.b_hi, st.b_lo, tid);
     if (s + 1 < nchunks) {
-      ta.fetch(A, lda, m0, M, (long)(s + 1) * GT_BK, K, tid);
-      tb.fetch(B, ldb, n0, N, (long)(s + 1) * GT_BK, K, tid);
+      ta.fetch(A, lda, m0, M, kbeg + (long)(s + 1) * GT_BK, kend, tid);
+      tb.fetch(B, ldb, n0, N, kbeg + (long)(s + 1) * GT_BK, kend, tid);
     }
     tc::fence_proxy_async();
     __syncthreads();
@@ -215,7 +219,7 @@ gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restric
 
 template <bool TA, bool TB, int BN>
 static int launch_gemm(const float* A, long lda, const float* B, long ldb, float* C, long ldc,
-                       int M, int N, int K, cudaStream_t st) {
+                       int M, int N, int K, int ksplit, int kper, long cstride, cudaStream_t st) {
   const size_t smem = sizeof(GtSmem<BN>) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<TA, TB, BN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -223,17 +227,78 @@ static int launch_gemm(const float* A, long lda, const float* B, long ldb, float
     set_error("gemm_tf32x3_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return PF_ERR_CUDA;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, GT_BM));
-  gemm_tf32x3_kernel<TA, TB, BN><<<grid, GT_THREADS, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, GT_BM), ksplit);
+  gemm_tf32x3_kernel<TA, TB, BN><<<grid, GT_THREADS, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K,
+                                                                 kper, cstride);
   return check_launch("gemm_tf32x3_kernel");
 }
 
 template <bool TA, bool TB>
 static int dispatch_bn(const float* A, long lda, const float* B, long ldb, float* C, long ldc,
-                       int M, int N, int K, cudaStream_t st) {
-  if (N > 128) return launch_gemm<TA, TB, 256>(A, lda, B, ldb, C, ldc, M, N, K, st);
-  if (N > 64) return launch_gemm<TA, TB, 128>(A, lda, B, ldb, C, ldc, M, N, K, st);
-  return launch_gemm<TA, TB, 64>(A, lda, B, ldb, C, ldc, M, N, K, st);
+                       int M, int N, int K, int ksplit, int kper, long cstride, cudaStream_t st) {
+  if (N > 128)
+    return launch_gemm<TA, TB, 256>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+  if (N > 64)
+    return launch_gemm<TA, TB, 128>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+  return launch_gemm<TA, TB, 64>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+}
+
+static int dispatch_gemm(const float* A, long lda, int transA, const float* B, long ldb, int transB,
+                         float* C, long ldc, int M, int N, int K, int ksplit, int kper,
+                         long cstride, cudaStream_t st) {
+  if (transA) {
+    if (transB)
+      return dispatch_bn<true, true>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+    return dispatch_bn<true, false>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+  }
+  if (transB)
+    return dispatch_bn<false, true>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+  return dispatch_bn<false, false>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+}
+
+// out[i] = sum_z part[z][i] in a fixed order (float4 per thread, double accumulation)
+// (the GEMM writes N of the ldw columns of a partial product: the padding is masked to zero)
+__global__ void gemm_splitk_reduce_kernel(const float* __restrict__ part, int ksplit, long count4,
+                                          long stride, int N, int ldw, float* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count4) return;
+  double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+  for (int z = 0; z < ksplit; ++z) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)z * stride) + i);
+    a += v.x; b += v.y; c += v.z; d += v.w;
+  }
+  const int col = (int)((i * 4) % ldw);
+  reinterpret_cast<float4*>(out)[i] =
+      make_float4(col + 0 < N ? (float)a : 0.f, col + 1 < N ? (float)b : 0.f,
+                  col + 2 < N ? (float)c : 0.f, col + 3 < N ? (float)d : 0.f);
+}
+
+static int check_gemm_args(const char* who, const float* A, long lda, int transA, const float* B,
+                           long ldb, int transB, const float* C, long ldc, int M, int N, int K) {
+  if (!(M > 0 && N > 0 && K > 0)) {
+    set_error("%s: empty problem %d x %d x %d", who, M, N, K);
+    return PF_ERR_ARG;
+  }
+  if (lda % 4 || ldb % 4 || ldc % 4) {
+    set_error("%s: leading dimensions must be multiples of 4 (lda=%ld ldb=%ld ldc=%ld)", who, lda,
+              ldb, ldc);
+    return PF_ERR_ARG;
+  }
+  if ((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) != 0) {
+    set_error("%s: operands must be 16-byte aligned", who);
+    return PF_ERR_ARG;
+  }
+  if (!(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N)) {
+    set_error("%s: leading dimension smaller than the row length", who);
+    return PF_ERR_ARG;
+  }
+  // an operand that is contiguous along K is read in float4 along K
+  if (!((transA && !transB) || K % 4 == 0)) {
+    set_error("%s: K=%d must be a multiple of 4 (zero padded) unless both operands are "
+              "contiguous along M / N", who, K);
+    return PF_ERR_ARG;
+  }
+  return PF_OK;
 }
 
 }  // namespace pf
@@ -243,23 +308,55 @@ using namespace pf;
 extern "C" int pf_gemm_tf32x3(const float* A, int64_t lda, int transA, const float* B, int64_t ldb,
                               int transB, float* C, int64_t ldc, int M, int N, int K,
                               void* stream) {
-  PF_REQUIRE(M > 0 && N > 0 && K > 0, "pf_gemm_tf32x3: empty problem %d x %d x %d", M, N, K);
-  PF_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0,
-             "pf_gemm_tf32x3: leading dimensions must be multiples of 4 (lda=%ld ldb=%ld ldc=%ld)",
-             (long)lda, (long)ldb, (long)ldc);
-  PF_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0,
-             "pf_gemm_tf32x3: operands must be 16-byte aligned");
-  PF_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N,
-             "pf_gemm_tf32x3: leading dimension smaller than the row length");
-  // an operand that is contiguous along K is read in float4 along K
-  PF_REQUIRE((transA && !transB) || K % 4 == 0,
-             "pf_gemm_tf32x3: K=%d must be a multiple of 4 (zero padded) unless both operands are "
-             "contiguous along M / N", K);
+  int rc = check_gemm_args("pf_gemm_tf32x3", A, lda, transA, B, ldb, transB, C, ldc, M, N, K);
+  if (rc) return rc;
+  return dispatch_gemm(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, 1, K, 0, as_stream(stream));
+}
+
+extern "C" int pf_gemm_splitk_plan(int M, int N, int K, int* ksplit, int64_t* workspace_bytes) {
+  PF_REQUIRE(M > 0 && N > 0 && K > 0, "pf_gemm_splitk_plan: empty problem %d x %d x %d", M, N, K);
+  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  const long tiles = (long)ceil_div(N, bn) * ceil_div(M, GT_BM);
+  // two waves of CTAs on a 148-SM part, but at least 8 K chunks per CTA
+  long want = (2L * 148 + tiles - 1) / tiles;
+  const long most = (K + 8L * GT_BK - 1) / (8L * GT_BK);
+  if (want > most) want = most;
+  if (want < 1) want = 1;
+  *ksplit = (int)want;
+  const long ldc = (N + 3) / 4 * 4;
+  *workspace_bytes = want > 1 ? (int64_t)want * M * ldc * sizeof(float) : 0;
+  return PF_OK;
+}
+
+extern "C" int pf_gemm_tf32x3_splitk(const float* A, int64_t lda, int transA, const float* B,
+                                     int64_t ldb, int transB, float* C, int64_t ldc, int M, int N,
+                                     int K, float* workspace, int64_t workspace_bytes,
+                                     void* stream) {
+  int rc = check_gemm_args("pf_gemm_tf32x3_splitk", A, lda, transA, B, ldb, transB, C, ldc, M, N, K);
+  if (rc) return rc;
+  int ksplit;
+  int64_t need;
+  pf_gemm_splitk_plan(M, N, K, &ksplit, &need);
   cudaStream_t st = as_stream(stream);
-  if (transA) {
-    if (transB) return dispatch_bn<true, true>(A, lda, B, ldb, C, ldc, M, N, K, st);
-    return dispatch_bn<true, false>(A, lda, B, ldb, C, ldc, M, N, K, st);
+  if (ksplit == 1)
+    return dispatch_gemm(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, 1, K, 0, st);
+  PF_REQUIRE(workspace != nullptr && workspace_bytes >= need && (((uintptr_t)workspace) & 15) == 0,
+             "pf_gemm_tf32x3_splitk: workspace of %ld bytes needed (16-byte aligned), got %ld",
+             (long)need, (long)workspace_bytes);
+  const long ldw = (N + 3) / 4 * 4;
+  long kper = ((long)K + ksplit - 1) / ksplit;
+  kper = (kper + GT_BK - 1) / GT_BK * GT_BK;
+  ksplit = (int)((K + kper - 1) / kper);
+  const long stride = (long)M * ldw;
+  rc = dispatch_gemm(A, lda, transA, B, ldb, transB, workspace, ldw, M, N, K, ksplit, (int)kper,
+                     stride, st);
+  if (rc) return rc;
+  if (ldc == ldw) {
+    const long count4 = stride / 4;
+    gemm_splitk_reduce_kernel<<<ceil_div(count4, 256), 256, 0, st>>>(workspace, ksplit, count4,
+                                                                     stride, N, (int)ldw, C);
+    return check_launch("gemm_splitk_reduce_kernel");
   }
-  if (transB) return dispatch_bn<false, true>(A, lda, B, ldb, C, ldc, M, N, K, st);
-  return dispatch_bn<false, false>(A, lda, B, ldb, C, ldc, M, N, K, st);
+  set_error("pf_gemm_tf32x3_splitk: ldc=%ld must equal N rounded up to 4 (%ld)", (long)ldc, ldw);
+  return PF_ERR_ARG;
 }

@@ -1,0 +1,203 @@
+"""NumPy stand-ins for the SIMM kernels of the C ABI (TEST INFRASTRUCTURE ONLY).
+
+Same role as tests/fake_kernels.py: every method is the specification of the CUDA kernel of
+the same name in pyfasst_b200/csrc/simm.cu / gemm_tc.cu, working on torch CPU tensors (views
+allowed).  The CPU tests run the SIMM host orchestration (pyfasst_b200/simm_engine.py) on these
+and compare it with the oracle and the reference's golden vectors; the `-m gpu` tests compare
+each CUDA kernel with its stand-in.  The product never imports this file.
+"""
+import numpy as np
+import torch
+
+EPS = np.float32(1e-20)
+
+
+def _np(t):
+    return None if t is None else t.numpy()
+
+
+class FakeSimmKernels(object):
+    name = "fake"
+
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.launches = 0
+
+    def launch_count(self):
+        return self.launches
+
+    # ---- dense products ---------------------------------------------------------------
+    def gemm_view(self, A, B, C, M, N, K, transA=False, transB=False, workspace=None):
+        self.launches += 1
+        a, b = _np(A), _np(B)
+        a = a[:K, :M].T if transA else a[:M, :K]
+        b = b[:N, :K].T if transB else b[:K, :N]
+        c = _np(C)
+        c[:M, :N] = (a.astype(np.float64) @ b.astype(np.float64)).astype(c.dtype)
+        if workspace is not None:
+            c[:M, N:] = 0
+
+    def gemm_splitk_workspace_bytes(self, M, N, K):
+        return 16
+
+    def simm_reduce_workspace_bytes(self):
+        return 16
+
+    def spec_power(self, W, H, V, N, accumulate):
+        self.launches += 1
+        w, h, v = _np(W), _np(H), _np(V)
+        K = w.shape[1]
+        p = (w.astype(np.float64) @ h[:K, :N].astype(np.float64)).astype(v.dtype)
+        if accumulate:
+            v[:, :N] += p
+        else:
+            v[:, :N] = p
+
+    def small_matmul(self, A, B, C):
+        self.launches += 1
+        a, b, c = _np(A), _np(B), _np(C)
+        c[:a.shape[0], :b.shape[1]] = (a.astype(np.float64) @ b.astype(np.float64)).astype(c.dtype)
+
+    # ---- planes ------------------------------------------------------------------------
+    def simm_lead_terms(self, other, hat, SX, a2, out, nch, F, N, ldn):
+        self.launches += 1
+        o, h, x, a, w = _np(other), _np(hat), _np(SX), _np(a2), _np(out)
+        num = np.zeros((F, N), np.float32)
+        den = np.zeros((F, N), np.float32)
+        for c in range(nch):
+            ih = 1 / np.maximum(h[:, c * ldn:c * ldn + N], EPS)
+            cc = a[c] * o[:, :N] * ih
+            den += cc
+            num += cc * x[:, c * ldn:c * ldn + N] * ih
+        w[:, :2 * ldn] = 0
+        w[:, :N] = num
+        w[:, ldn:ldn + N] = den
+
+    def simm_acc_terms(self, hat, SX, out, nch, sq_clamp, F, N, ldn):
+        self.launches += 1
+        h, x, w = _np(hat), _np(SX), _np(out)
+        w[:, :2 * nch * ldn] = 0
+        for c in range(nch):
+            hc, xc = h[:, c * ldn:c * ldn + N], x[:, c * ldn:c * ldn + N]
+            iv = 1 / np.maximum(hc, EPS)
+            t = xc / np.maximum(hc * hc, EPS) if sq_clamp else iv * xc * iv
+            w[:, c * ldn:c * ldn + N] = t
+            w[:, (nch + c) * ldn:(nch + c) * ldn + N] = iv
+
+    def simm_hat(self, SM, SF0, SPHI, a2, hat, nch, F, N, ldn):
+        self.launches += 1
+        m, s0, sp, a, h = _np(SM), _np(SF0), _np(SPHI), _np(a2), _np(hat)
+        lead = s0[:, :N] * sp[:, :N]
+        for c in range(nch):
+            h[:, c * ldn:(c + 1) * ldn] = 1
+            h[:, c * ldn:c * ldn + N] = np.maximum(a[c] * lead + m[:, c * ldn:c * ldn + N], EPS)
+
+    def simm_is_divergence(self, SX, hat, nch, F, N, ldn, workspace, out):
+        self.launches += 1
+        x, h = _np(SX), _np(hat)
+        tot = 0.0
+        for c in range(nch):
+            r = x[:, c * ldn:c * ldn + N] / h[:, c * ldn:c * ldn + N]
+            tot += np.sum((r - 1 - np.log(r)).astype(np.float64))
+        _np(out)[0] = tot
+
+    def simm_alpha_update(self, SX, hat, SF0, SPHI, F, N, ldn, omega, workspace, alpha, a2):
+        self.launches += 1
+        x, h, al, a2n = _np(SX), _np(hat), _np(alpha), _np(a2)
+        lead = _np(SF0)[:, :N] * _np(SPHI)[:, :N]
+        new = []
+        for c in range(2):
+            ih = 1 / np.maximum(h[:, c * ldn:c * ldn + N], EPS)
+            d = lead * ih
+            num = np.sum((d * x[:, c * ldn:c * ldn + N] * ih).astype(np.float64))
+            den = np.sum(d.astype(np.float64))
+            new.append(max(al[c] * (num / den) ** (omega * 0.1), 1e-20))
+        r = new[0] / max(new[0] + new[1], 0.001)
+        al[0], al[1] = r, 1 - r
+        a2n[0], a2n[1] = r * r, (1 - r) * (1 - r)
+
+    # ---- small matrices ------------------------------------------------------------------
+    def simm_update_rows(self, theta, C, nch, ldn, w, omega, floor_value, rows, N):
+        self.launches += 1
+        th, c = _np(theta), _np(C)
+        num = np.zeros((rows, N), np.float32)
+        den = np.zeros((rows, N), np.float32)
+        for ch in range(nch):
+            wc = np.float32(1) if w is None else _np(w)[ch, :rows, None]
+            num += wc * c[:rows, ch * ldn:ch * ldn + N]
+            den += wc * c[:rows, (nch + ch) * ldn:(nch + ch) * ldn + N]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = num / np.maximum(den, EPS)
+            g = ratio if omega == 1.0 else ratio ** np.float32(omega)
+            t = th[:rows, :N] * g
+        if floor_value > 0:
+            t = np.maximum(t, np.float32(floor_value))
+        th[:rows, :N] = t
+
+    def simm_hphi_normalise(self, HPHI, K, rowscale, N, s_out):
+        self.launches += 1
+        h = _np(HPHI)
+        if rowscale is not None:
+            h[:K, :N] *= _np(rowscale)[:K, None]
+        s = h[:K, :N].sum(axis=0)
+        pos = s > 0
+        h[:K, :N][:, pos] /= s[pos]
+        _np(s_out)[:N] = s
+
+    def simm_scale_columns(self, P, rows, N, s):
+        self.launches += 1
+        p = _np(P)
+        p[:rows, :N] *= _np(s)[:N]
+
+    def simm_scale_rows(self, P, rows, N, s):
+        self.launches += 1
+        p = _np(P)
+        p[:rows, :N] *= _np(s)[:rows, None]
+
+    def simm_hgamma_update(self, HGAMMA, WGAMMA, tn, td, F, P, K, omega, s_out):
+        self.launches += 1
+        hg, wg = _np(HGAMMA), _np(WGAMMA)[:F, :P].astype(np.float64)
+        num = wg.T @ _np(tn)[:F, :K].astype(np.float64)
+        den = wg.T @ _np(td)[:F, :K].astype(np.float64)
+        ratio = (num / np.maximum(den, 1e-20)).astype(np.float32)
+        hg[:P, :K] *= ratio if omega == 1.0 else ratio ** np.float32(omega)
+        s = hg[:P, :K].sum(axis=0)
+        pos = s > 0
+        hg[:P, :K][:, pos] /= s[pos]
+        _np(s_out)[:K] = s
+
+    def simm_wm_update(self, WM, R, D, nch, b2, clamp_den, omega, F, s_out):
+        self.launches += 1
+        wm, d = _np(WM), _np(D)
+        num = np.zeros((F, R), np.float32)
+        den = np.zeros((F, R), np.float32)
+        for c in range(nch):
+            wc = np.float32(1) if b2 is None else _np(b2)[c, None, :R]
+            num += wc * d[c, :, :R]
+            den += wc * d[nch + c, :, :R]
+        if clamp_den:
+            den = np.maximum(den, EPS)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = num / den
+            wm[:, :R] *= ratio if omega == 1.0 else ratio ** np.float32(omega)
+        s = wm[:, :R].astype(np.float64).sum(axis=0).astype(np.float32)
+        pos = s > 0
+        wm[:, :R][:, pos] /= s[pos]
+        _np(s_out)[:R] = s
+
+    def simm_beta_update(self, WM, R, D, F, omega, beta, b2):
+        self.launches += 1
+        wm, d, be, b2n = _np(WM)[:, :R].astype(np.float64), _np(D), _np(beta), _np(b2)
+        dg = [np.sum(wm * d[q, :, :R].astype(np.float64), axis=0) for q in range(4)]
+        bR = be[0, :R] * (dg[0] / dg[2]) ** (omega * 0.1)
+        bL = be[1, :R] * (dg[1] / dg[3]) ** (omega * 0.1)
+        bR = bR / np.maximum(bR + bL, 1e-20)
+        be[0, :R], be[1, :R] = bR, 1 - bR
+        b2n[0, :R], b2n[1, :R] = bR ** 2, (1 - bR) ** 2
+
+    def simm_wm_scaled(self, WM, R, b2, nch, F, WMs):
+        self.launches += 1
+        wm, out = _np(WM), _np(WMs)
+        out[:] = 0
+        for c in range(nch):
+            out[c, :, :R] = wm[:, :R] * (1 if b2 is None else _np(b2)[c, None, :R])
