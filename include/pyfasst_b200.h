@@ -216,23 +216,30 @@ int pf_gemm_tf32x3_splitk(const float* A, int64_t lda, int transA, const float* 
  *   work planes [F][2 nch ldn].  a2 = alpha^2 (float[nch], device; 1 for the mono model),
  *   b2 = beta^2 (float[nch][ldr], device).  Model: hat_c = a2_c SF0 SPHI + (WM b2_c) HM.
  * Producers write zero into the padding columns of the work planes. */
-/* out = (num | den): c_c = a2_c other/max(hat_c,eps), num = sum_c c_c SX_c/max(hat_c,eps),
- * den = sum_c c_c   (SIMM.py:304-305, :319-320, :352-353; :622-640, :685-700, :776-790) */
-int pf_simm_lead_terms(const float* other, const float* hat, const float* SX, const float* a2,
-                       float* out, int nch, int F, int64_t N, int64_t ldn, void* stream);
+/* hat_c = max(a2_c SF0 SPHI + SM_c, eps) is formed in registers by every consumer below (the
+ * hat planes are not stored).
+ * out = (num | den): c_c = a2_c other/hat_c, num = sum_c c_c SX_c/hat_c, den = sum_c c_c, with
+ * other = SPHI (other_is_sf0 = 0: HF0 update) or SF0 (1: HPHI / HGAMMA updates)
+ * (SIMM.py:304-305, :319-320, :352-353; :622-640, :685-700, :776-790) */
+int pf_simm_lead_terms(const float* SM, const float* SF0, const float* SPHI, const float* SX,
+                       const float* a2, int other_is_sf0, float* out, int nch, int F, int64_t N,
+                       int64_t ldn, void* stream);
 /* out = (T_0 .. T_{nch-1} | I_0 .. I_{nch-1}), T = SX/hat^2, I = 1/hat; sq_clamp selects the
  * stereo clamping max(hat^2, eps) (SIMM.py:741-750) against the mono one (:335-337) */
-int pf_simm_acc_terms(const float* hat, const float* SX, float* out, int nch, int sq_clamp, int F,
-                      int64_t N, int64_t ldn, void* stream);
-/* hat_c = max(a2_c SF0 SPHI + SM_c, eps)   (SIMM.py:313; :655-664) */
+int pf_simm_acc_terms(const float* SM, const float* SF0, const float* SPHI, const float* SX,
+                      const float* a2, float* out, int nch, int sq_clamp, int F, int64_t N,
+                      int64_t ldn, void* stream);
+/* hat_c = max(a2_c SF0 SPHI + SM_c, eps) written out (the separation masks read it)
+ * (SIMM.py:313; :655-664) */
 int pf_simm_hat(const float* SM, const float* SF0, const float* SPHI, const float* a2, float* hat,
                 int nch, int F, int64_t N, int64_t ldn, void* stream);
 int64_t pf_simm_reduce_workspace_bytes(void);
 /* out[0] = sum_c IS(SX_c | hat_c)   (ISDistortion, SIMM.py:35-44), float64, fixed order */
-int pf_simm_is_divergence(const float* SX, const float* hat, int nch, int F, int64_t N,
-                          int64_t ldn, double* workspace, double* out, void* stream);
+int pf_simm_is_divergence(const float* SX, const float* SM, const float* SF0, const float* SPHI,
+                          const float* a2, int nch, int F, int64_t N, int64_t ldn,
+                          double* workspace, double* out, void* stream);
 /* alpha update of Stereo_SIMM (SIMM.py:869-896): alpha double[2] and a2 float[2] on the device */
-int pf_simm_alpha_update(const float* SX, const float* hat, const float* SF0, const float* SPHI,
+int pf_simm_alpha_update(const float* SX, const float* SM, const float* SF0, const float* SPHI,
                          int F, int64_t N, int64_t ldn, double omega, double* workspace,
                          double* alpha, float* a2, void* stream);
 /* theta[r][n] *= (num/max(den,eps))^omega, num = sum_c w[c][r] C[r][c ldn + n],

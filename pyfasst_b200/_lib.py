@@ -64,11 +64,14 @@ SIGNATURES = {
     "pf_gemm_splitk_plan": [c_int, c_int, c_int, c_ip, ctypes.POINTER(c_i64)],
     "pf_gemm_tf32x3_splitk": [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int,
                               c_int, c_vp, c_i64, c_vp],
-    "pf_simm_lead_terms": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp],
-    "pf_simm_acc_terms": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_vp],
+    "pf_simm_lead_terms": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_i64, c_i64,
+                           c_vp],
+    "pf_simm_acc_terms": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_i64,
+                          c_vp],
     "pf_simm_hat": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp],
     "pf_simm_reduce_workspace_bytes": [],
-    "pf_simm_is_divergence": [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_vp],
+    "pf_simm_is_divergence": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp,
+                              c_vp],
     "pf_simm_alpha_update": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_dbl, c_vp, c_vp, c_vp,
                              c_vp],
     "pf_simm_update_rows": [c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_dbl, c_dbl,
@@ -352,24 +355,25 @@ class CudaKernels(object):
     def simm_reduce_workspace_bytes(self):
         return int(self.lib.pf_simm_reduce_workspace_bytes())
 
-    def simm_lead_terms(self, other, hat, SX, a2, out, nch, F, N, ldn):
-        self._call("pf_simm_lead_terms", self._pv(other), self._pv(hat), self._pv(SX),
-                   self._pv(a2), self._pv(out), nch, F, N, ldn)
+    def simm_lead_terms(self, SM, SF0, SPHI, SX, a2, other_is_sf0, out, nch, F, N, ldn):
+        self._call("pf_simm_lead_terms", self._pv(SM), self._pv(SF0), self._pv(SPHI),
+                   self._pv(SX), self._pv(a2), int(other_is_sf0), self._pv(out), nch, F, N, ldn)
 
-    def simm_acc_terms(self, hat, SX, out, nch, sq_clamp, F, N, ldn):
-        self._call("pf_simm_acc_terms", self._pv(hat), self._pv(SX), self._pv(out), nch,
-                   int(sq_clamp), F, N, ldn)
+    def simm_acc_terms(self, SM, SF0, SPHI, SX, a2, out, nch, sq_clamp, F, N, ldn):
+        self._call("pf_simm_acc_terms", self._pv(SM), self._pv(SF0), self._pv(SPHI),
+                   self._pv(SX), self._pv(a2), self._pv(out), nch, int(sq_clamp), F, N, ldn)
 
     def simm_hat(self, SM, SF0, SPHI, a2, hat, nch, F, N, ldn):
         self._call("pf_simm_hat", self._pv(SM), self._pv(SF0), self._pv(SPHI), self._pv(a2),
                    self._pv(hat), nch, F, N, ldn)
 
-    def simm_is_divergence(self, SX, hat, nch, F, N, ldn, workspace, out):
-        self._call("pf_simm_is_divergence", self._pv(SX), self._pv(hat), nch, F, N, ldn,
-                   self._pv(workspace), self._pv(out))
+    def simm_is_divergence(self, SX, SM, SF0, SPHI, a2, nch, F, N, ldn, workspace, out):
+        self._call("pf_simm_is_divergence", self._pv(SX), self._pv(SM), self._pv(SF0),
+                   self._pv(SPHI), self._pv(a2), nch, F, N, ldn, self._pv(workspace),
+                   self._pv(out))
 
-    def simm_alpha_update(self, SX, hat, SF0, SPHI, F, N, ldn, omega, workspace, alpha, a2):
-        self._call("pf_simm_alpha_update", self._pv(SX), self._pv(hat), self._pv(SF0),
+    def simm_alpha_update(self, SX, SM, SF0, SPHI, F, N, ldn, omega, workspace, alpha, a2):
+        self._call("pf_simm_alpha_update", self._pv(SX), self._pv(SM), self._pv(SF0),
                    self._pv(SPHI), F, N, ldn, float(omega), self._pv(workspace), self._pv(alpha),
                    self._pv(a2))
 

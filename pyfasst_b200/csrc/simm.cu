@@ -47,29 +47,50 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
   return d;
 }
 
-// ---- lead-side numerator / denominator planes ---------------------------------------------
-// c_c = a2_c other / max(hat_c, eps);  num = sum_c c_c SX_c / max(hat_c, eps);  den = sum_c c_c
-// (SIMM.py:304-305, :319-320, :352-353 with a2 = 1; Stereo: :622-640, :685-700, :776-790)
+// hat_c = max(a2_c SF0 SPHI + SM_c, eps) for 4 consecutive frames of row f, formed in registers
+// by every consumer: the hat planes are never stored (SIMM.py:313; Stereo :655-664).
 template <int NCH>
-__global__ void __launch_bounds__(SE_THREADS)
-simm_lead_terms_kernel(const float* __restrict__ other, const float* __restrict__ hat,
-                       const float* __restrict__ SX, const float* __restrict__ a2,
-                       float* __restrict__ out, long N, long ldn) {
-  const int f = blockIdx.y;
-  const long n0 = ((long)blockIdx.x * SE_THREADS + threadIdx.x) * 4;
-  if (n0 >= ldn) return;
-  float o[4], num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
-  unpack(ld4(other + (long)f * ldn + n0), o);
+__device__ __forceinline__ void load_model(const float* __restrict__ SM,
+                                           const float* __restrict__ SF0,
+                                           const float* __restrict__ SPHI,
+                                           const float* __restrict__ a2, long f, long n0, long ldn,
+                                           float (&s0)[4], float (&sp)[4], float (&h)[NCH][4]) {
+  unpack(ld4(SF0 + f * ldn + n0), s0);
+  unpack(ld4(SPHI + f * ldn + n0), sp);
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const float a = a2[c];
-    float h[4], x[4];
-    unpack(ld4(hat + ((long)f * NCH + c) * ldn + n0), h);
-    unpack(ld4(SX + ((long)f * NCH + c) * ldn + n0), x);
+    float m[4];
+    unpack(ld4(SM + (f * NCH + c) * ldn + n0), m);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[c][e] = fmaxf(fmaf(a, s0[e] * sp[e], m[e]), SIMM_EPS);
+  }
+}
+
+// ---- lead-side numerator / denominator planes ---------------------------------------------
+// c_c = a2_c other / max(hat_c, eps);  num = sum_c c_c SX_c / max(hat_c, eps);  den = sum_c c_c
+// with other = SPHI (HF0 update) or SF0 (HPHI / HGAMMA updates)
+// (SIMM.py:304-305, :319-320, :352-353 with a2 = 1; Stereo: :622-640, :685-700, :776-790)
+template <int NCH>
+__global__ void __launch_bounds__(SE_THREADS)
+simm_lead_terms_kernel(const float* __restrict__ SM, const float* __restrict__ SF0,
+                       const float* __restrict__ SPHI, const float* __restrict__ SX,
+                       const float* __restrict__ a2, int other_is_sf0, float* __restrict__ out,
+                       long N, long ldn) {
+  const long f = blockIdx.y;
+  const long n0 = ((long)blockIdx.x * SE_THREADS + threadIdx.x) * 4;
+  if (n0 >= ldn) return;
+  float s0[4], sp[4], h[NCH][4], num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+  load_model<NCH>(SM, SF0, SPHI, a2, f, n0, ldn, s0, sp, h);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float a = a2[c];
+    float x[4];
+    unpack(ld4(SX + (f * NCH + c) * ldn + n0), x);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float ih = 1.0f / fmaxf(h[e], SIMM_EPS);
-      const float cc = a * o[e] * ih;
+      const float ih = 1.0f / h[c][e];
+      const float cc = a * (other_is_sf0 ? s0[e] : sp[e]) * ih;
       den[e] += cc;
       num[e] += cc * x[e] * ih;
     }
@@ -77,8 +98,8 @@ simm_lead_terms_kernel(const float* __restrict__ other, const float* __restrict_
 #pragma unroll
   for (int e = 0; e < 4; ++e)
     if (n0 + e >= N) num[e] = den[e] = 0.f;
-  st4(out + (long)f * 2 * ldn + n0, num);
-  st4(out + (long)f * 2 * ldn + ldn + n0, den);
+  st4(out + f * 2 * ldn + n0, num);
+  st4(out + f * 2 * ldn + ldn + n0, den);
 }
 
 // ---- accompaniment-side planes  T_c = SX_c / hat_c^2,  I_c = 1 / hat_c ------------------------
@@ -86,24 +107,27 @@ simm_lead_terms_kernel(const float* __restrict__ other, const float* __restrict_
 // stereo (:741-763, :829-843, :909-916): T = SX / max(hat^2, eps), I = 1 / max(hat, eps)
 template <int NCH>
 __global__ void __launch_bounds__(SE_THREADS)
-simm_acc_terms_kernel(const float* __restrict__ hat, const float* __restrict__ SX,
-                      float* __restrict__ out, int sq_clamp, long N, long ldn) {
-  const int f = blockIdx.y;
+simm_acc_terms_kernel(const float* __restrict__ SM, const float* __restrict__ SF0,
+                      const float* __restrict__ SPHI, const float* __restrict__ SX,
+                      const float* __restrict__ a2, float* __restrict__ out, int sq_clamp, long N,
+                      long ldn) {
+  const long f = blockIdx.y;
   const long n0 = ((long)blockIdx.x * SE_THREADS + threadIdx.x) * 4;
   if (n0 >= ldn) return;
+  float s0[4], sp[4], h[NCH][4];
+  load_model<NCH>(SM, SF0, SPHI, a2, f, n0, ldn, s0, sp, h);
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    float h[4], x[4], t[4], iv[4];
-    unpack(ld4(hat + ((long)f * NCH + c) * ldn + n0), h);
-    unpack(ld4(SX + ((long)f * NCH + c) * ldn + n0), x);
+    float x[4], t[4], iv[4];
+    unpack(ld4(SX + (f * NCH + c) * ldn + n0), x);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      iv[e] = 1.0f / fmaxf(h[e], SIMM_EPS);
-      t[e] = sq_clamp ? x[e] / fmaxf(h[e] * h[e], SIMM_EPS) : iv[e] * x[e] * iv[e];
+      iv[e] = 1.0f / h[c][e];
+      t[e] = sq_clamp ? x[e] / fmaxf(h[c][e] * h[c][e], SIMM_EPS) : iv[e] * x[e] * iv[e];
       if (n0 + e >= N) t[e] = iv[e] = 0.f;
     }
-    st4(out + ((long)f * 2 * NCH + c) * ldn + n0, t);
-    st4(out + ((long)f * 2 * NCH + NCH + c) * ldn + n0, iv);
+    st4(out + (f * 2 * NCH + c) * ldn + n0, t);
+    st4(out + (f * 2 * NCH + NCH + c) * ldn + n0, iv);
   }
 }
 
@@ -114,23 +138,17 @@ __global__ void __launch_bounds__(SE_THREADS)
 simm_hat_kernel(const float* __restrict__ SM, const float* __restrict__ SF0,
                 const float* __restrict__ SPHI, const float* __restrict__ a2,
                 float* __restrict__ hat, long N, long ldn) {
-  const int f = blockIdx.y;
+  const long f = blockIdx.y;
   const long n0 = ((long)blockIdx.x * SE_THREADS + threadIdx.x) * 4;
   if (n0 >= ldn) return;
-  float s0[4], sp[4];
-  unpack(ld4(SF0 + (long)f * ldn + n0), s0);
-  unpack(ld4(SPHI + (long)f * ldn + n0), sp);
+  float s0[4], sp[4], h[NCH][4];
+  load_model<NCH>(SM, SF0, SPHI, a2, f, n0, ldn, s0, sp, h);
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    const float a = a2[c];
-    float m[4], h[4];
-    unpack(ld4(SM + ((long)f * NCH + c) * ldn + n0), m);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      h[e] = fmaxf(fmaf(a, s0[e] * sp[e], m[e]), SIMM_EPS);
-      if (n0 + e >= N) h[e] = 1.f;
-    }
-    st4(hat + ((long)f * NCH + c) * ldn + n0, h);
+    for (int e = 0; e < 4; ++e)
+      if (n0 + e >= N) h[c][e] = 1.f;
+    st4(hat + (f * NCH + c) * ldn + n0, h[c]);
   }
 }
 
@@ -141,9 +159,10 @@ simm_hat_kernel(const float* __restrict__ SM, const float* __restrict__ SF0,
 constexpr int SR_CTAS = 148 * 4;
 template <int NCH, int MODE>
 __global__ void __launch_bounds__(SE_THREADS)
-simm_plane_reduce_kernel(const float* __restrict__ SX, const float* __restrict__ hat,
+simm_plane_reduce_kernel(const float* __restrict__ SX, const float* __restrict__ SM,
                          const float* __restrict__ SF0, const float* __restrict__ SPHI,
-                         double* __restrict__ partial, int F, long N, long ldn) {
+                         const float* __restrict__ a2, double* __restrict__ partial, int F, long N,
+                         long ldn) {
   constexpr int NV = MODE == 0 ? 1 : 2 * NCH;
   __shared__ double s_red[SE_THREADS / 32];
   double acc[NV];
@@ -154,29 +173,22 @@ simm_plane_reduce_kernel(const float* __restrict__ SX, const float* __restrict__
   for (long i = (long)blockIdx.x * SE_THREADS + threadIdx.x; i < total;
        i += (long)gridDim.x * SE_THREADS) {
     const long f = i / per_row, n0 = (i % per_row) * 4;
-    float lead[4];
-    if (MODE == 1) {
-      float s0[4], sp[4];
-      unpack(ld4(SF0 + f * ldn + n0), s0);
-      unpack(ld4(SPHI + f * ldn + n0), sp);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) lead[e] = s0[e] * sp[e];
-    }
+    float s0[4], sp[4], h[NCH][4];
+    load_model<NCH>(SM, SF0, SPHI, a2, f, n0, ldn, s0, sp, h);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      float h[4], x[4];
-      unpack(ld4(hat + (f * NCH + c) * ldn + n0), h);
+      float x[4];
       unpack(ld4(SX + (f * NCH + c) * ldn + n0), x);
       float a = 0.f, b = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (n0 + e >= N) continue;
         if (MODE == 0) {
-          const float r = x[e] / h[e];
+          const float r = x[e] / h[c][e];
           a += r - 1.0f - logf(r);
         } else {
-          const float ih = 1.0f / fmaxf(h[e], SIMM_EPS);
-          const float d = lead[e] * ih;
+          const float ih = 1.0f / h[c][e];
+          const float d = s0[e] * sp[e] * ih;
           a += d * x[e] * ih;
           b += d;
         }
@@ -299,33 +311,40 @@ __global__ void simm_rowscale_kernel(float* __restrict__ P, long ld, const float
   P[(size_t)r * ld + n] *= s[r];
 }
 
-// ---- HGAMMA update (SIMM.py:354-362; Stereo :791-802), one CTA ---------------------------------------
+// ---- HGAMMA update (SIMM.py:354-362; Stereo :791-802) ------------------------------------------------
 // tn / td = (num | den) @ HPHI^T  [F][ldt] from the split-K GEMMs;
-// HGAMMA[p][k] *= (WGAMMA^T tn / max(WGAMMA^T td, eps))^omega, columns normalised to sum one,
-// s_out[k] = the column sums (they scale the rows of HPHI).
+// HGAMMA[p][k] *= (WGAMMA^T tn / max(WGAMMA^T td, eps))^omega  -- one CTA per entry (p, k) --
+// then (second kernel) the columns are normalised to sum one, s_out[k] = the column sums (they
+// scale the rows of HPHI).
 __global__ void __launch_bounds__(SE_THREADS)
 simm_hgamma_update_kernel(float* __restrict__ HG, int ldhg, const float* __restrict__ WG, int ldwg,
                           const float* __restrict__ tn, const float* __restrict__ td, int ldt,
-                          int F, int P, int K, float omega, float* __restrict__ s_out) {
-  for (int i = threadIdx.x; i < P * K; i += SE_THREADS) {
-    const int p = i / K, k = i % K;
-    double num = 0.0, den = 0.0;
-    for (int f = 0; f < F; ++f) {
-      const double wgv = (double)WG[(size_t)f * ldwg + p];
-      num += wgv * (double)tn[(size_t)f * ldt + k];
-      den += wgv * (double)td[(size_t)f * ldt + k];
-    }
+                          int F, int K, float omega) {
+  __shared__ double s_red[SE_THREADS / 32];
+  const int p = blockIdx.x / K, k = blockIdx.x % K;
+  double num = 0.0, den = 0.0;
+  for (int f = threadIdx.x; f < F; f += SE_THREADS) {
+    const double wgv = (double)WG[(size_t)f * ldwg + p];
+    num += wgv * (double)tn[(size_t)f * ldt + k];
+    den += wgv * (double)td[(size_t)f * ldt + k];
+  }
+  num = block_sum<SE_THREADS>(num, s_red);
+  den = block_sum<SE_THREADS>(den, s_red);
+  if (threadIdx.x == 0) {
     const float ratio = (float)(num / fmax(den, 1e-20));
     HG[(size_t)p * ldhg + k] *= omega == 1.0f ? ratio : powf(ratio, omega);
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += SE_THREADS) {
-    float s = 0.f;
-    for (int p = 0; p < P; ++p) s += HG[(size_t)p * ldhg + k];
-    if (s > 0.f)
-      for (int p = 0; p < P; ++p) HG[(size_t)p * ldhg + k] /= s;
-    s_out[k] = s;
-  }
+}
+
+__global__ void simm_hgamma_norm_kernel(float* __restrict__ HG, int ldhg, int P, int K,
+                                        float* __restrict__ s_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += HG[(size_t)p * ldhg + k];
+  if (s > 0.f)
+    for (int p = 0; p < P; ++p) HG[(size_t)p * ldhg + k] /= s;
+  s_out[k] = s;
 }
 
 // ---- WM update (SIMM.py:376-388; Stereo :829-866), one CTA per accompaniment component -------------
@@ -424,32 +443,33 @@ static int simm_check_plane(const char* who, int nch, int F, int64_t N, int64_t 
   return PF_OK;
 }
 
-extern "C" int pf_simm_lead_terms(const float* other, const float* hat, const float* SX,
-                                  const float* a2, float* out, int nch, int F, int64_t N,
-                                  int64_t ldn, void* stream) {
+extern "C" int pf_simm_lead_terms(const float* SM, const float* SF0, const float* SPHI,
+                                  const float* SX, const float* a2, int other_is_sf0, float* out,
+                                  int nch, int F, int64_t N, int64_t ldn, void* stream) {
   int rc = simm_check_plane("pf_simm_lead_terms", nch, F, N, ldn);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (nch == 1)
-    simm_lead_terms_kernel<1><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(other, hat, SX, a2,
-                                                                             out, N, ldn);
+    simm_lead_terms_kernel<1><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(
+        SM, SF0, SPHI, SX, a2, other_is_sf0, out, N, ldn);
   else
-    simm_lead_terms_kernel<2><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(other, hat, SX, a2,
-                                                                             out, N, ldn);
+    simm_lead_terms_kernel<2><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(
+        SM, SF0, SPHI, SX, a2, other_is_sf0, out, N, ldn);
   return check_launch("simm_lead_terms_kernel");
 }
 
-extern "C" int pf_simm_acc_terms(const float* hat, const float* SX, float* out, int nch,
+extern "C" int pf_simm_acc_terms(const float* SM, const float* SF0, const float* SPHI,
+                                 const float* SX, const float* a2, float* out, int nch,
                                  int sq_clamp, int F, int64_t N, int64_t ldn, void* stream) {
   int rc = simm_check_plane("pf_simm_acc_terms", nch, F, N, ldn);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (nch == 1)
-    simm_acc_terms_kernel<1><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(hat, SX, out, sq_clamp,
-                                                                            N, ldn);
+    simm_acc_terms_kernel<1><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(
+        SM, SF0, SPHI, SX, a2, out, sq_clamp, N, ldn);
   else
-    simm_acc_terms_kernel<2><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(hat, SX, out, sq_clamp,
-                                                                            N, ldn);
+    simm_acc_terms_kernel<2><<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, st>>>(
+        SM, SF0, SPHI, SX, a2, out, sq_clamp, N, ldn);
   return check_launch("simm_acc_terms_kernel");
 }
 
@@ -471,16 +491,17 @@ extern "C" int64_t pf_simm_reduce_workspace_bytes(void) {
   return (int64_t)SR_CTAS * 4 * sizeof(double);
 }
 
-extern "C" int pf_simm_is_divergence(const float* SX, const float* hat, int nch, int F, int64_t N,
+extern "C" int pf_simm_is_divergence(const float* SX, const float* SM, const float* SF0,
+                                     const float* SPHI, const float* a2, int nch, int F, int64_t N,
                                      int64_t ldn, double* workspace, double* out, void* stream) {
   int rc = simm_check_plane("pf_simm_is_divergence", nch, F, N, ldn);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (nch == 1)
-    simm_plane_reduce_kernel<1, 0><<<SR_CTAS, SE_THREADS, 0, st>>>(SX, hat, nullptr, nullptr,
+    simm_plane_reduce_kernel<1, 0><<<SR_CTAS, SE_THREADS, 0, st>>>(SX, SM, SF0, SPHI, a2,
                                                                   workspace, F, N, ldn);
   else
-    simm_plane_reduce_kernel<2, 0><<<SR_CTAS, SE_THREADS, 0, st>>>(SX, hat, nullptr, nullptr,
+    simm_plane_reduce_kernel<2, 0><<<SR_CTAS, SE_THREADS, 0, st>>>(SX, SM, SF0, SPHI, a2,
                                                                   workspace, F, N, ldn);
   rc = check_launch("simm_plane_reduce_kernel");
   if (rc) return rc;
@@ -488,14 +509,14 @@ extern "C" int pf_simm_is_divergence(const float* SX, const float* hat, int nch,
   return check_launch("simm_isdiv_finalize_kernel");
 }
 
-extern "C" int pf_simm_alpha_update(const float* SX, const float* hat, const float* SF0,
+extern "C" int pf_simm_alpha_update(const float* SX, const float* SM, const float* SF0,
                                     const float* SPHI, int F, int64_t N, int64_t ldn, double omega,
                                     double* workspace, double* alpha, float* a2, void* stream) {
   int rc = simm_check_plane("pf_simm_alpha_update", 2, F, N, ldn);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
-  simm_plane_reduce_kernel<2, 1><<<SR_CTAS, SE_THREADS, 0, st>>>(SX, hat, SF0, SPHI, workspace, F,
-                                                                N, ldn);
+  simm_plane_reduce_kernel<2, 1><<<SR_CTAS, SE_THREADS, 0, st>>>(SX, SM, SF0, SPHI, a2, workspace,
+                                                                F, N, ldn);
   rc = check_launch("simm_plane_reduce_kernel");
   if (rc) return rc;
   simm_alpha_finalize_kernel<<<1, SE_THREADS, 0, st>>>(workspace, SR_CTAS, omega, alpha, a2);
@@ -543,9 +564,12 @@ extern "C" int pf_simm_hgamma_update(float* HGAMMA, int ldhg, const float* WGAMM
                                      const float* tn, const float* td, int ldt, int F, int P,
                                      int K, double omega, float* s_out, void* stream) {
   PF_REQUIRE(F > 0 && P > 0 && K > 0, "pf_simm_hgamma_update: F=%d P=%d K=%d", F, P, K);
-  simm_hgamma_update_kernel<<<1, SE_THREADS, 0, as_stream(stream)>>>(
-      HGAMMA, ldhg, WGAMMA, ldwg, tn, td, ldt, F, P, K, (float)omega, s_out);
-  return check_launch("simm_hgamma_update_kernel");
+  simm_hgamma_update_kernel<<<P * K, SE_THREADS, 0, as_stream(stream)>>>(
+      HGAMMA, ldhg, WGAMMA, ldwg, tn, td, ldt, F, K, (float)omega);
+  int rc = check_launch("simm_hgamma_update_kernel");
+  if (rc) return rc;
+  simm_hgamma_norm_kernel<<<ceil_div(K, 64), 64, 0, as_stream(stream)>>>(HGAMMA, ldhg, P, K, s_out);
+  return check_launch("simm_hgamma_norm_kernel");
 }
 
 extern "C" int pf_simm_wm_update(float* WM, int ldr, int R, const float* D, int nch,

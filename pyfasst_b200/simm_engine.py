@@ -11,8 +11,9 @@ explicit flags below.
 Differences from the reference that are deliberate (all within float32 rounding):
   * after a column rescaling of HF0 (`HF0 *= sumHPHI`, SIMM.py:326, :365), SF0 = WF0 HF0 is
     rescaled by the same factors instead of being recomputed with an NF0-sized GEMM;
-  * hat is clamped to eps when it is formed, also before the first update (the reference clamps
-    it on use, SIMM.py:268 vs :304) -- identical unless hat < 1e-20.
+  * the model power hat is never stored: every kernel that needs it forms
+    max(alpha^2 SF0 SPHI + SM, eps) in registers, so it is clamped to eps also before the first
+    update (the reference clamps it on use, SIMM.py:268 vs :304) -- identical unless hat < 1e-20.
 """
 import numpy as np
 
@@ -65,7 +66,7 @@ class SimmEngine(object):
         for c, sx in enumerate(SX_list):
             self.SX[:, c * ldn:c * ldn + N] = torch.from_numpy(
                 np.ascontiguousarray(sx, dtype=np.float32)).to(self.dev)
-        self.hat, self.SM = zeros(F, nch * ldn), zeros(F, nch * ldn)
+        self.SM = zeros(F, nch * ldn)
         self.SF0, self.SPHI = zeros(F, ldn), zeros(F, ldn)
         self.work = zeros(F * 2 * nch * ldn)
         self.work_lead = self.work[:F * 2 * ldn].view(F, 2 * ldn)  # (num | den)
@@ -109,7 +110,6 @@ class SimmEngine(object):
         k.gemm_view(self.WF0, self.HF0, self.SF0, F, N, self.ldf0)
         k.spec_power(self.WPHI, self.HPHI, self.SPHI, N, False)
         self._model_acc()
-        self._hats()
         if self.compute_error:
             self._error(0)
 
@@ -121,21 +121,26 @@ class SimmEngine(object):
         for c in range(self.nch):
             k.gemm_view(self.WMs[c], self.HM, self.SM[:, c * ldn:(c + 1) * ldn], F, N, self.ldr)
 
-    def _hats(self):
-        self.k.simm_hat(self.SM, self.SF0, self.SPHI, self.a2, self.hat, self.nch, self.F, self.N,
+    # The model power hat_c = max(a2_c SF0 SPHI + SM_c, eps) is never stored: the kernels below
+    # form it in registers from the planes it is made of, which are kept current instead.
+    def hat_planes(self):
+        """hat as a [F, nch * ldn] device tensor (for the separation masks and tests)."""
+        hat = self.torch.zeros_like(self.SM)
+        self.k.simm_hat(self.SM, self.SF0, self.SPHI, self.a2, hat, self.nch, self.F, self.N,
                         self.ldn)
+        return hat
 
     def _error(self, slot):
-        self.k.simm_is_divergence(self.SX, self.hat, self.nch, self.F, self.N, self.ldn,
-                                  self.red_ws, self.reco[slot:slot + 1])
+        self.k.simm_is_divergence(self.SX, self.SM, self.SF0, self.SPHI, self.a2, self.nch, self.F,
+                                  self.N, self.ldn, self.red_ws, self.reco[slot:slot + 1])
 
-    def _lead_terms(self, other):
-        self.k.simm_lead_terms(other, self.hat, self.SX, self.a2, self.work_lead, self.nch, self.F,
-                               self.N, self.ldn)
+    def _lead_terms(self, other_is_sf0):
+        self.k.simm_lead_terms(self.SM, self.SF0, self.SPHI, self.SX, self.a2, other_is_sf0,
+                               self.work_lead, self.nch, self.F, self.N, self.ldn)
 
     def _acc_terms(self):
-        self.k.simm_acc_terms(self.hat, self.SX, self.work_acc, self.nch, self.stereo, self.F,
-                              self.N, self.ldn)
+        self.k.simm_acc_terms(self.SM, self.SF0, self.SPHI, self.SX, self.a2, self.work_acc,
+                              self.nch, self.stereo, self.F, self.N, self.ldn)
 
     def _acc_products(self):
         """D[q] = plane_q HM^T for the 2 nch accompaniment planes (contraction over frames)."""
@@ -154,22 +159,20 @@ class SimmEngine(object):
     def iterate(self):
         k, F, N, ldn, om = self.k, self.F, self.N, self.ldn, self.omega
         # HF0 (SIMM.py:303-315; :622-664)
-        self._lead_terms(self.SPHI)
+        self._lead_terms(False)
         k.gemm_view(self.WF0, self.work_lead, self.C_f0, self.NF0, 2 * ldn, F, transA=True)
         k.simm_update_rows(self.HF0, self.C_f0, 1, ldn, None, om, 0.0, self.NF0, N)
         k.gemm_view(self.WF0, self.HF0, self.SF0, F, N, self.ldf0)
-        self._hats()
         if self.compute_error:
             self._error(self.counter)
         self.counter += 1
         # HPHI (:319-331; :685-730)
-        self._lead_terms(self.SF0)
+        self._lead_terms(True)
         k.gemm_view(self.WPHI, self.work_lead, self.C_phi, self.K, 2 * ldn, F, transA=True)
         k.simm_update_rows(self.HPHI, self.C_phi, 1, ldn, None, om, 0.0, self.K, N)
         k.simm_hphi_normalise(self.HPHI, self.K, None, N, self.s_n)
         self._rescale_lead()
         k.spec_power(self.WPHI, self.HPHI, self.SPHI, N, False)
-        self._hats()
         if self.compute_error:
             self._error(self.counter)
         self.counter += 1
@@ -179,11 +182,10 @@ class SimmEngine(object):
         k.simm_update_rows(self.HM, self.C_hm, self.nch, ldn, self.b2, om,
                            0.0 if self.stereo else EPS, self.R, N)
         self._model_acc()
-        self._hats()
         self.counter += 1
         # HGAMMA (:351-372; :776-819)
         if self.update_hgamma:
-            self._lead_terms(self.SF0)
+            self._lead_terms(True)
             k.gemm_view(self.work_lead[:, :ldn], self.HPHI, self.tn, F, self.K, ldn, transB=True,
                         workspace=self.splitk_ws)
             k.gemm_view(self.work_lead[:, ldn:], self.HPHI, self.td, F, self.K, ldn, transB=True,
@@ -194,7 +196,6 @@ class SimmEngine(object):
             self._rescale_lead()
             k.small_matmul(self.WGAMMA, self.HGAMMA, self.WPHI)
             k.spec_power(self.WPHI, self.HPHI, self.SPHI, N, False)
-            self._hats()
             self.counter += 1
         # WM (:376-393; :829-866)
         self._acc_products()
@@ -205,20 +206,17 @@ class SimmEngine(object):
         else:  # mono quirk (:388): R == N, sumWM scales the COLUMNS of HM
             k.simm_scale_columns(self.HM, self.R, N, self.s_r)
         self._model_acc()
-        self._hats()
         self.counter += 1
         if not self.stereo:
             return
         # alpha (:869-896)
-        k.simm_alpha_update(self.SX, self.hat, self.SF0, self.SPHI, F, N, ldn, om, self.red_ws,
+        k.simm_alpha_update(self.SX, self.SM, self.SF0, self.SPHI, F, N, ldn, om, self.red_ws,
                             self.alpha, self.a2)
-        self._hats()
         self.counter += 1
         # beta (:909-941)
         self._acc_products()
         k.simm_beta_update(self.WM, self.R, self.D, F, om, self.beta, self.b2)
         self._model_acc()
-        self._hats()
         self.counter += 1
 
     # -- results (float64 NumPy, the reference's types) ----------------------------------------

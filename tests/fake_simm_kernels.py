@@ -59,9 +59,19 @@ class FakeSimmKernels(object):
         c[:a.shape[0], :b.shape[1]] = (a.astype(np.float64) @ b.astype(np.float64)).astype(c.dtype)
 
     # ---- planes ------------------------------------------------------------------------
-    def simm_lead_terms(self, other, hat, SX, a2, out, nch, F, N, ldn):
+    def _hat(self, SM, SF0, SPHI, a2, nch, N, ldn):
+        """hat_c = max(a2_c SF0 SPHI + SM_c, eps) as a [F, nch * ldn] array (padding = 1)."""
+        m, s0, sp, a = _np(SM), _np(SF0), _np(SPHI), _np(a2)
+        h = np.ones_like(m)
+        lead = s0[:, :N] * sp[:, :N]
+        for c in range(nch):
+            h[:, c * ldn:c * ldn + N] = np.maximum(a[c] * lead + m[:, c * ldn:c * ldn + N], EPS)
+        return h
+
+    def simm_lead_terms(self, SM, SF0, SPHI, SX, a2, other_is_sf0, out, nch, F, N, ldn):
         self.launches += 1
-        o, h, x, a, w = _np(other), _np(hat), _np(SX), _np(a2), _np(out)
+        h = self._hat(SM, SF0, SPHI, a2, nch, N, ldn)
+        o, x, a, w = _np(SF0 if other_is_sf0 else SPHI), _np(SX), _np(a2), _np(out)
         num = np.zeros((F, N), np.float32)
         den = np.zeros((F, N), np.float32)
         for c in range(nch):
@@ -73,9 +83,9 @@ class FakeSimmKernels(object):
         w[:, :N] = num
         w[:, ldn:ldn + N] = den
 
-    def simm_acc_terms(self, hat, SX, out, nch, sq_clamp, F, N, ldn):
+    def simm_acc_terms(self, SM, SF0, SPHI, SX, a2, out, nch, sq_clamp, F, N, ldn):
         self.launches += 1
-        h, x, w = _np(hat), _np(SX), _np(out)
+        h, x, w = self._hat(SM, SF0, SPHI, a2, nch, N, ldn), _np(SX), _np(out)
         w[:, :2 * nch * ldn] = 0
         for c in range(nch):
             hc, xc = h[:, c * ldn:c * ldn + N], x[:, c * ldn:c * ldn + N]
@@ -86,24 +96,21 @@ class FakeSimmKernels(object):
 
     def simm_hat(self, SM, SF0, SPHI, a2, hat, nch, F, N, ldn):
         self.launches += 1
-        m, s0, sp, a, h = _np(SM), _np(SF0), _np(SPHI), _np(a2), _np(hat)
-        lead = s0[:, :N] * sp[:, :N]
-        for c in range(nch):
-            h[:, c * ldn:(c + 1) * ldn] = 1
-            h[:, c * ldn:c * ldn + N] = np.maximum(a[c] * lead + m[:, c * ldn:c * ldn + N], EPS)
+        _np(hat)[:, :nch * ldn] = self._hat(SM, SF0, SPHI, a2, nch, N, ldn)
 
-    def simm_is_divergence(self, SX, hat, nch, F, N, ldn, workspace, out):
+    def simm_is_divergence(self, SX, SM, SF0, SPHI, a2, nch, F, N, ldn, workspace, out):
         self.launches += 1
-        x, h = _np(SX), _np(hat)
+        x, h = _np(SX), self._hat(SM, SF0, SPHI, a2, nch, N, ldn)
         tot = 0.0
         for c in range(nch):
             r = x[:, c * ldn:c * ldn + N] / h[:, c * ldn:c * ldn + N]
             tot += np.sum((r - 1 - np.log(r)).astype(np.float64))
         _np(out)[0] = tot
 
-    def simm_alpha_update(self, SX, hat, SF0, SPHI, F, N, ldn, omega, workspace, alpha, a2):
+    def simm_alpha_update(self, SX, SM, SF0, SPHI, F, N, ldn, omega, workspace, alpha, a2):
         self.launches += 1
-        x, h, al, a2n = _np(SX), _np(hat), _np(alpha), _np(a2)
+        x, al, a2n = _np(SX), _np(alpha), _np(a2)
+        h = self._hat(SM, SF0, SPHI, a2, 2, N, ldn)
         lead = _np(SF0)[:, :N] * _np(SPHI)[:, :N]
         new = []
         for c in range(2):

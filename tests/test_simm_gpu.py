@@ -67,17 +67,21 @@ def test_plane_kernels(nch, F, N):
     rng = np.random.default_rng(F + N + nch)
     ldn, pl = planes(rng, F, N, nch)
     a2 = np.array([0.3, 0.6], np.float32) if nch == 2 else np.ones(2, np.float32)
-    p = Pair(other=pl(1), hat=pl(nch), SX=pl(nch), SM=pl(nch), SF0=pl(1), SPHI=pl(1), a2=a2,
+    p = Pair(SX=pl(nch), SM=pl(nch), SF0=pl(1), SPHI=pl(1), a2=a2,
              lead=np.full((F, 2 * ldn), 7, np.float32), acc=np.full((F, 2 * nch * ldn), 7, np.float32),
              newhat=np.zeros((F, nch * ldn), np.float32), isd=np.zeros(1), ws=np.zeros(148 * 4 * 4))
-    p.run("simm_lead_terms", lambda d: (d["other"], d["hat"], d["SX"], d["a2"], d["lead"], nch, F, N, ldn))
-    p.check("lead")
+    for which in (0, 1):
+        p.run("simm_lead_terms", lambda d: (d["SM"], d["SF0"], d["SPHI"], d["SX"], d["a2"], which,
+                                            d["lead"], nch, F, N, ldn))
+        p.check("lead", rtol=5e-6)
     for sq in (0, 1):
-        p.run("simm_acc_terms", lambda d: (d["hat"], d["SX"], d["acc"], nch, sq, F, N, ldn))
-        p.check("acc")
+        p.run("simm_acc_terms", lambda d: (d["SM"], d["SF0"], d["SPHI"], d["SX"], d["a2"], d["acc"],
+                                           nch, sq, F, N, ldn))
+        p.check("acc", rtol=5e-6)
     p.run("simm_hat", lambda d: (d["SM"], d["SF0"], d["SPHI"], d["a2"], d["newhat"], nch, F, N, ldn))
     p.check("newhat")
-    p.run("simm_is_divergence", lambda d: (d["SX"], d["hat"], nch, F, N, ldn, d["ws"], d["isd"]))
+    p.run("simm_is_divergence", lambda d: (d["SX"], d["SM"], d["SF0"], d["SPHI"], d["a2"], nch, F, N,
+                                           ldn, d["ws"], d["isd"]))
     p.check("isd", rtol=1e-5)
     # the padding columns of the work planes are zero (they are contracted over n by the GEMMs)
     lead = p.gpu["lead"].cpu().numpy()
@@ -88,9 +92,9 @@ def test_alpha_update():
     rng = np.random.default_rng(3)
     F, N = 65, 333
     ldn, pl = planes(rng, F, N, 2)
-    p = Pair(hat=pl(2), SX=pl(2), SF0=pl(1), SPHI=pl(1), ws=np.zeros(148 * 4 * 4),
-             alpha=np.array([0.4, 0.6]), a2=np.zeros(2, np.float32))
-    p.run("simm_alpha_update", lambda d: (d["SX"], d["hat"], d["SF0"], d["SPHI"], F, N, ldn, 0.8,
+    p = Pair(SM=pl(2), SX=pl(2), SF0=pl(1), SPHI=pl(1), ws=np.zeros(148 * 4 * 4),
+             alpha=np.array([0.4, 0.6]), a2=np.array([0.16, 0.36], np.float32))
+    p.run("simm_alpha_update", lambda d: (d["SX"], d["SM"], d["SF0"], d["SPHI"], F, N, ldn, 0.8,
                                           d["ws"], d["alpha"], d["a2"]))
     p.check("alpha", rtol=1e-6)
     p.check("a2", rtol=1e-6)
