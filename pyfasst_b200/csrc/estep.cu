@@ -22,6 +22,8 @@
 // Layout: SoA planes, frames contiguous: X[4][F][ld] (re0, im0, re1, im1),
 // V[J][F][ld], hatW[J][F][ld]; one CTA owns one frequency and a run of frames,
 // a thread owns VEC consecutive frames (float4 / double2 accesses).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pf {
@@ -29,7 +31,9 @@ namespace pf {
 constexpr int ESTEP_THREADS = 128;
 constexpr int MAXJ = 6;
 constexpr int MAXR = 16;
-constexpr int PF_F32_FASTMATH = 2;  // float storage AND float per-bin algebra (experiments)
+constexpr int PF_F32_FASTMATH = 2;
+constexpr int ESTEP_DEFAULT_VARIANT = 3;
+constexpr int ESTEP_DEPTH = 3;  // passes in flight in the cp.async ring (OPT bit 2)  // float storage AND float per-bin algebra (experiments)
 
 __host__ __device__ constexpr int npairs(int J) { return J * (J + 1) / 2; }
 // accumulators per frequency: S (4 per pair), T (8 per source), sv (J), ll (1)
@@ -78,9 +82,17 @@ __global__ void spat_coef_kernel(const double2* __restrict__ A, SubMap map, int 
 
 // 1/x: for double, a float reciprocal refined by two Newton steps (4 DFMA) instead of
 // the ~20-instruction IEEE division; relative error < 1e-14.
-__device__ __forceinline__ float fast_rcp(float x) { return 1.0f / x; }
+// MUFU.RCP plus one Newton step (relative error ~1e-7, like the IEEE division, but without its
+// range check and slow-path call; the arguments here are clamped to >= 1e-10)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
 __device__ __forceinline__ double fast_rcp(double x) {
-  double r = (double)(1.0f / (float)x);
+  float r0;  // MUFU.RCP (2^-23 relative): no IEEE-division slow path to branch to
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)x));
+  double r = (double)r0;
   r = r * (2.0 - x * r);
   r = r * (2.0 - x * r);
   return r;
@@ -96,6 +108,98 @@ __device__ __forceinline__ double widen(float x) {
   return __hiloint2double((int)hi, (int)(f << 29));
 }
 __device__ __forceinline__ double widen(double x) { return x; }
+// the hardware conversion (F2F.F64.F32, XU pipe): one issue slot instead of five
+__device__ __forceinline__ double widen_hw(float x) { return (double)x; }
+__device__ __forceinline__ double widen_hw(double x) { return x; }
+
+// ---- packed float32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): the per-frequency moment sums are
+// 40% of the instructions of the E-step; two accumulators share one instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+// acc += a * b / acc += a  (in-out operand: the accumulator keeps its register pair)
+__device__ __forceinline__ void fma2_acc(f32x2& acc, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void add2_acc(f32x2& acc, f32x2 a) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a));
+}
+
+// The moment accumulators of one thread: S (4 per source pair), T (8 per source), sv (J), in
+// the order of the `partial` array.  Scalar version (any type) and packed float32 version.
+template <typename T, int J, bool PACK>
+struct Moments {
+  static constexpr int NP = J * (J + 1) / 2;
+  static constexpr int COUNT = 4 * NP + 9 * J;
+  T acc[COUNT];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < COUNT; ++i) acc[i] = (T)0;
+  }
+  __device__ __forceinline__ void add(const T (&pr)[NP], const T (&vt)[J], T t00, T t11, T t01r,
+                                      T t01i, const T (&u)[8]) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      acc[4 * p + 0] += pr[p] * t00;
+      acc[4 * p + 1] += pr[p] * t11;
+      acc[4 * p + 2] += pr[p] * t01r;
+      acc[4 * p + 3] += pr[p] * t01i;
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[4 * NP + 8 * j + e] += vt[j] * u[e];
+      acc[4 * NP + 8 * J + j] += vt[j];
+    }
+  }
+  __device__ __forceinline__ T get(int i) const { return acc[i]; }
+};
+
+template <int J>
+struct Moments<float, J, true> {
+  static constexpr int NP = J * (J + 1) / 2;
+  static constexpr int COUNT = 4 * NP + 9 * J;
+  static constexpr int NPK = (COUNT + 1) / 2;
+  f32x2 acc[NPK];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < NPK; ++i) acc[i] = 0ull;
+  }
+  __device__ __forceinline__ void add(const float (&pr)[NP], const float (&vt)[J], float t00,
+                                      float t11, float t01r, float t01i, const float (&u)[8]) {
+    const f32x2 ta = pack2(t00, t11), tb = pack2(t01r, t01i);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const f32x2 pp = pack2(pr[p], pr[p]);  // broadcast operand: no instruction
+      fma2_acc(acc[2 * p + 0], pp, ta);
+      fma2_acc(acc[2 * p + 1], pp, tb);
+    }
+    const f32x2 u0 = pack2(u[0], u[1]), u1 = pack2(u[2], u[3]);
+    const f32x2 u2 = pack2(u[4], u[5]), u3 = pack2(u[6], u[7]);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const f32x2 vv = pack2(vt[j], vt[j]);
+      fma2_acc(acc[2 * NP + 4 * j + 0], vv, u0);
+      fma2_acc(acc[2 * NP + 4 * j + 1], vv, u1);
+      fma2_acc(acc[2 * NP + 4 * j + 2], vv, u2);
+      fma2_acc(acc[2 * NP + 4 * j + 3], vv, u3);
+    }
+#pragma unroll
+    for (int j = 0; j < J; j += 2)
+      add2_acc(acc[2 * NP + 4 * J + j / 2], pack2(vt[j], j + 1 < J ? vt[j + 1] : 0.f));
+  }
+  __device__ __forceinline__ float get(int i) const {
+    float a, b;
+    unpack2(acc[i >> 1], a, b);
+    return (i & 1) ? b : a;
+  }
+};
 
 // Per-bin algebra shared by the E-step and the Wiener filter.
 // Sigma = s2 I + sum_j v_j R_j ; returns Sigma^-1 (i00, i11, i01) in the compute type C and
@@ -142,8 +246,10 @@ __device__ __forceinline__ void sigma_inverse(const C (&vj)[J], const D (&vd)[J]
 // a^H (y y^H - Sigma^-1) a cancels them down by the condition number of Sigma, which in
 // float32 costs eps*cond(Sigma) ~ 1e-2 at 50-60 dB bins.  The per-frequency moment sums
 // are accumulated in T (their rounding is random and averages out over frames).
-template <typename T, typename C, int J>
-__global__ void __launch_bounds__(ESTEP_THREADS)
+// OPT bit 0: packed float32 moment accumulation (FFMA2); bit 1: hardware float->double
+// conversion of the loaded values.  MINB: CTAs per SM the register allocation aims for.
+template <typename T, typename C, int J, int OPT, int MINB>
+__global__ void __launch_bounds__(ESTEP_THREADS, MINB)
 estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
                     const double* __restrict__ coef, const double* __restrict__ noise,
                     SubMap map, T* __restrict__ hatW, double* __restrict__ partial, int F,
@@ -170,9 +276,10 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 #pragma unroll
   for (int j = 0; j < J; ++j) invrank[j] = (T)map.invrank[j];
 
-  T acc[NA - 1];
-#pragma unroll
-  for (int i = 0; i < NA - 1; ++i) acc[i] = (T)0;
+  constexpr bool kPack = (OPT & 1) != 0 && sizeof(T) == 4;
+  constexpr bool kHwCvt = (OPT & 2) != 0;
+  Moments<T, J, kPack> mom;
+  mom.clear();
   double acc_ll = 0.0;
 
   const long plane = (long)F * ld;
@@ -181,9 +288,31 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   long end = begin + chunk;
   if (end > N) end = N;
 
-  // the loads of pass i+1 are issued before the arithmetic of pass i (register double
-  // buffering): with only two CTAs resident per SM the ~1 us HBM latency is otherwise exposed
-  constexpr bool kPrefetch = sizeof(T) == 4;
+  // Loads run ahead of the arithmetic: with only two CTAs resident per SM (the moment
+  // accumulators pin ~80 registers per thread) the ~1 us HBM latency is otherwise exposed.
+  //  * OPT bit 2: cp.async ring in shared memory, ESTEP_DEPTH passes ahead.  Every thread copies
+  //    and later reads back ITS OWN 16 bytes per plane, so no barrier is needed -- only
+  //    cp.async.wait_group on the thread's own groups (one group per pass, possibly empty).
+  //  * otherwise: register double buffering, one pass ahead (float32 planes only).
+  constexpr bool kRing = (OPT & 4) != 0 && sizeof(T) == 4;
+  constexpr bool kPrefetch = sizeof(T) == 4 && !kRing;
+  constexpr int NPL = 4 + J;
+  extern __shared__ __align__(16) unsigned char s_ring_raw[];
+  float4* s_ring = reinterpret_cast<float4*>(s_ring_raw);  // [ESTEP_DEPTH][NPL][ESTEP_THREADS]
+  const long stride = (long)ESTEP_THREADS * VEC;
+  const long first = begin + (long)threadIdx.x * VEC;
+  auto ring_issue = [&](long n, int slot) {
+    if (n < end) {
+      float4* dst = s_ring + (size_t)slot * NPL * ESTEP_THREADS + threadIdx.x;
+#pragma unroll
+      for (int pl = 0; pl < 4; ++pl)
+        cp_async16(dst + pl * ESTEP_THREADS, X + pl * plane + row + n, 16);
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+        cp_async16(dst + (4 + j) * ESTEP_THREADS, V + j * plane + row + n, 16);
+    }
+    cp_async_commit();
+  };
   T nx[4][VEC], nv[J][VEC];
   auto issue_loads = [&](long n) {
     load_vec<T>(X + 0 * plane + row + n, nx[0]);
@@ -193,38 +322,70 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 #pragma unroll
     for (int j = 0; j < J; ++j) load_vec<T>(V + j * plane + row + n, nv[j]);
   };
-  const long stride = (long)ESTEP_THREADS * VEC;
-  if (kPrefetch && begin + (long)threadIdx.x * VEC < end) issue_loads(begin + (long)threadIdx.x * VEC);
-  for (long n0 = begin + (long)threadIdx.x * VEC; n0 < end; n0 += stride) {
+  if (kRing) {
+#pragma unroll
+    for (int d = 0; d < ESTEP_DEPTH; ++d) ring_issue(first + d * stride, d);
+  }
+  if (kPrefetch && first < end) issue_loads(first);
+  int slot = 0;
+  for (long n0 = first; n0 < end; n0 += stride) {
     T x0r[VEC], x0i[VEC], x1r[VEC], x1i[VEC], v[J][VEC], w[J][VEC];
-    if (!kPrefetch) issue_loads(n0);
+    if (kRing) {
+      cp_async_wait<ESTEP_DEPTH - 1>();
+      const float4* src = s_ring + (size_t)slot * NPL * ESTEP_THREADS + threadIdx.x;
+      if (sizeof(T) == 4) {  // (the ring only exists for float32 planes)
+        float4 q;
+        q = src[0 * ESTEP_THREADS]; x0r[0] = q.x; x0r[1] = q.y; x0r[2] = q.z; x0r[3] = q.w;
+        q = src[1 * ESTEP_THREADS]; x0i[0] = q.x; x0i[1] = q.y; x0i[2] = q.z; x0i[3] = q.w;
+        q = src[2 * ESTEP_THREADS]; x1r[0] = q.x; x1r[1] = q.y; x1r[2] = q.z; x1r[3] = q.w;
+        q = src[3 * ESTEP_THREADS]; x1i[0] = q.x; x1i[1] = q.y; x1i[2] = q.z; x1i[3] = q.w;
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      x0r[e] = nx[0][e]; x0i[e] = nx[1][e]; x1r[e] = nx[2][e]; x1i[e] = nx[3][e];
+        for (int j = 0; j < J; ++j) {
+          q = src[(4 + j) * ESTEP_THREADS];
+          v[j][0] = q.x; v[j][1] = q.y; v[j][2] = q.z; v[j][3] = q.w;
+        }
+      }
+      ring_issue(n0 + ESTEP_DEPTH * stride, slot);  // refill the slot just consumed
+      slot = slot + 1 == ESTEP_DEPTH ? 0 : slot + 1;
+    } else {
+      if (!kPrefetch) issue_loads(n0);
 #pragma unroll
-      for (int j = 0; j < J; ++j) v[j][e] = nv[j][e];
+      for (int e = 0; e < VEC; ++e) {
+        x0r[e] = nx[0][e]; x0i[e] = nx[1][e]; x1r[e] = nx[2][e]; x1i[e] = nx[3][e];
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j][e] = nv[j][e];
+      }
+      if (kPrefetch && n0 + stride < end) issue_loads(n0 + stride);
     }
-    if (kPrefetch && n0 + stride < end) issue_loads(n0 + stride);
+    // frames beyond the end of the row: zero inputs contribute nothing to the moments and give
+    // hatW = 0; only the log-likelihood term is masked below (no branch around the algebra)
+    if (n0 + VEC > end) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        if (n0 + e >= end) {
+          x0r[e] = x0i[e] = x1r[e] = x1i[e] = (T)0;
+#pragma unroll
+          for (int j = 0; j < J; ++j) v[j][e] = (T)0;
+        }
+    }
 
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if (n0 + e >= end) {
-#pragma unroll
-        for (int j = 0; j < J; ++j) w[j][e] = (T)0;
-        continue;
-      }
+      const bool live = n0 + e < end;
       // Sigma_x = sum_j v_j R_j + s2 I and its inverse (audioModel.py:613-654)
       C vj[J], i00, i11, i01r, i01i;
       T vt[J], pr[NP], det;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         vt[j] = v[j][e];
-        vj[j] = (C)widen(vt[j]);
+        vj[j] = (C)(kHwCvt ? widen_hw(vt[j]) : widen(vt[j]));
       }
       sigma_inverse<C, T, J>(vj, vt, s_coef, s_dcoef, s2, pr, det, i00, i11, i01r, i01i);
       // y = Sigma^-1 x
-      const C a0r = (C)widen(x0r[e]), a0i = (C)widen(x0i[e]);
-      const C a1r = (C)widen(x1r[e]), a1i = (C)widen(x1i[e]);
+      const C a0r = (C)(kHwCvt ? widen_hw(x0r[e]) : widen(x0r[e]));
+      const C a0i = (C)(kHwCvt ? widen_hw(x0i[e]) : widen(x0i[e]));
+      const C a1r = (C)(kHwCvt ? widen_hw(x1r[e]) : widen(x1r[e]));
+      const C a1i = (C)(kHwCvt ? widen_hw(x1i[e]) : widen(x1i[e]));
       const C y0r = i00 * a0r + i01r * a1r - i01i * a1i;
       const C y0i = i00 * a0i + i01r * a1i + i01i * a1r;
       const C y1r = i01r * a0r + i01i * a0i + i11 * a1r;
@@ -234,9 +395,9 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
       // log-likelihood integrand log(det*pi) + x^H Sigma^-1 x (audioModel.py:660-664)
       const T quad = b0r * z0r + b0i * z0i + b1r * z1r + b1i * z1i;
       if (sizeof(T) == 8)
-        acc_ll += log((double)det) + 1.1447298858494002 + (double)quad;
+        acc_ll += live ? log((double)det) + 1.1447298858494002 + (double)quad : 0.0;
       else
-        acc_ll += (double)(__logf((float)det) + kLogPi + (float)quad);
+        acc_ll += (double)(live ? __logf((float)det) + kLogPi + (float)quad : 0.f);
       // M = y y^H - Sigma^-1
       const C m00 = y0r * y0r + y0i * y0i - i00;
       const C m11 = y1r * y1r + y1i * y1i - i11;
@@ -250,29 +411,13 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
                         (C)2 * (s_coef[4 * j + 2] * m01r + s_coef[4 * j + 3] * m01i));
         w[j][e] = pf_abs(vt[j] + vt[j] * vt[j] * (q * invrank[j]));
       }
-      // S_jk += v_j v_k M   (accumulated in T)
+      // S_jk += v_j v_k M ; U = x y^H ; T_j += v_j U ; sv_j += v_j   (accumulated in T)
       const T t00 = (T)m00, t11 = (T)m11, t01r = (T)m01r, t01i = (T)m01i;
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        acc[4 * p + 0] += pr[p] * t00;
-        acc[4 * p + 1] += pr[p] * t11;
-        acc[4 * p + 2] += pr[p] * t01r;
-        acc[4 * p + 3] += pr[p] * t01i;
-      }
-      // U = x y^H ; T_j += v_j U ; sv_j += v_j
-      const T u00r = b0r * z0r + b0i * z0i, u00i = b0i * z0r - b0r * z0i;
-      const T u01r = b0r * z1r + b0i * z1i, u01i = b0i * z1r - b0r * z1i;
-      const T u10r = b1r * z0r + b1i * z0i, u10i = b1i * z0r - b1r * z0i;
-      const T u11r = b1r * z1r + b1i * z1i, u11i = b1i * z1r - b1r * z1i;
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        T* t = acc + 4 * NP + 8 * j;
-        t[0] += vt[j] * u00r; t[1] += vt[j] * u00i;
-        t[2] += vt[j] * u01r; t[3] += vt[j] * u01i;
-        t[4] += vt[j] * u10r; t[5] += vt[j] * u10i;
-        t[6] += vt[j] * u11r; t[7] += vt[j] * u11i;
-        acc[4 * NP + 8 * J + j] += vt[j];
-      }
+      const T u[8] = {b0r * z0r + b0i * z0i, b0i * z0r - b0r * z0i,
+                      b0r * z1r + b0i * z1i, b0i * z1r - b0r * z1i,
+                      b1r * z0r + b1i * z0i, b1i * z0r - b1r * z0i,
+                      b1r * z1r + b1i * z1i, b1i * z1r - b1r * z1i};
+      mom.add(pr, vt, t00, t11, t01r, t01i, u);
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) store_vec<T>(hatW + j * plane + row + n0, w[j]);
@@ -283,7 +428,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   // (lanes are summed in the storage type: one 32-bit shuffle per step instead of two)
 #pragma unroll
   for (int i = 0; i < NA - 1; ++i) {
-    const T d = warp_sum(acc[i]);
+    const T d = warp_sum(mom.get(i));
     if (lane == 0) s_red[warp][i] = (double)d;
   }
   {
@@ -468,14 +613,55 @@ static int dispatch_wiener(int J, const void* X, const void* V, const double* co
   return PF_ERR_UNSUPPORTED;
 }
 
+// Tuning variant of the float32 kernel: PYFASST_ESTEP_VARIANT = OPT bits (1: packed moment
+// accumulation, 2: hardware float->double conversion, 4: cp.async ring), read once.
+static int estep_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PYFASST_ESTEP_VARIANT");
+    v = e != nullptr ? atoi(e) : ESTEP_DEFAULT_VARIANT;
+    if (v < 0 || v > 7) v = ESTEP_DEFAULT_VARIANT;
+  }
+  return v;
+}
+
+template <typename T, typename C, int J, int OPT>
+static int launch_estep_opt(const void* X, const void* V, const double* coef, const double* noise,
+                            const SubMap& map, void* hatW, double* partial, int F, long N,
+                            long ld, long chunk, int nsplit, cudaStream_t st) {
+  dim3 grid(nsplit, F);
+  size_t smem = 0;
+  if ((OPT & 4) != 0 && sizeof(T) == 4) {
+    smem = (size_t)ESTEP_DEPTH * (4 + J) * ESTEP_THREADS * 16;
+    cudaError_t e = cudaFuncSetAttribute(estep_stereo_kernel<T, C, J, OPT, 2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("estep_stereo_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return PF_ERR_CUDA;
+    }
+  }
+  estep_stereo_kernel<T, C, J, OPT, 2><<<grid, ESTEP_THREADS, smem, st>>>(
+      (const T*)X, (const T*)V, coef, noise, map, (T*)hatW, partial, F, N, ld, chunk, nsplit);
+  return check_launch("estep_stereo_kernel");
+}
+
 template <typename T, typename C, int J>
 static int launch_estep(const void* X, const void* V, const double* coef, const double* noise,
                         const SubMap& map, void* hatW, double* partial, int F, long N,
                         long ld, long chunk, int nsplit, cudaStream_t st) {
-  dim3 grid(nsplit, F);
-  estep_stereo_kernel<T, C, J><<<grid, ESTEP_THREADS, 0, st>>>(
-      (const T*)X, (const T*)V, coef, noise, map, (T*)hatW, partial, F, N, ld, chunk, nsplit);
-  return check_launch("estep_stereo_kernel");
+#define PF_ESTEP_ARGS X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st
+  if (sizeof(T) == 8) return launch_estep_opt<T, C, J, 0>(PF_ESTEP_ARGS);
+  switch (estep_variant()) {
+    case 0: return launch_estep_opt<T, C, J, 0>(PF_ESTEP_ARGS);
+    case 1: return launch_estep_opt<T, C, J, 1>(PF_ESTEP_ARGS);
+    case 2: return launch_estep_opt<T, C, J, 2>(PF_ESTEP_ARGS);
+    case 3: return launch_estep_opt<T, C, J, 3>(PF_ESTEP_ARGS);
+    case 4: return launch_estep_opt<T, C, J, 4>(PF_ESTEP_ARGS);
+    case 5: return launch_estep_opt<T, C, J, 5>(PF_ESTEP_ARGS);
+    case 6: return launch_estep_opt<T, C, J, 6>(PF_ESTEP_ARGS);
+    default: return launch_estep_opt<T, C, J, 7>(PF_ESTEP_ARGS);
+  }
+#undef PF_ESTEP_ARGS
 }
 
 template <typename T, typename C>
