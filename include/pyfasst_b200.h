@@ -82,12 +82,16 @@ int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch, int64_t L,
 /* Y       : dtype planes [2*nsig][F][ld]
  * synth   : double [wlen] synthesis window; norm : double [(N-1)*hop+wlen]
  *           = overlap-added synth*analysis (stft.py:117-129), host-built
- * out     : double [nsig][Lout] ; sample t reads frames covering t + wlen/2
+ * out     : double [nsig][Lout] ; sample t is the overlap-added sample t + drop: FASST drops
+ *           the first half window (drop = wlen/2, stft.py:123), the SIMM back end keeps it
+ *           (drop = 0, SeparateLeadStereo/separateLeadFunctions.py:163-233, whose patched
+ *           normalisation sequence :218-221 is simply passed in `norm`)
  * pcm     : optional int16 [Lout][nsig] interleaved, = (int16)trunc(out*maxdata)
- *           (audioModel.py:1227-1229) ; NULL to skip */
+ *           (audioModel.py:1227-1229), or round-half-even when pcm_round
+ *           (SeparateLeadStereoTF.py:1826-1827) ; NULL to skip */
 int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld, const double* synth,
              const double* norm, int wlen, int hop, int nfft, double* out, int64_t Lout,
-             int16_t* pcm, double maxdata, int dtype, void* stream);
+             int16_t* pcm, double maxdata, int64_t drop, int pcm_round, int dtype, void* stream);
 
 /* ---- K6: Wiener filter  (audioModel.py:1088-1236, :1327-1467) ----------------- */
 /* For every bin: Sigma = sum_j v_j R_j + s2 I, Y_g = (sum_{j in g} v_j R_j) Sigma^-1 x for
@@ -266,6 +270,18 @@ int pf_simm_wm_update(float* WM, int ldr, int R, const float* D, int nch, const 
 /* beta update of Stereo_SIMM from D = [4][F][ldr]  (SIMM.py:909-941); beta double[2][ldr] */
 int pf_simm_beta_update(const float* WM, int ldr, int R, const float* D, int F, double omega,
                         double* beta, float* b2, void* stream);
+/* SX_c = |X_c|^2 from STFT planes X [2 nch][F][ldx] (re, im per channel)
+ * (SeparateLeadStereoTF.py:843-917) */
+int pf_simm_power(const float* X, int64_t ldx, float* SX, int nch, int F, int64_t N, int64_t ldn,
+                  void* stream);
+/* Wiener masks of the lead / accompaniment separation applied to the mixture STFT
+ * (SeparateLeadStereoTF.py:1762-1871; eps_hat = 1e-9 there, SeparateLeadStereoTF.py:31):
+ *   Y[s = c]       = a2_c SF0 SPHI / max(hat_c, eps_hat) X_c      (lead, channel c)
+ *   Y[s = nch + c] = SM_c          / max(hat_c, eps_hat) X_c      (accompaniment)
+ * with hat_c = a2_c SF0 SPHI + SM_c; Y: planes [2 * 2 nch][F][ldx] (re, im per signal) */
+int pf_simm_masks(const float* SM, const float* SF0, const float* SPHI, const float* a2,
+                  const float* X, int64_t ldx, float* Y, double eps_hat, int nch, int F,
+                  int64_t N, int64_t ldn, void* stream);
 /* WMs[c][f][r] = WM[f][r] b2[c][r] (b2 = NULL: 1), zero in the padding columns r >= R */
 int pf_simm_wm_scaled(const float* WM, int ldr, int R, const float* b2, int nch, int F, float* WMs,
                       void* stream);

@@ -121,6 +121,41 @@ PATCHES = {
     "SeparateLeadStereo/SIMM/SIMM.py": [
         ("from string import join\n", ""),
     ],
+    # generateHannBasis (the smooth-filter dictionary WGAMMA, SeparateLeadStereoTF.py:506-512)
+    "sourcefilter/filter.py": [
+        ("        lengthSineWindow = 2.0 * np.floor(lengthSineWindow / 2.0) ",
+         "        lengthSineWindow = int(2.0 * np.floor(lengthSineWindow / 2.0))"),
+        ("        sizeBigWindow = 2.0 * numberFrequencyBins",
+         "        sizeBigWindow = 2 * int(numberFrequencyBins)"),
+        ("    bigWindow[(sizeBigWindow - lengthSineWindow / 2.0):\\\n"
+         "              (sizeBigWindow + lengthSineWindow / 2.0)] \\\n",
+         "    bigWindow[(sizeBigWindow - lengthSineWindow // 2):\\\n"
+         "              (sizeBigWindow + lengthSineWindow // 2)] \\\n"),
+    ],
+    # only stft / istft / sinebell of this module are executed (the SIMM front and back end,
+    # SeparateLeadStereoTF.py:761-917, :1762-1871); the other transforms are stubbed
+    "SeparateLeadStereo/separateLeadFunctions.py": [
+        ("from ..tftransforms import minqt\nfrom ..tftransforms import nsgt\n"
+         "from .. import audioObject as ao # for all these fancy transforms\n",
+         "minqt = nsgt = ao = None\n"),
+        ("from ..tools.utils import *\nfrom ..tools.distances import ISDistortion\n",
+         "from tools.utils import *\n"),
+        # float sizes / slice bounds that old numpy truncated (separateLeadFunctions.py:127-151)
+        ("    data = np.concatenate((np.zeros(lengthWindow / 2.0),\n"
+         "                           data,\n"
+         "                           np.zeros(lengthWindow / 2.0)))",
+         "    data = np.concatenate((np.zeros(int(lengthWindow / 2.0)),\n"
+         "                           data,\n"
+         "                           np.zeros(int(lengthWindow / 2.0))))"),
+        ("    numberFrames = np.ceil((lengthData - lengthWindow) / hopsize \\\n"
+         "                           + 1) + 1  ",
+         "    numberFrames = int(np.ceil((lengthData - lengthWindow) / hopsize \\\n"
+         "                           + 1) + 1)"),
+        ("    data = np.concatenate((data, np.zeros([newLengthData - lengthData])))",
+         "    data = np.concatenate((data, np.zeros([int(newLengthData - lengthData)])))"),
+        ("    numberFrequencies = nfft / 2.0 + 1\n    \n    if stop is None:",
+         "    numberFrequencies = int(nfft / 2.0 + 1)\n    \n    if stop is None:"),
+    ],
 }
 
 _GLOBAL_SUBS = [
@@ -153,7 +188,7 @@ def build(scratch=SCRATCH):
         with open(dst, "w") as fh:
             fh.write(_patch(rel, src))
     for pkg in ("tftransforms", "tools", "SeparateLeadStereo",
-                "SeparateLeadStereo/SIMM"):
+                "SeparateLeadStereo/SIMM", "sourcefilter"):
         open(os.path.join(scratch, pkg, "__init__.py"), "w").close()
     # the TF-transform registry: keep only the STFT entry (tft.py:74-80)
     with open(os.path.join(scratch, "tftransforms", "tft.py"), "w") as fh:
@@ -179,8 +214,6 @@ def load():
     sls = _stub("SeparateLeadStereo.SeparateLeadStereoTF")
     import SeparateLeadStereo
     SeparateLeadStereo.SeparateLeadStereoTF = sls
-    _stub("sourcefilter")
-    _stub("sourcefilter.filter", generateHannBasis=None)
     _stub("spatial")
     _stub("spatial.steering_vectors",
           gen_steer_vec_far_src_uniform_linear_array=None)
@@ -190,8 +223,25 @@ def load():
     import tools.signalTools as ref_st
     import tools.utils as ref_utils
     import tools.nmf as ref_nmf
+    import SeparateLeadStereo.separateLeadFunctions as ref_slf
+    import sourcefilter.filter as ref_filter
     return dict(audioModel=audioModel, stft=ref_stft, SIMM=ref_simm,
-                signalTools=ref_st, utils=ref_utils, nmf=ref_nmf)
+                signalTools=ref_st, utils=ref_utils, nmf=ref_nmf, slf=ref_slf, filter=ref_filter,
+                writeSeparatedSignals=_method_source(
+                    "SeparateLeadStereo/SeparateLeadStereoTF.py", "writeSeparatedSignals"))
+
+
+def _method_source(rel, name):
+    """The (print-stripped, dedented) source of one method of a reference class, for modules
+    that cannot be imported as a whole (SeparateLeadStereoTF needs the compiled Viterbi
+    extension): the caller exec()s it against a stand-in `self`."""
+    import textwrap
+    with open(os.path.join(REF, "pyfasst", rel)) as fh:
+        src = fh.read()
+    m = re.search(r"^    def %s\(.*?(?=^    def )" % name, src, re.S | re.M)
+    if m is None:
+        raise RuntimeError("method %s not found in %s" % (name, rel))
+    return textwrap.dedent(_strip_prints(_strip_inline_prints(m.group(0))))
 
 
 if __name__ == "__main__":

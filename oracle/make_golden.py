@@ -180,6 +180,72 @@ def run_simm(ref):
     print("simm alphaR", out["st_alphaR"], "err", out["st_recoError"][:3])
 
 
+def run_lead_sep(ref):
+    """The SIMM front / back end: slf.stft, slf.istft and SeparateLeadProcess.
+    writeSeparatedSignals (SeparateLeadStereoTF.py:1762-1871, executed from its own source
+    against a stand-in `self`: the module itself needs the compiled Viterbi extension)."""
+    slf, simm = ref["slf"], ref["SIMM"]
+    rng = np.random.default_rng(21)
+    fs, L, wlen, hop = 8000, 3000, 256, 32
+    t = np.arange(L) / fs
+    sig = np.stack([np.sin(2 * np.pi * 440 * t) * (1 + 0.5 * np.sin(2 * np.pi * 3 * t))
+                    + 0.3 * rng.standard_normal(L),
+                    0.6 * np.sin(2 * np.pi * 440 * t) + 0.4 * rng.standard_normal(L)], axis=1)
+    pcm = np.int16(np.round(0.8 * 32767 * sig / np.abs(sig).max()))
+    wavfile.write(os.path.join(GOLD, "mix_lead.wav"), fs, pcm)
+    scale = 1.2 * np.abs(pcm).max()
+    data = np.double(pcm) / scale
+    win = slf.sinebell(wlen)
+    XR, Fr, Nt = slf.stft(data[:, 0], window=win, hopsize=hop, nfft=wlen, fs=fs)
+    XL, _, _ = slf.stft(data[:, 1], window=win, hopsize=hop, nfft=wlen, fs=fs)
+    yR = slf.istft(XR, window=win, hopsize=hop, nfft=wlen)
+    F, N = XR.shape
+    NF0, P, K, R = 20, 8, 3, 4
+    WF0 = np.abs(rng.standard_normal((F, NF0))) ** 2
+    WF0 /= WF0.max(axis=0)
+    WGAMMA = np.abs(rng.standard_normal((F, P)))
+    init = dict(HGAMMA0=np.abs(rng.standard_normal((P, K))),
+                HPHI0=np.abs(rng.standard_normal((K, N))),
+                HF00=np.abs(rng.standard_normal((NF0, N))),
+                WM0=np.abs(rng.standard_normal((F, R))),
+                HM0=np.abs(rng.standard_normal((R, N))))
+    np.random.seed(9)
+    res = simm.Stereo_SIMM(np.abs(XR) ** 2, np.abs(XL) ** 2, WF0, WGAMMA, numberOfFilters=K,
+                           numberOfAccompanimentSpectralShapes=R, numberOfIterations=3,
+                           verbose=False, **init)
+    names = ("alphaR", "alphaL", "HGAMMA", "HPHI", "HF0", "betaR", "betaL", "HM", "WM")
+    params = dict(zip(names, res[:9]))
+    params.update(WF0=WF0, WGAMMA=WGAMMA)
+    written = {}
+
+    class Wav(object):
+        @staticmethod
+        def write(name, rate, arr):
+            written[name] = np.array(arr)
+
+    class Self(object):
+        pass
+    obj = Self()
+    obj.SIMMParams = params
+    obj.stftParams = dict(windowSizeInSamples=wlen, hopsize=hop, NFT=wlen)
+    obj.XR, obj.XL = XR, XL
+    obj.tfrepresentation = "stft"
+    obj.scaleData, obj.dataType, obj.fs = scale, pcm.dtype, fs
+    obj.files = dict(voc_output_file="out_lead.wav", mus_output_file="out_acc.wav")
+    ns = dict(np=np, slf=slf, wav=Wav, eps=10 ** -9, knownTransfos=["stft"])
+    exec(ref["writeSeparatedSignals"], ns)
+    ns["writeSeparatedSignals"](obj, suffix=".wav")
+    hann = ref["filter"].generateHannBasis(numberFrequencyBins=1025, sizeOfFourier=2048, Fs=44100,
+                                           frequencyScale='linear', numberOfBasis=30, overlap=.75)
+    hann2 = ref["filter"].generateHannBasis(129, 256, 8000, numberOfBasis=8)
+    out = dict(pcm=pcm, XR=XR, XL=XL, F=Fr, N=Nt, yR=yR, voc=written["out_lead.wav"],
+               hann_1025_30=hann, hann_129_8=hann2,
+               mus=written["out_acc.wav"], **init)
+    out.update({"p_" + k: np.asarray(v) for k, v in params.items()})
+    np.savez_compressed(os.path.join(GOLD, "lead_sep.npz"), **out)
+    print("lead_sep", XR.shape, written["out_lead.wav"].shape, np.abs(written["out_lead.wav"]).max())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = _py2shim.load()
@@ -196,6 +262,7 @@ def main():
     run_fasst(ref, "fasst_conv_r1", wavc, conv=True, rank=1, iters=6)
     run_fasst(ref, "fasst_conv_r2", wavc, conv=True, rank=2, iters=6, nbcomps=2)
     run_simm(ref)
+    run_lead_sep(ref)
 
 
 if __name__ == "__main__":

@@ -29,7 +29,7 @@ SIGNATURES = {
     "pf_stft": [c_vp, c_int, c_dbl, c_int, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp,
                 c_i64, c_i64, c_i64, c_vp, c_int, c_vp],
     "pf_istft": [c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64,
-                 c_vp, c_dbl, c_int, c_vp],
+                 c_vp, c_dbl, c_i64, c_int, c_int, c_vp],
     "pf_wiener_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_ip, c_int, c_int, c_i64,
                          c_i64, c_vp, c_vp, c_i64, c_int, c_vp],
     "pf_estep_plan": [c_int, c_i64, c_int, ctypes.POINTER(c_i64), c_ip, ctypes.POINTER(c_i64),
@@ -83,6 +83,9 @@ SIGNATURES = {
                               c_dbl, c_vp, c_vp],
     "pf_simm_wm_update": [c_vp, c_int, c_int, c_vp, c_int, c_vp, c_int, c_dbl, c_int, c_vp, c_vp],
     "pf_simm_beta_update": [c_vp, c_int, c_int, c_vp, c_int, c_dbl, c_vp, c_vp, c_vp],
+    "pf_simm_power": [c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_i64, c_vp],
+    "pf_simm_masks": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_int, c_int, c_i64,
+                      c_i64, c_vp],
     "pf_simm_wm_scaled": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
@@ -192,14 +195,17 @@ class CudaKernels(object):
                                 window.numel(), hop, nfft, self._p(X), frame0, N, ld,
                                 self._p(psd_sum), self.dtype_code(X), self._stream()), self.lib)
 
-    def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata):
+    def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata, drop=None, pcm_round=False):
+        """drop: overlap-added samples skipped at the start (default wlen/2, the FASST
+        convention); pcm_round: round half to even instead of truncating."""
         nsig = Y.shape[0] // 2
         F, ld = Y.shape[1], Y.shape[2]
         assert out.shape[0] == nsig
+        drop = synth.numel() // 2 if drop is None else int(drop)
         _check(self.lib.pf_istft(self._p(Y), nsig, F, N, ld, self._p(synth), self._p(norm),
                                  synth.numel(), hop, nfft, self._p(out), out.shape[1],
-                                 self._p(pcm), float(maxdata), self.dtype_code(Y),
-                                 self._stream()), self.lib)
+                                 self._p(pcm), float(maxdata), drop, int(pcm_round),
+                                 self.dtype_code(Y), self._stream()), self.lib)
 
     def wiener_stereo(self, X, V, A, src_of_sub, noise, group_of_src, ngroups, N, Y, workspace):
         J, F, ld = V.shape
@@ -404,6 +410,13 @@ class CudaKernels(object):
     def simm_beta_update(self, WM, R, D, F, omega, beta, b2):
         self._call("pf_simm_beta_update", self._pv(WM), WM.stride(0), R, self._pv(D), F,
                    float(omega), self._pv(beta), self._pv(b2))
+
+    def simm_power(self, X, SX, nch, F, N, ldn):
+        self._call("pf_simm_power", self._pv(X), X.stride(1), self._pv(SX), nch, F, N, ldn)
+
+    def simm_masks(self, SM, SF0, SPHI, a2, X, Y, eps_hat, nch, F, N, ldn):
+        self._call("pf_simm_masks", self._pv(SM), self._pv(SF0), self._pv(SPHI), self._pv(a2),
+                   self._pv(X), X.stride(1), self._pv(Y), float(eps_hat), nch, F, N, ldn)
 
     def simm_wm_scaled(self, WM, R, b2, nch, F, WMs):
         self._call("pf_simm_wm_scaled", self._pv(WM), WM.stride(0), R, self._pv(b2), nch, F,

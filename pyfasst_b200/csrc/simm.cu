@@ -425,6 +425,56 @@ __global__ void simm_wm_scaled_kernel(const float* __restrict__ WM, int ldr, int
     WMs[(size_t)c * F * ldr + i] = r < R ? WM[i] * (b2 ? b2[(size_t)c * ldr + r] : 1.0f) : 0.f;
 }
 
+// ---- front / back end of the separation (SeparateLeadStereoTF.py:843-917, :1762-1871) ------------
+// SX_c = |X_c|^2
+__global__ void __launch_bounds__(SE_THREADS)
+simm_power_kernel(const float* __restrict__ X, long ldx, float* __restrict__ SX, int nch, int F,
+                  long N, long ldn) {
+  const long f = blockIdx.y;
+  const long n0 = ((long)blockIdx.x * SE_THREADS + threadIdx.x) * 4;
+  if (n0 >= ldn) return;
+  for (int c = 0; c < nch; ++c) {
+    float p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      p[e] = 0.f;
+      if (n0 + e < N) {
+        const float re = X[((size_t)(2 * c) * F + f) * ldx + n0 + e];
+        const float im = X[((size_t)(2 * c + 1) * F + f) * ldx + n0 + e];
+        p[e] = re * re + im * im;
+      }
+    }
+    st4(SX + (f * nch + c) * ldn + n0, p);
+  }
+}
+
+// Y[c] = a2_c SF0 SPHI / hat_c X_c ; Y[nch + c] = SM_c / hat_c X_c
+template <int NCH>
+__global__ void __launch_bounds__(SE_THREADS)
+simm_masks_kernel(const float* __restrict__ SM, const float* __restrict__ SF0,
+                  const float* __restrict__ SPHI, const float* __restrict__ a2,
+                  const float* __restrict__ X, long ldx, float* __restrict__ Y, float eps_hat,
+                  int F, long N, long ldn) {
+  const long f = blockIdx.y;
+  const long n = (long)blockIdx.x * SE_THREADS + threadIdx.x;
+  if (n >= N) return;
+  const float lead = SF0[f * ldn + n] * SPHI[f * ldn + n];
+  const size_t plane = (size_t)F * ldx;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float sm = SM[(f * NCH + c) * ldn + n];
+    const float lv = a2[c] * lead;
+    const float ih = 1.0f / fmaxf(lv + sm, eps_hat);
+    const float re = X[(size_t)(2 * c) * plane + f * ldx + n];
+    const float im = X[(size_t)(2 * c + 1) * plane + f * ldx + n];
+    const float gl = lv * ih, gm = sm * ih;
+    Y[(size_t)(2 * c) * plane + f * ldx + n] = gl * re;
+    Y[(size_t)(2 * c + 1) * plane + f * ldx + n] = gl * im;
+    Y[(size_t)(2 * (NCH + c)) * plane + f * ldx + n] = gm * re;
+    Y[(size_t)(2 * (NCH + c) + 1) * plane + f * ldx + n] = gm * im;
+  }
+}
+
 }  // namespace pf
 
 using namespace pf;
@@ -587,6 +637,33 @@ extern "C" int pf_simm_beta_update(const float* WM, int ldr, int R, const float*
   PF_REQUIRE(F > 0 && R > 0 && ldr >= R, "pf_simm_beta_update: F=%d R=%d ldr=%d", F, R, ldr);
   simm_beta_update_kernel<<<R, SE_THREADS, 0, as_stream(stream)>>>(WM, ldr, D, F, omega, beta, b2);
   return check_launch("simm_beta_update_kernel");
+}
+
+extern "C" int pf_simm_power(const float* X, int64_t ldx, float* SX, int nch, int F, int64_t N,
+                             int64_t ldn, void* stream) {
+  int rc = simm_check_plane("pf_simm_power", nch, F, N, ldn);
+  if (rc) return rc;
+  PF_REQUIRE(ldx >= N, "pf_simm_power: ldx=%ld < N=%ld", (long)ldx, (long)N);
+  simm_power_kernel<<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, as_stream(stream)>>>(X, ldx, SX, nch,
+                                                                                  F, N, ldn);
+  return check_launch("simm_power_kernel");
+}
+
+extern "C" int pf_simm_masks(const float* SM, const float* SF0, const float* SPHI, const float* a2,
+                             const float* X, int64_t ldx, float* Y, double eps_hat, int nch, int F,
+                             int64_t N, int64_t ldn, void* stream) {
+  int rc = simm_check_plane("pf_simm_masks", nch, F, N, ldn);
+  if (rc) return rc;
+  PF_REQUIRE(ldx >= N, "pf_simm_masks: ldx=%ld < N=%ld", (long)ldx, (long)N);
+  dim3 grid(ceil_div(N, SE_THREADS), F);
+  cudaStream_t st = as_stream(stream);
+  if (nch == 1)
+    simm_masks_kernel<1><<<grid, SE_THREADS, 0, st>>>(SM, SF0, SPHI, a2, X, ldx, Y, (float)eps_hat,
+                                                     F, N, ldn);
+  else
+    simm_masks_kernel<2><<<grid, SE_THREADS, 0, st>>>(SM, SF0, SPHI, a2, X, ldx, Y, (float)eps_hat,
+                                                     F, N, ldn);
+  return check_launch("simm_masks_kernel");
 }
 
 extern "C" int pf_simm_wm_scaled(const float* WM, int ldr, int R, const float* b2, int nch, int F,

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(FFT_THREADS)
 istft_kernel(const T* __restrict__ Y, int F, long N, long ld, const double* __restrict__ synth,
              const double* __restrict__ norm, int wlen, int hop, int nfft, int log2m,
              const double2* __restrict__ tw, int seg_frames, double* __restrict__ out, long Lout,
-             int16_t* __restrict__ pcm, int nsig, double maxdata) {
+             int16_t* __restrict__ pcm, int nsig, double maxdata, long drop, int pcm_round) {
   constexpr int SG = Sector<T>::N;
   constexpr int ROW = 2 * SG + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -233,11 +233,17 @@ istft_kernel(const T* __restrict__ Y, int F, long N, long ld, const double* __re
   __syncthreads();
   for (int i = threadIdx.x; i < seg_len; i += FFT_THREADS) {
     const long tau = tau0 + i;
-    const long tout = tau - wlen / 2;  // the first half window is dropped (stft.py:123)
+    // FASST drops the first half window (stft.py:123, drop = wlen/2); the SIMM back end keeps
+    // it (separateLeadFunctions.py:224-232, drop = 0)
+    const long tout = tau - drop;
     if (tout < 0 || tout >= Lout) continue;
     const double v = seg[i] / __ldg(norm + tau);
     out[(size_t)sig * Lout + tout] = v;
-    if (pcm != nullptr) pcm[(size_t)tout * nsig + sig] = (int16_t)(int)(v * maxdata);
+    // np.int16(y * maxdata) truncates (audioModel.py:1227); np.round then cast rounds half to
+    // even (SeparateLeadStereoTF.py:1826-1827)
+    if (pcm != nullptr)
+      pcm[(size_t)tout * nsig + sig] =
+          (int16_t)(int)(pcm_round ? rint(v * maxdata) : v * maxdata);
   }
 }
 
@@ -341,7 +347,7 @@ static int dispatch_stft(int fmt, const void* pcm, int nch, double div, long L, 
 template <typename T>
 static int launch_istft(const void* Y, int nsig, int F, long N, long ld, const double* synth,
                         const double* norm, int wlen, int hop, int nfft, double* out, long Lout,
-                        int16_t* pcm, double maxdata, cudaStream_t st) {
+                        int16_t* pcm, double maxdata, long drop, int pcm_round, cudaStream_t st) {
   constexpr int SG = Sector<T>::N;
   const int M = nfft / 2;
   const double2* tw = twiddles(nfft, st);
@@ -365,7 +371,7 @@ static int launch_istft(const void* Y, int nsig, int F, long N, long ld, const d
   dim3 grid(ceil_div(total, (long)seg_frames * hop), nsig);
   istft_kernel<T><<<grid, FFT_THREADS, smem, st>>>((const T*)Y, F, N, ld, synth, norm, wlen, hop,
                                                   nfft, ilog2(M), tw, seg_frames, out, Lout, pcm,
-                                                  nsig, maxdata);
+                                                  nsig, maxdata, drop, pcm_round);
   return check_launch("istft_kernel");
 }
 
@@ -407,8 +413,8 @@ extern "C" int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch,
 
 extern "C" int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld,
                         const double* synth, const double* norm, int wlen, int hop, int nfft,
-                        double* out, int64_t Lout, int16_t* pcm, double maxdata, int dtype,
-                        void* stream) {
+                        double* out, int64_t Lout, int16_t* pcm, double maxdata, int64_t drop,
+                        int pcm_round, int dtype, void* stream) {
   int rc = check_fft_args("pf_istft", wlen, hop, nfft);
   if (rc) return rc;
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_istft: bad dtype %d", dtype);
@@ -416,10 +422,11 @@ extern "C" int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld,
   PF_REQUIRE(nsig >= 1 && nsig <= 65535 && N >= 1 && Lout >= 1, "pf_istft: nsig=%d N=%ld", nsig,
              (long)N);
   PF_REQUIRE(ld >= N && ld % 4 == 0, "pf_istft: ld=%ld must be >= N and a multiple of 4", (long)ld);
+  PF_REQUIRE(drop >= 0 && drop <= wlen, "pf_istft: drop=%ld outside [0, wlen]", (long)drop);
   cudaStream_t st = as_stream(stream);
   if (dtype == PF_F32)
     return launch_istft<float>(Y, nsig, F, N, ld, synth, norm, wlen, hop, nfft, out, Lout, pcm,
-                               maxdata, st);
+                               maxdata, drop, pcm_round, st);
   return launch_istft<double>(Y, nsig, F, N, ld, synth, norm, wlen, hop, nfft, out, Lout, pcm,
-                              maxdata, st);
+                              maxdata, drop, pcm_round, st);
 }

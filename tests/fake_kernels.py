@@ -58,7 +58,7 @@ class FakeKernels(object):
         if psd_sum is not None:
             _np(psd_sum)[:] = (Xo[:, :, :N].astype(np.float64) ** 2).sum(axis=(0, 2))
 
-    def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata):
+    def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata, drop=None, pcm_round=False):
         self.launches += 1
         Yn, ws, nrm = _np(Y), _np(synth), _np(norm)
         nsig = Yn.shape[0] // 2
@@ -72,11 +72,11 @@ class FakeKernels(object):
             data = np.zeros(total)
             for n in range(N):
                 data[n * hop:n * hop + wlen] += frames[n]
-            data = (data / nrm)[wlen // 2:]
+            data = (data / nrm)[wlen // 2 if drop is None else drop:]
             m = min(Lout, data.size)
             o[s, :m] = data[:m]
         if pcm is not None:
-            _np(pcm)[:] = np.int16(o.T * maxdata)
+            _np(pcm)[:] = np.int16(np.round(o.T * maxdata) if pcm_round else o.T * maxdata)
 
     def _spat(self, A, src_of_sub, J):
         """R_j = sum_r a_r a_r^H per frequency: [J, F] arrays r00, r11, r01."""

@@ -202,6 +202,24 @@ class FakeSimmKernels(object):
         be[0, :R], be[1, :R] = bR, 1 - bR
         b2n[0, :R], b2n[1, :R] = bR ** 2, (1 - bR) ** 2
 
+    def simm_power(self, X, SX, nch, F, N, ldn):
+        self.launches += 1
+        x, sx = _np(X), _np(SX)
+        sx[:, :nch * ldn] = 0
+        for c in range(nch):
+            sx[:, c * ldn:c * ldn + N] = x[2 * c, :, :N] ** 2 + x[2 * c + 1, :, :N] ** 2
+
+    def simm_masks(self, SM, SF0, SPHI, a2, X, Y, eps_hat, nch, F, N, ldn):
+        self.launches += 1
+        m, a, x, y = _np(SM), _np(a2), _np(X), _np(Y)
+        lead = _np(SF0)[:, :N] * _np(SPHI)[:, :N]
+        for c in range(nch):
+            lv, sm = a[c] * lead, m[:, c * ldn:c * ldn + N]
+            ih = 1 / np.maximum(lv + sm, np.float32(eps_hat))
+            for part in (0, 1):
+                y[2 * c + part, :, :N] = lv * ih * x[2 * c + part, :, :N]
+                y[2 * (nch + c) + part, :, :N] = sm * ih * x[2 * c + part, :, :N]
+
     def simm_wm_scaled(self, WM, R, b2, nch, F, WMs):
         self.launches += 1
         wm, out = _np(WM), _np(WMs)
