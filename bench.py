@@ -188,14 +188,20 @@ def run_reference(args, rank):
 
 def workload_config(args, note=None):
     L = int(round(args.duration_s * FS)) * args.gpus
+    model = "MultiChanNMFConv (convolutive mixing)" if getattr(args, "model", "inst") == "conv" \
+        else "MultiChanNMFInst_FASST"
+    shard = getattr(args, "shard", "time")
     cfg = {"workload": "configs[1]: synthetic %.0f-s stereo 44.1 kHz mix per GPU (x%d GPUs = %.0f s, "
-                       "weak scaling), MultiChanNMFInst_FASST %d sources x K=%d, spatial rank %d, "
+                       "weak scaling), %s %d sources x K=%d, spatial rank %d, "
                        "STFT %d/hop %d" % (args.duration_s, args.gpus, args.duration_s * args.gpus,
-                                           NSRC, NNMF, RANK, WLEN, HOP),
+                                           model, NSRC, NNMF, RANK, WLEN, HOP),
            "F": WLEN // 2 + 1, "N": n_frames(L), "tf_bins": (WLEN // 2 + 1) * n_frames(L),
            "sources": NSRC, "nmf_comps": NNMF, "spatial_rank": RANK,
-           "sharding": "frames over %d GPU(s); all-reduce of the per-frequency E-step statistics "
-                       "and of the FB numerators/denominators (NCCL)" % args.gpus,
+           "sharding": ("frames over %d GPU(s); all-reduce of the per-frequency E-step statistics "
+                        "and of the FB numerators/denominators (NCCL)" % args.gpus)
+           if shard == "time" else
+           ("frequency bins over %d GPU(s); all-reduce of the TW numerators/denominators, the "
+            "log-likelihood and the renormalisation maxima (NCCL)" % args.gpus),
            "l2": "inputs larger than L2 (X + V + hat_W planes >> 126 MB), no flush needed"}
     if note:
         cfg["note"] = note
@@ -234,16 +240,18 @@ def run_ours(args, rank, world):
     def make_audio(raw):
         a = ao.AudioObject("synthetic_mix.wav")
         a._samplerate = FS
-        a._set_raw(raw, compute_max=(world == 1))
+        a._set_raw(raw)  # the scaling factor is scanned on the device by the model
         return a
 
     def make_model(iters, raw=None):
         np.random.seed(0)
-        return am.MultiChanNMFInst_FASST(audio=make_audio(pcm if raw is None else raw),
-                                         nbComps=NSRC, nbNMFComps=NNMF, spatial_rank=RANK,
-                                         wlen=WLEN, hopsize=HOP, iter_num=iters,
-                                         ann_PSD_lim=[None, None], compute_dtype=dtype,
-                                         comm=comm, shard="time")
+        cls = am.MultiChanNMFConv if args.model == "conv" else am.MultiChanNMFInst_FASST
+        m = cls(audio=make_audio(pcm if raw is None else raw), nbComps=NSRC, nbNMFComps=NNMF,
+                spatial_rank=RANK, wlen=WLEN, hopsize=HOP, iter_num=iters,
+                ann_PSD_lim=[None, None], compute_dtype=dtype, comm=comm, shard=args.shard)
+        if args.model == "conv":
+            m.makeItConvolutive()
+        return m
 
     # ---- device-resident throughput (`value`) and per-phase / E-step kernel times -------
     model = make_model(args.steps + args.warmup)
@@ -303,7 +311,7 @@ def run_ours(args, rank, world):
         stages = {}
         barrier()
         t0 = time.perf_counter()
-        m.audioObject._set_raw(pinned, compute_max=(world == 1))  # host PCM -> AudioObject
+        m.audioObject._set_raw(pinned)  # host PCM -> AudioObject (no host pass over the samples)
         m.comp_transf_Cx()     # PCM host->device + STFT kernels (+ annealing limits D2H)
         torch.cuda.synchronize()
         stages["comp_transf_Cx_s"] = time.perf_counter() - t0
@@ -386,6 +394,11 @@ def main():
     ap.add_argument("--duration-s", type=float, default=600.0)
     ap.add_argument("--cpu-crop-s", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="inst", choices=["inst", "conv"],
+                    help="inst: MultiChanNMFInst_FASST (configs[1], default); conv: "
+                         "MultiChanNMFConv + makeItConvolutive (the model of configs[3])")
+    ap.add_argument("--shard", default="time", choices=["time", "freq"],
+                    help="multi-GPU partition: frames (default) or frequency bins")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per E-step launch from the committed ncu capture")
     args = ap.parse_args()

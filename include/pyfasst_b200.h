@@ -78,6 +78,11 @@ int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch, int64_t L,
             int64_t L_total, const double* window, int wlen, int hop, int nfft, void* X,
             int64_t frame0, int64_t N, int64_t ld, double* psd_sum, int dtype, void* stream);
 
+/* peak[0] = max |x| over `count` samples in the host layout `pcm_format`, as
+ * np.abs(data).max() gives it (audioObject.py:124-126: the scaling factor is 1.1 times this;
+ * the most negative integer, which np.abs wraps onto itself, is skipped). */
+int pf_pcm_peak(const void* pcm, int pcm_format, int64_t count, double* peak, void* stream);
+
 /* ---- K6: inverse STFT with overlap-add  (tftransforms/stft.py:71-131) --------- */
 /* Y       : dtype planes [2*nsig][F][ld]
  * synth   : double [wlen] synthesis window; norm : double [(N-1)*hop+wlen]

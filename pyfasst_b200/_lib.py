@@ -28,6 +28,7 @@ SIGNATURES = {
     "pf_set_device": [c_int],
     "pf_stft": [c_vp, c_int, c_dbl, c_int, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp,
                 c_i64, c_i64, c_i64, c_vp, c_int, c_vp],
+    "pf_pcm_peak": [c_vp, c_int, c_i64, c_vp, c_vp],
     "pf_istft": [c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64,
                  c_vp, c_dbl, c_i64, c_int, c_int, c_vp],
     "pf_wiener_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_ip, c_int, c_int, c_i64,
@@ -194,6 +195,13 @@ class CudaKernels(object):
                                 L if L_total is None else L_total, self._p(window),
                                 window.numel(), hop, nfft, self._p(X), frame0, N, ld,
                                 self._p(psd_sum), self.dtype_code(X), self._stream()), self.lib)
+
+    def pcm_peak(self, pcm, peak):
+        """peak[0] = max |x| of a device PCM tensor (any layout; the whole tensor is scanned)."""
+        torch = self.torch
+        fmt = {torch.float64: 0, torch.int16: 1, torch.int32: 2, torch.float32: 3}[pcm.dtype]
+        _check(self.lib.pf_pcm_peak(self._p(pcm), fmt, pcm.numel(), self._p(peak),
+                                    self._stream()), self.lib)
 
     def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata, drop=None, pcm_round=False):
         """drop: overlap-added samples skipped at the start (default wlen/2, the FASST

@@ -153,16 +153,20 @@ class FASST(object):
             if raw.dim() == 1:
                 raw = raw[:, None]
             nc = raw.shape[1]
-            if not hasattr(aobj, '_maxdata'):
-                # sharded scan of the scaling factor 1.1 max|x| (audioObject.py:124-126)
-                peak = torch.tensor([aobj._peak(s_lo, s_hi)], dtype=torch.float64, device=k.device)
-                if multi:
-                    self._comm.allreduce_max(peak)
-                aobj._maxdata = np.maximum(1.1 * float(peak.item()), 1e-10)
             raw = raw[s_lo:s_hi]
             if raw.dtype not in (torch.int16, torch.int32, torch.float32):
                 raw = raw.to(torch.float64).t().contiguous()  # planar float64 path
-            pcm, div = raw.to(k.device, non_blocking=True), float(aobj._maxdata)
+            pcm = raw.to(k.device, non_blocking=True)
+            if not hasattr(aobj, '_maxdata'):
+                # the scaling factor 1.1 max|x| (audioObject.py:124-126) from a scan of the
+                # samples already in HBM (a host scan of a 10-min mixture costs more than its
+                # STFT); sharded: every rank scans its own samples, then all-reduce MAX
+                peak = torch.zeros(1, dtype=torch.float64, device=k.device)
+                k.pcm_peak(pcm, peak)
+                if multi:
+                    self._comm.allreduce_max(peak)
+                aobj._maxdata = np.maximum(1.1 * float(peak.item()), 1e-10)
+            div = float(aobj._maxdata)
         if nc != 2:
             raise AttributeError("Nb channels " + str(nc) + " not implemented yet")
         F = nfft // 2 + 1
@@ -365,7 +369,7 @@ class FASST(object):
                 Yh[:, :, :Yn.shape[2]] = Yn
             Y = torch.tensor(Yh).to(eng.dev)
         L = self.audioObject.nframes
-        maxdata = float(self.audioObject._maxdata)
+        maxdata = float(self.audioObject._ensure_maxdata())
         hop, nfft = self.sig_repr_params['hopsize'], self.sig_repr_params['fsize']
         _, pcm = _stft.istft_planes(self._k(), Y, self.nbFramesSigRepr, self.tft.synthWindow,
                                     self.tft.window, hop, nfft, length=L, maxdata=maxdata)

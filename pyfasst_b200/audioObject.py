@@ -51,10 +51,12 @@ class AudioObject(object):
         self._samplerate, raw, self._encoding = wavread(self.filename)
         self._set_raw(raw)
 
-    def _set_raw(self, raw, compute_max=True):
+    def _set_raw(self, raw, compute_max=False):
         """Adopt an in-memory PCM array (numpy or a pinned torch tensor), [nframes, channels].
-        With compute_max=False the scaling factor `_maxdata` is left to the consumer (a sharded
-        model scans only its own samples and all-reduces the maximum)."""
+        The scaling factor `_maxdata` = 1.1 max|x| is computed lazily: by `_read` on the host
+        when the float64 `data` is asked for, or by the model on the device once the samples
+        are in HBM (FASST.comp_transf_Cx; a sharded model scans only its own samples and
+        all-reduces the maximum).  compute_max=True forces the host scan now."""
         self._raw = raw
         shape = tuple(raw.shape)
         if len(shape) == 2:
@@ -68,6 +70,13 @@ class AudioObject(object):
             del self._maxdata
         if compute_max:
             self._maxdata = np.maximum(1.1 * self._peak(0, self._nframes), 1e-10)
+
+    def _ensure_maxdata(self):
+        if not hasattr(self, '_maxdata'):
+            if not hasattr(self, '_raw'):
+                self._read_raw()
+            self._maxdata = np.maximum(1.1 * self._peak(0, self._nframes), 1e-10)
+        return self._maxdata
 
     def _peak(self, lo, hi):
         """max|x| over the samples [lo, hi) of `_raw`, as np.abs(data).max() gives it
@@ -89,8 +98,7 @@ class AudioObject(object):
         if not hasattr(self, '_raw'):
             self._read_raw()
         raw = self._raw.numpy() if hasattr(self._raw, "numpy") else np.asarray(self._raw)
-        if not hasattr(self, '_maxdata'):
-            self._maxdata = np.maximum(1.1 * self._peak(0, self._nframes), 1e-10)
+        self._ensure_maxdata()
         self._data = raw / self._maxdata
 
     def _write(self):

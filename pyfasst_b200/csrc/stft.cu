@@ -46,6 +46,28 @@ __device__ __forceinline__ void fft_inplace(double2* buf, const double2* __restr
   }
 }
 
+// the same transform on `nb` independent M-point sequences held back to back in buf: the
+// butterflies of all sequences are spread over the CTA, one barrier per stage for the batch
+__device__ __forceinline__ void fft_inplace_batch(double2* buf, const double2* __restrict__ tw,
+                                                  int M, int log2m, int nb) {
+  const int hm = M >> 1;
+  for (int half = 1, lh = 0; half < M; half <<= 1, ++lh) {
+    const int tstep = M >> lh;
+    for (int idx = threadIdx.x; idx < nb * hm; idx += FFT_THREADS) {
+      const int t = idx >> (log2m - 1), b = idx & (hm - 1);
+      const int grp = b >> lh, pos = b & (half - 1);
+      double2* base = buf + (size_t)t * M;
+      const int i0 = (grp << (lh + 1)) + pos, i1 = i0 + half;
+      const double2 w = __ldg(tw + pos * tstep);
+      const double2 tt = cmul_d(w, base[i1]);
+      const double2 u = base[i0];
+      base[i1] = make_double2(u.x - tt.x, u.y - tt.y);
+      base[i0] = make_double2(u.x + tt.x, u.y + tt.y);
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 struct Sector {  // elements of T in one 32-byte DRAM sector
   static constexpr int N = 32 / sizeof(T);
@@ -67,58 +89,55 @@ template <typename T, int FMT>
 __global__ void __launch_bounds__(FFT_THREADS)
 stft_kernel(const void* __restrict__ pcm, int nch, double div, long L, long sample0, long Ltot,
             long frame0, const double* __restrict__ window, int wlen, int hop, int nfft, int log2m,
-            const double2* __restrict__ tw, T* __restrict__ X, int F, long N, long ld) {
+            const double2* __restrict__ tw, T* __restrict__ X, int F, long N, long ld, int nb) {
   constexpr int TN = Sector<T>::N;
   constexpr int ROW = 2 * TN + 1;  // padded staging row: (re[TN], im[TN]) per bin
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int M = nfft / 2;
-  double2* buf = reinterpret_cast<double2*>(smem_raw);
-  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)M * sizeof(double2));
+  double2* buf = reinterpret_cast<double2*>(smem_raw);  // [nb][M]
+  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)nb * M * sizeof(double2));
   const int ch = blockIdx.y;
   const long n0 = (long)blockIdx.x * TN;
 
-  for (int t = 0; t < TN; ++t) {
-    const long n = n0 + t;
-    if (n >= N) {  // uniform per CTA
-      for (int k = threadIdx.x; k < F; k += FFT_THREADS) {
-        stage[k * ROW + t] = (T)0;
-        stage[k * ROW + TN + t] = (T)0;
-      }
-      continue;
-    }
-    // frame n covers samples n*hop - wlen/2 + i, i < wlen (stft.py:47-63)
+  // frame n covers samples n*hop - wlen/2 + i, i < wlen (stft.py:47-63); nb frames of the
+  // tile (all TN of them when they fit in shared memory) are framed, transformed and unpacked
+  // together: one barrier per FFT stage for the whole batch
+  for (int t0 = 0; t0 < TN; t0 += nb) {
+  for (int idx = threadIdx.x; idx < nb * M; idx += FFT_THREADS) {
+    const int tb = idx >> log2m, m = idx & (M - 1);
+    const long n = n0 + t0 + tb;
     const long base = (frame0 + n) * hop - wlen / 2;  // global sample index of the frame start
-    for (int m = threadIdx.x; m < M; m += FFT_THREADS) {
-      double v[2];
+    double v[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int i = 2 * m + e;
-        const long s = base + i;
-        const long sl = s - sample0;  // index into the window of samples we were given
-        v[e] = (i < wlen && s >= 0 && s < Ltot && sl >= 0 && sl < L)
-                   ? pcm_sample<FMT>(pcm, nch, L, ch, sl, div) * __ldg(window + i)
-                   : 0.0;
-      }
-      buf[__brev((unsigned)m) >> (32 - log2m)] = make_double2(v[0], v[1]);
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * m + e;
+      const long s = base + i;
+      const long sl = s - sample0;  // index into the window of samples we were given
+      v[e] = (n < N && i < wlen && s >= 0 && s < Ltot && sl >= 0 && sl < L)
+                 ? pcm_sample<FMT>(pcm, nch, L, ch, sl, div) * __ldg(window + i)
+                 : 0.0;
     }
-    __syncthreads();
-    fft_inplace(buf, tw, M);
-    // unpack: X[k] = Xe + W^k Xo, Xe = (Z[k]+conj Z[M-k])/2, Xo = -i (Z[k]-conj Z[M-k])/2
-    for (int k = threadIdx.x; k <= M; k += FFT_THREADS) {
-      const double2 a = buf[k & (M - 1)];
-      const double2 bq = buf[(M - k) & (M - 1)];
-      const double2 b = make_double2(bq.x, -bq.y);
-      const double2 xe = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
-      const double2 d = make_double2(0.5 * (a.x - b.x), 0.5 * (a.y - b.y));
-      const double2 xo = make_double2(d.y, -d.x);  // -i * d
-      const double2 w = (k < M) ? __ldg(tw + k) : make_double2(-1.0, 0.0);
-      const double2 r = cmul_d(w, xo);
-      stage[k * ROW + t] = (T)(xe.x + r.x);
-      stage[k * ROW + TN + t] = (T)(xe.y + r.y);
-    }
-    __syncthreads();
+    buf[(size_t)tb * M + (__brev((unsigned)m) >> (32 - log2m))] = make_double2(v[0], v[1]);
   }
   __syncthreads();
+  fft_inplace_batch(buf, tw, M, log2m, nb);
+  // unpack: X[k] = Xe + W^k Xo, Xe = (Z[k]+conj Z[M-k])/2, Xo = -i (Z[k]-conj Z[M-k])/2
+  for (int idx = threadIdx.x; idx < nb * F; idx += FFT_THREADS) {
+    const int tb = idx / F, k = idx - tb * F, t = t0 + tb;
+    const double2* z = buf + (size_t)tb * M;
+    const double2 a = z[k & (M - 1)];
+    const double2 bq = z[(M - k) & (M - 1)];
+    const double2 b = make_double2(bq.x, -bq.y);
+    const double2 xe = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+    const double2 d = make_double2(0.5 * (a.x - b.x), 0.5 * (a.y - b.y));
+    const double2 xo = make_double2(d.y, -d.x);  // -i * d
+    const double2 w = (k < M) ? __ldg(tw + k) : make_double2(-1.0, 0.0);
+    const double2 r = cmul_d(w, xo);
+    stage[k * ROW + t] = (T)(xe.x + r.x);
+    stage[k * ROW + TN + t] = (T)(xe.y + r.y);
+  }
+  __syncthreads();
+  }
   // write the tile: per (bin, re/im) one 32-byte sector
   const size_t plane = (size_t)F * ld;
   for (int i = threadIdx.x; i < F * 2 * TN; i += FFT_THREADS) {
@@ -151,6 +170,31 @@ __global__ void psd_sum_kernel(const T* __restrict__ X, int nplanes, int F, long
     double d = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) d += s_red[w];
     out[f] = d;
+  }
+}
+
+// peak[0] = max |x| over the samples as np.abs(data).max() gives it (audioObject.py:124-126):
+// for integer PCM the most negative value is skipped (np.abs wraps it onto itself, so it never
+// wins the max in the reference).  Non-negative doubles order like their bit patterns, so the
+// block maxima are combined with an integer atomicMax -- order independent, deterministic.
+template <typename S>
+__global__ void pcm_peak_kernel(const S* __restrict__ x, long count, S skip, int has_skip,
+                                unsigned long long* __restrict__ peak) {
+  double m = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long)gridDim.x * blockDim.x) {
+    const S v = x[i];
+    if (has_skip && v == skip) continue;
+    const double a = fabs((double)v);
+    m = a > m ? a : m;
+  }
+  m = warp_max(m);
+  __shared__ double s_red[32];
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = s_red[w] > m ? s_red[w] : m;
+    atomicMax(peak, (unsigned long long)__double_as_longlong(m));
   }
 }
 
@@ -305,7 +349,10 @@ static int launch_stft(const void* pcm, int nch, double div, long L, long sample
     set_error("pf_stft: cannot allocate the twiddle table");
     return PF_ERR_CUDA;
   }
-  const size_t smem = (size_t)M * sizeof(double2) + (size_t)F * (2 * TN + 1) * sizeof(T);
+  const size_t stage_bytes = (size_t)F * (2 * TN + 1) * sizeof(T);
+  int nb = TN;  // frames transformed together: as many as fit next to the staging tile
+  while (nb > 1 && (size_t)nb * M * sizeof(double2) + stage_bytes > 200 * 1024) nb /= 2;
+  const size_t smem = (size_t)nb * M * sizeof(double2) + stage_bytes;
   cudaError_t e = cudaFuncSetAttribute(stft_kernel<T, FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -315,7 +362,7 @@ static int launch_stft(const void* pcm, int nch, double div, long L, long sample
   dim3 grid(ceil_div(N, TN), nch);
   stft_kernel<T, FMT><<<grid, FFT_THREADS, smem, st>>>(pcm, nch, div, L, sample0, Ltot, frame0,
                                                       window, wlen, hop, nfft, ilog2(M), tw,
-                                                      (T*)X, F, N, ld);
+                                                      (T*)X, F, N, ld, nb);
   int rc = check_launch("stft_kernel");
   if (rc) return rc;
   if (psd_sum != nullptr) {
@@ -409,6 +456,37 @@ extern "C" int pf_stft(const void* pcm, int pcm_format, double pcm_div, int nch,
                                 wlen, hop, nfft, X, N, ld, psd_sum, st);
   return dispatch_stft<double>(pcm_format, pcm, nch, pcm_div, L, sample0, L_total, frame0, window,
                                wlen, hop, nfft, X, N, ld, psd_sum, st);
+}
+
+extern "C" int pf_pcm_peak(const void* pcm, int pcm_format, int64_t count, double* peak,
+                           void* stream) {
+  PF_REQUIRE(count > 0, "pf_pcm_peak: empty signal");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(peak, 0, sizeof(double), st);
+  if (e != cudaSuccess) {
+    set_error("pf_pcm_peak: %s", cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(peak);
+  const int grid = 148 * 8;
+  switch (pcm_format) {
+    case PF_PCM_F64_PLANAR:
+      pcm_peak_kernel<double><<<grid, 256, 0, st>>>((const double*)pcm, count, 0.0, 0, out);
+      break;
+    case PF_PCM_I16:
+      pcm_peak_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)pcm, count, INT16_MIN, 1, out);
+      break;
+    case PF_PCM_I32:
+      pcm_peak_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)pcm, count, INT32_MIN, 1, out);
+      break;
+    case PF_PCM_F32:
+      pcm_peak_kernel<float><<<grid, 256, 0, st>>>((const float*)pcm, count, 0.f, 0, out);
+      break;
+    default:
+      set_error("pf_pcm_peak: unknown PCM format %d", pcm_format);
+      return PF_ERR_ARG;
+  }
+  return check_launch("pcm_peak_kernel");
 }
 
 extern "C" int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld,

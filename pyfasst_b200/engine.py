@@ -238,9 +238,17 @@ class GemEngine(object):
                 "FB": self._upload(FB[self.f_lo:self.f_hi], self.tdtype),
                 "FW": self._upload(FW, self.tdtype),
                 "TW": TWd,
-                "W": self._zeros([self.F, Kw]),
-                "G": self._zeros([Kb, self.ld]),
             }
+            # Plain NMF (the standard models, audioModel.py:2377-2380) has FW = identity, fixed:
+            # W = FB FW and G = FW TW are then exact copies of FB and TW -- alias them instead
+            # of launching the two products.  (The renormalisation keeps FW at exactly the
+            # identity: it scales row k by c_k and divides column k by the same c_k.)
+            ent["FW_identity"] = Kb == Kw and np.array_equal(FW, np.eye(Kb))
+            if ent["FW_identity"]:
+                ent["W"], ent["G"] = ent["FB"], ent["TW"]
+            else:
+                ent["W"] = self._zeros([self.F, Kw])
+                ent["G"] = self._zeros([Kb, self.ld])
             self.spec.append(ent)
         self.omega = float(nmfUpdateCoeff)
         self._alloc_work()
@@ -299,9 +307,10 @@ class GemEngine(object):
         """W = FB FW, V_j = W H (comp_spat_comp_power, audioModel.py:430-498), G = FW H."""
         k = self.k
         for e in self.spec:
-            k.small_matmul(e["FB"], e["FW"], e["W"])
+            if not e["FW_identity"]:
+                k.small_matmul(e["FB"], e["FW"], e["W"])
             k.spec_power(e["W"], e["TW"], self.V[e["j"]], self.N, False)
-            if with_G and e["FB_free"]:
+            if with_G and e["FB_free"] and not e["FW_identity"]:
                 k.spec_power(e["FW"], e["TW"], e["G"], self.N, False)
 
     def estep(self):
@@ -353,7 +362,8 @@ class GemEngine(object):
                 k.sum_splits(pd, self.fb_nd[s, 1, :cnt])
             else:
                 k.mult_update_splits(e["FB"], pn, pd, F, e["Kb"], self.omega)
-                k.small_matmul(e["FB"], e["FW"], e["W"])
+                if not e["FW_identity"]:
+                    k.small_matmul(e["FB"], e["FW"], e["W"])
         if any_fb and self._tshard():
             self.comm.allreduce_sum(self.fb_nd)
             for s, e in enumerate(self.spec):
@@ -361,7 +371,8 @@ class GemEngine(object):
                     cnt = F * e["Kb"]
                     k.mult_update(e["FB"], self.fb_nd[s, 0, :cnt].view(F, e["Kb"]),
                                   self.fb_nd[s, 1, :cnt].view(F, e["Kb"]), F, e["Kb"], self.omega)
-                    k.small_matmul(e["FB"], e["FW"], e["W"])
+                    if not e["FW_identity"]:
+                        k.small_matmul(e["FB"], e["FW"], e["W"])
         # TW: contraction over the (local) frequencies with the updated W
         any_tw = False
         for s, e in enumerate(self.spec):

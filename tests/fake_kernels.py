@@ -58,6 +58,13 @@ class FakeKernels(object):
         if psd_sum is not None:
             _np(psd_sum)[:] = (Xo[:, :, :N].astype(np.float64) ** 2).sum(axis=(0, 2))
 
+    def pcm_peak(self, pcm, peak):
+        self.launches += 1
+        x = _np(pcm)
+        if np.issubdtype(x.dtype, np.signedinteger):
+            x = x[x != np.iinfo(x.dtype).min]
+        _np(peak)[0] = np.abs(x.astype(np.float64)).max() if x.size else 0.0
+
     def istft(self, Y, N, synth, norm, hop, nfft, out, pcm, maxdata, drop=None, pcm_round=False):
         self.launches += 1
         Yn, ws, nrm = _np(Y), _np(synth), _np(norm)
