@@ -29,6 +29,8 @@ constrained, TB empty; FB / TW / mixing parameters individually 'free' or 'fixed
 all spatial components instantaneous, or all convolutive and free (Q7).  Anything
 else raises NotImplementedError -- there is no CPU fallback.
 """
+import os
+
 import numpy as np
 
 EPS = 1e-10  # ref: audioModel.py:61
@@ -98,6 +100,34 @@ class GemEngine(object):
         self.X = None
         self.J = 0
         self.n_iter_done = 0
+        # The spectral components are independent of one another inside each phase of the
+        # M-step: their kernel chains run on side streams, so that the small kernels of one
+        # component (~30 % of the launches, a few microseconds each) overlap the bandwidth-bound
+        # kernels of the others.  PYFASST_STREAMS=0 keeps everything on one stream.
+        self._side = []
+        self._use_streams = self.dev.type == "cuda" and os.environ.get("PYFASST_STREAMS", "1") != "0"
+
+    # ------------------------------------------------------------------ streams
+    def _for_each(self, items, fn):
+        """fn(index, item) for every item; on a GPU each item's launches go to its own side
+        stream, forked from and joined back into the current stream (so the whole thing can
+        still be captured in a CUDA graph)."""
+        items = list(items)
+        if not self._use_streams or len(items) < 2:
+            for i, it in enumerate(items):
+                fn(i, it)
+            return
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.dev)
+        while len(self._side) < len(items):
+            self._side.append(torch.cuda.Stream(device=self.dev))
+        for i, it in enumerate(items):
+            st = self._side[i]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                fn(i, it)
+        for i in range(len(items)):
+            cur.wait_stream(self._side[i])
 
     # ------------------------------------------------------------------ allocation
     def _zeros(self, shape, dtype=None):
@@ -288,7 +318,7 @@ class GemEngine(object):
             chunk, nsplit = k.fb_plan(F, e["Kb"], N, code)
             self.fb_plan[id(e)] = (chunk, nsplit)
             fb_size = max(fb_size, nsplit * F * e["Kb"])
-        self.fb_part = self._zeros([2, fb_size], f64)
+        self.fb_part = self._zeros([S, 2, fb_size], f64)  # per component: they run concurrently
         self.fb_nd = self._zeros([S, 2, F * Kmax], f64)
         # TW update partial sums; the reduced num/den of all components share one
         # buffer so that a single all-reduce serves the whole iteration
@@ -297,21 +327,23 @@ class GemEngine(object):
             fchunk, fsplit = k.tw_plan(F, e["Kw"], N, code)
             self.tw_plan[id(e)] = (fchunk, fsplit)
             tw_size = max(tw_size, fsplit * e["Kw"] * ld)
-        self.tw_part = self._zeros([2, tw_size], f64)
-        # work plane for P' = W'H of the tensor-core TW path (float32 planes only)
-        self.scratch = self._zeros([F, ld]) if self.tdtype == torch.float32 else None
+        self.tw_part = self._zeros([S, 2, tw_size], f64)
+        # work planes for P' = W'H of the tensor-core TW path (float32 planes only)
+        self.scratch = self._zeros([S, F, ld]) if self.tdtype == torch.float32 else None
         self.tw_nd = self._zeros([S, 2, Kmax, ld], f64)
 
     # ------------------------------------------------------------------ pieces
     def compute_powers(self, with_G=True):
         """W = FB FW, V_j = W H (comp_spat_comp_power, audioModel.py:430-498), G = FW H."""
         k = self.k
-        for e in self.spec:
+
+        def powers(s, e):
             if not e["FW_identity"]:
                 k.small_matmul(e["FB"], e["FW"], e["W"])
             k.spec_power(e["W"], e["TW"], self.V[e["j"]], self.N, False)
             if with_G and e["FB_free"] and not e["FW_identity"]:
                 k.spec_power(e["FW"], e["TW"], e["G"], self.N, False)
+        self._for_each(self.spec, powers)
 
     def estep(self):
         """compute_suff_stat (audioModel.py:580-764) on the current parameters."""
@@ -346,16 +378,15 @@ class GemEngine(object):
         k, N, F = self.k, self.N, self.F
         # FB: contraction over the (local) frames.  Different components are independent given
         # hat_W and V, so under time sharding all FB sums are reduced with one all-reduce.
-        any_fb = False
-        for s, e in enumerate(self.spec):
-            if not e["FB_free"]:
-                continue
-            any_fb = True
+        fb = [(s, e) for s, e in enumerate(self.spec) if e["FB_free"]]
+
+        def fb_sums(_, se):
+            s, e = se
             j = e["j"]
             chunk, nsplit = self.fb_plan[id(e)]
             cnt = F * e["Kb"]
-            pn = self.fb_part[0, :nsplit * cnt].view(nsplit, F, e["Kb"])
-            pd = self.fb_part[1, :nsplit * cnt].view(nsplit, F, e["Kb"])
+            pn = self.fb_part[s, 0, :nsplit * cnt].view(nsplit, F, e["Kb"])
+            pd = self.fb_part[s, 1, :nsplit * cnt].view(nsplit, F, e["Kb"])
             k.fb_contract(self.hatW[j], self.V[j], self.V[j], e["G"], N, pn, pd, chunk, nsplit)
             if self._tshard():
                 k.sum_splits(pn, self.fb_nd[s, 0, :cnt])
@@ -364,39 +395,45 @@ class GemEngine(object):
                 k.mult_update_splits(e["FB"], pn, pd, F, e["Kb"], self.omega)
                 if not e["FW_identity"]:
                     k.small_matmul(e["FB"], e["FW"], e["W"])
-        if any_fb and self._tshard():
+
+        def fb_apply(_, se):
+            s, e = se
+            cnt = F * e["Kb"]
+            k.mult_update(e["FB"], self.fb_nd[s, 0, :cnt].view(F, e["Kb"]),
+                          self.fb_nd[s, 1, :cnt].view(F, e["Kb"]), F, e["Kb"], self.omega)
+            if not e["FW_identity"]:
+                k.small_matmul(e["FB"], e["FW"], e["W"])
+        # NB every FB update reads G_s = FW_s TW_s of its own component only, and no TW changes
+        # before all the FB updates are done (Gauss-Seidel order FB -> TW, Q2)
+        self._for_each(fb, fb_sums)
+        if fb and self._tshard():
             self.comm.allreduce_sum(self.fb_nd)
-            for s, e in enumerate(self.spec):
-                if e["FB_free"]:
-                    cnt = F * e["Kb"]
-                    k.mult_update(e["FB"], self.fb_nd[s, 0, :cnt].view(F, e["Kb"]),
-                                  self.fb_nd[s, 1, :cnt].view(F, e["Kb"]), F, e["Kb"], self.omega)
-                    if not e["FW_identity"]:
-                        k.small_matmul(e["FB"], e["FW"], e["W"])
+            self._for_each(fb, fb_apply)
         # TW: contraction over the (local) frequencies with the updated W
-        any_tw = False
-        for s, e in enumerate(self.spec):
-            if not e["TW_free"]:
-                continue
-            any_tw = True
+        tw = [(s, e) for s, e in enumerate(self.spec) if e["TW_free"]]
+
+        def tw_sums(_, se):
+            s, e = se
             j = e["j"]
             fchunk, fsplit = self.tw_plan[id(e)]
             cnt = e["Kw"] * self.ld
-            pn = self.tw_part[0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
-            pd = self.tw_part[1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+            pn = self.tw_part[s, 0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+            pd = self.tw_part[s, 1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
             k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit,
-                          self.scratch)
+                          None if self.scratch is None else self.scratch[s])
             if self._fshard():
                 k.sum_splits(pn, self.tw_nd[s, 0, :e["Kw"]])
                 k.sum_splits(pd, self.tw_nd[s, 1, :e["Kw"]])
             else:  # reduce the frequency splits inside the update kernel
                 k.mult_update_splits(e["TW"], pn, pd, e["Kw"], N, self.omega)
-        if any_tw and self._fshard():
+
+        def tw_apply(_, se):
+            s, e = se
+            k.mult_update(e["TW"], self.tw_nd[s, 0], self.tw_nd[s, 1], e["Kw"], N, self.omega)
+        self._for_each(tw, tw_sums)
+        if tw and self._fshard():
             self.comm.allreduce_sum(self.tw_nd)
-            for s, e in enumerate(self.spec):
-                if e["TW_free"]:
-                    k.mult_update(e["TW"], self.tw_nd[s, 0], self.tw_nd[s, 1], e["Kw"], N,
-                                  self.omega)
+            self._for_each(tw, tw_apply)
 
     def renormalize(self):
         """renormalize_parameters (audioModel.py:1980-2040)."""
@@ -405,14 +442,19 @@ class GemEngine(object):
         if self._fshard():
             self.comm.allreduce_sum(self.sums)
         k.spat_scale(self.A, self.src_of_sub, self.sums, self.counts)
-        for s, e in enumerate(self.spec):
+        def colmax(s, e):
             k.fb_scale_colmax(e["FB"], self.sums, self.counts, e["j"], self.colmax[s])
-        if self._fshard():
-            self.comm.allreduce_max(self.colmax)
-        for s, e in enumerate(self.spec):
+
+        def rescale(s, e):
             k.fw_renorm(e["FW"], self.colmax[s], self.wcol[s], self.w2[s])
             k.scale_matrix(e["FB"], self.F, e["Kb"], self.wcol[s], False, True)
             k.scale_matrix(e["TW"], e["Kw"], self.N, self.w2[s], True, False, self.totals[s:s + 1])
+        if self._fshard():
+            self._for_each(self.spec, colmax)
+            self.comm.allreduce_max(self.colmax)
+            self._for_each(self.spec, rescale)
+        else:
+            self._for_each(self.spec, lambda s, e: (colmax(s, e), rescale(s, e)))
         if self._tshard():
             self.comm.allreduce_sum(self.totals)
         k.check_totals(self.totals, EPS, self.flags)
