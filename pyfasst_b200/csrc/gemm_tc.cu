@@ -95,15 +95,22 @@ struct GtStage {
   unsigned char b_lo[BN * GT_BK * 4];
 };
 
-template <int BN>
+template <int BN, int STAGES>
 struct GtSmem {
-  GtStage<BN> stage[2];  // the write-out reuses stage[0] for its per-warp transpose tiles
+  GtStage<BN> stage[STAGES];  // the write-out reuses stage[0] for its per-warp transpose tiles
+};
+// CTAs per SM: two when the operand ring fits twice in shared memory (one-stage ring of the
+// short-K products, or the narrow BN = 64 tile) -- one CTA's write-out then overlaps the
+// other's loads and MMAs; TMEM: 2 x BN <= 512 columns.
+template <int BN, int STAGES>
+struct GtOcc {
+  static constexpr int value = (sizeof(GtSmem<BN, STAGES>) + 1024 <= 110 * 1024) ? 2 : 1;
 };
 static_assert(sizeof(GtStage<64>) >= (GT_THREADS / 32) * 32 * 36 * sizeof(float), "transpose tiles");
 
 // TA: A is stored [K][M] (A^T given); TB: B is stored [N][K] (B^T given)
-template <bool TA, bool TB, int BN>
-__global__ void __launch_bounds__(GT_THREADS, 1)
+template <bool TA, bool TB, int BN, int STAGES>
+__global__ void __launch_bounds__(GT_THREADS, GtOcc<BN, STAGES>::value)
 gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb,
                    float* __restrict__ C, long ldc, int M, int N, int K, int kper, long cstride) {
   extern __shared__ __align__(1024) unsigned char gt_smem[];
@@ -111,7 +118,7 @@ gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restric
   __shared__ uint64_t mbar_done;
   __shared__ uint32_t tmem_base;
   unsigned char* base = gt_smem + ((1024 - (tc::smem_u32(gt_smem) & 1023)) & 1023);
-  GtSmem<BN>& sm = *reinterpret_cast<GtSmem<BN>*>(base);
+  GtSmem<BN, STAGES>& sm = *reinterpret_cast<GtSmem<BN, STAGES>*>(base);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long m0 = (long)blockIdx.y * GT_BM, n0 = (long)blockIdx.x * BN;
   // split K: CTA z contracts k in [kbeg, kend) into the partial product C + z * cstride
@@ -139,9 +146,9 @@ gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restric
   ta.fetch(A, lda, m0, M, kbeg, kend, tid);
   tb.fetch(B, ldb, n0, N, kbeg, kend, tid);
   for (int s = 0; s < nchunks; ++s) {
-    const int b = s & 1;
+    const int b = s % STAGES;
     GtStage<BN>& st = sm.stage[b];
-    if (s >= 2) tc::mbar_wait(&mbar_free[b], (uint32_t)(((s >> 1) - 1) & 1));
+    if (s >= STAGES) tc::mbar_wait(&mbar_free[b], (uint32_t)((s / STAGES - 1) & 1));
     ta.store(st.a_hi, st.a_lo, tid);
     tb.store(st.b_hi, st.b_lo, tid);
     if (s + 1 < nchunks) {
@@ -217,20 +224,34 @@ gemm_tf32x3_kernel(const float* __restrict__ A, long lda, const float* __restric
   if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
 }
 
-template <bool TA, bool TB, int BN>
-static int launch_gemm(const float* A, long lda, const float* B, long ldb, float* C, long ldc,
-                       int M, int N, int K, int ksplit, int kper, long cstride, cudaStream_t st) {
-  const size_t smem = sizeof(GtSmem<BN>) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<TA, TB, BN>,
+template <bool TA, bool TB, int BN, int STAGES>
+static int launch_gemm_stages(const float* A, long lda, const float* B, long ldb, float* C,
+                              long ldc, int M, int N, int K, int ksplit, int kper, long cstride,
+                              cudaStream_t st) {
+  const size_t smem = sizeof(GtSmem<BN, STAGES>) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<TA, TB, BN, STAGES>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("gemm_tf32x3_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return PF_ERR_CUDA;
   }
   dim3 grid(ceil_div(N, BN), ceil_div(M, GT_BM), ksplit);
-  gemm_tf32x3_kernel<TA, TB, BN><<<grid, GT_THREADS, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K,
-                                                                 kper, cstride);
+  gemm_tf32x3_kernel<TA, TB, BN, STAGES><<<grid, GT_THREADS, smem, st>>>(A, lda, B, ldb, C, ldc, M,
+                                                                         N, K, kper, cstride);
   return check_launch("gemm_tf32x3_kernel");
+}
+
+template <bool TA, bool TB, int BN>
+static int launch_gemm(const float* A, long lda, const float* B, long ldb, float* C, long ldc,
+                       int M, int N, int K, int ksplit, int kper, long cstride, cudaStream_t st) {
+  // short contractions (at most two K chunks per CTA: the K = R products of the SIMM
+  // accompaniment model) take the one-stage ring and two CTAs per SM
+  const long kspan = ksplit > 1 ? kper : K;
+  if (kspan <= 2 * GT_BK)
+    return launch_gemm_stages<TA, TB, BN, 1>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride,
+                                             st);
+  return launch_gemm_stages<TA, TB, BN, 2>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride,
+                                           st);
 }
 
 template <bool TA, bool TB>
