@@ -40,6 +40,11 @@ if ROOT not in sys.path:
 FS = 44100
 WLEN, HOP = 2048, 512
 NSRC, NNMF, RANK = 4, 32, 2
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused E-step kernel on the
+# default workload, from the committed `ncu --set full` capture
+# profiles/r01/ncu_estep_stereo_kernel.txt (1.696969 GB + 0.835408 GB); the algorithmic figure is
+# 48 B x 52,974,050 bins = 2.543 GB, i.e. no wasted re-reads.
+ESTEP_DRAM_BYTES_PER_LAUNCH = 2.532377e9
 METRIC = "gem_tf_bins_iters_per_s"
 UNIT = "TF-bins*iters/s"
 
@@ -357,11 +362,15 @@ def run_ours(args, rank, world):
     bytes_per_bin = sz * (4 + 2 * NSRC)  # I^2 reals of x (=Cx, rank one) + V_j + hat_W_j
     local_bins = bins / float(world)  # frames are split evenly over the ranks
     achieved = bytes_per_bin * local_bins / (estep_ms * 1e-3) / 1e9
+    traffic = args.traffic
+    if traffic is None and world == 1 and args.dtype == "f32" and args.duration_s == 600.0:
+        traffic = ESTEP_DRAM_BYTES_PER_LAUNCH  # same workload as the committed capture
     roofline = {"bound": "hbm", "kernel": "estep_stereo_kernel", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "bytes_per_bin": bytes_per_bin, "ms_per_launch": estep_ms,
-                "traffic": args.traffic}
+                "algorithmic_bytes_per_launch": bytes_per_bin * local_bins,
+                "traffic": traffic}
 
     # ---- CPU baseline: the oracle on a bounded crop -----------------------------------------
     cpu = None

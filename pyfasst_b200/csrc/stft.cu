@@ -18,6 +18,8 @@
 // gather, deterministic, no atomics.  The segment is then divided by the overlap-added
 // window product (stft.py:117-129) and optionally truncated to int16
 // (audioModel.py:1227-1229).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pf {
@@ -350,8 +352,16 @@ static int launch_stft(const void* pcm, int nch, double div, long L, long sample
     return PF_ERR_CUDA;
   }
   const size_t stage_bytes = (size_t)F * (2 * TN + 1) * sizeof(T);
-  int nb = TN;  // frames transformed together: as many as fit next to the staging tile
-  while (nb > 1 && (size_t)nb * M * sizeof(double2) + stage_bytes > 200 * 1024) nb /= 2;
+  // frames transformed together (one barrier per FFT stage for the batch); limited so that two
+  // CTAs stay resident per SM
+  int nb = TN;
+  size_t budget = 110 * 1024;
+  if (const char* e = getenv("PYFASST_STFT_NB")) {  // tuning override
+    nb = atoi(e) > 0 ? atoi(e) : TN;
+    if (nb > TN) nb = TN;
+    budget = 200 * 1024;
+  }
+  while (nb > 1 && (size_t)nb * M * sizeof(double2) + stage_bytes > budget) nb /= 2;
   const size_t smem = (size_t)nb * M * sizeof(double2) + stage_bytes;
   cudaError_t e = cudaFuncSetAttribute(stft_kernel<T, FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
