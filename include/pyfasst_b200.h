@@ -131,6 +131,22 @@ int pf_estep_stereo(const void* X, const void* V, const void* A, const int* src_
                     void* hat_Rss, void* hat_Rxs, double* ll_f, void* workspace,
                     int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream);
 
+/* ---- K2 / K6 for I = 2..4 channels (extension: the reference is stereo only, audioModel.py:394,
+ * :605, :1127; definitions as oracle/fasst_oracle.py: estep_general -- batched I x I Hermitian
+ * inverse, determinant clamp on the generic determinant).  X: planes [2 I][F][ld]
+ * (re, im per channel), A: complex128 [R][I][F], hat_Rxs: complex128 [F][I][R]; everything
+ * else as pf_estep_stereo / pf_wiener_stereo (Y: planes [ngroups][2 I][F][ld]). */
+int pf_estep_multi_plan(int I, int J, int F, int64_t N, int64_t* chunk, int* nsplit,
+                        int64_t* workspace_bytes);
+int pf_estep_multi(const void* X, const void* V, const void* A, const int* src_of_sub, int R,
+                   int J, int I, const double* noise_psd, int F, int64_t N, int64_t ld, void* hatW,
+                   void* hat_Rss, void* hat_Rxs, double* ll_f, void* workspace,
+                   int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream);
+int pf_wiener_multi(const void* X, const void* V, const void* A, const int* src_of_sub, int R,
+                    int J, int I, const double* noise_psd, const int* group_of_src, int ngroups,
+                    int F, int64_t N, int64_t ld, void* Y, void* workspace,
+                    int64_t workspace_bytes, int dtype, void* stream);
+
 /* ---- K3: spatial M-step  (audioModel.py:766-889) ------------------------------- */
 /* Instantaneous mixing: f-summed real statistics (audioModel.py:816-826).
  * stats : double [I*n_upd + n_upd*n_upd]; under frequency sharding the caller
