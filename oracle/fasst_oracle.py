@@ -165,13 +165,16 @@ class OracleFASST(object):
     """Restatement of `FASST` + `MultiChanNMFInst_FASST` / `MultiChanNMFConv`.
 
     ref: audioModel.py:66-2294 (core), :2296-2508 (model structures).  Stereo
-    only, like the reference (audioModel.py:394,605,1127).
+    only, like the reference (audioModel.py:394,605,1127), unless
+    `generalised=True` (default for I != 2): the E-step and the Wiener gains then
+    use the batched I x I inverse of `estep_general` -- an EXTENSION with no
+    reference counterpart, proven equal to the stereo path at I = 2.
     """
 
     def __init__(self, audio, nbComps=3, nbNMFComps=4, spatial_rank=2,
                  wlen=2048, hopsize=512, iter_num=50, sim_ann_opt="ann",
                  ann_PSD_lim=None, nmfUpdateCoeff=1.0, lambdaCorr=0.0,
-                 init=True):
+                 init=True, generalised=None):
         if isinstance(audio, str):
             self.filename = audio
             self.fs, self.data, self.maxdata = read_audio(audio)
@@ -179,6 +182,7 @@ class OracleFASST(object):
             self.filename = "mix.wav"
             self.fs, self.data, self.maxdata = audio
         self.nframes_audio, self.channels = self.data.shape
+        self.generalised = (self.channels != 2) if generalised is None else generalised
         self.wlen = nextpow2(wlen)  # ref: audioModel.py:192-193
         self.hopsize = hopsize
         self.tft = STFT(linFTLen=self.wlen,
@@ -286,7 +290,7 @@ class OracleFASST(object):
 
     # -- ref: audioModel.py:384-428 ------------------------------------------ #
     def GEM_iteration(self):
-        if self.channels != 2:
+        if self.channels != 2 and not self.generalised:
             raise AttributeError("Nb channels %d not implemented yet"
                                  % self.channels)
         powers, mix, ranks = self.retrieve_subsrc_params()
@@ -339,6 +343,12 @@ class OracleFASST(object):
 
     # -- ref: audioModel.py:580-764 (E-step) --------------------------------- #
     def compute_suff_stat(self, spat_comp_powers, mix_matrix):
+        if self.generalised:
+            # EXTENSION (no reference for I != 2): the same definitions with a batched I x I
+            # inverse; identical to the stereo path at I = 2 (tests/test_oracle_golden.py)
+            hat_Rxs, hat_Rss, hat_Ws, loglik = estep_general(
+                self.X, spat_comp_powers, mix_matrix, self.noise["PSD"])
+            return None, hat_Rxs, hat_Rss, hat_Ws, loglik
         if self.channels != 2:
             raise ValueError("Nb channels not supported:%d" % self.channels)
         R = spat_comp_powers.shape[0]
@@ -552,8 +562,46 @@ class OracleFASST(object):
             WG[n, 1, 0] = np.conj(soff[n]) * idg[0] + sdiag[n, 1] * np.conj(iof)
         return WG
 
+    def separation_gains_general(self, spec_comp_ind=None):
+        """EXTENSION: WG[nsrc, I, I, F, N] = Sigma_n Sigma_x^-1 with a batched inverse (the clamp of
+        the determinant as in estep_general); equals separation_gains at I = 2."""
+        if spec_comp_ind is None:
+            spec_comp_ind = {j: [] for j in range(len(self.spat_comps))}
+            for s, spec in self.spec_comps.items():
+                spec_comp_ind[spec["spat_comp_ind"]].append(s)
+        nsrc, I = len(spec_comp_ind), self.channels
+        F, N = self.nbFreqsSigRepr, self.nbFramesSigRepr
+        Sn = np.zeros([nsrc, F, N, I, I], dtype=complex)
+        for n in range(nsrc):
+            spats = np.unique([self.spec_comps[s]["spat_comp_ind"] for s in spec_comp_ind[n]])
+            for j in spats:
+                V = self.comp_spat_comp_power(j, spec_comp_ind[n])
+                sc = self.spat_comps[j]
+                mc = sc["params"].T if sc["mix_type"] == "inst" else sc["params"]  # [rank, I(, F)]
+                mc = mc[:, :, None] * np.ones(F) if mc.ndim == 2 else mc
+                Rj = np.einsum("raf,rbf->fab", mc, np.conj(mc))
+                Sn[n] += V[:, :, None, None] * Rj[:, None]
+        Sx = Sn.sum(axis=0) + self.noise["PSD"][:, None, None, None] * np.eye(I)
+        det = np.real(np.linalg.det(Sx))
+        detc = np.sign(det + EPS) * np.maximum(np.abs(det), EPS)
+        Sinv = np.linalg.inv(Sx) * (det / detc)[..., None, None]
+        WG = np.einsum("sfnab,fnbc->sacfn", Sn, Sinv)
+        return WG
+
     def separate_signals(self, spec_comp_ind=None):
-        """Float separated signals [nsrc, L, 2] before PCM conversion."""
+        """Float separated signals [nsrc, L, I] before PCM conversion."""
+        if self.generalised:
+            WG = self.separation_gains_general(spec_comp_ind)
+            outs = []
+            for n in range(WG.shape[0]):
+                chans = []
+                for c1 in range(self.channels):
+                    self.tft.transfo = sum(WG[n, c1, c2] * self.X[c2]
+                                           for c2 in range(self.channels))
+                    self.tft.datalen_init = self.nframes_audio
+                    chans.append(self.tft.invertTransform())
+                outs.append(np.array(chans).T)
+            return np.array(outs)
         WG = self.separation_gains(spec_comp_ind)
         outs = []
         for n in range(WG.shape[0]):

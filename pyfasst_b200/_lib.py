@@ -37,6 +37,12 @@ SIGNATURES = {
                       c_int],
     "pf_estep_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_int, c_i64, c_i64, c_vp,
                         c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
+    "pf_estep_multi_plan": [c_int, c_int, c_int, c_i64, ctypes.POINTER(c_i64), c_ip,
+                            ctypes.POINTER(c_i64)],
+    "pf_estep_multi": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_int, c_vp, c_int, c_i64, c_i64, c_vp,
+                       c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
+    "pf_wiener_multi": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_int, c_vp, c_ip, c_int, c_int, c_i64,
+                        c_i64, c_vp, c_vp, c_i64, c_int, c_vp],
     "pf_mix_inst_stats": [c_vp, c_vp, c_vp, c_ip, c_int, c_ip, c_int, c_int, c_int, c_int, c_vp,
                           c_vp],
     "pf_mix_inst_solve": [c_vp, c_dbl, c_ip, c_int, c_int, c_int, c_vp, c_vp, c_vp],
@@ -243,6 +249,33 @@ class CudaKernels(object):
                                         self._p(Rxs), self._p(ll_f), self._p(workspace),
                                         workspace.numel() * workspace.element_size(),
                                         int(N_norm), code, self._stream()), self.lib)
+
+    # -- K2 / K6 for I = 2..4 channels (X: [2 I, F, ld], A: [R, I, F], Rxs: [F, I, R]) --------
+    def estep_multi_workspace_bytes(self, I, J, F, N):
+        chunk, nsplit, nbytes = c_i64(), c_int(), c_i64()
+        _check(self.lib.pf_estep_multi_plan(I, J, F, N, ctypes.byref(chunk), ctypes.byref(nsplit),
+                                            ctypes.byref(nbytes)), self.lib)
+        return nbytes.value
+
+    def estep_multi(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace,
+                    N_norm=0):
+        J, F, ld = V.shape
+        R, I = A.shape[0], A.shape[1]
+        assert X.shape[0] == 2 * I
+        _check(self.lib.pf_estep_multi(self._p(X), self._p(V), self._p(A), _iarr(src_of_sub), R, J,
+                                       I, self._p(noise), F, N, ld, self._p(hatW), self._p(Rss),
+                                       self._p(Rxs), self._p(ll_f), self._p(workspace),
+                                       workspace.numel() * workspace.element_size(), int(N_norm),
+                                       self.dtype_code(V), self._stream()), self.lib)
+
+    def wiener_multi(self, X, V, A, src_of_sub, noise, group_of_src, ngroups, N, Y, workspace):
+        J, F, ld = V.shape
+        R, I = A.shape[0], A.shape[1]
+        _check(self.lib.pf_wiener_multi(self._p(X), self._p(V), self._p(A), _iarr(src_of_sub), R, J,
+                                        I, self._p(noise), _iarr(group_of_src), ngroups, F, N, ld,
+                                        self._p(Y), self._p(workspace),
+                                        workspace.numel() * workspace.element_size(),
+                                        self.dtype_code(V), self._stream()), self.lib)
 
     # -- K3 ---------------------------------------------------------------------------
     def mix_inst_stats(self, Rss, Rxs, A, upd, oth, stats):

@@ -167,7 +167,9 @@ class FASST(object):
                     self._comm.allreduce_max(peak)
                 aobj._maxdata = np.maximum(1.1 * float(peak.item()), 1e-10)
             div = float(aobj._maxdata)
-        if nc != 2:
+        if nc < 2 or nc > 4:
+            # the reference accepts stereo only (audioModel.py:394, :605); 3 and 4 channels are
+            # an extension of this package (general-I kernels, csrc/estep_multi.cu)
             raise AttributeError("Nb channels " + str(nc) + " not implemented yet")
         F = nfft // 2 + 1
         psd = torch.zeros(F, dtype=torch.float64, device=k.device)
@@ -343,7 +345,8 @@ class FASST(object):
         """int16 [nbSources, L, 2]: the separated signals of `separate_comps` before they are
         written (device: Wiener filter K6 + inverse STFT with overlap-add)."""
         import torch
-        if self.audioObject.channels != 2:
+        nc = self.audioObject.channels
+        if nc < 2 or nc > 4:
             raise NotImplementedError()
         if spec_comp_ind is None:
             spec_comp_ind = {s: [s] for s in range(len(self.spec_comps))}
@@ -373,9 +376,9 @@ class FASST(object):
         hop, nfft = self.sig_repr_params['hopsize'], self.sig_repr_params['fsize']
         _, pcm = _stft.istft_planes(self._k(), Y, self.nbFramesSigRepr, self.tft.synthWindow,
                                     self.tft.window, hop, nfft, length=L, maxdata=maxdata)
-        # pcm: [L, 2*nbSources] with signal index = 2*source + channel
+        # pcm: [L, nc*nbSources] with signal index = nc*source + channel
         return np.ascontiguousarray(
-            pcm.cpu().numpy().reshape(L, nbSources, 2).transpose(1, 0, 2))
+            pcm.cpu().numpy().reshape(L, nbSources, nc).transpose(1, 0, 2))
 
 
 class MultiChanNMFInst_FASST(FASST):

@@ -16,7 +16,8 @@
 // At I = 4, J = 4 that is 293 accumulators per frequency -- too many for registers.  Each thread
 // therefore writes its bin's factors (v_j v_k, M, v_j, x y^H) to a shared-memory record, and the
 // warp accumulates the outer products cooperatively: lane l owns the accumulators l, l+32, ...
-// and walks the 32 records of the warp (2 shared loads + 1 FMA per accumulator and bin).
+// and walks the 32 records of the warp (2 shared loads + 1 FMA per accumulator and bin), in
+// float64.
 #include "common.cuh"
 
 namespace pf {
@@ -196,7 +197,11 @@ __device__ __forceinline__ void sigma_inverse_multi(const double (&v)[J], const 
   }
 }
 
-// ---- record of one bin in shared memory (type T) ---------------------------------------------------
+// ---- record of one bin in shared memory (float64 whatever the plane type) ----------------------------
+// The moment factors are kept and accumulated in float64: with R < I sub-sources, or in the
+// regime of the determinant clamp, M = y y^H - Sigma^-1 has entries ~ |x|^2 / s2^2 that cancel by
+// many orders of magnitude once contracted with the mixing vectors, and at ~500 FP64 operations
+// of per-bin algebra the 292 extra DFMAs per bin (spread over 32 lanes) do not show.
 //   [ pr (NP, padded to a multiple of 4) | M (I^2: diag, lower (re, im)) | v (J padded to 4) |
 //     U = x y^H (2 I^2: [a][b](re, im)) | 1 ]
 template <int I, int J>
@@ -209,8 +214,8 @@ struct Rec {
   static constexpr int U0 = V0 + (J + 3) / 4 * 4;
   static constexpr int ONE = U0 + NU;
   static constexpr int USED = ONE + 1;
-  // stride = 4 (mod 32) words: the 128-bit stores of 8 consecutive lanes hit disjoint banks
-  static constexpr int STRIDE = (USED + 31) / 32 * 32 + 4;
+  // stride = 5 (mod 16) doubles: the 64-bit accesses of a half warp hit disjoint banks
+  static constexpr int STRIDE = (USED + 15) / 16 * 16 + 5;
   static constexpr int NOUT = NP * NM + J * NU + J;  // accumulators (without ll)
   static constexpr int PER_LANE = (NOUT + 31) / 32;
 };
@@ -226,22 +231,22 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
   extern __shared__ __align__(16) unsigned char em_smem[];
   double* s_coef = reinterpret_cast<double*>(em_smem);                  // [J][NM]
   double* s_red = s_coef + J * NM;                                      // [warps][NA]
-  T* s_rec = reinterpret_cast<T*>(s_red + (EM_THREADS / 32) * NA);      // [warps][32][STRIDE]
+  double* s_rec = s_red + (EM_THREADS / 32) * NA;                       // [warps][32][STRIDE]
   const int f = blockIdx.y, split = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < J * NM; i += EM_THREADS) s_coef[i] = coef[(size_t)f * J * NM + i];
   __syncthreads();
   const double s2 = noise[f];
-  T* rec = s_rec + ((size_t)warp * 32 + lane) * RC::STRIDE;   // this thread's record
-  const T* wrec = s_rec + (size_t)warp * 32 * RC::STRIDE;     // the warp's 32 records
+  double* rec = s_rec + ((size_t)warp * 32 + lane) * RC::STRIDE;  // this thread's record
+  const double* wrec = s_rec + (size_t)warp * 32 * RC::STRIDE;    // the warp's 32 records
 
   // the accumulators this lane owns: o = lane + 32 m  ->  (offset of factor a, offset of factor b)
   int offa[RC::PER_LANE], offb[RC::PER_LANE];
-  T acc[RC::PER_LANE];
+  double acc[RC::PER_LANE];
 #pragma unroll
   for (int m = 0; m < RC::PER_LANE; ++m) {
     const int o = lane + 32 * m;
-    acc[m] = (T)0;
+    acc[m] = 0.0;
     if (o < RC::NP * NM) {
       offa[m] = RC::PR0 + o / NM;
       offb[m] = RC::M0 + o % NM;
@@ -311,31 +316,31 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
 #pragma unroll
       for (int j = 0; j < J; ++j)
 #pragma unroll
-        for (int k = j; k < J; ++k) rec[RC::PR0 + p++] = (T)(v[j] * v[k]);
+        for (int k = j; k < J; ++k) rec[RC::PR0 + p++] = v[j] * v[k];
 #pragma unroll
-      for (int i = 0; i < I; ++i) rec[RC::M0 + i] = (T)md[i];
+      for (int i = 0; i < I; ++i) rec[RC::M0 + i] = md[i];
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        rec[RC::M0 + I + 2 * t] = (T)mo[t].x;
-        rec[RC::M0 + I + 2 * t + 1] = (T)mo[t].y;
+        rec[RC::M0 + I + 2 * t] = mo[t].x;
+        rec[RC::M0 + I + 2 * t + 1] = mo[t].y;
       }
 #pragma unroll
-      for (int j = 0; j < J; ++j) rec[RC::V0 + j] = (T)v[j];
+      for (int j = 0; j < J; ++j) rec[RC::V0 + j] = v[j];
 #pragma unroll
       for (int a = 0; a < I; ++a)
 #pragma unroll
         for (int b = 0; b < I; ++b) {
           const double2 u = cmulc(x[a], y[b]);
-          rec[RC::U0 + 2 * (a * I + b)] = (T)u.x;
-          rec[RC::U0 + 2 * (a * I + b) + 1] = (T)u.y;
+          rec[RC::U0 + 2 * (a * I + b)] = u.x;
+          rec[RC::U0 + 2 * (a * I + b) + 1] = u.y;
         }
-      rec[RC::ONE] = (T)1;
+      rec[RC::ONE] = 1.0;
     }
     __syncwarp();
     // cooperative accumulation of the warp's 32 records
 #pragma unroll 4
     for (int b = 0; b < 32; ++b) {
-      const T* rb = wrec + (size_t)b * RC::STRIDE;
+      const double* rb = wrec + (size_t)b * RC::STRIDE;
 #pragma unroll
       for (int m = 0; m < RC::PER_LANE; ++m) acc[m] += rb[offa[m]] * rb[offb[m]];
     }
@@ -345,7 +350,7 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
 #pragma unroll
   for (int m = 0; m < RC::PER_LANE; ++m) {
     const int o = lane + 32 * m;
-    if (o < RC::NOUT) s_red[warp * NA + o] = (double)acc[m];
+    if (o < RC::NOUT) s_red[warp * NA + o] = acc[m];
   }
   {
     const double d = warp_sum(acc_ll);
@@ -491,8 +496,8 @@ wiener_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
 
 template <typename T, int I, int J>
 static size_t em_smem_bytes() {
-  return sizeof(double) * (J * I * I + (EM_THREADS / 32) * em_nacc(I, J)) +
-         sizeof(T) * (size_t)EM_THREADS * Rec<I, J>::STRIDE;
+  return sizeof(double) * (J * I * I + (EM_THREADS / 32) * em_nacc(I, J) +
+                           (size_t)EM_THREADS * Rec<I, J>::STRIDE);
 }
 
 template <typename T, int I, int J>

@@ -98,6 +98,7 @@ class GemEngine(object):
         if self.F <= 0 or self.N <= 0:
             raise ValueError("empty shard f=%r n=%r" % (f_range, n_range))
         self.X = None
+        self.I = 2  # channels; set_X_planes / set_X_host update it (3 and 4: general-I kernels)
         self.J = 0
         self.n_iter_done = 0
         # The spectral components are independent of one another inside each phase of the
@@ -162,17 +163,22 @@ class GemEngine(object):
 
     # ------------------------------------------------------------------ inputs
     def set_X_planes(self, X):
-        """X: device planes [4, F_local, ld] (re0, im0, re1, im1) of dtype self.tdtype."""
-        assert tuple(X.shape) == (4, self.F, self.ld) and X.dtype == self.tdtype
+        """X: device planes [2 I, F_local, ld] (re, im per channel) of dtype self.tdtype.
+        I = 2 is the reference's case; I = 3, 4 run the general-I kernels (an extension: the
+        reference raises for them, audioModel.py:394, :605)."""
+        assert X.dim() == 3 and tuple(X.shape[1:]) == (self.F, self.ld) and X.dtype == self.tdtype
+        assert X.shape[0] in (4, 6, 8), "2..4 channels"
         self.X = X
+        self.I = X.shape[0] // 2
 
     def set_X_host(self, Xc):
-        """Xc: complex [2, F_total, N_total] host array (e.g. an STFT computed elsewhere)."""
+        """Xc: complex [I, F_total, N_total] host array (e.g. an STFT computed elsewhere)."""
         Xc = np.asarray(Xc)[:, self.f_lo:self.f_hi, self.n_lo:self.n_hi]
-        planes = np.zeros([4, self.F, self.ld])
-        planes[0, :, :self.N], planes[1, :, :self.N] = Xc[0].real, Xc[0].imag
-        planes[2, :, :self.N], planes[3, :, :self.N] = Xc[1].real, Xc[1].imag
-        self.X = self._upload(planes, self.tdtype)
+        nch = Xc.shape[0]
+        planes = np.zeros([2 * nch, self.F, self.ld])
+        for c in range(nch):
+            planes[2 * c, :, :self.N], planes[2 * c + 1, :, :self.N] = Xc[c].real, Xc[c].imag
+        self.set_X_planes(self._upload(planes, self.tdtype))
 
     def set_noise(self, sim_ann_opt, lim0, lim1, psd):
         """Mirrors the noise handling of estim_param_a_post_model (audioModel.py:355-373)."""
@@ -213,20 +219,22 @@ class GemEngine(object):
             p = np.asarray(spat_comps[j]["params"])
             r = p.shape[1] if mix_types[j] == "inst" else p.shape[0]
             nc = p.shape[0] if mix_types[j] == "inst" else p.shape[1]
-            if nc != 2:
-                raise AttributeError("Nb channels %d not implemented yet" % nc)
+            if nc != self.I:
+                raise AttributeError("Nb channels %d not implemented yet" % nc
+                                     if nc not in (2, 3, 4) else
+                                     "mixing parameters for %d channels, signal has %d" % (nc, self.I))
             start = len(self.src_of_sub)
             self.ranks.append(list(range(start, start + r)))
             self.src_of_sub.extend([j] * r)
         R = len(self.src_of_sub)
-        A = np.zeros([R, 2, self.F], dtype=np.complex128)
+        A = np.zeros([R, self.I, self.F], dtype=np.complex128)
         for j in range(J):
             p = np.asarray(spat_comps[j]["params"])
             if mix_types[j] == "inst":
                 A[self.ranks[j]] = p.T[:, :, None]
             else:
                 if p.shape[2] != self.F_total:
-                    raise ValueError("convolutive params must be [rank, 2, F]")
+                    raise ValueError("convolutive params must be [rank, channels, F]")
                 A[self.ranks[j]] = p[:, :, self.f_lo:self.f_hi]
         self.J, self.R = J, R
         self.A = self._upload(A)
@@ -291,20 +299,24 @@ class GemEngine(object):
         self.hatW = self._zeros([J, F, ld])
         # hat_Rss, hat_Rxs and the per-frequency log-likelihood sums share one buffer so that
         # the time-sharded mode reduces them with a single all-reduce
-        self.estat = self._zeros([F * (2 * R * R + 4 * R + 1)], f64)
-        o1, o2 = 2 * F * R * R, 2 * F * R * R + 4 * F * R
+        I = self.I
+        self.estat = self._zeros([F * (2 * R * R + 2 * I * R + 1)], f64)
+        o1, o2 = 2 * F * R * R, 2 * F * R * R + 2 * I * F * R
         self.Rss = torch.view_as_complex(self.estat[:o1].view(F, R, R, 2))
-        self.Rxs = torch.view_as_complex(self.estat[o1:o2].view(F, 2, R, 2))
+        self.Rxs = torch.view_as_complex(self.estat[o1:o2].view(F, I, R, 2))
         self.ll_f = self.estat[o2:]
         self.ll_sum = self._zeros([1], f64)
         self.flags = self._zeros([1], torch.int32)
         self.iter_dev = self._zeros([1], torch.int32)
         code = k.dtype_code(self.V)
-        nbytes = k.estep_workspace_bytes(J, F, N, code)
+        # the stereo kernels for I = 2 (PYFASST_FORCE_MULTI=1: the general-I ones, for tests)
+        self.multi = I != 2 or os.environ.get("PYFASST_FORCE_MULTI") == "1"
+        nbytes = k.estep_multi_workspace_bytes(I, J, F, N) if self.multi else \
+            k.estep_workspace_bytes(J, F, N, code)
         self.ws = self._zeros([(nbytes + 7) // 8], f64)
-        self.stats = self._zeros([2 * R + R * R], f64)
+        self.stats = self._zeros([I * R + R * R], f64)
         self.sums = self._zeros([J], f64)
-        counts = np.array([len(self.ranks[j]) * 2 * self.F_total for j in range(J)], dtype=np.float64)
+        counts = np.array([len(self.ranks[j]) * I * self.F_total for j in range(J)], dtype=np.float64)
         self.counts = self._f64(counts)
         Kmax = max(max(e["Kb"], e["Kw"]) for e in self.spec)
         S = len(self.spec)
@@ -347,8 +359,9 @@ class GemEngine(object):
 
     def estep(self):
         """compute_suff_stat (audioModel.py:580-764) on the current parameters."""
-        self.k.estep_stereo(self.X, self.V, self.A, self.src_of_sub, self.noise, self.N,
-                            self.hatW, self.Rss, self.Rxs, self.ll_f, self.ws, self.N_total)
+        estep = self.k.estep_multi if self.multi else self.k.estep_stereo
+        estep(self.X, self.V, self.A, self.src_of_sub, self.noise, self.N, self.hatW, self.Rss,
+              self.Rxs, self.ll_f, self.ws, self.N_total)
         if self._tshard():  # means over all frames: sum the ranks' partial statistics
             self.comm.allreduce_sum(self.estat)
 
@@ -360,7 +373,7 @@ class GemEngine(object):
         if self.mix_type == "inst":
             upd = [r for j in range(self.J) if self.free_A[j] for r in self.ranks[j]]
             oth = [r for j in range(self.J) if not self.free_A[j] for r in self.ranks[j]]
-            n = 2 * len(upd) + len(upd) ** 2
+            n = self.I * len(upd) + len(upd) ** 2
             stats = self.stats[:n]
             k.mix_inst_stats(self.Rss, self.Rxs, self.A, upd, oth, stats)
             if self._fshard():
@@ -579,11 +592,12 @@ class GemEngine(object):
         return self._gather_f(self.noise, 0)
 
     def wiener(self, group_of_src, ngroups):
-        """Wiener-filtered STFTs Y[g] = Sigma_g Sigma_x^-1 x as planes [ngroups*4, F, ld]
+        """Wiener-filtered STFTs Y[g] = Sigma_g Sigma_x^-1 x as planes [ngroups * 2 I, F, ld]
         (compute_sigma_comp_2d / compute_inv_sigma_mix_2d / compute_Wiener_gain_2d,
         audioModel.py:1327-1467, with the last iteration's noise PSD, :1385)."""
         self.compute_powers(with_G=False)
-        Y = self._zeros([ngroups * 4, self.F, self.ld])
-        self.k.wiener_stereo(self.X, self.V, self.A, self.src_of_sub, self.noise, group_of_src,
-                             ngroups, self.N, Y, self.ws)
+        Y = self._zeros([ngroups * 2 * self.I, self.F, self.ld])
+        wiener = self.k.wiener_multi if self.multi else self.k.wiener_stereo
+        wiener(self.X, self.V, self.A, self.src_of_sub, self.noise, group_of_src, ngroups, self.N,
+               Y, self.ws)
         return Y

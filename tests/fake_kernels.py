@@ -145,6 +145,84 @@ class FakeKernels(object):
             Yn[4 * g + 2, :, :N] = g01r * y0r + g01i * y0i + g11 * y1r
             Yn[4 * g + 3, :, :N] = g01r * y0i - g01i * y0r + g11 * y1i
 
+    # ---- K2 / K6 for I = 2..4 channels ---------------------------------------------------
+    def _multi_core(self, X, V, A, src_of_sub, noise, N):
+        """Sigma^-1 (clamped, Q5 on the generic determinant) and y = Sigma^-1 x in float64."""
+        Xn = _np(X)[:, :, :N].astype(np.float64)
+        I = Xn.shape[0] // 2
+        x = np.transpose(Xn[0::2] + 1j * Xn[1::2], (1, 2, 0))       # [F, N, I]
+        Vn = _np(V)[:, :, :N].astype(np.float64)                    # [J, F, N]
+        J = Vn.shape[0]
+        An = _np(A)                                                  # [R, I, F]
+        Rj = np.zeros([J, An.shape[2], I, I], dtype=complex)
+        for r, j in enumerate(src_of_sub):
+            a = An[r].T                                              # [F, I]
+            Rj[j] += a[:, :, None] * np.conj(a[:, None, :])
+        Sig = np.einsum("jfn,jfab->fnab", Vn, Rj) + \
+            _np(noise)[:, None, None, None] * np.eye(I)[None, None]
+        det = np.real(np.linalg.det(Sig))
+        detc = np.maximum(det, EPS)
+        Sinv = np.linalg.inv(Sig) * (det / detc)[..., None, None]
+        y = np.einsum("fnab,fnb->fna", Sinv, x)
+        return x, Vn, Rj, Sinv, y, detc
+
+    def estep_multi_workspace_bytes(self, I, J, F, N):
+        return 64
+
+    def estep_multi(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace,
+                    N_norm=0):
+        self.launches += 3
+        Nn = N_norm if N_norm > 0 else N
+        x, Vn, Rj, Sinv, y, detc = self._multi_core(X, V, A, src_of_sub, noise, N)
+        J, F = Vn.shape[0], Vn.shape[1]
+        R = A.shape[0]
+        quad = np.real(np.sum(np.conj(x) * y, axis=2))
+        _np(ll_f)[:] = (np.log(detc) + np.log(np.pi) + quad).sum(1)
+        M = y[..., :, None] * np.conj(y[..., None, :]) - Sinv        # [F, N, I, I]
+        count = np.bincount(src_of_sub, minlength=J)
+        hw = _np(hatW)
+        hw[:] = 0
+        for j in range(J):
+            q = np.real(np.einsum("fnab,fba->fn", M, Rj[j]))
+            hw[j, :, :N] = np.abs(Vn[j] + Vn[j] * Vn[j] * q / count[j])
+        # moments: factors and sums in float64 whatever the plane type (the general-I kernel
+        # keeps its shared-memory records in float64)
+        U = x[..., :, None] * np.conj(y[..., None, :])
+        S = {}
+        for j in range(J):
+            for k in range(j, J):
+                S[j, k] = S[k, j] = np.einsum("fn,fnab->fab", Vn[j] * Vn[k], M)
+        T = [np.einsum("fn,fnab->fab", Vn[j], U) for j in range(J)]
+        sv = Vn.sum(2)
+        An = _np(A)
+        hRss, hRxs = _np(Rss), _np(Rxs)
+        for r1 in range(R):
+            j1 = src_of_sub[r1]
+            a1 = An[r1].T                                            # [F, I]
+            hRxs[:, :, r1] = np.einsum("fab,fb->fa", T[j1], a1) / Nn
+            for r2 in range(r1, R):
+                j2 = src_of_sub[r2]
+                a2 = An[r2].T
+                h = np.einsum("fa,fab,fb->f", np.conj(a1), S[j1, j2], a2) / Nn
+                if r1 == r2:
+                    h = np.real(h) + sv[j1] / Nn
+                hRss[:, r1, r2] = h
+                hRss[:, r2, r1] = np.conj(h)
+
+    def wiener_multi(self, X, V, A, src_of_sub, noise, group_of_src, ngroups, N, Y, workspace):
+        self.launches += 2
+        x, Vn, Rj, Sinv, y, detc = self._multi_core(X, V, A, src_of_sub, noise, N)
+        I = x.shape[2]
+        Yn = _np(Y)
+        Yn[:] = 0
+        for g in range(ngroups):
+            Sg = sum(np.einsum("fn,fab->fnab", Vn[j], Rj[j]) for j in range(Vn.shape[0])
+                     if group_of_src[j] == g)
+            out = np.einsum("fnab,fnb->fna", Sg, y)                  # [F, N, I]
+            for i in range(I):
+                Yn[2 * I * g + 2 * i, :, :N] = out[..., i].real
+                Yn[2 * I * g + 2 * i + 1, :, :N] = out[..., i].imag
+
     # ---- K2 ---------------------------------------------------------------------------
     def estep_workspace_bytes(self, J, F, N, dtype_code):
         return 64
@@ -211,7 +289,7 @@ class FakeKernels(object):
         if len(oth):
             for f in range(F):
                 rxs[f] -= np.dot(An[oth, :, f].T, hRss[f][np.ix_(oth, upd)])
-        rxs = np.real(rxs.sum(0))  # [2, Ku]
+        rxs = np.real(rxs.sum(0))  # [I, Ku]
         rss = np.real(hRss[:, np.vstack(upd), upd].sum(0))  # [Ku, Ku]
         _np(stats)[:] = np.concatenate([rxs.ravel(), rss.ravel()])
 
@@ -219,8 +297,9 @@ class FakeKernels(object):
         self.launches += 1
         st = _np(stats)
         Ku = len(upd)
-        rxs = st[:2 * Ku].reshape(2, Ku) / F_total
-        rss = st[2 * Ku:].reshape(Ku, Ku) / F_total
+        I = _np(A).shape[1]
+        rxs = st[:I * Ku].reshape(I, Ku) / F_total
+        rss = st[I * Ku:I * Ku + Ku * Ku].reshape(Ku, Ku) / F_total
         try:
             sol = np.linalg.solve(rss.T, rxs.T)
         except np.linalg.LinAlgError:
