@@ -50,13 +50,14 @@ UNIT = "TF-bins*iters/s"
 
 
 # --------------------------------------------------------------------------- workload
-def synth_mix(duration_s, seed=1234, fs=FS, nsrc=NSRC):
-    """Stereo int16 mixture: AR(2)-coloured Gaussian sources with random on/off
-    envelopes, instantaneous mixing, white noise at -40 dB."""
+def synth_mix(duration_s, seed=1234, fs=FS, nsrc=NSRC, channels=2):
+    """int16 mixture: AR(2)-coloured Gaussian sources with random on/off envelopes, white noise
+    at -40 dB.  Stereo: instantaneous mixing; more channels (configs[3]): every
+    source reaches every channel through its own random 64-tap FIR filter."""
     import scipy.signal as sps
     rng = np.random.default_rng(seed)
     L = int(round(duration_s * fs))
-    mix = np.zeros((L, 2))
+    mix = np.zeros((L, channels))
     for j in range(nsrc):
         r, th = 0.97 - 0.02 * j, np.pi * (0.05 + 0.11 * j)
         s = sps.lfilter([1.0], [1.0, -2 * r * np.cos(th), r * r], rng.standard_normal(L))
@@ -68,9 +69,14 @@ def synth_mix(duration_s, seed=1234, fs=FS, nsrc=NSRC):
         if env.size < L:
             env = np.pad(env, (0, L - env.size))
         s = s * env / (np.abs(s).max() + 1e-12)
-        ang = (j + 1) * np.pi / (2.0 * (nsrc + 1))
-        mix[:, 0] += np.sin(ang) * s
-        mix[:, 1] += np.cos(ang) * s
+        if channels == 2:
+            ang = (j + 1) * np.pi / (2.0 * (nsrc + 1))
+            mix[:, 0] += np.sin(ang) * s
+            mix[:, 1] += np.cos(ang) * s
+        else:
+            for c in range(channels):
+                h = rng.standard_normal(64) * np.exp(-np.arange(64) / 12.0)
+                mix[:, c] += sps.fftconvolve(s, h)[:L]
     mix += 10 ** (-40 / 20.0) * np.abs(mix).max() * rng.standard_normal(mix.shape)
     mix = 0.9 * mix / np.abs(mix).max()
     return np.int16(np.round(mix * 32767))
@@ -196,12 +202,16 @@ def workload_config(args, note=None):
     model = "MultiChanNMFConv (convolutive mixing)" if getattr(args, "model", "inst") == "conv" \
         else "MultiChanNMFInst_FASST"
     shard = getattr(args, "shard", "time")
-    cfg = {"workload": "configs[1]: synthetic %.0f-s stereo 44.1 kHz mix per GPU (x%d GPUs = %.0f s, "
+    nch, rank = getattr(args, "channels", 2), getattr(args, "rank", RANK)
+    cfg = {"workload": "%s: synthetic %.0f-s %s 44.1 kHz mix per GPU (x%d GPUs = %.0f s, "
                        "weak scaling), %s %d sources x K=%d, spatial rank %d, "
-                       "STFT %d/hop %d" % (args.duration_s, args.gpus, args.duration_s * args.gpus,
-                                           model, NSRC, NNMF, RANK, WLEN, HOP),
+                       "STFT %d/hop %d" % ("configs[1]" if nch == 2 else "configs[3]-like",
+                                           args.duration_s, "stereo" if nch == 2 else "%d-channel" % nch,
+                                           args.gpus, args.duration_s * args.gpus,
+                                           model, NSRC, NNMF, rank, WLEN, HOP),
+           "channels": nch,
            "F": WLEN // 2 + 1, "N": n_frames(L), "tf_bins": (WLEN // 2 + 1) * n_frames(L),
-           "sources": NSRC, "nmf_comps": NNMF, "spatial_rank": RANK,
+           "sources": NSRC, "nmf_comps": NNMF, "spatial_rank": rank,
            "sharding": ("frames over %d GPU(s); all-reduce of the per-frequency E-step statistics "
                         "and of the FB numerators/denominators (NCCL)" % args.gpus)
            if shard == "time" else
@@ -234,7 +244,7 @@ def run_ours(args, rank, world):
 
     # N = 1: the 10-min mixture of configs[1].  N > 1: weak scaling -- the mixture is N such
     # blocks back to back (one per GPU) and its frames are sharded over the ranks.
-    block = synth_mix(args.duration_s)
+    block = synth_mix(args.duration_s, channels=args.channels)
     pcm = block if world == 1 else np.ascontiguousarray(np.tile(block, (world, 1)))
     L = pcm.shape[0]
     F, N = WLEN // 2 + 1, n_frames(L)
@@ -252,7 +262,7 @@ def run_ours(args, rank, world):
         np.random.seed(0)
         cls = am.MultiChanNMFConv if args.model == "conv" else am.MultiChanNMFInst_FASST
         m = cls(audio=make_audio(pcm if raw is None else raw), nbComps=NSRC, nbNMFComps=NNMF,
-                spatial_rank=RANK, wlen=WLEN, hopsize=HOP, iter_num=iters,
+                spatial_rank=args.rank, wlen=WLEN, hopsize=HOP, iter_num=iters,
                 ann_PSD_lim=[None, None], compute_dtype=dtype, comm=comm, shard=args.shard)
         if args.model == "conv":
             m.makeItConvolutive()
@@ -359,13 +369,17 @@ def run_ours(args, rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     sz = 4 if args.dtype == "f32" else 8
-    bytes_per_bin = sz * (4 + 2 * NSRC)  # I^2 reals of x (=Cx, rank one) + V_j + hat_W_j
+    # 2 I reals of x (Cx = x x^H is rank one; = I^2 at I = 2) + V_j + hat_W_j
+    bytes_per_bin = sz * (2 * args.channels + 2 * NSRC)
     local_bins = bins / float(world)  # frames are split evenly over the ranks
     achieved = bytes_per_bin * local_bins / (estep_ms * 1e-3) / 1e9
     traffic = args.traffic
-    if traffic is None and world == 1 and args.dtype == "f32" and args.duration_s == 600.0:
+    if traffic is None and world == 1 and args.dtype == "f32" and args.duration_s == 600.0 \
+            and args.channels == 2 and args.rank == RANK:
         traffic = ESTEP_DRAM_BYTES_PER_LAUNCH  # same workload as the committed capture
-    roofline = {"bound": "hbm", "kernel": "estep_stereo_kernel", "achieved": achieved,
+    roofline = {"bound": "hbm",
+                "kernel": "estep_stereo_kernel" if args.channels == 2 else "estep_multi_kernel",
+                "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "bytes_per_bin": bytes_per_bin, "ms_per_launch": estep_ms,
@@ -374,7 +388,7 @@ def run_ours(args, rank, world):
 
     # ---- CPU baseline: the oracle on a bounded crop -----------------------------------------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.channels == 2:
         rate, cbins, cdt = cpu_gem_rate(args.cpu_crop_s, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": "1 GEM iteration of the oracle (NumPy float64 restatement of the "
@@ -407,6 +421,10 @@ def main():
     ap.add_argument("--model", default="inst", choices=["inst", "conv"],
                     help="inst: MultiChanNMFInst_FASST (configs[1], default); conv: "
                          "MultiChanNMFConv + makeItConvolutive (the model of configs[3])")
+    ap.add_argument("--channels", type=int, default=2, choices=[2, 3, 4],
+                    help="channels of the synthetic mixture (default 2 = configs[1]; 4 with "
+                         "--model conv --rank 4 = the model of configs[3]; the CPU arms are stereo)")
+    ap.add_argument("--rank", type=int, default=RANK, help="spatial rank of every source")
     ap.add_argument("--shard", default="time", choices=["time", "freq"],
                     help="multi-GPU partition: frames (default) or frequency bins")
     ap.add_argument("--traffic", type=float, default=None,

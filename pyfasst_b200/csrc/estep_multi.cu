@@ -23,6 +23,9 @@
 namespace pf {
 
 constexpr int EM_THREADS = 128;
+#ifndef EM_MINB
+#define EM_MINB 2
+#endif
 constexpr int EM_MAXJ = 6;
 constexpr int EM_MAXR = 24;
 constexpr int EM_MAXI = 4;
@@ -221,7 +224,7 @@ struct Rec {
 };
 
 template <typename T, int I, int J>
-__global__ void __launch_bounds__(EM_THREADS)
+__global__ void __launch_bounds__(EM_THREADS, EM_MINB)
 estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
                    const double* __restrict__ coef, const double* __restrict__ noise, MultiMap map,
                    T* __restrict__ hatW, double* __restrict__ partial, int F, long N, long ld,
@@ -241,27 +244,28 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
   const double* wrec = s_rec + (size_t)warp * 32 * RC::STRIDE;    // the warp's 32 records
 
   // the accumulators this lane owns: o = lane + 32 m  ->  (offset of factor a, offset of factor b)
-  int offa[RC::PER_LANE], offb[RC::PER_LANE];
-  double acc[RC::PER_LANE];
-#pragma unroll
-  for (int m = 0; m < RC::PER_LANE; ++m) {
+  // of the record; recomputed for every pass (a few integer operations per 32 bins) so that they
+  // do not occupy registers during the per-bin algebra
+  auto offsets = [&](int m, int& oa, int& ob) {
     const int o = lane + 32 * m;
-    acc[m] = 0.0;
     if (o < RC::NP * NM) {
-      offa[m] = RC::PR0 + o / NM;
-      offb[m] = RC::M0 + o % NM;
+      oa = RC::PR0 + o / NM;
+      ob = RC::M0 + o % NM;
     } else if (o < RC::NP * NM + J * RC::NU) {
       const int q = o - RC::NP * NM;
-      offa[m] = RC::V0 + q / RC::NU;
-      offb[m] = RC::U0 + q % RC::NU;
+      oa = RC::V0 + q / RC::NU;
+      ob = RC::U0 + q % RC::NU;
     } else if (o < RC::NOUT) {
-      offa[m] = RC::V0 + (o - RC::NP * NM - J * RC::NU);
-      offb[m] = RC::ONE;
-    } else {  // beyond the last accumulator: 0 * 1
-      offa[m] = RC::ONE;
-      offb[m] = RC::ONE;
+      oa = RC::V0 + (o - RC::NP * NM - J * RC::NU);
+      ob = RC::ONE;
+    } else {  // beyond the last accumulator: 1 * 1, never stored
+      oa = RC::ONE;
+      ob = RC::ONE;
     }
-  }
+  };
+  double acc[RC::PER_LANE];
+#pragma unroll
+  for (int m = 0; m < RC::PER_LANE; ++m) acc[m] = 0.0;
   double acc_ll = 0.0;
 
   const long plane = (long)F * ld, row = (long)f * ld;
@@ -338,11 +342,16 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
     }
     __syncwarp();
     // cooperative accumulation of the warp's 32 records
-#pragma unroll 4
-    for (int b = 0; b < 32; ++b) {
-      const double* rb = wrec + (size_t)b * RC::STRIDE;
+    {
+      int offa[RC::PER_LANE], offb[RC::PER_LANE];
 #pragma unroll
-      for (int m = 0; m < RC::PER_LANE; ++m) acc[m] += rb[offa[m]] * rb[offb[m]];
+      for (int m = 0; m < RC::PER_LANE; ++m) offsets(m, offa[m], offb[m]);
+#pragma unroll 4
+      for (int b = 0; b < 32; ++b) {
+        const double* rb = wrec + (size_t)b * RC::STRIDE;
+#pragma unroll
+        for (int m = 0; m < RC::PER_LANE; ++m) acc[m] += rb[offa[m]] * rb[offb[m]];
+      }
     }
     __syncwarp();
   }
