@@ -307,6 +307,22 @@ int pf_simm_masks(const float* SM, const float* SF0, const float* SPHI, const fl
 int pf_simm_wm_scaled(const float* WM, int ldr, int R, const float* b2, int nch, int F, float* WMs,
                       void* stream);
 
+/* ---- IS-NMF initialisers  (tools/nmf.py:24-159, audioModel.py:2091-2222; eps = 1e-10) -----------
+ * float32, layout as the SIMM kernels; the contractions are pf_gemm_tf32x3(_splitk). */
+/* out = (T | I) [F][2 ldn]: T = SX / max(hat^2, eps), I = 1 / max(hat, eps) */
+int pf_nmf_is_terms(const float* hat, const float* SX, float* out, double eps, int F, int64_t N,
+                    int64_t ldn, void* stream);
+/* H[k][n] *= C[k][n] / max(C[k][ldn + n], eps)   (C = W^T (T | I)) */
+int pf_nmf_update_rows(float* H, int64_t ldh, const float* C, int64_t ldc, int64_t ldn, double eps,
+                       int rows, int64_t N, void* stream);
+/* W *= D[0] / max(D[1], eps) (D = [2][F][ldk]: T H^T, I H^T); columns normalised to sum one
+ * (a zero sum counts as one); s_out[k] = the sums */
+int pf_nmf_w_update(float* W, int ldk, int K, const float* D, double eps, int F, float* s_out,
+                    void* stream);
+/* out[f][n] = mean_c |X_c[f][n]|^2 from STFT planes X [2 nch][F][ldx]  (audioModel.py:2150-2158) */
+int pf_mono_power(const float* X, int64_t ldx, int nch, float* out, int F, int64_t N, int64_t ldn,
+                  void* stream);
+
 /* ---- tcgen05 self-test (pins the descriptor / layout conventions of csrc/tc.cuh) ------ */
 /* D[128][N] = A B^T in tf32 (split3: 3xTF32, fp32-class accuracy).  A: a_mn ? [K][128] :
  * [128][K]; B: b_mn ? [K][N] : [N][K]; float32 device buffers; N, K multiples of 32. */

@@ -246,6 +246,28 @@ def run_lead_sep(ref):
     print("lead_sep", XR.shape, written["out_lead.wav"].shape, np.abs(written["out_lead.wav"]).max())
 
 
+def run_nmf(ref):
+    """tools/nmf.py: NMF_decomposition and NMF_decomp_init (the step before GEM)."""
+    nmf = ref["nmf"]
+    rng = np.random.default_rng(8)
+    F, N, K = 65, 120, 6
+    Wt = np.abs(rng.standard_normal((F, K))) ** 2
+    Ht = np.abs(rng.standard_normal((K, N))) ** 2
+    SX = Wt @ Ht * (1 + 0.1 * rng.standard_normal((F, N))) ** 2 + 1e-6
+    np.random.seed(12)
+    W0 = np.random.randn(F, K) ** 2          # the draws NMF_decomposition makes (nmf.py:34-35)
+    H0 = np.random.randn(K, N) ** 2
+    np.random.seed(12)
+    W1, H1 = nmf.NMF_decomposition(SX, nbComps=K, niter=5)
+    Wi = np.abs(rng.standard_normal((F, K))) + 0.1
+    Hi = np.abs(rng.standard_normal((K, N))) + 0.1
+    W2, H2 = nmf.NMF_decomp_init(SX, nbComps=K, niter=5, Winit=Wi, Hinit=Hi)
+    W3, H3 = nmf.NMF_decomp_init(SX, nbComps=K, niter=5, Winit=Wi, Hinit=Hi.T, updateW=False)
+    np.savez_compressed(os.path.join(GOLD, "nmf.npz"), SX=SX, W0=W0, H0=H0, W1=W1, H1=H1, Wi=Wi,
+                        Hi=Hi, W2=W2, H2=H2, W3=W3, H3=H3)
+    print("nmf", W1.shape, H1.shape, float(np.abs(W3 - Wi).max()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = _py2shim.load()
@@ -263,6 +285,7 @@ def main():
     run_fasst(ref, "fasst_conv_r2", wavc, conv=True, rank=2, iters=6, nbcomps=2)
     run_simm(ref)
     run_lead_sep(ref)
+    run_nmf(ref)
 
 
 if __name__ == "__main__":

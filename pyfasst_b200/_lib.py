@@ -93,6 +93,10 @@ SIGNATURES = {
     "pf_simm_power": [c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_i64, c_vp],
     "pf_simm_masks": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_int, c_int, c_i64,
                       c_i64, c_vp],
+    "pf_nmf_is_terms": [c_vp, c_vp, c_vp, c_dbl, c_int, c_i64, c_i64, c_vp],
+    "pf_nmf_update_rows": [c_vp, c_i64, c_vp, c_i64, c_i64, c_dbl, c_int, c_i64, c_vp],
+    "pf_nmf_w_update": [c_vp, c_int, c_int, c_vp, c_dbl, c_int, c_vp, c_vp],
+    "pf_mono_power": [c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_i64, c_vp],
     "pf_simm_wm_scaled": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
@@ -458,6 +462,23 @@ class CudaKernels(object):
     def simm_masks(self, SM, SF0, SPHI, a2, X, Y, eps_hat, nch, F, N, ldn):
         self._call("pf_simm_masks", self._pv(SM), self._pv(SF0), self._pv(SPHI), self._pv(a2),
                    self._pv(X), X.stride(1), self._pv(Y), float(eps_hat), nch, F, N, ldn)
+
+    # -- IS-NMF initialisers ---------------------------------------------------------------
+    def nmf_is_terms(self, hat, SX, out, eps, F, N, ldn):
+        self._call("pf_nmf_is_terms", self._pv(hat), self._pv(SX), self._pv(out), float(eps), F, N,
+                   ldn)
+
+    def nmf_update_rows(self, H, C, ldn, eps, rows, N):
+        self._call("pf_nmf_update_rows", self._pv(H), H.stride(0), self._pv(C), C.stride(0), ldn,
+                   float(eps), rows, N)
+
+    def nmf_w_update(self, W, K, D, eps, F, s_out):
+        self._call("pf_nmf_w_update", self._pv(W), W.stride(0), K, self._pv(D), float(eps), F,
+                   self._pv(s_out))
+
+    def mono_power(self, X, out, F, N, ldn):
+        self._call("pf_mono_power", self._pv(X), X.stride(1), X.shape[0] // 2, self._pv(out), F, N,
+                   ldn)
 
     def simm_wm_scaled(self, WM, R, b2, nch, F, WMs):
         self._call("pf_simm_wm_scaled", self._pv(WM), WM.stride(0), R, self._pv(b2), nch, F,

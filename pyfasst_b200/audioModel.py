@@ -306,6 +306,74 @@ class FASST(object):
         eng.check_flags()
         eng.read_model(self.spat_comps, self.spec_comps)
 
+    # ------------------------------------------------------------------ NMF initialisation
+    def _mono_power(self):
+        """Device plane [F, ldn] float32: mean over the channels of |X_c|^2, the one-channel
+        power spectrum the initialisers factorise (ref: audioModel.py:2150-2158)."""
+        import torch
+        if self._X is None:
+            self.comp_transf_Cx()
+        if self._comm is not None and self._comm.world > 1:
+            raise NotImplementedError("NMF initialisation of a sharded model")
+        k = self._k()
+        F, N = self.nbFreqsSigRepr, self.nbFramesSigRepr
+        ldn = (N + 3) // 4 * 4
+        X = self._X if self._X.dtype == torch.float32 else self._X.to(torch.float32)
+        out = torch.zeros((F, ldn), dtype=torch.float32, device=k.device)
+        k.mono_power(X, out, F, N, ldn)
+        return out
+
+    def initialize_all_spec_comps_with_NMF(self, sameInitAll=False, **kwargs):
+        """IS-NMF of the one-channel mixture as initial FB / TW of every spectral component
+        (ref: audioModel.py:2091-2116)."""
+        if sameInitAll:
+            return self.initialize_all_spec_comps_with_NMF_same(**kwargs)
+        return self.initialize_all_spec_comps_with_NMF_indiv(**kwargs)
+
+    def initialize_all_spec_comps_with_NMF_indiv(self, niter=10, updateFreqBasis=True,
+                                                 updateTimeWeight=True, **kwargs):
+        """One NMF with the stacked FB / TW of all components as initial point; every component
+        receives its slice back (ref: audioModel.py:2118-2183)."""
+        from .tools.nmf import NMF_decomp_init
+        eps = 1e-10
+        nb = [sc['factor'][0]['FB'].shape[1] for sc in self.spec_comps.values()]
+        total = int(np.sum(nb))
+        FBinit = np.zeros([self.nbFreqsSigRepr, total])
+        TWinit = np.zeros([total, self.nbFramesSigRepr])
+        for ind, sc in self.spec_comps.items():
+            lo = int(np.sum(nb[:ind]))
+            FBinit[:, lo:lo + nb[ind]] = sc['factor'][0]['FB']
+            TWinit[lo:lo + nb[ind]] = sc['factor'][0]['TW']
+        W, H = NMF_decomp_init(SX=self._mono_power(), nbComps=total, niter=niter,
+                               verbose=self.verbose, Winit=FBinit, Hinit=TWinit,
+                               updateW=updateFreqBasis, updateH=updateTimeWeight,
+                               kernels=self._k(), nframes=self.nbFramesSigRepr)
+        for ind, sc in self.spec_comps.items():
+            lo = int(np.sum(nb[:ind]))
+            if updateFreqBasis:
+                sc['factor'][0]['FB'] = np.maximum(W[:, lo:lo + nb[ind]], eps)
+            if updateTimeWeight:
+                sc['factor'][0]['TW'] = np.maximum(H[lo:lo + nb[ind]], eps)
+        self.renormalize_parameters()
+
+    def initialize_all_spec_comps_with_NMF_same(self, niter=10, **kwargs):
+        """The same W / H (most energetic components first) for every spectral component
+        (ref: audioModel.py:2185-2222)."""
+        from .tools.nmf import NMF_decomposition
+        if not np.all([len(sc['factor']) == 1 for sc in self.spec_comps.values()]):
+            raise NotImplementedError("NMF init not implemented for multi factor models.")
+        nb = [sc['factor'][0]['FB'].shape[1] for sc in self.spec_comps.values()]
+        W, H = NMF_decomposition(SX=self._mono_power(), verbose=self.verbose,
+                                 nbComps=int(np.max(nb)), niter=niter, kernels=self._k(),
+                                 nframes=self.nbFramesSigRepr)
+        order = np.argsort(H.sum(axis=1))[::-1]
+        W, H = W[:, order], H[order]
+        for sc in self.spec_comps.values():
+            ncomp = sc['factor'][0]['FB'].shape[1]
+            sc['factor'][0]['FB'][:] = W[:, :ncomp]
+            sc['factor'][0]['TW'][:] = H[:ncomp]
+        self.renormalize_parameters()
+
     # ------------------------------------------------------------------ K6
     def separate_spat_comps(self, dir_results=None, suffix=None):
         """One separated (stereo) signal per spatial component (ref: audioModel.py:1063-1086)."""

@@ -475,6 +475,81 @@ simm_masks_kernel(const float* __restrict__ SM, const float* __restrict__ SF0,
   }
 }
 
+// ---- IS-NMF initialisers (pyfasst/tools/nmf.py:24-159; eps = 1e-10 there) ------------------------------
+// out = (T | I):  T = SX / max(hat^2, eps),  I = 1 / max(hat, eps);  zero in the padding
+__global__ void __launch_bounds__(SE_THREADS)
+nmf_is_terms_kernel(const float* __restrict__ hat, const float* __restrict__ SX,
+                    float* __restrict__ out, float eps, long N, long ldn) {
+  const long f = blockIdx.y;
+  const long n0 = ((long)blockIdx.x * SE_THREADS + threadIdx.x) * 4;
+  if (n0 >= ldn) return;
+  float h[4], x[4], t[4], iv[4];
+  unpack(ld4(hat + f * ldn + n0), h);
+  unpack(ld4(SX + f * ldn + n0), x);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    t[e] = x[e] / fmaxf(h[e] * h[e], eps);
+    iv[e] = 1.0f / fmaxf(h[e], eps);
+    if (n0 + e >= N) t[e] = iv[e] = 0.f;
+  }
+  st4(out + f * 2 * ldn + n0, t);
+  st4(out + f * 2 * ldn + ldn + n0, iv);
+}
+
+// H[k][n] *= C[k][n] / max(C[k][ldn + n], eps)   (nmf.py:54-60, :151-157)
+__global__ void nmf_update_rows_kernel(float* __restrict__ H, long ldh, const float* __restrict__ C,
+                                       long ldc, long ldn, float eps, int rows, long N) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (n >= N || r >= rows) return;
+  H[(size_t)r * ldh + n] *= C[(size_t)r * ldc + n] / fmaxf(C[(size_t)r * ldc + ldn + n], eps);
+}
+
+// W[f][k] *= D[0][f][k] / max(D[1][f][k], eps); s = sum_f W[f][k] (0 -> 1); W[:, k] /= s;
+// s_out[k] = s (it scales row k of H)   (nmf.py:40-51, :133-146).  One CTA per column.
+__global__ void __launch_bounds__(SE_THREADS)
+nmf_w_update_kernel(float* __restrict__ W, int ldk, const float* __restrict__ D, float eps, int F,
+                    float* __restrict__ s_out) {
+  __shared__ double s_red[SE_THREADS / 32];
+  __shared__ float s_sum;
+  const int k = blockIdx.x;
+  const size_t plane = (size_t)F * ldk;
+  double acc = 0.0;
+  for (int f = threadIdx.x; f < F; f += SE_THREADS) {
+    const float v = W[(size_t)f * ldk + k] *
+                    (D[(size_t)f * ldk + k] / fmaxf(D[plane + (size_t)f * ldk + k], eps));
+    W[(size_t)f * ldk + k] = v;
+    acc += (double)v;
+  }
+  const double total = block_sum<SE_THREADS>(acc, s_red);
+  if (threadIdx.x == 0) {
+    s_sum = total == 0.0 ? 1.0f : (float)total;
+    s_out[k] = s_sum;
+  }
+  __syncthreads();
+  const float s = s_sum;
+  for (int f = threadIdx.x; f < F; f += SE_THREADS) W[(size_t)f * ldk + k] /= s;
+}
+
+// out[f][n] = mean over channels of |X_c|^2: the one-channel power spectrum the NMF
+// initialisers factorise (audioModel.py:2150-2158)
+__global__ void __launch_bounds__(SE_THREADS)
+mono_power_kernel(const float* __restrict__ X, long ldx, int nch, float* __restrict__ out, int F,
+                  long N, long ldn) {
+  const long f = blockIdx.y;
+  const long n = (long)blockIdx.x * SE_THREADS + threadIdx.x;
+  if (n >= ldn) return;
+  float p = 0.f;
+  if (n < N) {
+    for (int c = 0; c < 2 * nch; ++c) {
+      const float v = X[((size_t)c * F + f) * ldx + n];
+      p += v * v;
+    }
+    p /= (float)nch;
+  }
+  out[f * ldn + n] = p;
+}
+
 }  // namespace pf
 
 using namespace pf;
@@ -664,6 +739,41 @@ extern "C" int pf_simm_masks(const float* SM, const float* SF0, const float* SPH
     simm_masks_kernel<2><<<grid, SE_THREADS, 0, st>>>(SM, SF0, SPHI, a2, X, ldx, Y, (float)eps_hat,
                                                      F, N, ldn);
   return check_launch("simm_masks_kernel");
+}
+
+extern "C" int pf_nmf_is_terms(const float* hat, const float* SX, float* out, double eps, int F,
+                               int64_t N, int64_t ldn, void* stream) {
+  int rc = simm_check_plane("pf_nmf_is_terms", 1, F, N, ldn);
+  if (rc) return rc;
+  nmf_is_terms_kernel<<<SIMM_PLANE_GRID(ldn, F), SE_THREADS, 0, as_stream(stream)>>>(
+      hat, SX, out, (float)eps, N, ldn);
+  return check_launch("nmf_is_terms_kernel");
+}
+
+extern "C" int pf_nmf_update_rows(float* H, int64_t ldh, const float* C, int64_t ldc, int64_t ldn,
+                                  double eps, int rows, int64_t N, void* stream) {
+  PF_REQUIRE(rows > 0 && N > 0 && ldc >= 2 * ldn, "pf_nmf_update_rows: rows=%d N=%ld ldc=%ld", rows,
+             (long)N, (long)ldc);
+  dim3 grid(ceil_div(N, 256), rows);
+  nmf_update_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(H, ldh, C, ldc, ldn, (float)eps, rows,
+                                                            N);
+  return check_launch("nmf_update_rows_kernel");
+}
+
+extern "C" int pf_nmf_w_update(float* W, int ldk, int K, const float* D, double eps, int F,
+                               float* s_out, void* stream) {
+  PF_REQUIRE(F > 0 && K > 0 && ldk >= K, "pf_nmf_w_update: F=%d K=%d ldk=%d", F, K, ldk);
+  nmf_w_update_kernel<<<K, SE_THREADS, 0, as_stream(stream)>>>(W, ldk, D, (float)eps, F, s_out);
+  return check_launch("nmf_w_update_kernel");
+}
+
+extern "C" int pf_mono_power(const float* X, int64_t ldx, int nch, float* out, int F, int64_t N,
+                             int64_t ldn, void* stream) {
+  PF_REQUIRE(nch >= 1 && F > 0 && N > 0 && ldn >= N && ldx >= N, "pf_mono_power: nch=%d F=%d N=%ld",
+             nch, F, (long)N);
+  dim3 grid(ceil_div(ldn, SE_THREADS), F);
+  mono_power_kernel<<<grid, SE_THREADS, 0, as_stream(stream)>>>(X, ldx, nch, out, F, N, ldn);
+  return check_launch("mono_power_kernel");
 }
 
 extern "C" int pf_simm_wm_scaled(const float* WM, int ldr, int R, const float* b2, int nch, int F,

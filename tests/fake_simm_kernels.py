@@ -220,6 +220,35 @@ class FakeSimmKernels(object):
                 y[2 * c + part, :, :N] = lv * ih * x[2 * c + part, :, :N]
                 y[2 * (nch + c) + part, :, :N] = sm * ih * x[2 * c + part, :, :N]
 
+    # ---- IS-NMF initialisers ------------------------------------------------------------------
+    def nmf_is_terms(self, hat, SX, out, eps, F, N, ldn):
+        self.launches += 1
+        h, x, w = _np(hat)[:, :N], _np(SX)[:, :N], _np(out)
+        e = np.float32(eps)
+        w[:, :2 * ldn] = 0
+        w[:, :N] = x / np.maximum(h * h, e)
+        w[:, ldn:ldn + N] = 1 / np.maximum(h, e)
+
+    def nmf_update_rows(self, H, C, ldn, eps, rows, N):
+        self.launches += 1
+        h, c = _np(H), _np(C)
+        h[:rows, :N] *= c[:rows, :N] / np.maximum(c[:rows, ldn:ldn + N], np.float32(eps))
+
+    def nmf_w_update(self, W, K, D, eps, F, s_out):
+        self.launches += 1
+        w, d = _np(W), _np(D)
+        w[:, :K] *= d[0, :, :K] / np.maximum(d[1, :, :K], np.float32(eps))
+        s = w[:, :K].astype(np.float64).sum(axis=0).astype(np.float32)
+        s[s == 0] = 1
+        w[:, :K] /= s
+        _np(s_out)[:K] = s
+
+    def mono_power(self, X, out, F, N, ldn):
+        self.launches += 1
+        x, o = _np(X), _np(out)
+        o[:, :ldn] = 0
+        o[:, :N] = (x[:, :, :N].astype(np.float32) ** 2).sum(axis=0) / np.float32(x.shape[0] // 2)
+
     def simm_wm_scaled(self, WM, R, b2, nch, F, WMs):
         self.launches += 1
         wm, out = _np(WM), _np(WMs)
