@@ -323,6 +323,14 @@ int pf_nmf_w_update(float* W, int ldk, int K, const float* D, double eps, int F,
 int pf_mono_power(const float* X, int64_t ldx, int nch, float* out, int F, int64_t N, int64_t ldn,
                   void* stream);
 
+/* ---- Viterbi melody tracking  (SeparateLeadStereo/tracking/_tracking.pyx:11-93) ----------------
+ * log_density_ns: float64 [N][S] (frame major), log_prior [S], log_trans [S][S] (row = from);
+ * path: int64 [N].  Same recursion and tie breaking (smallest index among equal maxima) as the
+ * reference's Cython module: the path is bit-identical. */
+int64_t pf_viterbi_workspace_bytes(int S, int64_t N);
+int pf_viterbi(const double* log_density_ns, const double* log_prior, const double* log_trans, int S,
+               int64_t N, void* workspace, int64_t workspace_bytes, long long* path, void* stream);
+
 /* ---- tcgen05 self-test (pins the descriptor / layout conventions of csrc/tc.cuh) ------ */
 /* D[128][N] = A B^T in tf32 (split3: 3xTF32, fp32-class accuracy).  A: a_mn ? [K][128] :
  * [128][K]; B: b_mn ? [K][N] : [N][K]; float32 device buffers; N, K multiples of 32. */

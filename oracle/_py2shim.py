@@ -228,7 +228,36 @@ def load():
     return dict(audioModel=audioModel, stft=ref_stft, SIMM=ref_simm,
                 signalTools=ref_st, utils=ref_utils, nmf=ref_nmf, slf=ref_slf, filter=ref_filter,
                 writeSeparatedSignals=_method_source(
-                    "SeparateLeadStereo/SeparateLeadStereoTF.py", "writeSeparatedSignals"))
+                    "SeparateLeadStereo/SeparateLeadStereoTF.py", "writeSeparatedSignals"),
+                runViterbi=_method_source(
+                    "SeparateLeadStereo/SeparateLeadStereoTF.py", "runViterbi"),
+                initiateHF0WithIndexBestPath=_method_source(
+                    "SeparateLeadStereo/SeparateLeadStereoTF.py", "initiateHF0WithIndexBestPath"))
+
+
+class OldNumpy(object):
+    """`np` as the reference's Python-2-era code expects it, for exec()ing method sources:
+    removed aliases (np.Inf) and float array sizes (old NumPy truncated them with a warning).
+    Everything else is today's NumPy."""
+
+    def __init__(self):
+        import numpy
+        self._np = numpy
+        self.Inf = numpy.inf
+
+    def __getattr__(self, name):
+        return getattr(self._np, name)
+
+    def _size(self, shape):
+        if isinstance(shape, (list, tuple)):
+            return [int(v) for v in shape]
+        return int(shape)
+
+    def ones(self, shape, *a, **k):
+        return self._np.ones(self._size(shape), *a, **k)
+
+    def zeros(self, shape, *a, **k):
+        return self._np.zeros(self._size(shape), *a, **k)
 
 
 def _method_source(rel, name):

@@ -268,6 +268,88 @@ def run_nmf(ref):
     print("nmf", W1.shape, H1.shape, float(np.abs(W3 - Wi).max()))
 
 
+def run_viterbi():
+    """The reference's Cython tracker (compiled by oracle/build_ref.py) on small HMMs, ties
+    included (integer log-probabilities) and on a melody-like problem built as runViterbi does
+    (SeparateLeadStereoTF.py:1183-1215)."""
+    from oracle import build_ref
+    trk = build_ref.load()
+    rng = np.random.default_rng(17)
+    out = {}
+    for tag, (S, N, ties) in {"a": (7, 40, False), "b": (33, 300, False), "c": (12, 200, True),
+                              "d": (1, 5, False)}.items():
+        dens = rng.standard_normal((S + 1, N))
+        prior = np.log(np.ones(S + 1) / (S + 1))
+        trans = np.log(rng.random((S + 1, S + 1)) + 1e-3)
+        if ties:  # exactly equal candidates: the smallest predecessor index must win
+            dens, trans = np.round(dens), np.round(trans)
+        out.update({tag + "_dens": dens, tag + "_prior": prior, tag + "_trans": trans,
+                    tag + "_path": trk.viterbiTracking(S, N, dens, prior, trans)})
+    # melody-like: banded Toeplitz transitions, log of a sparse non-negative HF0 (with -inf)
+    NF0, N, step = 60, 400, 4
+    t = np.exp(-np.floor(np.arange(NF0) / step))
+    cut = min(NF0, 2 * 5 * step)
+    t[cut:] = t[cut - 1]
+    T = np.zeros([NF0 + 1, NF0 + 1])
+    b = np.arange(NF0)
+    T[:NF0, :NF0] = t[np.abs(b[None, :] - b[:, None])]
+    T[:NF0, NF0], T[NF0, :NF0], T[NF0, NF0] = t[cut - 1] * 1e-90, t[cut - 1] * 1e-80, t[cut - 1] * 1e-100
+    T = T / T.sum(axis=1)[:, None]
+    HF0 = np.abs(rng.standard_normal((NF0, N))) ** 4
+    HF0[rng.random((NF0, N)) < 0.2] = 0.0
+    with np.errstate(divide="ignore"):
+        logH = np.zeros([NF0 + 1, N])
+        logH[:NF0] = np.log(HF0)
+    logH[NF0] = -100
+    prior = np.log(np.ones(NF0 + 1) / (NF0 + 1.0))
+    out.update(m_dens=logH, m_prior=prior, m_trans=np.log(T),
+               m_path=trk.viterbiTracking(NF0, N, logH, prior, np.log(T)))
+    np.savez_compressed(os.path.join(GOLD, "viterbi.npz"), **out)
+    print("viterbi", {k: v[:8] for k, v in out.items() if k.endswith("path")})
+
+
+def run_melody(ref):
+    """SeparateLeadProcess.runViterbi and initiateHF0WithIndexBestPath
+    (SeparateLeadStereoTF.py:1150-1368), executed from their own source against a stand-in
+    `self`, with the reference's Cython tracker compiled by oracle/build_ref.py."""
+    import tempfile
+    from oracle import build_ref
+    trk = build_ref.load()
+    rng = np.random.default_rng(23)
+    NF0, N, step, fs, hop = 61, 250, 4, 8000, 32
+    F0Table = 100.0 * 2 ** (np.arange(NF0) / (12.0 * step))
+    HF0 = np.abs(rng.standard_normal((NF0, N))) ** 6
+    line = np.clip((30 + 20 * np.sin(np.arange(N) / 25.0)).astype(int), 0, NF0 - 1)
+    HF0[line, np.arange(N)] += 50.0
+    HF0[rng.random((NF0, N)) < 0.15] = 0.0
+    HF0[:, 100:110] = 0.0      # silent frames: the log floor (:1205)
+    HF0[0, 200:205] = 1e4      # the decoded line touches state 0 -> "no melody" (:1311, :1364)
+    out = {}
+    for tag, search in (("full", (None, None)), ("band", (130.0, 200.0))):
+        class Self(object):
+            pass
+        obj = Self()
+        obj.SIMMParams = dict(HF0=HF0.copy(), NF0=NF0, chirpPerF0=1, minF0=100, maxF0=float(
+            F0Table[-1]) + 1, stepNotes=step, F0Table=F0Table)
+        obj.trackingParams = dict(minF0search=search[0] or 100, maxF0search=search[1] or 1e9)
+        obj.stftParams = dict(hopsize=float(hop))
+        obj.fs, obj.N, obj.verbose, obj.scopeAllowedHF0 = fs, N, False, 4.0
+        obj.computeNFrames = lambda: N
+        tmp = tempfile.mkdtemp()
+        obj.files = dict(pitch_output_file=os.path.join(tmp, "pitches.txt"))
+        ns = dict(np=_py2shim.OldNumpy(), viterbiTrackingArray=trk.viterbiTracking, eps=10 ** -9)
+        exec(ref["runViterbi"], ns)
+        exec(ref["initiateHF0WithIndexBestPath"], ns)
+        ns["runViterbi"](obj)
+        ns["initiateHF0WithIndexBestPath"](obj)
+        out.update({tag + "_path": obj.indexBestPath, tag + "_freq": obj.freqMelody,
+                    tag + "_HF00": obj.SIMMParams["HF00"],
+                    tag + "_pitches": np.loadtxt(obj.files["pitch_output_file"])})
+    np.savez_compressed(os.path.join(GOLD, "melody.npz"), HF0=HF0, F0Table=F0Table, NF0=NF0,
+                        N=N, stepNotes=step, fs=fs, hopsize=hop, **out)
+    print("melody", out["full_path"][:10], out["band_path"][:10], out["full_HF00"].sum())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = _py2shim.load()
@@ -286,6 +368,8 @@ def main():
     run_simm(ref)
     run_lead_sep(ref)
     run_nmf(ref)
+    run_viterbi()
+    run_melody(ref)
 
 
 if __name__ == "__main__":

@@ -98,13 +98,16 @@ SIGNATURES = {
     "pf_nmf_w_update": [c_vp, c_int, c_int, c_vp, c_dbl, c_int, c_vp, c_vp],
     "pf_mono_power": [c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_i64, c_vp],
     "pf_simm_wm_scaled": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp],
+    "pf_viterbi_workspace_bytes": [c_int, c_i64],
+    "pf_viterbi": [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_ll_reduce": [c_vp, c_int, c_vp, c_vp],
     "pf_ll_store": [c_vp, c_dbl, c_vp, c_vp, c_int, c_vp],
 }
 _RESTYPE = {"pf_last_error": ctypes.c_char_p, "pf_launch_count": ctypes.c_ulonglong,
-            "pf_simm_reduce_workspace_bytes": ctypes.c_int64}
+            "pf_simm_reduce_workspace_bytes": ctypes.c_int64,
+            "pf_viterbi_workspace_bytes": ctypes.c_int64}
 
 _lib = None
 
@@ -387,7 +390,7 @@ class CudaKernels(object):
         if t is None:
             return None
         assert t.is_cuda and t.dtype in (self.torch.float32, self.torch.float64)
-        assert t.dim() == 1 or t.stride(-1) == 1, "rows must be contiguous"
+        assert t.dim() == 1 or t.is_contiguous() or t.stride(-1) == 1, "rows must be contiguous"
         return t.data_ptr()
 
     def _call(self, name, *args):
@@ -462,6 +465,19 @@ class CudaKernels(object):
     def simm_masks(self, SM, SF0, SPHI, a2, X, Y, eps_hat, nch, F, N, ldn):
         self._call("pf_simm_masks", self._pv(SM), self._pv(SF0), self._pv(SPHI), self._pv(a2),
                    self._pv(X), X.stride(1), self._pv(Y), float(eps_hat), nch, F, N, ldn)
+
+    # -- Viterbi ------------------------------------------------------------------------------
+    def viterbi(self, log_density, log_prior, log_trans):
+        """log_density: device float64 [S, N]; returns the device int64 path [N]."""
+        torch = self.torch
+        S, N = log_density.shape
+        dens = log_density.t().contiguous()  # frame major (layout plumbing)
+        ws = torch.empty((int(self.lib.pf_viterbi_workspace_bytes(S, N)) + 7) // 8,
+                         dtype=torch.float64, device=log_density.device)
+        path = torch.empty(N, dtype=torch.int64, device=log_density.device)
+        self._call("pf_viterbi", self._pv(dens), self._pv(log_prior), self._pv(log_trans), S, N,
+                   self._pv(ws), ws.numel() * 8, path.data_ptr())
+        return path
 
     # -- IS-NMF initialisers ---------------------------------------------------------------
     def nmf_is_terms(self, hat, SX, out, eps, F, N, ldn):

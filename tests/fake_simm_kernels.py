@@ -220,6 +220,23 @@ class FakeSimmKernels(object):
                 y[2 * c + part, :, :N] = lv * ih * x[2 * c + part, :, :N]
                 y[2 * (nch + c) + part, :, :N] = sm * ih * x[2 * c + part, :, :N]
 
+    # ---- Viterbi --------------------------------------------------------------------------------
+    def viterbi(self, log_density, log_prior, log_trans):
+        self.launches += 2
+        dens, prior, trans = _np(log_density), _np(log_prior), _np(log_trans)
+        S, N = dens.shape
+        cum = prior + dens[:, 0]
+        ante = np.zeros((N, S), dtype=np.int64)
+        for n in range(1, N):
+            cand = cum[:, None] + trans          # [from, to]
+            ante[n] = np.argmax(cand, axis=0)    # first maximum, like the strict `>` scan
+            cum = cand[ante[n], np.arange(S)] + dens[:, n]
+        path = np.zeros(N, dtype=np.int64)
+        path[-1] = np.argmax(cum)
+        for n in range(N - 2, -1, -1):
+            path[n] = ante[n + 1, path[n + 1]]
+        return torch.from_numpy(path)
+
     # ---- IS-NMF initialisers ------------------------------------------------------------------
     def nmf_is_terms(self, hat, SX, out, eps, F, N, ldn):
         self.launches += 1
