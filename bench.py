@@ -198,7 +198,8 @@ def run_reference(args, rank):
 
 
 def workload_config(args, note=None):
-    L = int(round(args.duration_s * FS)) * args.gpus
+    blocks = getattr(args, "blocks", 1)
+    L = int(round(args.duration_s * FS)) * args.gpus * blocks
     model = "MultiChanNMFConv (convolutive mixing)" if getattr(args, "model", "inst") == "conv" \
         else "MultiChanNMFInst_FASST"
     shard = getattr(args, "shard", "time")
@@ -206,8 +207,9 @@ def workload_config(args, note=None):
     cfg = {"workload": "%s: synthetic %.0f-s %s 44.1 kHz mix per GPU (x%d GPUs = %.0f s, "
                        "weak scaling), %s %d sources x K=%d, spatial rank %d, "
                        "STFT %d/hop %d" % ("configs[1]" if nch == 2 else "configs[3]-like",
-                                           args.duration_s, "stereo" if nch == 2 else "%d-channel" % nch,
-                                           args.gpus, args.duration_s * args.gpus,
+                                           args.duration_s * blocks,
+                                           "stereo" if nch == 2 else "%d-channel" % nch,
+                                           args.gpus, args.duration_s * args.gpus * blocks,
                                            model, NSRC, NNMF, rank, WLEN, HOP),
            "channels": nch,
            "F": WLEN // 2 + 1, "N": n_frames(L), "tf_bins": (WLEN // 2 + 1) * n_frames(L),
@@ -245,7 +247,10 @@ def run_ours(args, rank, world):
     # N = 1: the 10-min mixture of configs[1].  N > 1: weak scaling -- the mixture is N such
     # blocks back to back (one per GPU) and its frames are sharded over the ranks.
     block = synth_mix(args.duration_s, channels=args.channels)
-    pcm = block if world == 1 else np.ascontiguousarray(np.tile(block, (world, 1)))
+    # (--blocks B: B such blocks per GPU, e.g. --duration-s 450 --blocks 8 on one GPU is the
+    # same 1-hour mixture as --duration-s 450 on 8 GPUs: strong-scaling pairs)
+    reps = world * args.blocks
+    pcm = block if reps == 1 else np.ascontiguousarray(np.tile(block, (reps, 1)))
     L = pcm.shape[0]
     F, N = WLEN // 2 + 1, n_frames(L)
     bins = F * N
@@ -319,7 +324,8 @@ def run_ours(args, rank, world):
     torch.cuda.empty_cache()
 
     # ---- end to end through the public API with host buffers (`e2e`) ---------------------
-    pinned = torch.from_numpy(pcm).pin_memory()  # the mixture as a host buffer (int16 PCM)
+    # the mixture as a host buffer (int16 PCM)
+    pinned = None if args.no_e2e else torch.from_numpy(pcm).pin_memory()
 
     def api_run(iters):
         m = make_model(iters)  # constructor = reference behaviour (reads the WAV, STFT, init)
@@ -341,20 +347,22 @@ def run_ours(args, rank, world):
                 for sp in m.spec_comps.values() for f in sp["factor"].values())
         return t1 - t0, npar, ll, stages
 
-    for _ in range(2):  # warm-up: library state and the caching allocator's block sizes
-        api_run(max(1, args.warmup))
-    dt, npar, ll_api, stages = api_run(args.steps)
-    dt_t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-    dt = float(dt_t.item())
-    h2d = (pcm.nbytes + npar) / float(args.steps)
-    d2h = (npar + 8 * args.steps + 8 * F) / float(args.steps)
-    e2e = {"value": bins * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "wall_s": dt, "stages": stages,
-           "what": "AudioObject._set_raw(pinned int16 PCM) + comp_transf_Cx() + "
-                   "estim_param_a_post_model() with iter_num=steps; host numpy/PCM in, host "
-                   "numpy parameters and log-likelihoods out"}
+    e2e = None
+    if not args.no_e2e:  # (scaling-evidence runs may skip it; the driver's runs never do)
+        for _ in range(2):  # warm-up: library state and the caching allocator's block sizes
+            api_run(max(1, args.warmup))
+        dt, npar, ll_api, stages = api_run(args.steps)
+        dt_t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t.item())
+        h2d = (pcm.nbytes + npar) / float(args.steps)
+        d2h = (npar + 8 * args.steps + 8 * F) / float(args.steps)
+        e2e = {"value": bins * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "wall_s": dt, "stages": stages,
+               "what": "AudioObject._set_raw(pinned int16 PCM) + comp_transf_Cx() + "
+                       "estim_param_a_post_model() with iter_num=steps; host numpy/PCM in, host "
+                       "numpy parameters and log-likelihoods out"}
 
     if rank != 0:
         if world > 1:
@@ -374,7 +382,7 @@ def run_ours(args, rank, world):
     local_bins = bins / float(world)  # frames are split evenly over the ranks
     achieved = bytes_per_bin * local_bins / (estep_ms * 1e-3) / 1e9
     traffic = args.traffic
-    if traffic is None and world == 1 and args.dtype == "f32" and args.duration_s == 600.0 \
+    if traffic is None and world == 1 and args.dtype == "f32" and args.duration_s == 600.0 and args.blocks == 1 \
             and args.channels == 2 and args.rank == RANK:
         traffic = ESTEP_DRAM_BYTES_PER_LAUNCH  # same workload as the committed capture
     roofline = {"bound": "hbm",
@@ -418,6 +426,11 @@ def main():
     ap.add_argument("--duration-s", type=float, default=600.0)
     ap.add_argument("--cpu-crop-s", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="skip the end-to-end leg (scaling-evidence runs only)")
+    ap.add_argument("--blocks", type=int, default=1,
+                    help="blocks of --duration-s per GPU (strong-scaling pairs: N GPUs x B "
+                         "blocks = the same mixture)")
     ap.add_argument("--model", default="inst", choices=["inst", "conv"],
                     help="inst: MultiChanNMFInst_FASST (configs[1], default); conv: "
                          "MultiChanNMFConv + makeItConvolutive (the model of configs[3])")

@@ -110,6 +110,39 @@ def test_estep_stereo(ck, fk, dt, F, N, J, rank, consistent):
     assert_allclose(rss1, np.conj(np.transpose(rss1, (0, 2, 1))), atol=1e-14 * np.abs(rss1).max())
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("F,N,J,rank", [(5, 77, 1, 1), (3, 1000, 3, 1), (4, 2600, 4, 2),
+                                        (2, 7001, 2, 3), (3, 4, 4, 1), (2, 20003, 4, 2)])
+def test_estep_stereo_warp_specialised(ck, fk, monkeypatch, cfg, F, N, J, rank):
+    """The warp-specialised float32 E-step (algebra warps + moment warps, records through shared
+    memory) against the kernel specification AND against the fused kernel: same per-bin algebra;
+    the moment sums only differ by the order of the float32 additions."""
+    dt = torch.float32
+    rng = np.random.default_rng(F * 1000 + N)
+    ld, R, src, X, V, A, noise = problem(rng, dt, F, N, J, rank, consistent=True)
+    outs = []
+    for k, dev, kern in ((fk, "cpu", None), (ck, "cuda", "fused"), (ck, "cuda", "ws")):
+        if kern is not None:
+            monkeypatch.setenv("PYFASST_ESTEP_KERNEL", kern)
+            monkeypatch.setenv("PYFASST_ESTEP_WSCFG", str(cfg))
+        hatW = torch.zeros((J, F, ld), dtype=dt, device=dev)
+        Rss = torch.zeros((F, R, R), dtype=torch.complex128, device=dev)
+        Rxs = torch.zeros((F, 2, R), dtype=torch.complex128, device=dev)
+        ll = torch.zeros(F, dtype=torch.float64, device=dev)
+        ws = torch.zeros((k.estep_workspace_bytes(J, F, N, k.dtype_code(V)) + 7) // 8,
+                         dtype=torch.float64, device=dev)
+        k.estep_stereo(X.to(dev), V.to(dev), A.to(dev), src, noise.to(dev), N, hatW, Rss, Rxs, ll, ws)
+        outs.append([t.cpu().numpy() for t in (hatW, Rss, Rxs, ll)])
+    (hw0, rss0, rxs0, ll0), (hw1, rss1, rxs1, ll1), (hw2, rss2, rxs2, ll2) = outs
+    assert rel(hw2[:, :, :N], hw0[:, :, :N]) < 1e-6
+    assert (hw2[:, :, N:] == 0).all(), "padding frames must stay zero"
+    assert rel(hw2, hw1) < 1e-6, "same per-bin algebra as the fused kernel"
+    assert rel(rss2, rss0) < 1e-4 and rel(rxs2, rxs0) < 1e-4
+    assert rel(rss2, rss1) < 1e-4 and rel(rxs2, rxs1) < 1e-4
+    assert_allclose(ll2, ll0, rtol=1e-6, atol=1e-6 * N)
+    assert_allclose(rss2, np.conj(np.transpose(rss2, (0, 2, 1))), atol=1e-14 * np.abs(rss2).max())
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 def test_wiener_stereo(ck, fk, dt):
     rng = np.random.default_rng(5)
