@@ -331,6 +331,21 @@ int64_t pf_viterbi_workspace_bytes(int S, int64_t N);
 int pf_viterbi(const double* log_density_ns, const double* log_prior, const double* log_trans, int S,
                int64_t N, void* workspace, int64_t workspace_bytes, long long* path, void* stream);
 
+/* ---- Glottal-source F0 dictionary WF0  (SeparateLeadStereo/separateLeadFunctions.py:
+ * generate_ODGD_spec :888-949, generate_ODGD_spec_chirped :1010-1072, the column loops of
+ * generate_WF0_chirped :237-345 and generate_WF0_TR_chirped :696-886) -----------------------
+ * Column c = power spectrum of one windowed frame of the KLGLOTT88 waveform
+ *   x_c(t) = Re sum_{h=1}^{npart[c]} A_h exp(2 pi i h (f1[c] tau + (f2[c]-f1[c]) tau^2 / (2 T))),
+ *   tau = t / fs, T = Lsig / fs, A_h the glottal amplitudes (:917-929) of F0 = (f1+f2)/2 with
+ *   opening coefficient Ot; f1 = f2 gives the plain (unchirped) comb.
+ * out[c][r] = | sum_{k < wlen} window[k] x_c(t_begin + k) exp(-2 pi i r k / nfft) |^2, r < rows
+ *   (x_c = 0 outside [0, Lsig)).  f1, f2: double [ncols]; npart: int32 [ncols], all <=
+ *   max_partials <= 2048; window: double [wlen], wlen <= nfft <= 8192; out: double [ncols][rows];
+ *   all device pointers. */
+int pf_wf0_combs(const double* f1, const double* f2, const int* npart, int ncols, int max_partials,
+                 double fs, double Ot, int64_t Lsig, int64_t t_begin, const double* window,
+                 int wlen, int nfft, int rows, double* out, void* stream);
+
 /* ---- tcgen05 self-test (pins the descriptor / layout conventions of csrc/tc.cuh) ------ */
 /* D[128][N] = A B^T in tf32 (split3: 3xTF32, fp32-class accuracy).  A: a_mn ? [K][128] :
  * [128][K]; B: b_mn ? [K][N] : [N][K]; float32 device buffers; N, K multiples of 32. */

@@ -115,7 +115,10 @@ PATCHES = {
          "    data = data / normalisationSeq"),
         ("self.freqbins = self.ftlen / 2 + 1", "self.freqbins = self.ftlen // 2 + 1"),
     ],
-    "tools/utils.py": [],
+    "tools/utils.py": [
+        # scipy moved the window functions to scipy.signal.windows (same function)
+        ("spsig.blackmanharris(M)", "spsig.windows.blackmanharris(M)"),
+    ],
     "tools/signalTools.py": [],
     "tools/nmf.py": [],
     "SeparateLeadStereo/SIMM/SIMM.py": [
@@ -155,6 +158,26 @@ PATCHES = {
          "    data = np.concatenate((data, np.zeros([int(newLengthData - lengthData)])))"),
         ("    numberFrequencies = nfft / 2.0 + 1\n    \n    if stop is None:",
          "    numberFrequencies = int(nfft / 2.0 + 1)\n    \n    if stop is None:"),
+        # the F0 dictionary generators (generate_WF0_chirped :237-345, generate_WF0_TR_chirped
+        # :696-886, generate_ODGD_spec :888-949): float count that old numpy truncated when it
+        # was used as a size / index (all the generators share the line)
+        ("numberOfF0 = np.ceil(12.0 * stepNotes * np.log2(maxF0 / minF0)) + 1",
+         "numberOfF0 = int(np.ceil(12.0 * stepNotes * np.log2(maxF0 / minF0)) + 1)"),
+        # `array == 'sinebell'` was a scalar False in old numpy (the window may be an array)
+        ("    if analysisWindowType=='sinebell':\n        analysisWindow = sinebell(lengthOdgd)\n"
+         "    elif analysisWindowType=='hanning' or \\\n             analysisWindowType=='hanning':",
+         "    if isinstance(analysisWindowType, str) and analysisWindowType=='sinebell':\n"
+         "        analysisWindow = sinebell(lengthOdgd)\n"
+         "    elif isinstance(analysisWindowType, str) and analysisWindowType=='hanning':"),
+        ("    elif analysisWindowType=='rectangular':\n        analysisWindow = np.ones(lengthOdgd)\n"
+         "    elif len(analysisWindowType)==lengthOdgd:",
+         "    elif isinstance(analysisWindowType, str) and analysisWindowType=='rectangular':\n"
+         "        analysisWindow = np.ones(lengthOdgd)\n"
+         "    elif len(analysisWindowType)==lengthOdgd:"),
+        # old np.fft.rfft cast a complex input to float (ComplexWarning: the imaginary part is
+        # discarded); today's raises.  The STFT object receives the complex waveform (:846, :877)
+        ("transform.computeTransform(data=odgd)\n",
+         "transform.computeTransform(data=np.real(odgd))\n"),
     ],
 }
 

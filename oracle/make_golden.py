@@ -350,6 +350,39 @@ def run_melody(ref):
     print("melody", out["full_path"][:10], out["band_path"][:10], out["full_HF00"].sum())
 
 
+def run_wf0(ref):
+    """The glottal-source F0 dictionary: generate_WF0_TR_chirped with the
+    reference's own STFT object (what SeparateLeadProcess.computeWF0 runs for
+    tfrepresentation='stft', SeparateLeadStereoTF.py:661-684), with and without chirps, and the
+    older generate_WF0_chirped (separateLeadFunctions.py:237-345); the .npz cache names the
+    reference writes are recorded too."""
+    import tempfile
+    slf, st, ut = ref["slf"], ref["stft"], ref["utils"]
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        fs, nft = 8000, 256
+        tr = st.STFT(linFTLen=nft, atomHopFactor=0.25, winFunc=ut.sqrt_blackmanharris, fs=fs)
+        t1, w1, _ = slf.generate_WF0_TR_chirped(tr, minF0=100, maxF0=800, stepNotes=2, Ot=0.5,
+                                                perF0=1, depthChirpInSemiTone=0.5, loadWF0=False)
+        t2, w2, _ = slf.generate_WF0_TR_chirped(tr, minF0=100, maxF0=800, stepNotes=1, Ot=0.5,
+                                                perF0=3, depthChirpInSemiTone=0.5, loadWF0=False)
+        t3, w3 = slf.generate_WF0_chirped(100, 800, fs, Nfft=256, stepNotes=1, lengthWindow=256,
+                                          Ot=0.5, perF0=2, depthChirpInSemiTone=.15,
+                                          loadWF0=False, analysisWindow='sinebell')
+        # a hop that is not ftlen / 4 and a window shorter than the transform would need another
+        # transform class; the reference's STFT ties window length to linFTLen
+        tr2 = st.STFT(linFTLen=512, atomHopFactor=0.125, winFunc=np.hanning, fs=16000)
+        t4, w4, _ = slf.generate_WF0_TR_chirped(tr2, minF0=60, maxF0=500, stepNotes=1, Ot=0.25,
+                                                perF0=2, depthChirpInSemiTone=0.5, loadWF0=False)
+        names = sorted(os.listdir("."))
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "wf0.npz"), t1=t1, w1=w1, t2=t2, w2=w2, t3=t3, w3=w3,
+                        t4=t4, w4=w4, cache_names=np.array(names))
+    print("wf0", w1.shape, w2.shape, w3.shape, w4.shape, names)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = _py2shim.load()
@@ -370,6 +403,7 @@ def main():
     run_nmf(ref)
     run_viterbi()
     run_melody(ref)
+    run_wf0(ref)
 
 
 if __name__ == "__main__":

@@ -14,9 +14,10 @@ tracking/_tracking.py), `initiateHF0WithIndexBestPath` (:1321-1368) -- and the c
 stage `estimStereoSIMMParamsWriteSeps` / `overlapAddChunks` / `checkChunkSize` (:1370-1583,
 :1880-1899), i.e. the whole of `autoMelSepAndWrite` (:1142-1148).
 
-Not here (8f row 4): the generation of the glottal F0 dictionary -- `WF0` (F x NF0, and
-optionally `F0Table`) must be given to the constructor; `computeWF0` raises NotImplementedError
-without it.  Only `tfrepresentation='stft'`.
+And (8f row 4) the glottal F0 dictionary: `computeWF0` (:587-700) generates it on the GPU
+(separateLeadFunctions.generate_WF0_TR_chirped, csrc/wf0.cu) with the reference's `.npz` cache,
+unless `WF0` (F x NF0, and optionally `F0Table`) is given to the constructor.  Only
+`tfrepresentation='stft'`.
 """
 import os
 
@@ -24,6 +25,8 @@ import numpy as np
 import scipy.io.wavfile as wav
 
 from . import separateLeadFunctions as slf
+from ..tftransforms.stft import STFT
+from ..tools.utils import sqrt_blackmanharris
 from .SIMM import SIMM
 from .tracking._tracking import viterbiTracking as viterbiTrackingArray
 
@@ -35,12 +38,17 @@ class SeparateLeadProcess(object):
                  numCompAccomp=40, minF0=39, maxF0=2000, stepNotes=16, chirpPerF0=1,
                  K_numFilters=4, P_numAtomFilters=30, imageCanvas=None, wavCanvas=None,
                  progressBar=None, verbose=True, outputDirSuffix='/', minF0search=None,
-                 maxF0search=None, tfrepresentation='stft', initHF00='random', freeMemory=True,
-                 WF0=None, F0Table=None, kernels=None):
+                 maxF0search=None, tfrepresentation='stft', cqtfmax=4000, cqtfmin=50, cqtbins=48,
+                 cqtWinFunc=sqrt_blackmanharris, cqtAtomHopFactor=0.25, initHF00='random',
+                 freeMemory=True, WF0=None, F0Table=None, kernels=None):
         if tfrepresentation != 'stft':
             raise NotImplementedError("pyfasst_b200: only tfrepresentation='stft'")
         # per-instance (the reference shares these dicts between instances, :259-261)
         self.files, self.stftParams, self.SIMMParams = {}, {}, {}
+        # the transform object of the dictionary (ref: :334-339; the cqt* values other than the
+        # window and the hop factor are ignored by the STFT, tftransforms/stft.py:360-362)
+        self.stftParams.update(cqtfmin=cqtfmin, cqtfmax=cqtfmax, cqtbins=cqtbins,
+                               cqtWinFunc=cqtWinFunc, cqtAtomHopFactor=cqtAtomHopFactor)
         self.verbose = verbose
         self.tfrepresentation = tfrepresentation
         self.displayEvolution = False
@@ -89,13 +97,25 @@ class SeparateLeadProcess(object):
         f['pitch_output_file'] = str(f['pathBaseName'] + '_pitches.txt')
 
     def computeWF0(self):
-        """The F0 dictionary.  Its generation (KLGLOTT88 glottal source, ref: :587-700,
-        separateLeadFunctions.py:696-949) is not on this path: it must be supplied."""
+        """The F0 dictionary (ref: :587-700, the `stft` branch :661-684): glottal harmonic combs
+        through the STFT transform object, columns normalised to sum one -- generated on the
+        GPU (or read from the reference's .npz cache in the working directory) unless WF0 was
+        given to the constructor."""
         WF0 = self.SIMMParams['WF0']
         if WF0 is None:
-            raise NotImplementedError(
-                "pyfasst_b200: the glottal F0 dictionary generator is not implemented; pass "
-                "WF0 (F x NF0) to SeparateLeadProcess")
+            self.mqt = STFT(linFTLen=int(self.stftParams['NFT']),
+                            atomHopFactor=self.stftParams['cqtAtomHopFactor'],
+                            winFunc=self.stftParams['cqtWinFunc'], fs=self.fs,
+                            kernels=self._kernels)
+            self.SIMMParams['F0Table'], WF0, self.mqt = slf.generate_WF0_TR_chirped(
+                transform=self.mqt, minF0=self.SIMMParams['minF0'],
+                maxF0=self.SIMMParams['maxF0'], stepNotes=self.SIMMParams['stepNotes'], Ot=0.5,
+                perF0=self.SIMMParams['chirpPerF0'], depthChirpInSemiTone=0.5, loadWF0=True,
+                verbose=self.verbose, kernels=self._kernels)
+            WF0 = self.SIMMParams['WF0'] = WF0 / np.sum(WF0, axis=0)
+            self.SIMMParams['NF0'] = self.SIMMParams['F0Table'].size
+            self.F = WF0.shape[0]
+            return
         if WF0.shape[0] != self.F:
             raise ValueError("WF0 must have NFT/2+1 = %d rows, got %d" % (self.F, WF0.shape[0]))
         self.SIMMParams['NF0'] = WF0.shape[1] // self.SIMMParams['chirpPerF0']

@@ -1,17 +1,22 @@
 """Time-frequency front / back end of the SeparateLeadStereo (SIMM) path, drop-in for the
 functions of pyfasst/SeparateLeadStereo/separateLeadFunctions.py that the path uses:
 `stft` (:90-161), `istft` (:163-233), `sinebell`, `nextpow2`, `generateHannBasis`
-(pyfasst/sourcefilter/filter.py:9-73).  The transforms run on the GPU (csrc/stft.cu, shared
+(pyfasst/sourcefilter/filter.py:9-73), and the glottal-source F0 dictionary generators
+`generate_WF0_chirped` (:237-345) / `generate_WF0_TR_chirped` (:696-886) with their `.npz`
+cache files.  The transforms run on the GPU (csrc/stft.cu, shared
 with the FASST front end -- the two conventions differ only in the window, in the patched
 normalisation sequence of the inverse and in whether the leading half window is kept, quirk
 Q9 of SURVEY.md); there is no CPU fallback.
 
-Out of scope: generate_WF0_chirped / the KLGLOTT88 source model.
+Out of scope: the constant-Q variants generate_WF0_MinQT_chirped / _NSGTMinQT_chirped (other
+transforms).
 """
+import os
+
 import numpy as np
 
 from ..tftransforms import stft as _stft
-from ..tools.utils import nextpow2, sinebell  # noqa: F401  (re-exported like the reference)
+from ..tools.utils import hann, nextpow2, sinebell  # noqa: F401  (re-exported like the reference)
 
 
 def stft(data, window=sinebell(2048), hopsize=256.0, nfft=2048.0, fs=44100.0, start=0,
@@ -112,3 +117,117 @@ def generateHannBasis(numberFrequencyBins, sizeOfFourier, Fs, frequencyScale='li
     for p in range(numberOfBasis):
         WGAMMA[:, p] = bigWindow[np.int32(freq - centers[p] + big)]
     return WGAMMA
+
+
+# ---- glottal-source F0 dictionary (KLGLOTT88) ------------------------------------------------
+def _f0_table(minF0, maxF0, stepNotes):
+    """F0 candidates, `stepNotes` per semitone (ref: separateLeadFunctions.py:313-316)."""
+    minF0, maxF0, stepNotes = np.double(minF0), np.double(maxF0), np.double(stepNotes)
+    numberOfF0 = int(np.ceil(12.0 * stepNotes * np.log2(maxF0 / minF0)) + 1)
+    return minF0 * (2 ** (np.arange(numberOfF0, dtype=np.double) / (12 * stepNotes)))
+
+
+def _comb_columns(F0Table, Fs, perF0, depthChirpInSemiTone):
+    """(F1, F2, partials) of every column: the plain comb of each F0 followed by its perF0 - 1
+    chirps, F0 the mean of F1 and F2 (ref: :318-341; partialMax :911, :1038)."""
+    f1, f2 = [], []
+    for F0 in F0Table:
+        f1.append(F0)
+        f2.append(F0)
+        for chirpNumber in range(int(perF0) - 1):
+            F2 = F0 * (2 ** ((chirpNumber + 1.0) * depthChirpInSemiTone / (12.0 * (perF0 - 1.0))))
+            f1.append(2.0 * F0 - F2)
+            f2.append(F2)
+    f1, f2 = np.array(f1), np.array(f2)
+    npart = np.floor((np.double(Fs) / 2) / np.maximum(f1, f2)).astype(np.int32)
+    return f1, f2, npart
+
+
+def _combs(kernels, F0Table, Fs, perF0, depth, Ot, Lsig, t_begin, window, nfft, rows, plain_window=None):
+    """WF0 [rows, NF0 * perF0] from the comb kernel (csrc/wf0.cu)."""
+    k = kernels or _stft.default_kernels()
+    f1, f2, npart = _comb_columns(F0Table, Fs, perF0, depth)
+    W = k.wf0_combs(f1, f2, npart, Fs, Ot, Lsig, t_begin, window, nfft, rows)
+    W = np.ascontiguousarray(W.cpu().numpy().T)
+    if plain_window is not None and perF0 > 1:
+        # generate_WF0_chirped windows the plain combs with `analysisWindow` but the chirped
+        # ones with the sinebell default of generate_ODGD_spec_chirped (:335-339)
+        plain = np.arange(F0Table.size) * int(perF0)
+        Wp = k.wf0_combs(f1[plain], f2[plain], npart[plain], Fs, Ot, Lsig, t_begin, plain_window,
+                         nfft, rows)
+        W[:, plain] = Wp.cpu().numpy().T
+    return W
+
+
+def generate_WF0_chirped(minF0, maxF0, Fs, Nfft=2048, stepNotes=4, lengthWindow=2048, Ot=0.5,
+                         perF0=1, depthChirpInSemiTone=0.5, loadWF0=True, analysisWindow='hanning',
+                         kernels=None):
+    """F0Table, WF0 = generate_WF0_chirped(...)  (ref: separateLeadFunctions.py:237-345): the
+    `Nfft` x (NF0 perF0) dictionary of glottal harmonic combs, |FFT|^2 of the windowed KLGLOTT88
+    waveform of every F0 (and of its perF0 - 1 chirps), cached in the working directory under
+    the reference's file name."""
+    filename = str('').join(['wf0_', '_minF0-', str(minF0), '_maxF0-', str(maxF0), '_Fs-', str(Fs),
+                             '_Nfft-', str(Nfft), '_stepNotes-', str(stepNotes), '_Ot-', str(Ot),
+                             '_perF0-', str(perF0), '_depthChirp-', str(depthChirpInSemiTone),
+                             '_analysisWindow-', analysisWindow, '.npz'])
+    if os.path.isfile(filename) and loadWF0:
+        struc = np.load(filename)
+        return struc['F0Table'], struc['WF0']
+    windows = {'sinebell': sinebell, 'hanning': hann, 'rectangular': np.ones}
+    if analysisWindow not in windows:
+        raise ValueError("Analysis window not understood.")
+    lengthWindow, Nfft = int(lengthWindow), int(Nfft)
+    F0Table = _f0_table(minF0, maxF0, stepNotes)
+    chirp_win = sinebell(lengthWindow)
+    plain_win = windows[analysisWindow](lengthWindow)
+    WF0 = _combs(kernels, F0Table, Fs, perF0, depthChirpInSemiTone, Ot, lengthWindow, 0,
+                 chirp_win if perF0 > 1 else plain_win, Nfft, Nfft,
+                 plain_window=None if analysisWindow == 'sinebell' else plain_win)
+    np.savez(filename, F0Table=F0Table, WF0=WF0)
+    return F0Table, WF0
+
+
+def generate_WF0_TR_chirped(transform, minF0, maxF0, stepNotes=4, Ot=0.5, perF0=1,
+                            depthChirpInSemiTone=0.5, loadWF0=True, verbose=False, kernels=None):
+    """F0Table, WF0, transform = generate_WF0_TR_chirped(transform, ...)  (ref: :696-886) for an
+    STFT transform object (tftransforms.stft.STFT): every comb is the power of the STFT frame
+    in the middle of a waveform of 2 linFTLen samples (old NumPy's rfft kept the real part of
+    the complex waveform).  Cached under the reference's file name (F0Table and WF0 only)."""
+    if hasattr(transform, 'cqtkernel') or hasattr(transform, 'octaveNr'):
+        raise NotImplementedError("pyfasst_b200: only the STFT transform (DESIGN.md section 8)")
+    try:
+        lengthWindow = (transform.freqbins - 1) * 2 * 2  # "just to be sure" (:763)
+    except AttributeError:
+        raise AttributeError('There is something utterly wrong with the desired TF '
+                             'representation...\nNo freqbins attribute!')
+    # the reference's cache name: the scalar / function attributes of the transform (:768-799)
+    keep = ('fmin', 'fmax', 'bins', 'fs', 'winFunc', 'freqbins', 'atomHopFactor')
+    attributes = []
+    for key, v in transform.__dict__.items():
+        if key in keep and np.isscalar(v):
+            attributes.append(key.lower() + '-' + str(v))
+        elif key in keep and callable(v):
+            attributes.append(v.__name__)
+    attributes.sort()
+    filename = str('').join(['wf0_%s_' % transform.transformname, '_minF0-', str(minF0),
+                             '_maxF0-', str(maxF0), '_stepNotes-', str(int(stepNotes)),
+                             '_Ot-', str(Ot), '_perF0-', str(int(perF0)),
+                             '_depthChirp-', str(depthChirpInSemiTone),
+                             '_lengthWindow-%d' % lengthWindow, '_', str('_').join(attributes),
+                             '.npz'])
+    if os.path.isfile(filename) and loadWF0:
+        struc = np.load(filename, allow_pickle=True)
+        return struc['F0Table'], struc['WF0'], transform
+    Nfft = (transform.freqbins - 1) * 2
+    hop = int(transform.fthop)
+    window = np.asarray(transform.window, dtype=np.float64)
+    # the frame nearest to the middle of the waveform; frame n is centred on sample n hop
+    # (tftransforms/stft.py:40-63; midindex :849-850)
+    nframes = int(np.ceil(lengthWindow / np.double(hop)) + 2)
+    midindex = int(np.argmin((lengthWindow / 2. - np.arange(nframes) * float(hop)) ** 2))
+    t_begin = midindex * hop - window.size // 2
+    F0Table = _f0_table(minF0, maxF0, stepNotes)
+    WF0 = _combs(kernels, F0Table, transform.fs, perF0, depthChirpInSemiTone, Ot, lengthWindow,
+                 t_begin, window, Nfft, transform.freqbins)
+    np.savez(filename, F0Table=F0Table, WF0=WF0)
+    return F0Table, WF0, transform

@@ -100,6 +100,8 @@ SIGNATURES = {
     "pf_simm_wm_scaled": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_viterbi_workspace_bytes": [c_int, c_i64],
     "pf_viterbi": [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp],
+    "pf_wf0_combs": [c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_i64, c_i64, c_vp, c_int, c_int,
+                     c_int, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "pf_noise_anneal": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_ll_reduce": [c_vp, c_int, c_vp, c_vp],
@@ -478,6 +480,22 @@ class CudaKernels(object):
         self._call("pf_viterbi", self._pv(dens), self._pv(log_prior), self._pv(log_trans), S, N,
                    self._pv(ws), ws.numel() * 8, path.data_ptr())
         return path
+
+    # -- glottal-source F0 dictionary ------------------------------------------------------------
+    def wf0_combs(self, f1, f2, npart, fs, Ot, Lsig, t_begin, window, nfft, rows):
+        """f1, f2 (float64), npart (int32): host arrays [ncols]; window: host float64 [wlen].
+        Returns the device float64 array [ncols, rows] of comb power spectra."""
+        torch = self.torch
+        dev = self.device
+        f1d = torch.tensor(np.ascontiguousarray(f1, dtype=np.float64)).to(dev)
+        f2d = torch.tensor(np.ascontiguousarray(f2, dtype=np.float64)).to(dev)
+        npd = torch.tensor(np.ascontiguousarray(npart, dtype=np.int32)).to(dev)
+        wd = torch.tensor(np.ascontiguousarray(window, dtype=np.float64)).to(dev)
+        out = torch.empty((f1d.numel(), int(rows)), dtype=torch.float64, device=dev)
+        self._call("pf_wf0_combs", self._pv(f1d), self._pv(f2d), npd.data_ptr(), f1d.numel(),
+                   int(np.max(npart)) if len(npart) else 0, float(fs), float(Ot), int(Lsig),
+                   int(t_begin), self._pv(wd), wd.numel(), int(nfft), int(rows), self._pv(out))
+        return out
 
     # -- IS-NMF initialisers ---------------------------------------------------------------
     def nmf_is_terms(self, hat, SX, out, eps, F, N, ldn):

@@ -220,6 +220,34 @@ class FakeSimmKernels(object):
                 y[2 * c + part, :, :N] = lv * ih * x[2 * c + part, :, :N]
                 y[2 * (nch + c) + part, :, :N] = sm * ih * x[2 * c + part, :, :N]
 
+    # ---- glottal-source F0 dictionary -----------------------------------------------------------
+    def wf0_combs(self, f1, f2, npart, fs, Ot, Lsig, t_begin, window, nfft, rows):
+        """Specification of wf0_comb_kernel (csrc/wf0.cu): power spectrum of one windowed frame
+        of the KLGLOTT88 waveform per column, float64."""
+        self.launches += 1
+        f1, f2 = np.asarray(f1, dtype=np.float64), np.asarray(f2, dtype=np.float64)
+        window = np.asarray(window, dtype=np.float64)
+        wlen = window.size
+        out = np.zeros((f1.size, rows))
+        t = t_begin + np.arange(wlen)
+        inside = (t >= 0) & (t < Lsig)
+        tau = t / float(fs)
+        for c in range(f1.size):
+            P = int(npart[c])
+            frame = np.zeros(wlen)
+            if P > 0:
+                h = np.arange(1, P + 1)
+                z = 1j * 2.0 * np.pi * h * Ot
+                E = np.exp(-z)
+                amp = (f1[c] + f2[c]) / 2.0 * 27 / 4 * (E + 2 * (1 + 2 * E) / z
+                                                          - 6 * (1 - E) / z ** 2) / z
+                cyc = f1[c] * tau + (f2[c] - f1[c]) * tau ** 2 / (2.0 * Lsig / fs)
+                x = np.real(np.sum(amp[:, None] * np.exp(2j * np.pi * np.outer(h, cyc)), axis=0))
+                frame = np.where(inside, x, 0.0) * window
+            spec = np.fft.fft(frame, nfft)
+            out[c] = np.abs(spec[np.arange(rows) % nfft]) ** 2
+        return torch.tensor(out)
+
     # ---- Viterbi --------------------------------------------------------------------------------
     def viterbi(self, log_density, log_prior, log_trans):
         self.launches += 2
