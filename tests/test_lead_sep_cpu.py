@@ -124,10 +124,24 @@ def test_estim_stereo_simm_params(tmp_path):
     check_estimation(tmp_path, AllFakeKernels())
 
 
+def test_constructor_builds_the_f0_dictionary(tmp_path, monkeypatch):
+    """Without a WF0 argument the constructor generates the glottal F0 dictionary like the
+    reference's computeWF0 (SeparateLeadStereoTF.py:661-684): STFT transform object with the
+    sqrt-Blackman-Harris window, combs normalised to sum one."""
+    from oracle import wf0_oracle as wo
+    from pyfasst_b200.tools.utils import sqrt_blackmanharris
+    monkeypatch.chdir(tmp_path)
+    p = make_process(tmp_path, AllFakeKernels(), dict(p_WF0=None), minF0=100, maxF0=800,
+                     stepNotes=2)
+    table, W = wo.generate_WF0_TR_chirped(WLEN, WLEN // 4, sqrt_blackmanharris, FS, 100, 800, 2,
+                                          0.5, 1, 0.5)
+    assert_allclose(p.SIMMParams['F0Table'], table, rtol=0, atol=0)
+    assert_allclose(p.SIMMParams['WF0'], wo.normalise(W), rtol=0, atol=1e-12)
+    assert p.SIMMParams['NF0'] == table.size and p.F == WLEN // 2 + 1
+
+
 def test_constructor_errors(tmp_path):
     g = load()
-    with pytest.raises(NotImplementedError):  # the F0 dictionary generator is not on this path
-        make_process(tmp_path, AllFakeKernels(), dict(p_WF0=None))
     with pytest.raises(ValueError):
         make_process(tmp_path, AllFakeKernels(), dict(p_WF0=g["p_WF0"][:-1]))
     with pytest.raises(NotImplementedError):
