@@ -203,6 +203,23 @@ int pf_mult_update_splits(void* theta, int64_t ldt, const double* num_partial,
                           int64_t ldnd, int rows, int64_t cols, double omega, int dtype,
                           void* stream);
 
+/* ---- K4 for general factor structures (several factors per spectral component, free FW, large
+ * dictionaries: multiChanSourceF0Filter, audioModel.py:2551-2760).  The planes of
+ * update_spectral_components (audioModel.py:1513-1520, :1565-1571) are formed once and contracted
+ * with pf_gemm_tf32x3(_splitk). */
+/* out [F][2 ld] = ( hatW / max(P,eps)^2 * max(O,eps) | max(O,eps) / max(P,eps) ), eps = 1e-10,
+ * zero in the padding columns n >= N */
+int pf_gem_ratio_planes(const void* hatW, const void* P, const void* O, void* out, int F,
+                        int64_t N, int64_t ld, int dtype, void* stream);
+/* out (=, +=) a * b elementwise on [F][ld] planes (b = NULL: a); zero in the padding */
+int pf_mul_planes(const void* a, const void* b, void* out, int F, int64_t N, int64_t ld,
+                  int accumulate, int dtype, void* stream);
+/* theta[r][c] *= (num[r][c] / max(den[r][c], 1e-10))^omega with num / den of theta's type
+ * (GEMM outputs)  (audioModel.py:1573, :1631, :1725) */
+int pf_mult_update_same(void* theta, int64_t ldt, const void* num, int64_t ldn, const void* den,
+                        int64_t ldd, int rows, int64_t cols, double omega, int dtype,
+                        void* stream);
+
 /* ---- K5: renormalisation  (audioModel.py:1980-2040) ----------------------------- */
 int pf_spat_energy(const void* A, const int* src_of_sub, int R, int J, int I, int F,
                    double* sums, void* stream);

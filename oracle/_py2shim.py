@@ -176,6 +176,9 @@ PATCHES = {
          "    elif len(analysisWindowType)==lengthOdgd:"),
         # old np.fft.rfft cast a complex input to float (ComplexWarning: the imaginary part is
         # discarded); today's raises.  The STFT object receives the complex waveform (:846, :877)
+        # np.load of the .npz cache (it holds the pickled transform object): pickles were allowed
+        # by default in the NumPy of the time
+        ("struc = np.load(filename)", "struc = np.load(filename, allow_pickle=True)"),
         ("transform.computeTransform(data=odgd)\n",
          "transform.computeTransform(data=np.real(odgd))\n"),
     ],

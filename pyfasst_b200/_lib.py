@@ -100,6 +100,9 @@ SIGNATURES = {
     "pf_simm_wm_scaled": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_viterbi_workspace_bytes": [c_int, c_i64],
     "pf_viterbi": [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp],
+    "pf_gem_ratio_planes": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp],
+    "pf_mul_planes": [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_vp],
+    "pf_mult_update_same": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
     "pf_wf0_combs": [c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_i64, c_i64, c_vp, c_int, c_int,
                      c_int, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
@@ -176,7 +179,9 @@ class CudaKernels(object):
     def _p(self, t):
         if t is None:
             return None
-        assert t.is_cuda and t.is_contiguous(), "kernel arguments must be contiguous CUDA tensors"
+        # (2-D views with contiguous rows are fine: every matrix argument carries its stride)
+        assert t.is_cuda and (t.is_contiguous() or (t.dim() == 2 and t.stride(1) == 1)), \
+            "kernel arguments must be CUDA tensors with contiguous rows"
         return t.data_ptr()
 
     def _stream(self):
@@ -545,6 +550,23 @@ class CudaKernels(object):
         _check(self.lib.pf_scale_matrix(self._p(M), M.stride(0), rows, cols, self._p(s),
                                         int(by_row), int(divide), self._p(total),
                                         self.dtype_code(M), self._stream()), self.lib)
+
+    # -- general factor structures -----------------------------------------------------------------
+    def gem_ratio_planes(self, hatW, P, O, out, N):
+        F, ld = hatW.shape
+        _check(self.lib.pf_gem_ratio_planes(self._p(hatW), self._p(P), self._p(O), self._p(out), F,
+                                            N, ld, self.dtype_code(hatW), self._stream()), self.lib)
+
+    def mul_planes(self, a, b, out, N, accumulate=False):
+        F, ld = a.shape
+        _check(self.lib.pf_mul_planes(self._p(a), self._p(b), self._p(out), F, N, ld,
+                                      int(accumulate), self.dtype_code(a), self._stream()), self.lib)
+
+    def mult_update_same(self, theta, num, den, rows, cols, omega):
+        _check(self.lib.pf_mult_update_same(self._p(theta), theta.stride(0), self._p(num),
+                                            num.stride(0), self._p(den), den.stride(0), rows, cols,
+                                            float(omega), self.dtype_code(theta), self._stream()),
+               self.lib)
 
     def check_totals(self, totals, eps, flags):
         _check(self.lib.pf_check_totals(self._p(totals), totals.numel(), float(eps),

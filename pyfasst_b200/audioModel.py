@@ -2,7 +2,7 @@
 
 Same class names, constructor arguments, public methods and user-visible state as the
 reference (`FASST` audioModel.py:66-2294, `MultiChanNMFInst_FASST` :2296-2420,
-`MultiChanNMFConv` :2422-2508): `spat_comps`, `spec_comps` and `noise` stay plain
+`MultiChanNMFConv` :2422-2508, `multiChanSourceF0Filter` :2551-3014): `spat_comps`, `spec_comps` and `noise` stay plain
 NumPy-holding dicts that the user may read and edit between calls
 (doc/source/description.rst:125-197).  Every numerical method packs that state into HBM,
 runs the sm_100a kernels through the C ABI (GemEngine, pyfasst_b200/engine.py) and
@@ -24,6 +24,7 @@ import numpy as np
 
 from . import audioObject as ao
 from .engine import GemEngine
+from .engine_general import GeneralGemEngine
 from .tftransforms.tft import tftransforms
 from .tftransforms import stft as _stft
 
@@ -102,14 +103,29 @@ class FASST(object):
         the source of truth at every public-method entry)."""
         if self._X is None:
             self.comp_transf_Cx()
-        eng = GemEngine(self._k(), self.nbFreqsSigRepr, self.nbFramesSigRepr,
-                        dtype=self.compute_dtype, comm=self._comm, shard=self._shard)
+        cls = GeneralGemEngine if self._general_structure() else GemEngine
+        eng = cls(self._k(), self.nbFreqsSigRepr, self.nbFramesSigRepr,
+                  dtype=self.compute_dtype, comm=self._comm, shard=self._shard)
         eng.set_X_planes(self._X)
         lim = self.noise['ann_PSD_lim']
         opt = self.noise['sim_ann_opt'] if psd_mode is None else psd_mode
         eng.set_noise(opt, lim[0], lim[1], self.noise['PSD'])
         eng.set_model(self.spat_comps, self.spec_comps, self.nmfUpdateCoeff)
         return eng
+
+    def _general_structure(self):
+        """True when the spectral structure is not the single-factor NMF of the standard models
+        (several factors, free FW, several spectral components per source, shared or large
+        dictionaries): GeneralGemEngine (engine_general.py) runs those."""
+        owners = []
+        for spec in self.spec_comps.values():
+            owners.append(spec['spat_comp_ind'])
+            if len(spec['factor']) != 1:
+                return True
+            fac = list(spec['factor'].values())[0]
+            if fac['FW_frdm_prior'] == 'free' or np.shape(fac['FW'])[0] > 64:
+                return True
+        return sorted(owners) != list(range(len(self.spat_comps)))
 
     # ------------------------------------------------------------------ K1
     def comp_transf_Cx(self):
@@ -544,3 +560,121 @@ class MultiChanNMFConv(MultiChanNMFInst_FASST):
                                            dtype=complex)
             for r in range(self.rank[nspat]):
                 spat_comp['params'][r] = A[spat_ind].T
+
+
+class multiChanSourceF0Filter(FASST):
+    """Multichannel source/filter model (ref: audioModel.py:2551-3014): `nbComps - 1` sources
+    with a two-factor spectral component -- glottal-comb dictionary x smooth filters -- and one
+    residual NMF component.  The dictionary WF0 is generated on the GPU
+    (SeparateLeadStereo.separateLeadFunctions.generate_WF0_TR_chirped) and SHARED by all the
+    sources, like the reference's `self.sourceFreqComps` (quirk Q11: the renormalisation rescales
+    the shared array once per source).  Estimation runs on GeneralGemEngine.
+
+    Not here: `sparsity` (reweigh_sparsity_constraint, :2981-3014), `initSpecCompsWithLabelAndFiles`
+    (needs the external gmm-gsmm module) and `initializeFreeMats`."""
+
+    def __init__(self, audio, nbComps=3, nbNMFResComps=1, nbFilterComps=20, nbFilterWeigs=[4, ],
+                 minF0=39, maxF0=2000, minF0search=80, maxF0search=800, stepnoteF0=16,
+                 chirpPerF0=1, spatial_rank=1, sparsity=None, **kwargs):
+        from .SeparateLeadStereo import separateLeadFunctions as slf
+        super(multiChanSourceF0Filter, self).__init__(audio=audio, **kwargs)
+        if sparsity is not None:
+            raise NotImplementedError("pyfasst_b200: the sparsity re-weighting of the source "
+                                      "activations (audioModel.py:2981-3014) is not implemented")
+        self.comp_transf_Cx()
+        self.sourceParams = {'minF0': minF0, 'maxF0': maxF0, 'stepnoteF0': stepnoteF0,
+                             'chirpPerF0': chirpPerF0, 'minF0search': minF0search,
+                             'maxF0search': maxF0search}
+        self.nbComps = nbComps
+        self.nbNMFResComps = nbNMFResComps
+        self.nbFilterComps = nbFilterComps
+        if len(nbFilterWeigs) < self.nbComps - 1:
+            self.nbFilterWeigs = [nbFilterWeigs[0], ] * self.nbComps
+        else:
+            self.nbFilterWeigs = nbFilterWeigs
+        self.spatial_rank = np.atleast_1d(spatial_rank)
+        if self.spatial_rank.size < self.nbComps:
+            self.spatial_rank = [self.spatial_rank[0], ] * self.nbComps
+        # the source dictionary is shared among all the components (:2613-2635)
+        self.F0Table, WF0, _ = slf.generate_WF0_TR_chirped(
+            transform=self.tft, minF0=minF0, maxF0=maxF0, stepNotes=stepnoteF0, Ot=0.5,
+            perF0=chirpPerF0, depthChirpInSemiTone=0.5, loadWF0=True, verbose=self.verbose,
+            kernels=self._kernels)
+        WF0 = np.array(WF0)
+        for n in range(WF0.shape[1]):  # patterns in low-energy bins are set to eps (:2624-2627)
+            WF0[WF0[:, n] < WF0[:, n].max() * 1e-4, n] = eps
+        self.sourceFreqComps = np.ascontiguousarray(
+            np.hstack([WF0[:self.nbFreqsSigRepr], np.vstack(np.ones(self.nbFreqsSigRepr))]))
+        self.nbSourceComps = self.sourceFreqComps.shape[1]
+        self.sourceFreqWeights = np.eye(self.nbSourceComps)
+        self.filterFreqComps = slf.generateHannBasis(
+            numberFrequencyBins=self.nbFreqsSigRepr, sizeOfFourier=self.sig_repr_params['fsize'],
+            Fs=self.audioObject.samplerate, frequencyScale='linear',
+            numberOfBasis=self.nbFilterComps)
+        self.sparsity = sparsity
+        self._initialize_structures()
+
+    def _initialize_structures(self, seed=None):
+        """ref: audioModel.py:2650-2772, same np.random call order."""
+        np.random.seed(seed)
+        self.rank = self.spatial_rank
+        nc = self.audioObject.channels
+        rnd = lambda *shape: 0.75 * np.abs(np.random.randn(*shape)) + 0.25
+        self.spat_comps, self.spec_comps = {}, {}
+        for j in range(self.nbComps - 1):
+            params = np.random.randn(nc, self.rank[j])
+            if nc == 2:
+                ang = (j + 1) * np.pi / (2. * self.nbComps)
+                params = np.array([np.sin(ang) + np.random.randn(self.rank[j]) * np.sqrt(0.01),
+                                   np.cos(ang) + np.random.randn(self.rank[j]) * np.sqrt(0.01)])
+            self.spat_comps[j] = {'time_dep': 'indep', 'mix_type': 'inst',
+                                  'frdm_prior': 'free', 'params': params}
+            source = {'FB': self.sourceFreqComps, 'FW': self.sourceFreqWeights,
+                      'TW': rnd(self.nbSourceComps, self.nbFramesSigRepr), 'TB': [],
+                      'FB_frdm_prior': 'fixed', 'FW_frdm_prior': 'fixed',
+                      'TW_frdm_prior': 'free', 'TB_frdm_prior': [], 'TW_constr': 'NMF'}
+            filt = {'FB': self.filterFreqComps,
+                    'FW': rnd(self.nbFilterComps, self.nbFilterWeigs[j]),
+                    'TW': rnd(self.nbFilterWeigs[j], self.nbFramesSigRepr), 'TB': [],
+                    'FB_frdm_prior': 'fixed', 'FW_frdm_prior': 'free',
+                    'TW_frdm_prior': 'free', 'TB_frdm_prior': [], 'TW_constr': 'NMF'}
+            self.spec_comps[j] = {'spat_comp_ind': j, 'factor': {0: source, 1: filt}}
+        # residual component: single-factor NMF (:2709-2745)
+        self.resSpatialRank = self.rank[-1]
+        j = self.nbComps - 1
+        self.spat_comps[j] = {'time_dep': 'indep', 'mix_type': 'inst', 'frdm_prior': 'free',
+                              'params': np.random.randn(nc, self.resSpatialRank)}
+        res = {'FB': rnd(self.nbFreqsSigRepr, self.nbNMFResComps),
+               'FW': np.eye(self.nbNMFResComps),
+               'TW': rnd(self.nbNMFResComps, self.nbFramesSigRepr), 'TB': [],
+               'FB_frdm_prior': 'free', 'FW_frdm_prior': 'fixed',
+               'TW_frdm_prior': 'free', 'TB_frdm_prior': [], 'TW_constr': 'NMF'}
+        self.spec_comps[j] = {'spat_comp_ind': j, 'factor': {0: res}}
+        for j in range(self.nbComps):
+            self.spec_comps[j]['sparsity'] = False
+        self.renormalize_parameters()
+
+    def setSpecCompFB(self, compNb, FB, FB_frdm_prior='fixed'):
+        """ref: audioModel.py:2858-2876"""
+        speccomp = self.spec_comps[compNb]['factor'][0]
+        if self.nbFreqsSigRepr != FB.shape[0]:
+            raise AttributeError("Size of provided FB is not consistent with inner attributes")
+        speccomp['FB'] = np.copy(FB)
+        ncomp = FB.shape[1]
+        speccomp['FW'] = np.eye(ncomp)
+        speccomp['TW'] = 0.75 * np.abs(np.random.randn(ncomp, self.nbFramesSigRepr)) + 0.25
+        speccomp['FB_frdm_prior'] = FB_frdm_prior
+
+    def makeItConvolutive(self):
+        """ref: audioModel.py:2910-2931"""
+        nc = self.audioObject.channels
+        for nspat, (spat_ind, spat_comp) in enumerate(self.spat_comps.items()):
+            if spat_comp['mix_type'] != 'inst':
+                warnings.warn("Spatial component %d " % spat_ind +
+                              "already not instantaneous, skipping...")
+                continue
+            spat_comp['mix_type'] = 'conv'
+            inst = np.asarray(spat_comp['params'])
+            spat_comp['params'] = np.zeros([self.rank[nspat], nc, self.nbFreqsSigRepr],
+                                           dtype=complex)
+            spat_comp['params'][:] = np.atleast_2d(inst.T)[:, :, None]

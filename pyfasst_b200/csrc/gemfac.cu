@@ -1,0 +1,118 @@
+// K4 for general factor structures (source/filter models: several factors per spectral component,
+// free FW, large dictionaries), sm_100a.
+//
+// The reference's update_spectral_components (pyfasst/audioModel.py:1469-1727) is, for every free
+// matrix of every factor, two dense contractions of the planes
+//     num_plane = hat_W / P^2 * O ,   den_plane = O / P        (P, O clamped at eps, :1513-1520)
+// with the other matrices of the factor.  The fast path (nmf.cu / nmf_tc.cu) fuses the planes
+// into the contractions for single-factor NMF with K <= 32; here the planes are formed once
+// (one bandwidth-bound pass) and contracted by the tensor-core GEMM of gemm_tc.cu, which is what
+// the K = 1093 glottal dictionary of multiChanSourceF0Filter (audioModel.py:2551-2760) needs.
+#include "common.cuh"
+
+namespace pf {
+
+constexpr int GF_THREADS = 256;
+constexpr double GF_EPS = 1e-10;  // audioModel.py:72
+
+// out[f][0:ld] = hatW / max(P,eps)^2 * max(O,eps), out[f][ld:2ld] = max(O,eps) / max(P,eps);
+// zero in the padding columns n >= N (the planes are contracted over n with padded lengths)
+template <typename T>
+__global__ void __launch_bounds__(GF_THREADS)
+gem_ratio_planes_kernel(const T* __restrict__ hatW, const T* __restrict__ P,
+                        const T* __restrict__ O, T* __restrict__ out, int F, long N, long ld) {
+  const long n = (long)blockIdx.x * GF_THREADS + threadIdx.x;
+  const int f = blockIdx.y;
+  if (n >= ld) return;
+  T num = (T)0, den = (T)0;
+  if (n < N) {
+    const size_t i = (size_t)f * ld + n;
+    const T p = pf_max(P[i], (T)GF_EPS);
+    const T o = pf_max(O[i], (T)GF_EPS);
+    const T ip = (T)1 / p;
+    den = o * ip;
+    num = hatW[i] * ip * ip * o;
+  }
+  out[(size_t)f * 2 * ld + n] = num;
+  out[(size_t)f * 2 * ld + ld + n] = den;
+}
+
+// out (=, +=) a * b  (b == NULL: a), zero in the padding
+template <typename T>
+__global__ void __launch_bounds__(GF_THREADS)
+mul_planes_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int F,
+                  long N, long ld, int accumulate) {
+  const long n = (long)blockIdx.x * GF_THREADS + threadIdx.x;
+  const int f = blockIdx.y;
+  if (n >= ld) return;
+  const size_t i = (size_t)f * ld + n;
+  T v = (T)0;
+  if (n < N) {
+    v = a[i];
+    if (b != nullptr) v *= b[i];
+    if (accumulate) v += out[i];
+  }
+  out[i] = v;
+}
+
+// theta[r][c] *= (num[r][c] / max(den[r][c], eps))^omega, num / den in the type of theta
+template <typename T>
+__global__ void __launch_bounds__(GF_THREADS)
+mult_update_same_kernel(T* __restrict__ theta, long ldt, const T* __restrict__ num, long ldn,
+                        const T* __restrict__ den, long ldd, int rows, long cols, double omega) {
+  const long c = (long)blockIdx.x * GF_THREADS + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= cols) return;
+  const double ratio = (double)num[(size_t)r * ldn + c] /
+                       fmax((double)den[(size_t)r * ldd + c], GF_EPS);
+  const double g = omega == 1.0 ? ratio : pow(ratio, omega);
+  theta[(size_t)r * ldt + c] = (T)((double)theta[(size_t)r * ldt + c] * g);
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" int pf_gem_ratio_planes(const void* hatW, const void* P, const void* O, void* out, int F,
+                                   int64_t N, int64_t ld, int dtype, void* stream) {
+  PF_REQUIRE(F > 0 && N > 0 && ld >= N, "pf_gem_ratio_planes: F=%d N=%ld ld=%ld", F, (long)N,
+             (long)ld);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_gem_ratio_planes: bad dtype %d", dtype);
+  dim3 grid(ceil_div(ld, GF_THREADS), F);
+  if (dtype == PF_F32)
+    gem_ratio_planes_kernel<float><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (const float*)hatW, (const float*)P, (const float*)O, (float*)out, F, N, ld);
+  else
+    gem_ratio_planes_kernel<double><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (const double*)hatW, (const double*)P, (const double*)O, (double*)out, F, N, ld);
+  return check_launch("gem_ratio_planes_kernel");
+}
+
+extern "C" int pf_mul_planes(const void* a, const void* b, void* out, int F, int64_t N, int64_t ld,
+                             int accumulate, int dtype, void* stream) {
+  PF_REQUIRE(F > 0 && N > 0 && ld >= N, "pf_mul_planes: F=%d N=%ld ld=%ld", F, (long)N, (long)ld);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_mul_planes: bad dtype %d", dtype);
+  dim3 grid(ceil_div(ld, GF_THREADS), F);
+  if (dtype == PF_F32)
+    mul_planes_kernel<float><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (const float*)a, (const float*)b, (float*)out, F, N, ld, accumulate);
+  else
+    mul_planes_kernel<double><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (const double*)a, (const double*)b, (double*)out, F, N, ld, accumulate);
+  return check_launch("mul_planes_kernel");
+}
+
+extern "C" int pf_mult_update_same(void* theta, int64_t ldt, const void* num, int64_t ldn,
+                                   const void* den, int64_t ldd, int rows, int64_t cols,
+                                   double omega, int dtype, void* stream) {
+  PF_REQUIRE(rows > 0 && cols > 0, "pf_mult_update_same: rows=%d cols=%ld", rows, (long)cols);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_mult_update_same: bad dtype %d", dtype);
+  dim3 grid(ceil_div(cols, GF_THREADS), rows);
+  if (dtype == PF_F32)
+    mult_update_same_kernel<float><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (float*)theta, ldt, (const float*)num, ldn, (const float*)den, ldd, rows, cols, omega);
+  else
+    mult_update_same_kernel<double><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (double*)theta, ldt, (const double*)num, ldn, (const double*)den, ldd, rows, cols, omega);
+  return check_launch("mult_update_same_kernel");
+}

@@ -238,6 +238,15 @@ class GemEngine(object):
                 A[self.ranks[j]] = p[:, :, self.f_lo:self.f_hi]
         self.J, self.R = J, R
         self.A = self._upload(A)
+        self.omega = float(nmfUpdateCoeff)
+        self._set_spectral(spec_comps)
+        self._alloc_work()
+
+    def _set_spectral(self, spec_comps):
+        """Spectral components of the fast path: one per spatial component, single NMF factor,
+        fixed FW (the structures of MultiChanNMFInst_FASST / MultiChanNMFConv,
+        audioModel.py:2355-2391).  Anything else: GeneralGemEngine (engine_general.py)."""
+        J = self.J
         # spectral components: one per spatial component, single NMF factor
         S = len(spec_comps)
         if sorted(spec_comps.keys()) != list(range(S)):
@@ -288,10 +297,12 @@ class GemEngine(object):
                 ent["W"] = self._zeros([self.F, Kw])
                 ent["G"] = self._zeros([Kb, self.ld])
             self.spec.append(ent)
-        self.omega = float(nmfUpdateCoeff)
-        self._alloc_work()
 
     def _alloc_work(self):
+        self._alloc_common()
+        self._alloc_spectral()
+
+    def _alloc_common(self):
         torch, k = self.torch, self.k
         F, ld, J, R, N = self.F, self.ld, self.J, self.R, self.N
         f64, c128 = torch.float64, torch.complex128
@@ -318,6 +329,12 @@ class GemEngine(object):
         self.sums = self._zeros([J], f64)
         counts = np.array([len(self.ranks[j]) * I * self.F_total for j in range(J)], dtype=np.float64)
         self.counts = self._f64(counts)
+
+    def _alloc_spectral(self):
+        torch, k = self.torch, self.k
+        F, ld, N = self.F, self.ld, self.N
+        f64 = torch.float64
+        code = k.dtype_code(self.V)
         Kmax = max(max(e["Kb"], e["Kw"]) for e in self.spec)
         S = len(self.spec)
         self.colmax = self._zeros([S, Kmax], f64)

@@ -429,6 +429,35 @@ class FakeKernels(object):
         if total is not None:
             _np(total)[0] += m[:rows, :cols].astype(np.float64).sum()
 
+    # ---- general factor structures (csrc/gemfac.cu) ---------------------------------------
+    def gem_ratio_planes(self, hatW, P, O, out, N):
+        self.launches += 1
+        F, ld = hatW.shape
+        p = np.maximum(_np(P)[:, :N].astype(np.float64), EPS)
+        o = np.maximum(_np(O)[:, :N].astype(np.float64), EPS)
+        on = _np(out)
+        on[:] = 0
+        on[:, :N] = _np(hatW)[:, :N] / p ** 2 * o
+        on[:, ld:ld + N] = o / p
+
+    def mul_planes(self, a, b, out, N, accumulate=False):
+        self.launches += 1
+        v = _np(a)[:, :N].astype(np.float64)
+        if b is not None:
+            v = v * _np(b)[:, :N]
+        on = _np(out)
+        if accumulate:
+            v = v + on[:, :N]
+        on[:, :N] = v
+        on[:, N:] = 0
+
+    def mult_update_same(self, theta, num, den, rows, cols, omega):
+        self.launches += 1
+        th = _np(theta)
+        ratio = _np(num)[:rows, :cols].astype(np.float64) / np.maximum(
+            _np(den)[:rows, :cols].astype(np.float64), EPS)
+        th[:rows, :cols] = th[:rows, :cols].astype(np.float64) * ratio ** omega
+
     def check_totals(self, totals, eps, flags):
         self.launches += 1
         tt = _np(totals)
