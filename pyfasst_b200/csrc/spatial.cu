@@ -265,6 +265,37 @@ __global__ void fw_renorm_kernel(T* __restrict__ FW, int ldfw, int Kb, int Kw,
   }
 }
 
+// The same for large FW (the K x K weights of a large dictionary): rows scaled by one CTA each,
+// column means by one CTA each; the division by w2 is a scale_matrix launch.
+template <typename T>
+__global__ void fw_scale_rows_kernel(T* __restrict__ FW, int ldfw, int Kw,
+                                     const double* __restrict__ colmax,
+                                     double* __restrict__ w_out) {
+  const int r = blockIdx.x;
+  double w = colmax[r];
+  if (w == 0.0) w = 1.0;
+  if (threadIdx.x == 0) w_out[r] = w;
+  for (int c = threadIdx.x; c < Kw; c += blockDim.x)
+    FW[(size_t)r * ldfw + c] = (T)((double)FW[(size_t)r * ldfw + c] * w);
+}
+template <typename T>
+__global__ void fw_col_means_kernel(const T* __restrict__ FW, int ldfw, int Kb,
+                                    double* __restrict__ w2_out) {
+  const int c = blockIdx.x;
+  double s = 0.0;
+  for (int r = threadIdx.x; r < Kb; r += blockDim.x) s += (double)FW[(size_t)r * ldfw + c];
+  __shared__ double s_red[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) d += s_red[w];
+    d /= Kb;
+    w2_out[c] = d == 0.0 ? 1.0 : d;
+  }
+}
+
 // M[r][c] *= (by_row ? s[r] : s[c]) or /= ; optional sum of the result (TW restart test,
 // audioModel.py:2023): one atomic per CTA after a block reduction
 template <typename T>
@@ -366,7 +397,7 @@ extern "C" int pf_fb_scale_colmax(void* FB, int ldw, int F, int K, const double*
                                   const double* counts, int j, double* colmax, int dtype,
                                   void* stream) {
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_fb_scale_colmax: bad dtype %d", dtype);
-  PF_REQUIRE(K >= 1 && K <= 64, "pf_fb_scale_colmax: K=%d (max 64)", K);
+  PF_REQUIRE(K >= 1 && K <= 65535, "pf_fb_scale_colmax: K=%d", K);
   if (dtype == PF_F32)
     fb_scale_colmax_kernel<float><<<K, 256, 0, as_stream(stream)>>>((float*)FB, ldw, F, K, sums,
                                                                    counts, j, colmax);
@@ -379,7 +410,20 @@ extern "C" int pf_fb_scale_colmax(void* FB, int ldw, int F, int K, const double*
 extern "C" int pf_fw_renorm(void* FW, int ldfw, int Kb, int Kw, const double* colmax, double* w,
                             double* w2, int dtype, void* stream) {
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_fw_renorm: bad dtype %d", dtype);
-  PF_REQUIRE(Kb >= 1 && Kb <= 64 && Kw >= 1 && Kw <= 64, "pf_fw_renorm: Kb=%d Kw=%d (max 64)", Kb, Kw);
+  PF_REQUIRE(Kb >= 1 && Kb <= 65535 && Kw >= 1 && Kw <= 65535, "pf_fw_renorm: Kb=%d Kw=%d", Kb, Kw);
+  if (Kb > 64 || Kw > 64) {  // large weights: three launches instead of one CTA
+    cudaStream_t st = as_stream(stream);
+    if (dtype == PF_F32) {
+      fw_scale_rows_kernel<float><<<Kb, 256, 0, st>>>((float*)FW, ldfw, Kw, colmax, w);
+      fw_col_means_kernel<float><<<Kw, 256, 0, st>>>((const float*)FW, ldfw, Kb, w2);
+    } else {
+      fw_scale_rows_kernel<double><<<Kb, 256, 0, st>>>((double*)FW, ldfw, Kw, colmax, w);
+      fw_col_means_kernel<double><<<Kw, 256, 0, st>>>((const double*)FW, ldfw, Kb, w2);
+    }
+    int rc = check_launch("fw_col_means_kernel");
+    if (rc) return rc;
+    return pf_scale_matrix(FW, ldfw, Kb, Kw, w2, 0, 1, nullptr, dtype, stream);
+  }
   if (dtype == PF_F32)
     fw_renorm_kernel<float><<<1, 256, 0, as_stream(stream)>>>((float*)FW, ldfw, Kb, Kw, colmax, w, w2);
   else

@@ -123,7 +123,10 @@ class GeneralGemEngine(GemEngine):
 
     def _refresh_factor(self, fc):
         """W = FB FW and the factor's power P = W TW from the current matrices."""
-        self.k.small_matmul(fc["FB"], fc["FW"], fc["W"])
+        if fc["Kb4"] * fc["Kw4"] <= 4096:
+            self.k.small_matmul(fc["FB"], fc["FW"], fc["W"])
+        else:  # the weights of a large dictionary: tensor-core GEMM
+            self._gemm(fc["FB"], fc["FW"], fc["W"], self.F, fc["Kw4"], fc["Kb4"])
         if fc["Kw"] <= 32:
             self.k.spec_power(fc["W"][:, :fc["Kw"]], fc["TW"][:fc["Kw"]], fc["P"], self.N, False)
         else:
@@ -183,7 +186,10 @@ class GeneralGemEngine(GemEngine):
                     # Q3: the power of ALL the spectral components of the source (:1521-1523)
                     self._refresh_src(j)
                     k.gem_ratio_planes(self.hatW[j], self.V[j], self.other, self.planes, N)
-                    k.small_matmul(fc["FW"], fc["TW"], fc["G"])          # (FW TW), :1531-1540
+                    if Kb4 * Kw4 <= 4096:                                # (FW TW), :1531-1540
+                        k.small_matmul(fc["FW"], fc["TW"], fc["G"])
+                    else:
+                        self._gemm(fc["FW"], fc["TW"], fc["G"], Kb4, ld, Kw4)
                     T = self.tnd[:2 * F * Kb4].view(2 * F, Kb4)
                     self._gemm(self.planes.view(2 * F, ld), fc["G"], T, 2 * F, Kb4, ld,
                                transB=True, splitk=True)

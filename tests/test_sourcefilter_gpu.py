@@ -49,3 +49,29 @@ def test_model_against_reference(tmp_path, monkeypatch):
 def test_float64_is_refused():
     with pytest.raises(NotImplementedError):
         cpu.build(ck(), 1, "float64").estim_param_a_post_model()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_renormalisation_kernels_with_large_dictionaries(dt):
+    """fb_scale_colmax / fw_renorm beyond 64 columns (the 1093-comb dictionary and its square
+    weight matrix), on row-strided views like GeneralGemEngine passes them."""
+    rng = np.random.default_rng(11)
+    F, Kb, Kw = 50, 150, 131
+    FBp = torch.tensor(np.abs(rng.standard_normal((F, 152)))).to(dt)
+    FWp = torch.tensor(np.abs(rng.standard_normal((152, 132)))).to(dt)
+    FWp[7, :] = 0
+    FBp[:, 9] = 0  # a zero column: its maximum counts as one
+    sums = torch.tensor([3.0, 5.0], dtype=torch.float64)
+    counts = torch.tensor([2.0, 4.0], dtype=torch.float64)
+    outs = []
+    for k, dev in ((FakeKernels(), "cpu"), (ck(), "cuda")):
+        FB, FW = FBp.clone().to(dev), FWp.clone().to(dev)
+        colmax = torch.zeros(152, dtype=torch.float64, device=dev)
+        w = torch.zeros(152, dtype=torch.float64, device=dev)
+        w2 = torch.zeros(132, dtype=torch.float64, device=dev)
+        k.fb_scale_colmax(FB[:, :Kb], sums.to(dev), counts.to(dev), 1, colmax)
+        k.fw_renorm(FW[:Kb, :Kw], colmax, w, w2)
+        outs.append([t.cpu().numpy() for t in (FB, FW, colmax, w, w2)])
+    tol = 1e-6 if dt == torch.float32 else 1e-13
+    for a, b in zip(outs[1], outs[0]):
+        assert np.abs(a - b).max() / np.abs(b).max() < tol
