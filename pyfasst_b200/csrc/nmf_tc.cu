@@ -503,9 +503,268 @@ tw_contract_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ 
   if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
+// ============================ TW update, P' formed in the kernel =========================
+// The same contractions, but P' = W' H is not read from a plane: a first MMA forms
+//     P'[128 n][16 f] = H^T[128 n][32 k] W'^T[32 k][16 f]
+// in TMEM (A = the CTA's H tile, MN-major, staged once; B = the step's W' rows, K-major), every
+// thread reads the P' values of ITS elements back with tcgen05.ld, forms the two operands and
+// the main MMAs follow as above.  Per source and iteration this removes the spec_power launch
+// (4 B/bin written) and the P' read (4 B/bin): 8 instead of 16 B/bin for the TW update.
+// Thread mapping (dictated by TMEM: a warp reads the 32 lanes (w & 3) * 32 ..): thread = one
+// frame n = 32 (w & 3) + lane and the 8 frequency rows (w >> 2) * 8 .. + 7 of the step.
+// The P' MMA of step s + 1 is issued before the main MMAs of step s (double-buffered P').
+constexpr int TWF_THREADS = 256;
+constexpr int TWF_FR = 16;
+constexpr int TWF_NT = 128;
+constexpr uint32_t TWF_LBO = TWF_FR * 128, TWF_SBO = 512;   // a1 / a2 / b tiles (K = 16 rows)
+constexpr uint32_t TWF_HLBO = 32 * 128;                     // H tile (K = 32 rows)
+
+struct TwfStage {
+  unsigned char a1_hi[TWF_FR * TWF_NT * 4];
+  unsigned char a1_lo[TWF_FR * TWF_NT * 4];
+  unsigned char a2_hi[TWF_FR * TWF_NT * 4];
+  unsigned char a2_lo[TWF_FR * TWF_NT * 4];
+  unsigned char b_hi[TWF_FR * 32 * 4];
+  unsigned char b_lo[TWF_FR * 32 * 4];
+};
+struct TwfSmem {
+  TwfStage st[2];
+  unsigned char h_hi[32 * TWF_NT * 4];   // H tile, MN-major [32 k][128 n]
+  unsigned char h_lo[32 * TWF_NT * 4];
+  unsigned char wp_hi[TWF_FR * 32 * 4];  // W' rows of the NEXT step, K-major [16 f][32 k]
+  unsigned char wp_lo[TWF_FR * 32 * 4];
+};
+
+// Variants tried on configs[1] (profiles/r01/ncu_tw_contract_fused_tc_kernel.txt): this one, one
+// CTA-wide barrier per step, 229 us per launch; row pointers + precomputed shared-memory
+// addresses (98 M instead of 113 M instructions) 240 us; mbarrier hand-over to a dedicated MMA
+// warp with P' issued two steps ahead 293 us (96 registers, spills), to thread 0 390 us.
+__global__ void __launch_bounds__(TWF_THREADS, 2)
+tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ Op, long ld,
+                            const float* __restrict__ W, int ldw, const float* __restrict__ H,
+                            long ldh, int K, int F, long N, int fchunk, int fsplit,
+                            double* __restrict__ num, double* __restrict__ den, long ldo) {
+  extern __shared__ __align__(1024) unsigned char twf_smem[];
+  __shared__ uint64_t mbar_free[2];
+  __shared__ uint64_t mbar_p[2];
+  __shared__ uint64_t mbar_done;
+  __shared__ uint32_t tmem_base;
+  unsigned char* base = twf_smem + ((1024 - (tc::smem_u32(twf_smem) & 1023)) & 1023);
+  TwfSmem& sm = *reinterpret_cast<TwfSmem*>(base);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long nb = (long)blockIdx.x * TWF_NT;
+  const int split = blockIdx.y;
+  const int fb = split * fchunk;
+  int fe = fb + fchunk;
+  if (fe > F) fe = F;
+  const int nsteps = (fe - fb + TWF_FR - 1) / TWF_FR;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 128);
+  if (tid == 0) {
+    tc::mbar_init(&mbar_free[0], 1);
+    tc::mbar_init(&mbar_free[1], 1);
+    tc::mbar_init(&mbar_p[0], 1);
+    tc::mbar_init(&mbar_p[1], 1);
+    tc::mbar_init(&mbar_done, 1);
+    tc::fence_mbar_init();
+  }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // H tile 32 k x 128 n (zero beyond K and beyond the row): 4 float4 per thread
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + q * TWF_THREADS;  // 0 .. 1023
+    const int k = i >> 5, c = (i & 31) * 4;
+    const long n = nb + c;
+    const float4 h = (k < K && n + 4 <= ldh) ? ldg4(H + (long)k * ldh + n) : zero4;
+    st_split4(sm.h_hi, sm.h_lo, tc::mnmajor_off(k, c, TWF_HLBO, TWF_SBO), h);
+  }
+  // W rows: threads 0..127 hold 4 consecutive k of one of the 16 rows of a step
+  const int wrow = tid >> 3, wk = (tid & 7) * 4;
+  const uint32_t woff = tc::mnmajor_off(wrow, wk, TWF_LBO, TWF_SBO);   // main B (f = K index)
+  const uint32_t wpoff = tc::kmajor_off(wrow, wk);                      // P' B  (f = N index)
+  auto load_w = [&](int step) {
+    float4 w = zero4;
+    if (tid < 128 && step < nsteps) {
+      const int f = fb + step * TWF_FR + wrow;
+      if (f < fe) {
+        const float* wr = W + (long)f * ldw;
+        w.x = (wk + 0 < K) ? __ldg(wr + wk + 0) : 0.f;
+        w.y = (wk + 1 < K) ? __ldg(wr + wk + 1) : 0.f;
+        w.z = (wk + 2 < K) ? __ldg(wr + wk + 2) : 0.f;
+        w.w = (wk + 3 < K) ? __ldg(wr + wk + 3) : 0.f;
+      }
+    }
+    return w;
+  };
+  auto stage_wp = [&](float4 w) {
+    float4 hi, lo;
+    tc::split_tf32(w.x, hi.x, lo.x); tc::split_tf32(w.y, hi.y, lo.y);
+    tc::split_tf32(w.z, hi.z, lo.z); tc::split_tf32(w.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(sm.wp_hi + wpoff) = hi;
+    *reinterpret_cast<float4*>(sm.wp_lo + wpoff) = lo;
+  };
+  // plane elements of this thread: frame n, rows fhalf * 8 .. + 7 of the step
+  const int nl = (warp & 3) * 32 + lane, fhalf = warp >> 2;
+  const long n = nb + nl;
+  const bool n_ok = n < ld;
+  float hw_n[8], o_n[8];
+  auto fetch = [&](int step) {
+    const int f0 = fb + step * TWF_FR + fhalf * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int f = f0 + q;
+      const bool ok = n_ok && f < fe;
+      const long off = (long)f * ld + n;
+      hw_n[q] = ok ? __ldg(hatW + off) : 0.f;
+      o_n[q] = ok ? __ldg(Op + off) : 0.f;
+    }
+  };
+  float4 w_cur = load_w(0), w_nxt = load_w(1), w_nn;
+  if (tid < 128) stage_wp(w_cur);
+  tc::fence_proxy_async();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = tc::idesc_tf32(128, 32, 1, 1);
+  const uint32_t idesc_p = tc::idesc_tf32(128, 16, 1, 0);
+  // P'(step) -> TMEM columns 64 + 16 (step & 1) .. + 15; W' rows are in wp_hi / wp_lo
+  auto issue_p = [&](int step) {
+    const uint32_t hh = tc::smem_u32(sm.h_hi), hl = tc::smem_u32(sm.h_lo);
+    const uint32_t wh = tc::smem_u32(sm.wp_hi), wl = tc::smem_u32(sm.wp_lo);
+    const uint32_t d = tmem + 64u + 16u * (uint32_t)(step & 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t dah = tc::smem_desc_mnmajor(hh + j * 1024, TWF_HLBO, TWF_SBO);
+      const uint64_t dal = tc::smem_desc_mnmajor(hl + j * 1024, TWF_HLBO, TWF_SBO);
+      const uint64_t dbh = tc::smem_desc_kmajor(wh + j * 32), dbl = tc::smem_desc_kmajor(wl + j * 32);
+      tc::mma_tf32(d, dah, dbh, idesc_p, j > 0 ? 1u : 0u);
+      tc::mma_tf32(d, dah, dbl, idesc_p, 1u);
+      tc::mma_tf32(d, dal, dbh, idesc_p, 1u);
+    }
+    tc::mma_commit(&mbar_p[step & 1]);
+  };
+  if (nsteps > 0) {
+    fetch(0);
+    if (tid == 0) issue_p(0);
+  }
+  for (int s = 0; s < nsteps; ++s) {
+    const int b = s & 1;
+    float hw[8], o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { hw[q] = hw_n[q]; o[q] = o_n[q]; }
+    if (s + 1 < nsteps) fetch(s + 1);
+    w_nn = load_w(s + 2);
+    // the main MMAs of step s-2 must have finished reading this ring slot
+    if (s >= 2) tc::mbar_wait(&mbar_free[b], (uint32_t)(((s >> 1) - 1) & 1));
+    // P'(s): its MMA was issued one step ago; it also frees wp_hi / wp_lo
+    tc::mbar_wait(&mbar_p[b], (uint32_t)((s >> 1) & 1));
+    tc::fence_after_thread_sync();
+    uint32_t pv[8];
+    tc::tmem_ld_32x8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 64u + 16u * (uint32_t)b +
+                         8u * (uint32_t)fhalf, pv);
+    tc::tmem_ld_wait();
+    TwfStage& st = sm.st[b];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      // rows beyond the shard (all-zero loads) contribute nothing: W is zero there as well
+      const float oc = fmaxf(o[q], kEpsF);
+      const float rp = fast_rcpf(fmaxf(__uint_as_float(pv[q]), kEpsF));
+      const float e2 = oc * rp;                // other / P'            (audioModel.py:1694-1701)
+      const float e1 = oc * (hw[q] * rp * rp);  // other * hat_W / P'^2  (audioModel.py:1714-1720)
+      const uint32_t off = tc::mnmajor_off(fhalf * 8 + q, nl, TWF_LBO, TWF_SBO);
+      float hi, lo;
+      tc::split_tf32(e1, hi, lo);
+      *reinterpret_cast<float*>(st.a1_hi + off) = hi;
+      *reinterpret_cast<float*>(st.a1_lo + off) = lo;
+      tc::split_tf32(e2, hi, lo);
+      *reinterpret_cast<float*>(st.a2_hi + off) = hi;
+      *reinterpret_cast<float*>(st.a2_lo + off) = lo;
+    }
+    if (tid < 128) {
+      st_split4(st.b_hi, st.b_lo, woff, w_cur);
+      stage_wp(w_nxt);  // W' rows of step s + 1 for the next P' MMA
+    }
+    w_cur = w_nxt;
+    w_nxt = w_nn;
+    tc::fence_proxy_async();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+      if (s + 1 < nsteps) issue_p(s + 1);
+      const uint32_t a1h = tc::smem_u32(st.a1_hi), a1l = tc::smem_u32(st.a1_lo);
+      const uint32_t a2h = tc::smem_u32(st.a2_hi), a2l = tc::smem_u32(st.a2_lo);
+      const uint32_t bh = tc::smem_u32(st.b_hi), bl = tc::smem_u32(st.b_lo);
+#pragma unroll
+      for (int j = 0; j < TWF_FR / 8; ++j) {
+        const uint64_t dbh = tc::smem_desc_mnmajor(bh + j * 1024, TWF_LBO, TWF_SBO);
+        const uint64_t dbl = tc::smem_desc_mnmajor(bl + j * 1024, TWF_LBO, TWF_SBO);
+        const uint64_t d1h = tc::smem_desc_mnmajor(a1h + j * 1024, TWF_LBO, TWF_SBO);
+        const uint64_t d1l = tc::smem_desc_mnmajor(a1l + j * 1024, TWF_LBO, TWF_SBO);
+        const uint64_t d2h = tc::smem_desc_mnmajor(a2h + j * 1024, TWF_LBO, TWF_SBO);
+        const uint64_t d2l = tc::smem_desc_mnmajor(a2l + j * 1024, TWF_LBO, TWF_SBO);
+        const uint32_t acc = (s > 0 || j > 0) ? 1u : 0u;
+        tc::mma_tf32(tmem, d1h, dbh, idesc, acc);
+        tc::mma_tf32(tmem, d1h, dbl, idesc, 1u);
+        tc::mma_tf32(tmem, d1l, dbh, idesc, 1u);
+        tc::mma_tf32(tmem + 32, d2h, dbh, idesc, acc);
+        tc::mma_tf32(tmem + 32, d2h, dbl, idesc, 1u);
+        tc::mma_tf32(tmem + 32, d2l, dbh, idesc, 1u);
+      }
+      tc::mma_commit(&mbar_free[b]);
+      if (s == nsteps - 1) tc::mma_commit(&mbar_done);
+    }
+  }
+  if (nsteps > 0) tc::mbar_wait(&mbar_done, 0);
+  tc::fence_after_thread_sync();
+  if (warp < 4) {
+    const long no = nb + warp * 32 + lane;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      uint32_t v[32];
+      if (nsteps > 0) {
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(which * 32), v);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      double* out = which ? den : num;
+      if (no < ldo) {
+        const bool live = no < N;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k < K) out[((size_t)split * K + k) * ldo + no] = live ? (double)__uint_as_float(v[k]) : 0.0;
+      }
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
 }  // namespace pf
 
 using namespace pf;
+
+// TW update contractions for float32 planes, K <= 32, P' = W' H formed in the kernel
+int pf_tw_contract_fused_tc(const float* hatW, const float* O, long ld, const float* W, int ldw,
+                            const float* H, long ldh, int K, int F, long N, int fchunk, int fsplit,
+                            double* num, double* den, long ldo, cudaStream_t st) {
+  const size_t smem = sizeof(TwfSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tw_contract_fused_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("tw_contract_fused_tc_kernel: %zu bytes of shared memory: %s", smem,
+              cudaGetErrorString(e));
+    return PF_ERR_CUDA;
+  }
+  dim3 grid(ceil_div(N, TWF_NT), fsplit);
+  tw_contract_fused_tc_kernel<<<grid, TWF_THREADS, smem, st>>>(hatW, O, ld, W, ldw, H, ldh, K, F, N,
+                                                             fchunk, fsplit, num, den, ldo);
+  return check_launch("tw_contract_fused_tc_kernel");
+}
 
 // host side: called from pf_nmf_fb_contract (nmf.cu) for float32 planes with P == O
 int pf_fb_contract_tc(const float* hatW, const float* P, long ld, const float* G, long ldg, int K,

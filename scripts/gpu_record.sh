@@ -24,11 +24,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
 echo "ncu launch-list exit $?"
 CMD2="python scripts/profile_driver.py --iters 4"
 $CMD2 > gpurun_out/${TAG}_driver_plain.log 2>&1 || { echo "driver failed"; exit 1; }
-for kern in ${KERNELS:-estep_stereo_kernel tw_contract_tc_kernel fb_contract_tc_kernel spec_power_tc_kernel}; do
+for kern in ${KERNELS:-estep_stereo_kernel tw_contract_fused_tc_kernel fb_contract_tc_kernel spec_power_tc_kernel}; do
   ncu --set full --clock-control none --import-source on -k regex:$kern -s 2 -c 1 \
       -f -o gpurun_out/${TAG}_prof_$kern $CMD2 > gpurun_out/${TAG}_ncu_$kern.log 2>&1
   echo "ncu $kern exit $?"
 done
+[ "${SKIP_SIMM:-0}" = "1" ] && exit 0
 # SIMM (configs[2]): bench line, launch list, and the dense contraction kernel
 python scripts/bench_simm.py --steps 3 --warmup 3 > gpurun_out/${TAG}_simm_bench.json 2> gpurun_out/${TAG}_simm_bench.err; echo "simm bench exit $?"
 CMD3="python scripts/bench_simm.py --steps 1 --warmup 3 --no-cpu-baseline"
