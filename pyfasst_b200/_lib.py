@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpyfasst_b200.so")
+# PYFASST_B200_LIB: another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PYFASST_B200_LIB") or os.path.join(HERE, "libpyfasst_b200.so")
 
 PF_F32, PF_F64 = 0, 1
 PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2

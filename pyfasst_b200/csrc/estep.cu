@@ -69,7 +69,11 @@ __global__ void spat_coef_kernel(const double2* __restrict__ A, SubMap map, int 
 // OPT bit 0: packed float32 moment accumulation (FFMA2); bit 1: hardware float->double
 // conversion of the loaded values.  MINB: CTAs per SM the register allocation aims for.
 template <typename T, typename C, int J, int OPT, int MINB>
+#ifdef PF_ESTEP_MAXNREG
+__global__ void __maxnreg__(PF_ESTEP_MAXNREG)
+#else
 __global__ void __launch_bounds__(ESTEP_THREADS, MINB)
+#endif
 estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
                     const double* __restrict__ coef, const double* __restrict__ noise,
                     SubMap map, T* __restrict__ hatW, double* __restrict__ partial, int F,
@@ -450,14 +454,14 @@ static int launch_estep_opt(const void* X, const void* V, const double* coef, co
   size_t smem = 0;
   if ((OPT & 4) != 0 && sizeof(T) == 4) {
     smem = (size_t)ESTEP_DEPTH * (4 + J) * ESTEP_THREADS * 16;
-    cudaError_t e = cudaFuncSetAttribute(estep_stereo_kernel<T, C, J, OPT, 2>,
+    cudaError_t e = cudaFuncSetAttribute(estep_stereo_kernel<T, C, J, OPT, ESTEP_MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("estep_stereo_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return PF_ERR_CUDA;
     }
   }
-  estep_stereo_kernel<T, C, J, OPT, 2><<<grid, ESTEP_THREADS, smem, st>>>(
+  estep_stereo_kernel<T, C, J, OPT, ESTEP_MINB><<<grid, ESTEP_THREADS, smem, st>>>(
       (const T*)X, (const T*)V, coef, noise, map, (T*)hatW, partial, F, N, ld, chunk, nsplit);
   return check_launch("estep_stereo_kernel");
 }

@@ -7,7 +7,14 @@
 
 namespace pf {
 
-constexpr int ESTEP_THREADS = 128;
+#ifndef PF_ESTEP_THREADS
+#define PF_ESTEP_THREADS 128
+#endif
+#ifndef PF_ESTEP_MINB
+#define PF_ESTEP_MINB 2
+#endif
+constexpr int ESTEP_THREADS = PF_ESTEP_THREADS;
+constexpr int ESTEP_MINB = PF_ESTEP_MINB;  // CTAs per SM the register allocation aims for
 constexpr int MAXJ = 6;
 constexpr int MAXR = 16;
 constexpr int PF_F32_FASTMATH = 2;

@@ -518,34 +518,39 @@ constexpr int TWF_FR = 16;
 constexpr int TWF_NT = 128;
 constexpr uint32_t TWF_LBO = TWF_FR * 128, TWF_SBO = 512;   // a1 / a2 / b tiles (K = 16 rows)
 constexpr uint32_t TWF_HLBO = 32 * 128;                     // H tile (K = 32 rows)
+constexpr int TWF_PB = 64;   // rows per P' MMA block (= its UMMA N): 4 steps share 12 MMAs
 
-struct TwfStage {
+struct TwfSmem {
+  // operand tiles of the main MMAs (ONE stage: the MMAs of a step are short and have finished
+  // by the time the next step's operands are formed)
   unsigned char a1_hi[TWF_FR * TWF_NT * 4];
   unsigned char a1_lo[TWF_FR * TWF_NT * 4];
   unsigned char a2_hi[TWF_FR * TWF_NT * 4];
   unsigned char a2_lo[TWF_FR * TWF_NT * 4];
   unsigned char b_hi[TWF_FR * 32 * 4];
   unsigned char b_lo[TWF_FR * 32 * 4];
-};
-struct TwfSmem {
-  TwfStage st[2];
   unsigned char h_hi[32 * TWF_NT * 4];   // H tile, MN-major [32 k][128 n]
   unsigned char h_lo[32 * TWF_NT * 4];
-  unsigned char wp_hi[TWF_FR * 32 * 4];  // W' rows of the NEXT step, K-major [16 f][32 k]
-  unsigned char wp_lo[TWF_FR * 32 * 4];
+  unsigned char wp_hi[TWF_PB * 32 * 4];  // W' rows of the next P' block, K-major [64 f][32 k]
+  unsigned char wp_lo[TWF_PB * 32 * 4];
+  float ptile[2][TWF_FR][TWF_NT];        // P' of a step, [f][n] (transposed out of TMEM)
 };
 
-// Variants tried on configs[1] (profiles/r01/ncu_tw_contract_fused_tc_kernel.txt): this one, one
-// CTA-wide barrier per step, 229 us per launch; row pointers + precomputed shared-memory
-// addresses (98 M instead of 113 M instructions) 240 us; mbarrier hand-over to a dedicated MMA
-// warp with P' issued two steps ahead 293 us (96 registers, spills), to thread 0 390 us.
+// Variants measured on configs[1] (profiles/r01): thread = one frame x 8 rows straight out of
+// TMEM (4-byte accesses) 229 us per launch; the same with fewer address instructions 240 us; with
+// an mbarrier hand-over to a dedicated MMA warp 293 us; this one -- P' transposed through
+// shared memory one step ahead so that the threads keep 16-byte accesses -- 220 us; that one
+// with the MMA issue moved to a ninth warp 322 us (9 warps of 112 registers: three of them land
+// on one scheduler's 16 K registers, so only ONE CTA fits per SM -- the same holds for every
+// 288-thread variant above).
 __global__ void __launch_bounds__(TWF_THREADS, 2)
 tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ Op, long ld,
                             const float* __restrict__ W, int ldw, const float* __restrict__ H,
                             long ldh, int K, int F, long N, int fchunk, int fsplit,
                             double* __restrict__ num, double* __restrict__ den, long ldo) {
   extern __shared__ __align__(1024) unsigned char twf_smem[];
-  __shared__ uint64_t mbar_free[2];
+  __shared__ uint64_t s_desc[28];
+  __shared__ uint64_t mbar_free;
   __shared__ uint64_t mbar_p[2];
   __shared__ uint64_t mbar_done;
   __shared__ uint32_t tmem_base;
@@ -559,10 +564,9 @@ tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restr
   if (fe > F) fe = F;
   const int nsteps = (fe - fb + TWF_FR - 1) / TWF_FR;
 
-  if (warp == 0) tc::tmem_alloc(&tmem_base, 128);
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
   if (tid == 0) {
-    tc::mbar_init(&mbar_free[0], 1);
-    tc::mbar_init(&mbar_free[1], 1);
+    tc::mbar_init(&mbar_free, 1);
     tc::mbar_init(&mbar_p[0], 1);
     tc::mbar_init(&mbar_p[1], 1);
     tc::mbar_init(&mbar_done, 1);
@@ -581,7 +585,6 @@ tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restr
   // W rows: threads 0..127 hold 4 consecutive k of one of the 16 rows of a step
   const int wrow = tid >> 3, wk = (tid & 7) * 4;
   const uint32_t woff = tc::mnmajor_off(wrow, wk, TWF_LBO, TWF_SBO);   // main B (f = K index)
-  const uint32_t wpoff = tc::kmajor_off(wrow, wk);                      // P' B  (f = N index)
   auto load_w = [&](int step) {
     float4 w = zero4;
     if (tid < 128 && step < nsteps) {
@@ -596,114 +599,173 @@ tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restr
     }
     return w;
   };
-  auto stage_wp = [&](float4 w) {
-    float4 hi, lo;
-    tc::split_tf32(w.x, hi.x, lo.x); tc::split_tf32(w.y, hi.y, lo.y);
-    tc::split_tf32(w.z, hi.z, lo.z); tc::split_tf32(w.w, hi.w, lo.w);
-    *reinterpret_cast<float4*>(sm.wp_hi + wpoff) = hi;
-    *reinterpret_cast<float4*>(sm.wp_lo + wpoff) = lo;
-  };
-  // plane elements of this thread: frame n, rows fhalf * 8 .. + 7 of the step
-  const int nl = (warp & 3) * 32 + lane, fhalf = warp >> 2;
-  const long n = nb + nl;
-  const bool n_ok = n < ld;
-  float hw_n[8], o_n[8];
-  auto fetch = [&](int step) {
-    const int f0 = fb + step * TWF_FR + fhalf * 8;
+  // W' rows of one P' block (64 rows x 32 k = 512 float4: two per thread), K-major tile
+  auto stage_wp_block = [&](int blk) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int f = f0 + q;
-      const bool ok = n_ok && f < fe;
-      const long off = (long)f * ld + n;
-      hw_n[q] = ok ? __ldg(hatW + off) : 0.f;
-      o_n[q] = ok ? __ldg(Op + off) : 0.f;
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * TWF_THREADS;  // 0 .. 511
+      const int r = i >> 3, kk = (i & 7) * 4;
+      const int f = fb + blk * TWF_PB + r;
+      float4 w = zero4;
+      if (f < fe) {
+        const float* wr = W + (long)f * ldw;
+        w.x = (kk + 0 < K) ? __ldg(wr + kk + 0) : 0.f;
+        w.y = (kk + 1 < K) ? __ldg(wr + kk + 1) : 0.f;
+        w.z = (kk + 2 < K) ? __ldg(wr + kk + 2) : 0.f;
+        w.w = (kk + 3 < K) ? __ldg(wr + kk + 3) : 0.f;
+      }
+      float4 hi, lo;
+      tc::split_tf32(w.x, hi.x, lo.x); tc::split_tf32(w.y, hi.y, lo.y);
+      tc::split_tf32(w.z, hi.z, lo.z); tc::split_tf32(w.w, hi.w, lo.w);
+      const uint32_t off = tc::kmajor_off(r, kk);
+      *reinterpret_cast<float4*>(sm.wp_hi + off) = hi;
+      *reinterpret_cast<float4*>(sm.wp_lo + off) = lo;
     }
   };
-  float4 w_cur = load_w(0), w_nxt = load_w(1), w_nn;
-  if (tid < 128) stage_wp(w_cur);
+  // plane elements of this thread: float4 (f, n4) of the 16 x 128 tiles, 2 per plane and step
+  int prow[2], pcol[2];
+  uint32_t poff[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = tid + q * TWF_THREADS;  // 0 .. 511
+    prow[q] = i >> 5;
+    pcol[q] = (i & 31) * 4;
+    poff[q] = tc::mnmajor_off(prow[q], pcol[q], TWF_LBO, TWF_SBO);
+  }
+  float4 hw_n[2], o_n[2];
+  auto fetch = [&](int step) {
+    const int f0 = fb + step * TWF_FR;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int f = f0 + prow[q];
+      const long n = nb + pcol[q];
+      const bool ok = (f < fe) && (n + 4 <= ld);
+      const long off = (long)f * ld + n;
+      hw_n[q] = ok ? ldg4(hatW + off) : zero4;
+      o_n[q] = ok ? ldg4(Op + off) : zero4;
+    }
+  };
+  // TMEM -> ptile: this thread's TMEM lane is frame nl, it moves rows fhalf * 8 .. + 7
+  const int nl = (warp & 3) * 32 + lane, fhalf = warp >> 2;
+  const uint32_t tmem_lane = (uint32_t)((warp & 3) * 32) << 16;
+
+  const int nblocks = (nsteps + 3) / 4;
+  float4 w_cur = load_w(0), w_n1 = load_w(1);
+  stage_wp_block(0);
   tc::fence_proxy_async();
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = tmem_base;
   const uint32_t idesc = tc::idesc_tf32(128, 32, 1, 1);
-  const uint32_t idesc_p = tc::idesc_tf32(128, 16, 1, 0);
-  // P'(step) -> TMEM columns 64 + 16 (step & 1) .. + 15; W' rows are in wp_hi / wp_lo
-  auto issue_p = [&](int step) {
+  const uint32_t idesc_p = tc::idesc_tf32(128, TWF_PB, 1, 0);
+  // every shared-memory descriptor is loop invariant (one operand stage): thread 0 builds them
+  // once; issuing a step is then 28 shared loads + 36 MMAs instead of ~400 ALU instructions on
+  // the critical path of warp 0
+  if (tid == 0) {
     const uint32_t hh = tc::smem_u32(sm.h_hi), hl = tc::smem_u32(sm.h_lo);
     const uint32_t wh = tc::smem_u32(sm.wp_hi), wl = tc::smem_u32(sm.wp_lo);
-    const uint32_t d = tmem + 64u + 16u * (uint32_t)(step & 1);
+    for (int j = 0; j < 4; ++j) {
+      s_desc[j] = tc::smem_desc_mnmajor(hh + j * 1024, TWF_HLBO, TWF_SBO);
+      s_desc[4 + j] = tc::smem_desc_mnmajor(hl + j * 1024, TWF_HLBO, TWF_SBO);
+      s_desc[8 + j] = tc::smem_desc_kmajor(wh + j * 32);
+      s_desc[12 + j] = tc::smem_desc_kmajor(wl + j * 32);
+    }
+    const uint32_t a1h = tc::smem_u32(sm.a1_hi), a1l = tc::smem_u32(sm.a1_lo);
+    const uint32_t a2h = tc::smem_u32(sm.a2_hi), a2l = tc::smem_u32(sm.a2_lo);
+    const uint32_t bh = tc::smem_u32(sm.b_hi), bl = tc::smem_u32(sm.b_lo);
+    for (int j = 0; j < TWF_FR / 8; ++j) {
+      s_desc[16 + 6 * j + 0] = tc::smem_desc_mnmajor(bh + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 1] = tc::smem_desc_mnmajor(bl + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 2] = tc::smem_desc_mnmajor(a1h + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 3] = tc::smem_desc_mnmajor(a1l + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 4] = tc::smem_desc_mnmajor(a2h + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 5] = tc::smem_desc_mnmajor(a2l + j * 1024, TWF_LBO, TWF_SBO);
+    }
+  }
+  // P'(block) -> TMEM columns 64 + 64 (block & 1) .. + 63; W' rows are in wp_hi / wp_lo
+  auto issue_p = [&](int blk) {
+    const int step = blk;  // (mbarrier slot = block parity)
+    const uint32_t d = tmem + 64u + (uint32_t)TWF_PB * (uint32_t)(blk & 1);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint64_t dah = tc::smem_desc_mnmajor(hh + j * 1024, TWF_HLBO, TWF_SBO);
-      const uint64_t dal = tc::smem_desc_mnmajor(hl + j * 1024, TWF_HLBO, TWF_SBO);
-      const uint64_t dbh = tc::smem_desc_kmajor(wh + j * 32), dbl = tc::smem_desc_kmajor(wl + j * 32);
+      const uint64_t dah = s_desc[j], dal = s_desc[4 + j], dbh = s_desc[8 + j], dbl = s_desc[12 + j];
       tc::mma_tf32(d, dah, dbh, idesc_p, j > 0 ? 1u : 0u);
       tc::mma_tf32(d, dah, dbl, idesc_p, 1u);
       tc::mma_tf32(d, dal, dbh, idesc_p, 1u);
     }
     tc::mma_commit(&mbar_p[step & 1]);
   };
+  // P' of a step: wait for the MMA of its block, move this thread's 8 values from TMEM to
+  // ptile[step & 1]
+  auto p_to_smem = [&](int step) {
+    const int blk = step >> 2, bb = blk & 1;
+    tc::mbar_wait(&mbar_p[bb], (uint32_t)((blk >> 1) & 1));
+    tc::fence_after_thread_sync();
+    uint32_t pv[8];
+    tc::tmem_ld_32x8(tmem + tmem_lane + 64u + (uint32_t)TWF_PB * (uint32_t)bb +
+                         16u * (uint32_t)(step & 3) + 8u * (uint32_t)fhalf, pv);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sm.ptile[step & 1][fhalf * 8 + q][nl] = __uint_as_float(pv[q]);
+  };
   if (nsteps > 0) {
     fetch(0);
     if (tid == 0) issue_p(0);
+    p_to_smem(0);                       // (also: the P' MMA of block 0 has finished reading wp)
+    tc::fence_before_thread_sync();
+    __syncthreads();                    // ptile[0] complete
   }
   for (int s = 0; s < nsteps; ++s) {
-    const int b = s & 1;
-    float hw[8], o[8];
+    float4 hw[2], o[2], p[2];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { hw[q] = hw_n[q]; o[q] = o_n[q]; }
+    for (int q = 0; q < 2; ++q) { hw[q] = hw_n[q]; o[q] = o_n[q]; }
     if (s + 1 < nsteps) fetch(s + 1);
-    w_nn = load_w(s + 2);
-    // the main MMAs of step s-2 must have finished reading this ring slot
-    if (s >= 2) tc::mbar_wait(&mbar_free[b], (uint32_t)(((s >> 1) - 1) & 1));
-    // P'(s): its MMA was issued one step ago; it also frees wp_hi / wp_lo
-    tc::mbar_wait(&mbar_p[b], (uint32_t)((s >> 1) & 1));
-    tc::fence_after_thread_sync();
-    uint32_t pv[8];
-    tc::tmem_ld_32x8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 64u + 16u * (uint32_t)b +
-                         8u * (uint32_t)fhalf, pv);
-    tc::tmem_ld_wait();
-    TwfStage& st = sm.st[b];
+    const float4 w_n2 = load_w(s + 2);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 2; ++q)
+      p[q] = *reinterpret_cast<const float4*>(&sm.ptile[s & 1][prow[q]][pcol[q]]);
+    float4 e1[2], e2[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
       // rows beyond the shard (all-zero loads) contribute nothing: W is zero there as well
-      const float oc = fmaxf(o[q], kEpsF);
-      const float rp = fast_rcpf(fmaxf(__uint_as_float(pv[q]), kEpsF));
-      const float e2 = oc * rp;                // other / P'            (audioModel.py:1694-1701)
-      const float e1 = oc * (hw[q] * rp * rp);  // other * hat_W / P'^2  (audioModel.py:1714-1720)
-      const uint32_t off = tc::mnmajor_off(fhalf * 8 + q, nl, TWF_LBO, TWF_SBO);
-      float hi, lo;
-      tc::split_tf32(e1, hi, lo);
-      *reinterpret_cast<float*>(st.a1_hi + off) = hi;
-      *reinterpret_cast<float*>(st.a1_lo + off) = lo;
-      tc::split_tf32(e2, hi, lo);
-      *reinterpret_cast<float*>(st.a2_hi + off) = hi;
-      *reinterpret_cast<float*>(st.a2_lo + off) = lo;
+      auto e12 = [&](float hwv, float ov, float pvv, float& a, float& c) {
+        const float oc = fmaxf(ov, kEpsF);
+        const float rp = fast_rcpf(fmaxf(pvv, kEpsF));
+        c = oc * rp;                // other / P'            (audioModel.py:1694-1701)
+        a = oc * (hwv * rp * rp);   // other * hat_W / P'^2  (audioModel.py:1714-1720)
+      };
+      e12(hw[q].x, o[q].x, p[q].x, e1[q].x, e2[q].x);
+      e12(hw[q].y, o[q].y, p[q].y, e1[q].y, e2[q].y);
+      e12(hw[q].z, o[q].z, p[q].z, e1[q].z, e2[q].z);
+      e12(hw[q].w, o[q].w, p[q].w, e1[q].w, e2[q].w);
     }
-    if (tid < 128) {
-      st_split4(st.b_hi, st.b_lo, woff, w_cur);
-      stage_wp(w_nxt);  // W' rows of step s + 1 for the next P' MMA
+    // the main MMAs of the previous step must have finished reading the operand tiles
+    if (s >= 1) tc::mbar_wait(&mbar_free, (uint32_t)((s - 1) & 1));
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      st_split4(sm.a1_hi, sm.a1_lo, poff[q], e1[q]);
+      st_split4(sm.a2_hi, sm.a2_lo, poff[q], e2[q]);
     }
-    w_cur = w_nxt;
-    w_nxt = w_nn;
+    if (tid < 128) st_split4(sm.b_hi, sm.b_lo, woff, w_cur);
+    if (s + 1 < nsteps) p_to_smem(s + 1);  // its block's MMA was issued >= 2 steps ago
+    // second step of a block: stage the W' rows of the next block (wp is free: the MMA of the
+    // current block completed before its first rows were read) -- its MMA follows this barrier
+    const bool next_block = (s & 3) == 1 && (s >> 2) + 1 < nblocks;
+    if (next_block) stage_wp_block((s >> 2) + 1);
+    w_cur = w_n1;
+    w_n1 = w_n2;
     tc::fence_proxy_async();
     tc::fence_before_thread_sync();
     __syncthreads();
     if (tid == 0) {
       tc::fence_after_thread_sync();
-      if (s + 1 < nsteps) issue_p(s + 1);
-      const uint32_t a1h = tc::smem_u32(st.a1_hi), a1l = tc::smem_u32(st.a1_lo);
-      const uint32_t a2h = tc::smem_u32(st.a2_hi), a2l = tc::smem_u32(st.a2_lo);
-      const uint32_t bh = tc::smem_u32(st.b_hi), bl = tc::smem_u32(st.b_lo);
+      if (next_block) issue_p((s >> 2) + 1);
 #pragma unroll
       for (int j = 0; j < TWF_FR / 8; ++j) {
-        const uint64_t dbh = tc::smem_desc_mnmajor(bh + j * 1024, TWF_LBO, TWF_SBO);
-        const uint64_t dbl = tc::smem_desc_mnmajor(bl + j * 1024, TWF_LBO, TWF_SBO);
-        const uint64_t d1h = tc::smem_desc_mnmajor(a1h + j * 1024, TWF_LBO, TWF_SBO);
-        const uint64_t d1l = tc::smem_desc_mnmajor(a1l + j * 1024, TWF_LBO, TWF_SBO);
-        const uint64_t d2h = tc::smem_desc_mnmajor(a2h + j * 1024, TWF_LBO, TWF_SBO);
-        const uint64_t d2l = tc::smem_desc_mnmajor(a2l + j * 1024, TWF_LBO, TWF_SBO);
+        const uint64_t dbh = s_desc[16 + 6 * j + 0], dbl = s_desc[16 + 6 * j + 1];
+        const uint64_t d1h = s_desc[16 + 6 * j + 2], d1l = s_desc[16 + 6 * j + 3];
+        const uint64_t d2h = s_desc[16 + 6 * j + 4], d2l = s_desc[16 + 6 * j + 5];
         const uint32_t acc = (s > 0 || j > 0) ? 1u : 0u;
         tc::mma_tf32(tmem, d1h, dbh, idesc, acc);
         tc::mma_tf32(tmem, d1h, dbl, idesc, 1u);
@@ -712,7 +774,7 @@ tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restr
         tc::mma_tf32(tmem + 32, d2h, dbl, idesc, 1u);
         tc::mma_tf32(tmem + 32, d2l, dbh, idesc, 1u);
       }
-      tc::mma_commit(&mbar_free[b]);
+      tc::mma_commit(&mbar_free);
       if (s == nsteps - 1) tc::mma_commit(&mbar_done);
     }
   }
@@ -741,7 +803,7 @@ tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restr
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace pf

@@ -601,9 +601,37 @@ class GemEngine(object):
             fac = spec_comps[s]["factor"]
             fac = fac[list(fac.keys())[0]]
             f64 = self.torch.float64
-            fac["FB"] = self._gather_f(e["FB"].to(f64), 0)
+            fac["FB"] = self._to_host(self._gather_dev(e["FB"].to(f64), 0, self.F_total, "freq"),
+                                      fac["FB"])
             fac["FW"] = e["FW"].to(f64).cpu().numpy()
-            fac["TW"] = self._gather_n(e["TW"][:, :self.N].to(f64), 1)
+            fac["TW"] = self._to_host(
+                self._gather_dev(e["TW"][:, :self.N].to(f64), 1, self.N_total, "time"), fac["TW"])
+
+    def _to_host(self, t, old):
+        """Device tensor -> host array.  When the user-visible array it replaces has the same
+        shape and is a writable C-contiguous float64 array, the copy lands in it IN PLACE (the
+        reference updates its parameter arrays in place as well, audioModel.py:1573, :1725): the
+        pages are already mapped, which halves the device-to-host time of the 10-minute TW
+        matrices compared with a freshly allocated array."""
+        if isinstance(old, np.ndarray) and old.dtype == np.float64 and old.flags.c_contiguous \
+                and old.flags.writeable and old.shape == tuple(t.shape) and t.is_cuda:
+            self.torch.from_numpy(old).copy_(t)
+            return old
+        return t.cpu().numpy()
+
+    def _gather_dev(self, t, axis, total, which):
+        """Like _gather, but the result stays a device tensor (replicated / unsharded case) or
+        is the gathered device tensor."""
+        if not self._sharded() or self.shard != which:
+            return t
+        shards = shard_bounds(total, self.comm.world)
+        smax = max(hi - lo for lo, hi in shards)
+        t = t.movedim(axis, 0)
+        pad = t.new_zeros((smax,) + tuple(t.shape[1:]))
+        pad[:t.shape[0]] = t
+        parts = self.comm.allgather(pad)
+        full = self.torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, shards)], dim=0)
+        return full.movedim(0, axis)
 
     def noise_psd(self):
         return self._gather_f(self.noise, 0)
