@@ -255,11 +255,32 @@ class FASST(object):
 
     def comp_spat_comp_power(self, spat_comp_ind, spec_comp_ind=[], factor_ind=[]):
         """V = power of one spatial component [F, N] (ref: audioModel.py:430-498)."""
-        if len(factor_ind) or (len(spec_comp_ind) and any(
-                self.spec_comps[s]['spat_comp_ind'] != spat_comp_ind for s in spec_comp_ind)):
-            raise NotImplementedError("factor / foreign spectral-component selection")
         eng = self._engine(psd_mode='fixed')
         eng.compute_powers(with_G=False)
+        if isinstance(eng, GeneralGemEngine):
+            # sum over the selected spectral components of this spatial component of the product
+            # of the selected factors; an empty list selects everything (Q1, :476-497)
+            V = None
+            specs = list(spec_comp_ind) if len(spec_comp_ind) else list(range(len(eng.spec)))
+            for s_ind in specs:
+                sp = eng.spec[s_ind]
+                if sp["j"] != spat_comp_ind:
+                    continue
+                keys = [fc["key"] for fc in sp["fac"]]
+                which = list(factor_ind) if len(factor_ind) else keys
+                C = None
+                for fc in sp["fac"]:
+                    if fc["key"] in which:
+                        C = fc["P"].clone() if C is None else C * fc["P"]
+                if C is None:
+                    C = eng.torch.ones_like(sp["fac"][0]["P"])
+                V = C if V is None else V + C
+            if V is None:
+                V = eng.torch.zeros_like(eng.V[0])
+            return V[:, :self.nbFramesSigRepr].cpu().numpy().astype(np.float64)
+        if (len(factor_ind) and list(factor_ind) != [0]) or (len(spec_comp_ind) and any(
+                self.spec_comps[s]['spat_comp_ind'] != spat_comp_ind for s in spec_comp_ind)):
+            raise NotImplementedError("factor / foreign spectral-component selection")
         V = eng._gather_f(eng.V[spat_comp_ind], 0)
         return V[:, :self.nbFramesSigRepr].astype(np.float64)
 

@@ -115,3 +115,33 @@ def test_sparsity_is_refused():
     with pytest.raises(NotImplementedError):
         am.multiChanSourceF0Filter(audio=WAV, kernels=AllFakeKernels(), sparsity=[3, ],
                                    wlen=256, hopsize=64)
+
+
+def check_separation_and_powers(kernels, dtype, tol_pow, max_lsb, tmp_path, monkeypatch):
+    """comp_spat_comp_power (with factor selection) and the Wiener separation of the source/filter
+    model against the oracle, both loaded with the reference's final parameters."""
+    monkeypatch.chdir(tmp_path)
+    g = load()
+    m = build(kernels, 1, dtype)
+    m.spat_comps, m.spec_comps = structure_from(g, "final")
+    np.random.seed(0)
+    o = fo.OracleFASST(WAV, nbComps=3, nbNMFComps=2, spatial_rank=1, wlen=256, hopsize=64, iter_num=1)
+    o.spat_comps, o.spec_comps = structure_from(g, "final")
+    for j, specs, facs in ((0, [], []), (1, [1], [0]), (1, [1], [1]), (2, [], [])):
+        a = m.comp_spat_comp_power(j, specs, facs)
+        b = o.comp_spat_comp_power(j, specs, facs)
+        assert np.abs(a - b).max() / np.abs(b).max() < tol_pow, (j, specs, facs)
+    # a component of another source contributes nothing (audioModel.py:476-478)
+    assert np.abs(m.comp_spat_comp_power(0, [1])).max() == 0
+    noise = np.array(g["final_TW0_0"]).mean() * 0 + 1e-3 * np.ones(129)
+    m.noise['PSD'], o.noise['PSD'] = noise.copy(), noise.copy()
+    pcm = m.separate_comps_pcm()
+    ref = o.separate_signals()
+    for n in range(3):
+        want = fo.pcm_from_float(ref[n], o.maxdata)
+        diff = np.abs(pcm[n].astype(int) - want.astype(int))
+        assert diff.max() <= max_lsb, (n, diff.max())
+
+
+def test_separation_and_powers_on_kernel_spec(tmp_path, monkeypatch):
+    check_separation_and_powers(AllFakeKernels(), "float64", 1e-10, 1, tmp_path, monkeypatch)

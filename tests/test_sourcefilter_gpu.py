@@ -75,3 +75,7 @@ def test_renormalisation_kernels_with_large_dictionaries(dt):
     tol = 1e-6 if dt == torch.float32 else 1e-13
     for a, b in zip(outs[1], outs[0]):
         assert np.abs(a - b).max() / np.abs(b).max() < tol
+
+
+def test_separation_and_powers(tmp_path, monkeypatch):
+    cpu.check_separation_and_powers(ck(), "float32", 2e-6, 4, tmp_path, monkeypatch)
