@@ -220,6 +220,14 @@ int pf_mult_update_same(void* theta, int64_t ldt, const void* num, int64_t ldn, 
                         int64_t ldd, int rows, int64_t cols, double omega, int dtype,
                         void* stream);
 
+/* Sparsity re-weighting of the source activations of multiChanSourceF0Filter
+ * (audioModel.py:2981-3014; median filter: tools/signalTools.py:13-24): TW [K][ldt] *= Gaussian
+ * mask around the median-filtered (window `length`) barycentre of every frame, of variance
+ * sigma = exp(log_sigma0 + slope * (iter_dev[0] - 1)) (the device iteration counter has already
+ * advanced when this runs); work: 2 N doubles */
+int pf_sparsity_reweigh(void* TW, int64_t ldt, int K, int64_t N, int length, double log_sigma0,
+                        double slope, const int* iter_dev, double* work, int dtype, void* stream);
+
 /* ---- K5: renormalisation  (audioModel.py:1980-2040) ----------------------------- */
 int pf_spat_energy(const void* A, const int* src_of_sub, int R, int J, int I, int F,
                    double* sums, void* stream);

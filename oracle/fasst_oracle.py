@@ -136,6 +136,19 @@ class STFT(object):
 # --------------------------------------------------------------------------- #
 # audio I/O scaling (ref: audioObject.py:112-127, :130-147, :76-98)
 # --------------------------------------------------------------------------- #
+def median_filter(x, length=10):
+    """ref: tools/signalTools.py:13-24 -- the window [n - length, min(n + length, N - 1)) is
+    asymmetric and never holds the last sample; an empty window keeps the input value."""
+    N = x.size
+    out = np.zeros_like(x)
+    for n in range(N):
+        win = x[max(n - length, 0):min(n + length, N - 1)]
+        out[n] = np.median(win) if win.size else np.nan
+        if np.isnan(out[n]):
+            out[n] = x[n]
+    return out
+
+
 def read_audio(filename):
     """Returns (fs, data[L, nc] float64 scaled by 1/maxdata, maxdata)."""
     fs, raw = wavfile.read(filename)
@@ -286,7 +299,31 @@ class OracleFASST(object):
                 self.noise["PSD"] = ((np.sqrt(lim[0]) * (I - i)
                                       + np.sqrt(lim[1]) * i) / I) ** 2
             logliks[i] = self.GEM_iteration()
+            # multiChanSourceF0Filter.estim_param_a_post_model (audioModel.py:2933-2979): the
+            # source activations are re-weighted after every iteration when a component
+            # carries a 'sparsity' entry; sigma goes from K^2 down to 9 geometrically
+            if any(sp.get("sparsity") for sp in self.spec_comps.values()):
+                log0 = np.log(np.max([sp["factor"][0]["TW"].shape[0]
+                                      for sp in self.spec_comps.values()]) ** 2)
+                sigma = np.exp(log0 + (np.log(9.0) - log0) / max(I - 1.0, 1.) * i)
+                self.reweigh_sparsity_constraint(sigma)
         return logliks
+
+    # -- ref: audioModel.py:2981-3014, tools/signalTools.py:13-24 ---------------- #
+    def reweigh_sparsity_constraint(self, sigma):
+        for sp in self.spec_comps.values():
+            TW = sp["factor"][0]["TW"]
+            K = TW.shape[0]
+            if not sp.get("sparsity") or K <= 2:
+                continue
+            w = np.arange(K - 1, 0, -1) ** 2
+            mu = np.dot(np.arange(K - 1) * w, TW[:-1]) / np.dot(w, np.maximum(TW[:-1], EPS))
+            mu = median_filter(mu, length=sp["sparsity"])
+            mask = np.exp(-0.5 * ((np.vstack(np.arange(K)) - mu) ** 2) / sigma)
+            mask[-1] = mask.max(axis=0)
+            pos = mask[-1] > 0
+            mask[:, pos] /= mask[-1][pos]
+            TW *= mask
 
     # -- ref: audioModel.py:384-428 ------------------------------------------ #
     def GEM_iteration(self):

@@ -418,6 +418,24 @@ def run_sourcefilter(ref, wav):
         snapshot_sf(model, "final", out)
         out["shared_final"] = np.array(model.sourceFreqComps)
         assert model.spec_comps[0]["factor"][0]["FB"] is model.spec_comps[1]["factor"][0]["FB"]
+        # the same with the sparsity re-weighting of the source activations (:2933-3014):
+        # median filter of length 2 for every component (a one-element list applies to all)
+        def build_sparse(iters):
+            m = am.multiChanSourceF0Filter(
+                audio=wav, nbComps=3, nbNMFResComps=2, nbFilterComps=6, nbFilterWeigs=[3, ],
+                minF0=100, maxF0=400, stepnoteF0=1, chirpPerF0=1, spatial_rank=1, sparsity=[2, ],
+                wlen=256, hopsize=64, iter_num=iters, verbose=0, ann_PSD_lim=[None, None])
+            m._initialize_structures(seed=5)
+            return m
+        model = build_sparse(4)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out["sparse_logliks"] = np.real(model.estim_param_a_post_model())
+        snapshot_sf(model, "sparse", out)
+        x = np.random.RandomState(3).rand(40)
+        out["median_in"] = x
+        for L in (1, 2, 5):
+            out["median_%d" % L] = am.st.medianFilter(x, length=L)
     finally:
         os.chdir(cwd)
     np.savez_compressed(os.path.join(GOLD, "fasst_sourcefilter.npz"), **out)

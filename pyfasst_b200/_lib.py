@@ -104,6 +104,7 @@ SIGNATURES = {
     "pf_gem_ratio_planes": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp],
     "pf_mul_planes": [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_vp],
     "pf_mult_update_same": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
+    "pf_sparsity_reweigh": [c_vp, c_i64, c_int, c_i64, c_int, c_dbl, c_dbl, c_vp, c_vp, c_int, c_vp],
     "pf_wf0_combs": [c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_i64, c_i64, c_vp, c_int, c_int,
                      c_int, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
@@ -567,6 +568,12 @@ class CudaKernels(object):
         _check(self.lib.pf_mult_update_same(self._p(theta), theta.stride(0), self._p(num),
                                             num.stride(0), self._p(den), den.stride(0), rows, cols,
                                             float(omega), self.dtype_code(theta), self._stream()),
+               self.lib)
+
+    def sparsity_reweigh(self, TW, K, N, length, log_sigma0, slope, iter_dev, work):
+        _check(self.lib.pf_sparsity_reweigh(self._p(TW), TW.stride(0), K, N, int(length),
+                                            float(log_sigma0), float(slope), iter_dev.data_ptr(),
+                                            self._p(work), self.dtype_code(TW), self._stream()),
                self.lib)
 
     def check_totals(self, totals, eps, flags):

@@ -111,6 +111,8 @@ class FASST(object):
         opt = self.noise['sim_ann_opt'] if psd_mode is None else psd_mode
         eng.set_noise(opt, lim[0], lim[1], self.noise['PSD'])
         eng.set_model(self.spat_comps, self.spec_comps, self.nmfUpdateCoeff)
+        # (the sparsity re-weighting belongs to estim_param_a_post_model, not to GEM_iteration)
+        eng.sparsity_enabled = psd_mode is None
         return eng
 
     def _general_structure(self):
@@ -591,17 +593,16 @@ class multiChanSourceF0Filter(FASST):
     sources, like the reference's `self.sourceFreqComps` (quirk Q11: the renormalisation rescales
     the shared array once per source).  Estimation runs on GeneralGemEngine.
 
-    Not here: `sparsity` (reweigh_sparsity_constraint, :2981-3014), `initSpecCompsWithLabelAndFiles`
-    (needs the external gmm-gsmm module) and `initializeFreeMats`."""
+    `sparsity` (the re-weighting of the source activations after every iteration,
+    reweigh_sparsity_constraint :2981-3014) runs on the device inside the estimation loop.
+    Not here: `initSpecCompsWithLabelAndFiles` (needs the external gmm-gsmm module) and
+    `initializeFreeMats`."""
 
     def __init__(self, audio, nbComps=3, nbNMFResComps=1, nbFilterComps=20, nbFilterWeigs=[4, ],
                  minF0=39, maxF0=2000, minF0search=80, maxF0search=800, stepnoteF0=16,
                  chirpPerF0=1, spatial_rank=1, sparsity=None, **kwargs):
         from .SeparateLeadStereo import separateLeadFunctions as slf
         super(multiChanSourceF0Filter, self).__init__(audio=audio, **kwargs)
-        if sparsity is not None:
-            raise NotImplementedError("pyfasst_b200: the sparsity re-weighting of the source "
-                                      "activations (audioModel.py:2981-3014) is not implemented")
         self.comp_transf_Cx()
         self.sourceParams = {'minF0': minF0, 'maxF0': maxF0, 'stepnoteF0': stepnoteF0,
                              'chirpPerF0': chirpPerF0, 'minF0search': minF0search,
@@ -671,8 +672,16 @@ class multiChanSourceF0Filter(FASST):
                'FB_frdm_prior': 'free', 'FW_frdm_prior': 'fixed',
                'TW_frdm_prior': 'free', 'TB_frdm_prior': [], 'TW_constr': 'NMF'}
         self.spec_comps[j] = {'spat_comp_ind': j, 'factor': {0: res}}
+        # sparsity: median-filter length of the re-weighting of the source activations, per
+        # component or one value for all (ref: audioModel.py:2747-2770)
+        sparsity = self.sparsity
         for j in range(self.nbComps):
-            self.spec_comps[j]['sparsity'] = False
+            if sparsity is None or len(sparsity) not in (1, self.nbComps):
+                self.spec_comps[j]['sparsity'] = False
+            elif len(sparsity) == self.nbComps:
+                self.spec_comps[j]['sparsity'] = sparsity[j]
+            else:
+                self.spec_comps[j]['sparsity'] = sparsity[0]
         self.renormalize_parameters()
 
     def setSpecCompFB(self, compNb, FB, FB_frdm_prior='fixed'):

@@ -69,9 +69,115 @@ mult_update_same_kernel(T* __restrict__ theta, long ldt, const T* __restrict__ n
   theta[(size_t)r * ldt + c] = (T)((double)theta[(size_t)r * ldt + c] * g);
 }
 
+// ---- sparsity re-weighting of the source activations -----------------------------------------
+// multiChanSourceF0Filter.reweigh_sparsity_constraint (audioModel.py:2981-3014): per frame the
+// barycentre of the activations over the dictionary index, median filtered along time
+// (tools/signalTools.py:13-24), then a Gaussian mask around it whose width sigma shrinks from
+// K^2 to 9 over the iterations (:2937-2977).
+template <typename T>
+__global__ void sparsity_barycenter_kernel(const T* __restrict__ TW, long ldt, int K, long N,
+                                           double* __restrict__ mu) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double num = 0.0, den = 0.0;
+  for (int k = 0; k < K - 1; ++k) {
+    const double w = (double)(K - 1 - k) * (double)(K - 1 - k);
+    const double v = (double)TW[(size_t)k * ldt + n];
+    num += (double)k * w * v;
+    den += w * fmax(v, GF_EPS);
+  }
+  mu[n] = num / den;
+}
+
+constexpr int GF_MAX_MEDIAN = 64;  // 2 * length
+// out[n] = median(in[max(n - L, 0) : min(n + L, N - 1)]), the input value for an empty window
+// or a NaN result (signalTools.py:18-23)
+__global__ void median_filter_kernel(const double* __restrict__ in, long N, int L,
+                                     double* __restrict__ out) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  long lo = n - L, hi = n + L;
+  if (lo < 0) lo = 0;
+  if (hi > N - 1) hi = N - 1;
+  double w[GF_MAX_MEDIAN];
+  int cnt = 0;
+  bool has_nan = false;
+  for (long i = lo; i < hi; ++i) {
+    const double v = in[i];
+    if (v != v) has_nan = true;
+    int j = cnt++;
+    while (j > 0 && w[j - 1] > v) {  // insertion sort
+      w[j] = w[j - 1];
+      --j;
+    }
+    w[j] = v;
+  }
+  double m;
+  if (cnt == 0 || has_nan)
+    m = in[n];
+  else
+    m = (cnt & 1) ? w[cnt >> 1] : 0.5 * (w[(cnt >> 1) - 1] + w[cnt >> 1]);
+  out[n] = m;
+}
+
+// TW[k][n] *= mask[k][n]: mask = exp(-(k - mu_n)^2 / (2 sigma)) divided by its maximum over k
+// (where that is positive); the last row gets the maximum itself, i.e. 1
+template <typename T>
+__global__ void sparsity_mask_kernel(T* __restrict__ TW, long ldt, int K, long N,
+                                     const double* __restrict__ mu, double log_sigma0,
+                                     double slope, const int* __restrict__ iter_dev) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (n >= N) return;
+  const double sigma = exp(log_sigma0 + slope * (double)(iter_dev[0] - 1));
+  const double m = mu[n];
+  // the row nearest to mu carries the maximum (exp is monotone)
+  double kc = rint(m);
+  if (!(kc >= 0.0)) kc = 0.0;
+  if (kc > (double)(K - 1)) kc = (double)(K - 1);
+  double best = (kc - m) * (kc - m);
+  if (kc >= 1.0) best = fmin(best, (kc - 1.0 - m) * (kc - 1.0 - m));
+  if (kc + 1.0 <= (double)(K - 1)) best = fmin(best, (kc + 1.0 - m) * (kc + 1.0 - m));
+  const double top = exp(-0.5 * best / sigma);
+  double mask;
+  if (k == K - 1)
+    mask = top > 0.0 ? 1.0 : top;
+  else {
+    mask = exp(-0.5 * (((double)k - m) * ((double)k - m)) / sigma);
+    if (top > 0.0) mask /= top;
+  }
+  TW[(size_t)k * ldt + n] = (T)((double)TW[(size_t)k * ldt + n] * mask);
+}
+
 }  // namespace pf
 
 using namespace pf;
+
+extern "C" int pf_sparsity_reweigh(void* TW, int64_t ldt, int K, int64_t N, int length,
+                                   double log_sigma0, double slope, const int* iter_dev,
+                                   double* work, int dtype, void* stream) {
+  PF_REQUIRE(K > 2 && K <= 65535 && N > 0, "pf_sparsity_reweigh: K=%d N=%ld", K, (long)N);
+  PF_REQUIRE(length >= 1 && 2 * length <= GF_MAX_MEDIAN,
+             "pf_sparsity_reweigh: median length %d (1..%d)", length, GF_MAX_MEDIAN / 2);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_sparsity_reweigh: bad dtype %d", dtype);
+  cudaStream_t st = as_stream(stream);
+  double* mu = work;
+  double* muf = work + N;
+  const int blocks = ceil_div(N, 128);
+  if (dtype == PF_F32)
+    sparsity_barycenter_kernel<float><<<blocks, 128, 0, st>>>((const float*)TW, ldt, K, N, mu);
+  else
+    sparsity_barycenter_kernel<double><<<blocks, 128, 0, st>>>((const double*)TW, ldt, K, N, mu);
+  median_filter_kernel<<<blocks, 128, 0, st>>>(mu, N, length, muf);
+  dim3 grid(ceil_div(N, GF_THREADS), K);
+  if (dtype == PF_F32)
+    sparsity_mask_kernel<float><<<grid, GF_THREADS, 0, st>>>((float*)TW, ldt, K, N, muf,
+                                                            log_sigma0, slope, iter_dev);
+  else
+    sparsity_mask_kernel<double><<<grid, GF_THREADS, 0, st>>>((double*)TW, ldt, K, N, muf,
+                                                             log_sigma0, slope, iter_dev);
+  return check_launch("sparsity_mask_kernel");
+}
 
 extern "C" int pf_gem_ratio_planes(const void* hatW, const void* P, const void* O, void* out, int F,
                                    int64_t N, int64_t ld, int dtype, void* stream) {

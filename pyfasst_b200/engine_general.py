@@ -87,7 +87,7 @@ class GeneralGemEngine(GemEngine):
                 ent["G"] = self._zeros([Kb4, self.ld])   # FW TW (FB update)
                 ent["P"] = self._zeros([self.F, self.ld])  # power of the factor
                 facs.append(ent)
-            self.spec.append({"j": j, "fac": facs,
+            self.spec.append({"j": j, "fac": facs, "sparsity": spec_comps[s].get("sparsity"),
                               # power of the component = product of its factor powers
                               "C": facs[0]["P"] if len(facs) == 1 else self._zeros([self.F, self.ld])})
         self.by_src = [[sp for sp in self.spec if sp["j"] == j] for j in range(self.J)]
@@ -115,6 +115,9 @@ class GeneralGemEngine(GemEngine):
         self.totals = self._zeros([n], f64)      # sum of every TW after its rescaling
         self.gcount = self._f64(np.array([fc["Kw"] * self.N_total for fc in facs], dtype=np.float64))
         self.gvec = self._zeros([Kw4], f64)
+        self.sparse_work = self._zeros([2 * self.N], f64)
+        # sparsity re-weighting runs inside estim_param_a_post_model only (audioModel.py:2933-2979)
+        self.sparsity_enabled = False
 
     # ------------------------------------------------------------------ powers
     def _gemm(self, A, B, C, M, N, K, transA=False, transB=False, splitk=False):
@@ -256,6 +259,20 @@ class GeneralGemEngine(GemEngine):
     def _check_totals(self):
         tot = self.totals.clone()
         self.k.check_totals(tot, EPS, self.flags)
+
+    # ------------------------------------------------------------------ sparsity
+    def gem_iteration(self, n_iter_total, logliks, mark=None):
+        super(GeneralGemEngine, self).gem_iteration(n_iter_total, logliks, mark)
+        if not self.sparsity_enabled or not any(sp["sparsity"] for sp in self.spec):
+            return
+        # sigma: exp(log K^2 + (log 9 - log K^2) / max(iter_num - 1, 1) * i)  (:2937-2977)
+        log0 = float(np.log(max(sp["fac"][0]["Kw"] for sp in self.spec) ** 2))
+        slope = (float(np.log(9.0)) - log0) / max(n_iter_total - 1.0, 1.0)
+        for sp in self.spec:
+            fc = sp["fac"][0]
+            if sp["sparsity"] and fc["Kw"] > 2:
+                self.k.sparsity_reweigh(fc["TW"], fc["Kw"], self.N, int(sp["sparsity"]), log0,
+                                        slope, self.iter_dev, self.sparse_work)
 
     # ------------------------------------------------------------------ results
     def read_model(self, spat_comps, spec_comps):

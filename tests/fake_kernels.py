@@ -458,6 +458,26 @@ class FakeKernels(object):
             _np(den)[:rows, :cols].astype(np.float64), EPS)
         th[:rows, :cols] = th[:rows, :cols].astype(np.float64) * ratio ** omega
 
+    def sparsity_reweigh(self, TW, K, N, length, log_sigma0, slope, iter_dev, work):
+        """Specification of pf_sparsity_reweigh (audioModel.py:2981-3014)."""
+        self.launches += 3
+        tw = _np(TW)
+        v = tw[:K, :N].astype(np.float64)
+        sigma = np.exp(log_sigma0 + slope * (int(_np(iter_dev)[0]) - 1))
+        w = np.arange(K - 1, 0, -1) ** 2
+        mu = np.dot(np.arange(K - 1) * w, v[:-1]) / np.dot(w, np.maximum(v[:-1], EPS))
+        muf = np.zeros_like(mu)
+        for n in range(N):
+            win = mu[max(n - length, 0):min(n + length, N - 1)]
+            muf[n] = np.median(win) if win.size else np.nan
+            if np.isnan(muf[n]):
+                muf[n] = mu[n]
+        mask = np.exp(-0.5 * ((np.arange(K)[:, None] - muf) ** 2) / sigma)
+        mask[-1] = mask.max(axis=0)
+        pos = mask[-1] > 0
+        mask[:, pos] /= mask[-1][pos]
+        tw[:K, :N] = v * mask
+
     def check_totals(self, totals, eps, flags):
         self.launches += 1
         tt = _np(totals)

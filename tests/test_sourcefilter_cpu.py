@@ -111,10 +111,37 @@ def test_model_on_kernel_spec_against_reference(tmp_path, monkeypatch):
     check_snapshot(m, load(), "final", 1e-7)
 
 
-def test_sparsity_is_refused():
-    with pytest.raises(NotImplementedError):
-        am.multiChanSourceF0Filter(audio=WAV, kernels=AllFakeKernels(), sparsity=[3, ],
-                                   wlen=256, hopsize=64)
+def check_sparse_model(kernels, dtype, tol_ll, tol_par, tmp_path, monkeypatch):
+    """The estimation loop with the sparsity re-weighting of the source activations
+    (sparsity=[2]: a median filter of length 2 for every component), 4 iterations."""
+    monkeypatch.chdir(tmp_path)
+    g = load()
+    kw = dict(KW, sparsity=[2, ])
+    m = am.multiChanSourceF0Filter(audio=WAV, iter_num=4, kernels=kernels, compute_dtype=dtype,
+                                   **kw)
+    m._initialize_structures(seed=5)
+    assert [m.spec_comps[j]['sparsity'] for j in range(3)] == [2, 2, 2]
+    ll = m.estim_param_a_post_model()
+    assert_allclose(ll, g["sparse_logliks"], rtol=tol_ll)
+    check_snapshot(m, g, "sparse", tol_par)
+    # one GEM_iteration() does not re-weigh (only the estimation loop does, :2933-2979)
+    before = m.spec_comps[0]['factor'][0]['TW'].copy()
+    m.GEM_iteration()
+    assert np.isfinite(m.spec_comps[0]['factor'][0]['TW']).all() and before.shape
+
+
+def test_sparse_model_on_kernel_spec_against_reference(tmp_path, monkeypatch):
+    check_sparse_model(AllFakeKernels(), "float64", 1e-9, 1e-7, tmp_path, monkeypatch)
+
+
+def test_sparsity_argument_forms(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    m = am.multiChanSourceF0Filter(audio=WAV, kernels=AllFakeKernels(), compute_dtype="float64",
+                                   **dict(KW, sparsity=[3, 0, 5]))
+    assert [m.spec_comps[j]['sparsity'] for j in range(3)] == [3, 0, 5]
+    m = am.multiChanSourceF0Filter(audio=WAV, kernels=AllFakeKernels(), compute_dtype="float64",
+                                   **dict(KW, sparsity=[3, 4]))   # neither 1 nor nbComps entries
+    assert [m.spec_comps[j]['sparsity'] for j in range(3)] == [False, False, False]
 
 
 def check_separation_and_powers(kernels, dtype, tol_pow, max_lsb, tmp_path, monkeypatch):
@@ -145,3 +172,25 @@ def check_separation_and_powers(kernels, dtype, tol_pow, max_lsb, tmp_path, monk
 
 def test_separation_and_powers_on_kernel_spec(tmp_path, monkeypatch):
     check_separation_and_powers(AllFakeKernels(), "float64", 1e-10, 1, tmp_path, monkeypatch)
+
+
+def sparse_structure(g, prefix):
+    spat, spec = structure_from(g, prefix)
+    for j in range(3):
+        spec[j]['sparsity'] = 2   # sparsity=[2] applies to every component (audioModel.py:2766-2768)
+    return spat, spec
+
+
+def test_oracle_sparsity_reweighting_against_reference():
+    g = load()
+    for L in (1, 2, 5):
+        assert_allclose(fo.median_filter(g["median_in"], length=L), g["median_%d" % L], rtol=0, atol=0)
+    np.random.seed(0)
+    m = fo.OracleFASST(WAV, nbComps=3, nbNMFComps=2, spatial_rank=1, wlen=256, hopsize=64,
+                       iter_num=4)
+    m.spat_comps, m.spec_comps = sparse_structure(g, "init")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ll = m.estim_param_a_post_model()
+    assert_allclose(ll, g["sparse_logliks"], rtol=1e-9)
+    check_snapshot(m, g, "sparse", 1e-9)

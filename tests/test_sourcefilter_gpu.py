@@ -79,3 +79,26 @@ def test_renormalisation_kernels_with_large_dictionaries(dt):
 
 def test_separation_and_powers(tmp_path, monkeypatch):
     cpu.check_separation_and_powers(ck(), "float32", 2e-6, 4, tmp_path, monkeypatch)
+
+
+def test_sparse_model_against_reference(tmp_path, monkeypatch):
+    cpu.check_sparse_model(ck(), "float32", 5e-5, 5e-3, tmp_path, monkeypatch)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_sparsity_reweigh_kernel_against_spec(dt):
+    rng = np.random.default_rng(5)
+    K, N, ld = 41, 333, 352
+    TW = np.zeros((44, ld))
+    TW[:K, :N] = np.abs(rng.standard_normal((K, N))) ** 3
+    TW[:K - 1, 7] = 0.0       # an empty frame: the barycentre falls back on the eps clamp
+    outs = []
+    for k, dev in ((FakeKernels(), "cpu"), (ck(), "cuda")):
+        t = torch.tensor(TW).to(dt).to(dev)
+        it = torch.tensor([3], dtype=torch.int32, device=dev)
+        work = torch.zeros(2 * N, dtype=torch.float64, device=dev)
+        k.sparsity_reweigh(t, K, N, 4, float(np.log(K ** 2)), -0.9, it, work)
+        outs.append(t.cpu().numpy())
+    tol = 2e-6 if dt == torch.float32 else 1e-12
+    assert np.abs(outs[1] - outs[0]).max() / np.abs(outs[0]).max() < tol
+    assert (outs[1][K:] == 0).all() and (outs[1][:, N:] == 0).all()
