@@ -30,44 +30,64 @@ __device__ __forceinline__ double2 cmul_d(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// in-place radix-2 decimation-in-time FFT of M points held bit-reversed in buf;
-// tw[k] = exp(-2 pi i k / (2M)), k < M.  All threads of the CTA take part.
-__device__ __forceinline__ void fft_inplace(double2* buf, const double2* __restrict__ tw, int M) {
-  for (int half = 1; half < M; half <<= 1) {
-    const int tstep = M / half;
-    for (int b = threadIdx.x; b < M / 2; b += FFT_THREADS) {
-      const int grp = b / half, pos = b - grp * half;
-      const int i0 = grp * 2 * half + pos, i1 = i0 + half;
-      const double2 w = __ldg(tw + pos * tstep);
-      const double2 t = cmul_d(w, buf[i1]);
-      const double2 u = buf[i0];
-      buf[i1] = make_double2(u.x - t.x, u.y - t.y);
-      buf[i0] = make_double2(u.x + t.x, u.y + t.y);
+// Two consecutive radix-2 stages (half = 1 << lh and 2 half) on the four elements they couple:
+// the same butterflies in the same order as two separate passes -- bit-identical results --
+// with one shared-memory round trip and one barrier instead of two.
+__device__ __forceinline__ void fft_two_stages(double2* base, const double2* __restrict__ tw,
+                                               int M, int lh, int q) {
+  const int half = 1 << lh;
+  const int grp = q >> lh, pos = q & (half - 1);
+  const int i0 = (grp << (lh + 2)) + pos, i1 = i0 + half, i2 = i1 + half, i3 = i2 + half;
+  const double2 wa = __ldg(tw + pos * (M >> lh));
+  const double2 wb0 = __ldg(tw + pos * (M >> (lh + 1)));
+  const double2 wb1 = __ldg(tw + (pos + half) * (M >> (lh + 1)));
+  const double2 a0 = base[i0], a1 = base[i1], a2 = base[i2], a3 = base[i3];
+  const double2 t1 = cmul_d(wa, a1), t3 = cmul_d(wa, a3);
+  const double2 p0 = make_double2(a0.x + t1.x, a0.y + t1.y);
+  const double2 p1 = make_double2(a0.x - t1.x, a0.y - t1.y);
+  const double2 p2 = make_double2(a2.x + t3.x, a2.y + t3.y);
+  const double2 p3 = make_double2(a2.x - t3.x, a2.y - t3.y);
+  const double2 u2 = cmul_d(wb0, p2), u3 = cmul_d(wb1, p3);
+  base[i0] = make_double2(p0.x + u2.x, p0.y + u2.y);
+  base[i2] = make_double2(p0.x - u2.x, p0.y - u2.y);
+  base[i1] = make_double2(p1.x + u3.x, p1.y + u3.y);
+  base[i3] = make_double2(p1.x - u3.x, p1.y - u3.y);
+}
+__device__ __forceinline__ void fft_one_stage(double2* base, const double2* __restrict__ tw,
+                                              int M, int lh, int b) {
+  const int half = 1 << lh;
+  const int grp = b >> lh, pos = b & (half - 1);
+  const int i0 = (grp << (lh + 1)) + pos, i1 = i0 + half;
+  const double2 w = __ldg(tw + pos * (M >> lh));
+  const double2 t = cmul_d(w, base[i1]);
+  const double2 u = base[i0];
+  base[i1] = make_double2(u.x - t.x, u.y - t.y);
+  base[i0] = make_double2(u.x + t.x, u.y + t.y);
+}
+
+// in-place radix-2 decimation-in-time FFT of `nb` independent M-point sequences held bit-reversed,
+// back to back, in buf; tw[k] = exp(-2 pi i k / (2M)), k < M.  All threads of the CTA take part;
+// the stages run two at a time (one barrier per pair for the whole batch).
+__device__ __forceinline__ void fft_inplace_batch(double2* buf, const double2* __restrict__ tw,
+                                                  int M, int log2m, int nb) {
+  int lh = 0;
+  for (; lh + 1 < log2m; lh += 2) {
+    for (int idx = threadIdx.x; idx < nb * (M >> 2); idx += FFT_THREADS) {
+      const int t = idx >> (log2m - 2), q = idx & ((M >> 2) - 1);
+      fft_two_stages(buf + (size_t)t * M, tw, M, lh, q);
+    }
+    __syncthreads();
+  }
+  if (lh < log2m) {  // odd number of stages: the last one alone
+    for (int idx = threadIdx.x; idx < nb * (M >> 1); idx += FFT_THREADS) {
+      const int t = idx >> (log2m - 1), b = idx & ((M >> 1) - 1);
+      fft_one_stage(buf + (size_t)t * M, tw, M, lh, b);
     }
     __syncthreads();
   }
 }
-
-// the same transform on `nb` independent M-point sequences held back to back in buf: the
-// butterflies of all sequences are spread over the CTA, one barrier per stage for the batch
-__device__ __forceinline__ void fft_inplace_batch(double2* buf, const double2* __restrict__ tw,
-                                                  int M, int log2m, int nb) {
-  const int hm = M >> 1;
-  for (int half = 1, lh = 0; half < M; half <<= 1, ++lh) {
-    const int tstep = M >> lh;
-    for (int idx = threadIdx.x; idx < nb * hm; idx += FFT_THREADS) {
-      const int t = idx >> (log2m - 1), b = idx & (hm - 1);
-      const int grp = b >> lh, pos = b & (half - 1);
-      double2* base = buf + (size_t)t * M;
-      const int i0 = (grp << (lh + 1)) + pos, i1 = i0 + half;
-      const double2 w = __ldg(tw + pos * tstep);
-      const double2 tt = cmul_d(w, base[i1]);
-      const double2 u = base[i0];
-      base[i1] = make_double2(u.x - tt.x, u.y - tt.y);
-      base[i0] = make_double2(u.x + tt.x, u.y + tt.y);
-    }
-    __syncthreads();
-  }
+__device__ __forceinline__ void fft_inplace(double2* buf, const double2* __restrict__ tw, int M) {
+  fft_inplace_batch(buf, tw, M, 31 - __clz(M), 1);
 }
 
 template <typename T>
