@@ -172,12 +172,25 @@ def cpu_gem_rate(crop_s, iters, warm=0):
     return bins * iters / dt, bins, dt
 
 
+def host_threads():
+    """Gives the BLAS behind NumPy every host core (torchrun exports OMP_NUM_THREADS=1 to its
+    workers) and returns the number of threads it will actually use -- the `cores` of the CPU
+    arm."""
+    want = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
+        return max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
+    except Exception:  # noqa: BLE001 -- without threadpoolctl the environment decides
+        return int(os.environ.get("OMP_NUM_THREADS", want))
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     crop_s = args.cpu_crop_s
+    cores = host_threads()
     rate, bins, dt = cpu_gem_rate(crop_s, args.steps, args.warmup)
-    cores = os.cpu_count()
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -397,8 +410,9 @@ def run_ours(args, rank, world):
     # ---- CPU baseline: the oracle on a bounded crop -----------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline and args.channels == 2:
+        cores = host_threads()
         rate, cbins, cdt = cpu_gem_rate(args.cpu_crop_s, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "1 GEM iteration of the oracle (NumPy float64 restatement of the "
                          "reference) on a %.1f s crop (%d bins, %.1f s)" %
                          (args.cpu_crop_s, cbins, cdt)}
