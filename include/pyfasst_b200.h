@@ -94,6 +94,10 @@ int pf_pcm_peak(const void* pcm, int pcm_format, int64_t count, double* peak, vo
  * pcm     : optional int16 [Lout][nsig] interleaved, = (int16)trunc(out*maxdata)
  *           (audioModel.py:1227-1229), or round-half-even when pcm_round
  *           (SeparateLeadStereoTF.py:1826-1827) ; NULL to skip */
+/* norm [hop (N-1) + wlen] = overlap-added prod = synth * analysis window, frames accumulated in
+ * ascending order like the reference (stft.py:112-121); zeros -> 1 and the edge patch of the
+ * SIMM inverse (separateLeadFunctions.py:218-221) are applied by the caller */
+int pf_overlap_norm(const double* prod, int wlen, int hop, int64_t N, double* norm, void* stream);
 int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld, const double* synth,
              const double* norm, int wlen, int hop, int nfft, double* out, int64_t Lout,
              int16_t* pcm, double maxdata, int64_t drop, int pcm_round, int dtype, void* stream);

@@ -63,7 +63,12 @@ def istft_planes(kernels, Y, N, window, analysisWindow, hopsize, nfft, originalD
     total = hopsize * (N - 1) + window.size
     length = total if originalDataLen is None else min(int(originalDataLen), total)
     dev = Y.device
-    norm = torch.tensor(overlap_norm(window, analysisWindow, hopsize, N)).to(dev)
+    # overlap_norm() on the device: sums, then the reference's edge patch and zeros -> 1
+    norm = kernels.overlap_norm(np.asarray(window) * np.asarray(analysisWindow), hopsize, N)
+    wlen = window.size
+    norm[:wlen] = norm[wlen:2 * wlen].clone()
+    norm[-wlen:] = norm[-2 * wlen:-wlen].clone()
+    norm[norm == 0] = 1.0
     synth = torch.tensor(np.asarray(window, dtype=np.float64)).to(dev)
     out = torch.zeros([nsig, length], dtype=torch.float64, device=dev)
     pcm = None if scale is None else torch.zeros([length, nsig], dtype=torch.int16, device=dev)

@@ -105,6 +105,7 @@ SIGNATURES = {
     "pf_mul_planes": [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_vp],
     "pf_mult_update_same": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
     "pf_sparsity_reweigh": [c_vp, c_i64, c_int, c_i64, c_int, c_dbl, c_dbl, c_vp, c_vp, c_int, c_vp],
+    "pf_overlap_norm": [c_vp, c_int, c_int, c_i64, c_vp, c_vp],
     "pf_wf0_combs": [c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_i64, c_i64, c_vp, c_int, c_int,
                      c_int, c_vp, c_vp],
     "pf_tc_selftest": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
@@ -487,6 +488,16 @@ class CudaKernels(object):
         self._call("pf_viterbi", self._pv(dens), self._pv(log_prior), self._pv(log_trans), S, N,
                    self._pv(ws), ws.numel() * 8, path.data_ptr())
         return path
+
+    def overlap_norm(self, prod, hop, N):
+        """Device float64 [hop (N-1) + wlen]: the overlap-added window product of the inverse
+        STFT (prod: host float64 [wlen])."""
+        torch = self.torch
+        pd = torch.tensor(np.ascontiguousarray(prod, dtype=np.float64)).to(self.device)
+        norm = torch.empty(int(hop) * (int(N) - 1) + pd.numel(), dtype=torch.float64,
+                           device=self.device)
+        self._call("pf_overlap_norm", self._pv(pd), pd.numel(), int(hop), int(N), self._pv(norm))
+        return norm
 
     # -- glottal-source F0 dictionary ------------------------------------------------------------
     def wf0_combs(self, f1, f2, npart, fs, Ot, Lsig, t_begin, window, nfft, rows):

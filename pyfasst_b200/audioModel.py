@@ -483,9 +483,10 @@ class FASST(object):
         hop, nfft = self.sig_repr_params['hopsize'], self.sig_repr_params['fsize']
         _, pcm = _stft.istft_planes(self._k(), Y, self.nbFramesSigRepr, self.tft.synthWindow,
                                     self.tft.window, hop, nfft, length=L, maxdata=maxdata)
-        # pcm: [L, nc*nbSources] with signal index = nc*source + channel
-        return np.ascontiguousarray(
-            pcm.cpu().numpy().reshape(L, nbSources, nc).transpose(1, 0, 2))
+        # pcm: [L, nc*nbSources] with signal index = nc*source + channel; the re-ordering to
+        # [source, L, channel] happens on the device (a strided host copy of the 423 MB of a
+        # 10-minute 4-source separation took 0.3 s)
+        return pcm.view(L, nbSources, nc).permute(1, 0, 2).contiguous().cpu().numpy()
 
 
 class MultiChanNMFInst_FASST(FASST):

@@ -171,6 +171,21 @@ stft_kernel(const void* __restrict__ pcm, int nch, double div, long L, long samp
   }
 }
 
+// norm[t] = sum over the frames n covering sample t, in ascending n (the reference's accumulation
+// order, stft.py:112-121), of prod[t - n hop]: the overlap-added window product of istft
+__global__ void overlap_norm_kernel(const double* __restrict__ prod, int wlen, int hop, long N,
+                                    long total, double* __restrict__ norm) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  long n_lo = t - wlen + 1;
+  n_lo = n_lo <= 0 ? 0 : (n_lo + hop - 1) / hop;
+  long n_hi = t / hop;
+  if (n_hi > N - 1) n_hi = N - 1;
+  double acc = 0.0;
+  for (long n = n_lo; n <= n_hi; ++n) acc += prod[t - n * hop];
+  norm[t] = acc;
+}
+
 // psd_sum[f] = sum over planes and frames of X^2 (audioModel.py:304-319), fixed order
 template <typename T>
 __global__ void psd_sum_kernel(const T* __restrict__ X, int nplanes, int F, long N, long ld,
@@ -537,4 +552,14 @@ extern "C" int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld,
                                maxdata, drop, pcm_round, st);
   return launch_istft<double>(Y, nsig, F, N, ld, synth, norm, wlen, hop, nfft, out, Lout, pcm,
                               maxdata, drop, pcm_round, st);
+}
+
+extern "C" int pf_overlap_norm(const double* prod, int wlen, int hop, int64_t N, double* norm,
+                               void* stream) {
+  PF_REQUIRE(wlen > 0 && hop > 0 && N > 0, "pf_overlap_norm: wlen=%d hop=%d N=%ld", wlen, hop,
+             (long)N);
+  const long total = (long)hop * (N - 1) + wlen;
+  overlap_norm_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(prod, wlen, hop, N,
+                                                                         total, norm);
+  return check_launch("overlap_norm_kernel");
 }

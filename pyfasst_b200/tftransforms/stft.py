@@ -77,7 +77,10 @@ def istft_planes(kernels, Y, N, window, analysisWindow, hopsize, nfft, length=No
     if length is None:
         length = total - wlen // 2
     dev = Y.device
-    norm = torch.tensor(overlap_norm(window, analysisWindow, hopsize, N)).to(dev)
+    # the overlap-added window product is formed on the device (a host loop over the frames of a
+    # 10-minute signal plus the upload of its 212 MB took longer than the transform itself)
+    norm = kernels.overlap_norm(np.asarray(window) * np.asarray(analysisWindow), hopsize, N)
+    norm[norm == 0] = 1.0
     synth = torch.tensor(np.asarray(window, dtype=np.float64)).to(dev)
     out = torch.zeros([nsig, length], dtype=torch.float64, device=dev)
     pcm = None

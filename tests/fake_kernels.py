@@ -58,6 +58,14 @@ class FakeKernels(object):
         if psd_sum is not None:
             _np(psd_sum)[:] = (Xo[:, :, :N].astype(np.float64) ** 2).sum(axis=(0, 2))
 
+    def overlap_norm(self, prod, hop, N):
+        self.launches += 1
+        prod = np.asarray(prod, dtype=np.float64)
+        norm = np.zeros(hop * (N - 1) + prod.size)
+        for n in range(N):
+            norm[n * hop:n * hop + prod.size] += prod
+        return torch.tensor(norm)
+
     def pcm_peak(self, pcm, peak):
         self.launches += 1
         x = _np(pcm)
