@@ -25,9 +25,7 @@ here) and prints the same line with "impl": "reference".
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 

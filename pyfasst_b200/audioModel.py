@@ -17,7 +17,6 @@ Extra keyword arguments (not in the reference):
                     (frequency bins; the TW numerators/denominators are all-reduced)
     use_cuda_graph: replay the GEM iteration as a CUDA graph
 """
-import os
 import warnings
 
 import numpy as np
