@@ -119,6 +119,12 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   //    cp.async.wait_group on the thread's own groups (one group per pass, possibly empty).
   //  * otherwise: register double buffering, one pass ahead (float32 planes only).
   constexpr bool kRing = (OPT & 4) != 0 && sizeof(T) == 4;
+  //  * OPT bit 3 (with the ring): the inputs of a pass STAY in the ring slot -- every bin reads
+  //    its 4 + J scalars from shared memory when its turn comes and writes hatW back over V --
+  //    so that no float4 input / output / prefetch registers are live across the per-bin
+  //    algebra and three CTAs fit on an SM.  Lane l visits its four bins rotated by l / 8:
+  //    the 4-byte accesses at a 16-byte stride are then bank-conflict free.
+  constexpr bool kSmemIO = kRing && (OPT & 8) != 0;
   constexpr bool kPrefetch = sizeof(T) == 4 && !kRing;
   constexpr int NPL = 4 + J;
   extern __shared__ __align__(16) unsigned char s_ring_raw[];
@@ -152,9 +158,21 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   }
   if (kPrefetch && first < end) issue_loads(first);
   int slot = 0;
+  const int rot = (threadIdx.x >> 3) & 3;
   for (long n0 = first; n0 < end; n0 += stride) {
     T x0r[VEC], x0i[VEC], x1r[VEC], x1i[VEC], v[J][VEC], w[J][VEC];
-    if (kRing) {
+    float* sb = reinterpret_cast<float*>(s_ring + (size_t)slot * NPL * ESTEP_THREADS + threadIdx.x);
+    if (kSmemIO) {
+      cp_async_wait<ESTEP_DEPTH - 1>();
+      if (n0 + VEC > end) {  // frames beyond the end of the row: zero inputs (own slot, no barrier)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          if (n0 + e >= end) {
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) sb[pl * ESTEP_THREADS * 4 + e] = 0.f;
+          }
+      }
+    } else if (kRing) {
       cp_async_wait<ESTEP_DEPTH - 1>();
       const float4* src = s_ring + (size_t)slot * NPL * ESTEP_THREADS + threadIdx.x;
       if (sizeof(T) == 4) {  // (the ring only exists for float32 planes)
@@ -183,7 +201,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
     }
     // frames beyond the end of the row: zero inputs contribute nothing to the moments and give
     // hatW = 0; only the log-likelihood term is masked below (no branch around the algebra)
-    if (n0 + VEC > end) {
+    if (!kSmemIO && n0 + VEC > end) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e)
         if (n0 + e >= end) {
@@ -195,7 +213,16 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const bool live = n0 + e < end;
+      const int es = kSmemIO ? ((e + rot) & 3) : e;  // the bin of the vector this step works on
+      const bool live = n0 + es < end;
+      if (kSmemIO) {
+        x0r[e] = (T)sb[0 * ESTEP_THREADS * 4 + es];
+        x0i[e] = (T)sb[1 * ESTEP_THREADS * 4 + es];
+        x1r[e] = (T)sb[2 * ESTEP_THREADS * 4 + es];
+        x1i[e] = (T)sb[3 * ESTEP_THREADS * 4 + es];
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j][e] = (T)sb[(4 + j) * ESTEP_THREADS * 4 + es];
+      }
       // Sigma_x = sum_j v_j R_j + s2 I and its inverse (audioModel.py:613-654)
       C vj[J], i00, i11, i01r, i01i;
       T vt[J], pr[NP], det;
@@ -234,6 +261,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         const T q = (T)(s_coef[4 * j + 0] * m00 + s_coef[4 * j + 1] * m11 +
                         (C)2 * (s_coef[4 * j + 2] * m01r + s_coef[4 * j + 3] * m01i));
         w[j][e] = pf_abs(vt[j] + vt[j] * vt[j] * (q * invrank[j]));
+        if (kSmemIO) sb[(4 + j) * ESTEP_THREADS * 4 + es] = (float)w[j][e];
       }
       // S_jk += v_j v_k M ; U = x y^H ; T_j += v_j U ; sv_j += v_j   (accumulated in T)
       const T t00 = (T)m00, t11 = (T)m11, t01r = (T)m01r, t01i = (T)m01i;
@@ -243,8 +271,19 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
                       b1r * z1r + b1i * z1i, b1i * z1r - b1r * z1i};
       mom.add(pr, vt, t00, t11, t01r, t01i, u);
     }
+    if (kSmemIO) {
+      if (sizeof(T) == 4) {
 #pragma unroll
-    for (int j = 0; j < J; ++j) store_vec<T>(hatW + j * plane + row + n0, w[j]);
+        for (int j = 0; j < J; ++j)
+          *reinterpret_cast<float4*>(hatW + j * plane + row + n0) =
+              *reinterpret_cast<const float4*>(sb + (4 + j) * ESTEP_THREADS * 4);
+      }
+      ring_issue(n0 + ESTEP_DEPTH * stride, slot);  // refill the slot just consumed
+      slot = slot + 1 == ESTEP_DEPTH ? 0 : slot + 1;
+    } else {
+#pragma unroll
+      for (int j = 0; j < J; ++j) store_vec<T>(hatW + j * plane + row + n0, w[j]);
+    }
   }
 
   // fixed-order block reduction in double (H8: deterministic, no float atomics)
@@ -442,7 +481,7 @@ static int dispatch_wiener(int J, const void* X, const void* V, const double* co
 static int estep_variant() {
   const char* e = getenv("PYFASST_ESTEP_VARIANT");
   int v = e != nullptr ? atoi(e) : ESTEP_DEFAULT_VARIANT;
-  if (v < 0 || v > 7) v = ESTEP_DEFAULT_VARIANT;
+  if (v < 0 || (v > 7 && v != 15)) v = ESTEP_DEFAULT_VARIANT;
   return v;
 }
 
@@ -452,16 +491,17 @@ static int launch_estep_opt(const void* X, const void* V, const double* coef, co
                             long ld, long chunk, int nsplit, cudaStream_t st) {
   dim3 grid(nsplit, F);
   size_t smem = 0;
+  constexpr int MINB = (OPT & 8) != 0 ? ESTEP_MINB_SMEMIO : ESTEP_MINB;
   if ((OPT & 4) != 0 && sizeof(T) == 4) {
     smem = (size_t)ESTEP_DEPTH * (4 + J) * ESTEP_THREADS * 16;
-    cudaError_t e = cudaFuncSetAttribute(estep_stereo_kernel<T, C, J, OPT, ESTEP_MINB>,
+    cudaError_t e = cudaFuncSetAttribute(estep_stereo_kernel<T, C, J, OPT, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("estep_stereo_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return PF_ERR_CUDA;
     }
   }
-  estep_stereo_kernel<T, C, J, OPT, ESTEP_MINB><<<grid, ESTEP_THREADS, smem, st>>>(
+  estep_stereo_kernel<T, C, J, OPT, MINB><<<grid, ESTEP_THREADS, smem, st>>>(
       (const T*)X, (const T*)V, coef, noise, map, (T*)hatW, partial, F, N, ld, chunk, nsplit);
   return check_launch("estep_stereo_kernel");
 }
@@ -480,6 +520,7 @@ static int launch_estep(const void* X, const void* V, const double* coef, const 
     case 4: return launch_estep_opt<T, C, J, 4>(PF_ESTEP_ARGS);
     case 5: return launch_estep_opt<T, C, J, 5>(PF_ESTEP_ARGS);
     case 6: return launch_estep_opt<T, C, J, 6>(PF_ESTEP_ARGS);
+    case 15: return launch_estep_opt<T, C, J, 15>(PF_ESTEP_ARGS);
     default: return launch_estep_opt<T, C, J, 7>(PF_ESTEP_ARGS);
   }
 #undef PF_ESTEP_ARGS

@@ -15,6 +15,10 @@ namespace pf {
 #endif
 constexpr int ESTEP_THREADS = PF_ESTEP_THREADS;
 constexpr int ESTEP_MINB = PF_ESTEP_MINB;  // CTAs per SM the register allocation aims for
+#ifndef PF_ESTEP_MINB_SMEMIO
+#define PF_ESTEP_MINB_SMEMIO 3
+#endif
+constexpr int ESTEP_MINB_SMEMIO = PF_ESTEP_MINB_SMEMIO;  // same, shared-memory-resident I/O variant
 constexpr int MAXJ = 6;
 constexpr int MAXR = 16;
 constexpr int PF_F32_FASTMATH = 2;
