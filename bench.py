@@ -40,9 +40,9 @@ WLEN, HOP = 2048, 512
 NSRC, NNMF, RANK = 4, 32, 2
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused E-step kernel on the
 # default workload, from the committed `ncu --set full` capture
-# profiles/r01/ncu_estep_stereo_kernel.txt (1.696969 GB + 0.835408 GB); the algorithmic figure is
+# profiles/r01/ncu_estep_stereo_kernel.txt (1.697144 GB + 0.823602 GB); the algorithmic figure is
 # 48 B x 52,974,050 bins = 2.543 GB, i.e. no wasted re-reads.
-ESTEP_DRAM_BYTES_PER_LAUNCH = 2.532377e9
+ESTEP_DRAM_BYTES_PER_LAUNCH = 2.520746e9
 METRIC = "gem_tf_bins_iters_per_s"
 UNIT = "TF-bins*iters/s"
 

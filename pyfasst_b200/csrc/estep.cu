@@ -88,11 +88,13 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   const int split = blockIdx.x;
   __shared__ C s_coef[NC];
   __shared__ T s_dcoef[NP];  // the mixed discriminants in the storage type (determinant)
+  __shared__ T s_fcoef[4 * J];  // R_j in the storage type (OPT bit 4)
   __shared__ double s_red[ESTEP_THREADS / 32][NA];
   if (threadIdx.x < NC) {
     const double c = coef[(size_t)f * NC + threadIdx.x];
     s_coef[threadIdx.x] = (C)c;
     if (threadIdx.x >= 4 * J) s_dcoef[threadIdx.x - 4 * J] = (T)c;
+    else s_fcoef[threadIdx.x] = (T)c;
   }
   __syncthreads();
   const C s2 = (C)noise[f];
@@ -102,14 +104,26 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 
   constexpr bool kPack = (OPT & 1) != 0 && sizeof(T) == 4;
   constexpr bool kHwCvt = (OPT & 2) != 0;
+  // OPT bit 4: fewer float<->double conversions (XU pipe, 16 results/clk/SM: the busiest pipe of
+  // this kernel).  Sigma is ALSO formed in the storage type (16 FFMA): the determinant needs no
+  // narrowed s00/s11, and the float copy of M = y y^H - Sigma^-1 that feeds the moment sums is
+  // formed from the narrowed y and the float Sigma^-1 instead of narrowing the four entries of
+  // the float64 M (which still feeds tr(M R_j), where the cancellation happens).  The
+  // log-likelihood integrand is summed in float over the VEC bins of a pass and widened once.
+  constexpr bool kLean = (OPT & 16) != 0 && sizeof(T) == 4 && sizeof(C) == 8;
+  const T s2t = (T)noise[f];
   Moments<T, J, kPack> mom;
   mom.clear();
   double acc_ll = 0.0;
 
   const long plane = (long)F * ld;
   const long row = (long)f * ld;
-  const long begin = (long)split * chunk;
-  long end = begin + chunk;
+  // OPT bit 5: the splits of a row take its passes in turn (split s works on passes s, s + nsplit,
+  // ...) instead of one contiguous run of frames each: the CTAs of a row, which are launched
+  // together, then read and write ONE contiguous region of every plane at any moment.
+  constexpr bool kInterleave = (OPT & 32) != 0;
+  const long begin = kInterleave ? (long)split * ESTEP_THREADS * VEC : (long)split * chunk;
+  long end = kInterleave ? N : begin + chunk;
   if (end > N) end = N;
 
   // Loads run ahead of the arithmetic: with only two CTAs resident per SM (the moment
@@ -129,7 +143,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   constexpr int NPL = 4 + J;
   extern __shared__ __align__(16) unsigned char s_ring_raw[];
   float4* s_ring = reinterpret_cast<float4*>(s_ring_raw);  // [ESTEP_DEPTH][NPL][ESTEP_THREADS]
-  const long stride = (long)ESTEP_THREADS * VEC;
+  const long stride = (long)ESTEP_THREADS * VEC * (kInterleave ? nsplit : 1);
   const long first = begin + (long)threadIdx.x * VEC;
   auto ring_issue = [&](long n, int slot) {
     if (n < end) {
@@ -211,6 +225,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         }
     }
 
+    float pass_ll = 0.f;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const int es = kSmemIO ? ((e + rot) & 3) : e;  // the bin of the vector this step works on
@@ -231,7 +246,40 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         vt[j] = v[j][e];
         vj[j] = (C)(kHwCvt ? widen_hw(vt[j]) : widen(vt[j]));
       }
-      sigma_inverse<C, T, J>(vj, vt, s_coef, s_dcoef, s2, pr, det, i00, i11, i01r, i01i);
+      T f00 = s2t, f11 = s2t, f01r = (T)0, f01i = (T)0, idet_t = (T)0;
+      if (kLean) {
+        C s00 = s2, s11 = s2, s01r = (C)0, s01i = (C)0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          s00 += vj[j] * s_coef[4 * j + 0];
+          s11 += vj[j] * s_coef[4 * j + 1];
+          s01r += vj[j] * s_coef[4 * j + 2];
+          s01i += vj[j] * s_coef[4 * j + 3];
+          f00 += vt[j] * s_fcoef[4 * j + 0];
+          f11 += vt[j] * s_fcoef[4 * j + 1];
+          f01r += vt[j] * s_fcoef[4 * j + 2];
+          f01i += vt[j] * s_fcoef[4 * j + 3];
+        }
+        det = s2t * (f00 + (f11 - s2t));
+        int p = 0;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+          for (int k = j; k < J; ++k) {
+            pr[p] = vt[j] * vt[k];
+            det += pr[p] * s_dcoef[p];
+            ++p;
+          }
+        det = pf_max(det, (T)1e-10);
+        idet_t = fast_rcp(det);
+        const C idet = (C)idet_t;
+        i00 = s11 * idet;
+        i11 = s00 * idet;
+        i01r = -s01r * idet;
+        i01i = -s01i * idet;
+      } else {
+        sigma_inverse<C, T, J>(vj, vt, s_coef, s_dcoef, s2, pr, det, i00, i11, i01r, i01i);
+      }
       // y = Sigma^-1 x
       const C a0r = (C)(kHwCvt ? widen_hw(x0r[e]) : widen(x0r[e]));
       const C a0i = (C)(kHwCvt ? widen_hw(x0i[e]) : widen(x0i[e]));
@@ -247,6 +295,8 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
       const T quad = b0r * z0r + b0i * z0i + b1r * z1r + b1i * z1i;
       if (sizeof(T) == 8)
         acc_ll += live ? log((double)det) + 1.1447298858494002 + (double)quad : 0.0;
+      else if (kLean)
+        pass_ll += live ? __logf((float)det) + kLogPi + (float)quad : 0.f;
       else
         acc_ll += (double)(live ? __logf((float)det) + kLogPi + (float)quad : 0.f);
       // M = y y^H - Sigma^-1
@@ -264,13 +314,22 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         if (kSmemIO) sb[(4 + j) * ESTEP_THREADS * 4 + es] = (float)w[j][e];
       }
       // S_jk += v_j v_k M ; U = x y^H ; T_j += v_j U ; sv_j += v_j   (accumulated in T)
-      const T t00 = (T)m00, t11 = (T)m11, t01r = (T)m01r, t01i = (T)m01i;
+      T t00, t11, t01r, t01i;
+      if (kLean) {
+        t00 = z0r * z0r + z0i * z0i - f11 * idet_t;
+        t11 = z1r * z1r + z1i * z1i - f00 * idet_t;
+        t01r = z0r * z1r + z0i * z1i + f01r * idet_t;
+        t01i = z0i * z1r - z0r * z1i + f01i * idet_t;
+      } else {
+        t00 = (T)m00; t11 = (T)m11; t01r = (T)m01r; t01i = (T)m01i;
+      }
       const T u[8] = {b0r * z0r + b0i * z0i, b0i * z0r - b0r * z0i,
                       b0r * z1r + b0i * z1i, b0i * z1r - b0r * z1i,
                       b1r * z0r + b1i * z0i, b1i * z0r - b1r * z0i,
                       b1r * z1r + b1i * z1i, b1i * z1r - b1r * z1i};
       mom.add(pr, vt, t00, t11, t01r, t01i, u);
     }
+    if (kLean) acc_ll += (double)pass_ll;
     if (kSmemIO) {
       if (sizeof(T) == 4) {
 #pragma unroll
@@ -477,11 +536,12 @@ static int dispatch_wiener(int J, const void* X, const void* V, const double* co
 }
 
 // Tuning variant of the float32 kernel: PYFASST_ESTEP_VARIANT = OPT bits (1: packed moment
-// accumulation, 2: hardware float->double conversion, 4: cp.async ring).
+// accumulation, 2: hardware float->double conversion, 4: cp.async ring, 8: shared-memory-resident
+// I/O (15 only), 16: fewer conversions (19 only), 32: interleaved splits (35 only)).
 static int estep_variant() {
   const char* e = getenv("PYFASST_ESTEP_VARIANT");
   int v = e != nullptr ? atoi(e) : ESTEP_DEFAULT_VARIANT;
-  if (v < 0 || (v > 7 && v != 15)) v = ESTEP_DEFAULT_VARIANT;
+  if (v < 0 || (v > 7 && v != 15 && v != 19 && v != 35)) v = ESTEP_DEFAULT_VARIANT;
   return v;
 }
 
@@ -511,7 +571,7 @@ static int launch_estep(const void* X, const void* V, const double* coef, const 
                         const SubMap& map, void* hatW, double* partial, int F, long N,
                         long ld, long chunk, int nsplit, cudaStream_t st) {
 #define PF_ESTEP_ARGS X, V, coef, noise, map, hatW, partial, F, N, ld, chunk, nsplit, st
-  if (sizeof(T) == 8) return launch_estep_opt<T, C, J, 0>(PF_ESTEP_ARGS);
+  if (sizeof(T) == 8) return launch_estep_opt<T, C, J, 32>(PF_ESTEP_ARGS);  // interleaved splits
   switch (estep_variant()) {
     case 0: return launch_estep_opt<T, C, J, 0>(PF_ESTEP_ARGS);
     case 1: return launch_estep_opt<T, C, J, 1>(PF_ESTEP_ARGS);
@@ -521,6 +581,8 @@ static int launch_estep(const void* X, const void* V, const double* coef, const 
     case 5: return launch_estep_opt<T, C, J, 5>(PF_ESTEP_ARGS);
     case 6: return launch_estep_opt<T, C, J, 6>(PF_ESTEP_ARGS);
     case 15: return launch_estep_opt<T, C, J, 15>(PF_ESTEP_ARGS);
+    case 19: return launch_estep_opt<T, C, J, 19>(PF_ESTEP_ARGS);
+    case 35: return launch_estep_opt<T, C, J, 35>(PF_ESTEP_ARGS);
     default: return launch_estep_opt<T, C, J, 7>(PF_ESTEP_ARGS);
   }
 #undef PF_ESTEP_ARGS
@@ -552,11 +614,17 @@ extern "C" int pf_estep_plan(int J, int64_t N, int dtype, int64_t* chunk, int* n
   const long vec = dtype == PF_F64 ? 2 : 4;
   const bool ws = estep_use_ws(J, (long)N, dtype);
   const long pass = ws ? estep_ws_pass() : ESTEP_THREADS * vec;
-  // aim for ~32 passes per CTA (16 for the warp-specialised kernel, whose pass is 6x longer) so
-  // the end-of-CTA reduction is amortised, while keeping at least ~4 CTAs per SM in flight on a
-  // 148-SM part
+  // aim for ~64 passes per CTA (16 for the warp-specialised kernel, whose pass is 6x longer) so
+  // that the start and the end-of-CTA reduction are amortised (one CTA costs about one pass on
+  // top of its passes: 64 instead of 32 passes per CTA is 0.716 -> 0.702 ms on configs[1],
+  // profiles/r01/estep_interleave_experiment.txt), while keeping at least ~4 CTAs per SM in
+  // flight on a 148-SM part
   long passes = (N + pass - 1) / pass;
-  long per_cta = ws ? estep_ws_passes_per_cta() : 32;
+  long per_cta = ws ? estep_ws_passes_per_cta() : 64;
+  if (!ws) {  // tuning: PYFASST_ESTEP_PASSES = passes per CTA (a power of two)
+    const char* e = getenv("PYFASST_ESTEP_PASSES");
+    if (e != nullptr && atoi(e) >= 1 && atoi(e) <= 1024) per_cta = atoi(e);
+  }
   long want_ctas = 148L * 8;
   while (per_cta > 1 && (long)F * ((passes + per_cta - 1) / per_cta) < want_ctas) per_cta /= 2;
   long c = per_cta * pass;

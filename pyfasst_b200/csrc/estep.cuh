@@ -22,8 +22,11 @@ constexpr int ESTEP_MINB_SMEMIO = PF_ESTEP_MINB_SMEMIO;  // same, shared-memory-
 constexpr int MAXJ = 6;
 constexpr int MAXR = 16;
 constexpr int PF_F32_FASTMATH = 2;
-constexpr int ESTEP_DEFAULT_VARIANT = 3;
-constexpr int ESTEP_DEPTH = 3;  // passes in flight in the cp.async ring (OPT bit 2)  // float storage AND float per-bin algebra (experiments)
+constexpr int ESTEP_DEFAULT_VARIANT = 35;  // packed moments + hardware conversions + interleaved splits
+#ifndef PF_ESTEP_DEPTH
+#define PF_ESTEP_DEPTH 3
+#endif
+constexpr int ESTEP_DEPTH = PF_ESTEP_DEPTH;  // passes in flight in the cp.async ring (OPT bit 2)  // float storage AND float per-bin algebra (experiments)
 
 __host__ __device__ constexpr int npairs(int J) { return J * (J + 1) / 2; }
 // accumulators per frequency: S (4 per pair), T (8 per source), sv (J), ll (1)
