@@ -157,14 +157,25 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
     }
     cp_async_commit();
   };
+  // OPT bit 6: streaming cache hints (ld.global.cs / st.global.cs): every plane is touched once
+  constexpr bool kStream = (OPT & 64) != 0 && sizeof(T) == 4;
   T nx[4][VEC], nv[J][VEC];
+  auto ld_plane = [&](const T* p, T (&out)[VEC]) {
+    if (kStream) {
+      const float4 q = __ldcs(reinterpret_cast<const float4*>(p));
+      out[0] = (T)q.x; out[1] = (T)q.y;
+      if (VEC == 4) { out[VEC - 2] = (T)q.z; out[VEC - 1] = (T)q.w; }
+    } else {
+      load_vec<T>(p, out);
+    }
+  };
   auto issue_loads = [&](long n) {
-    load_vec<T>(X + 0 * plane + row + n, nx[0]);
-    load_vec<T>(X + 1 * plane + row + n, nx[1]);
-    load_vec<T>(X + 2 * plane + row + n, nx[2]);
-    load_vec<T>(X + 3 * plane + row + n, nx[3]);
+    ld_plane(X + 0 * plane + row + n, nx[0]);
+    ld_plane(X + 1 * plane + row + n, nx[1]);
+    ld_plane(X + 2 * plane + row + n, nx[2]);
+    ld_plane(X + 3 * plane + row + n, nx[3]);
 #pragma unroll
-    for (int j = 0; j < J; ++j) load_vec<T>(V + j * plane + row + n, nv[j]);
+    for (int j = 0; j < J; ++j) ld_plane(V + j * plane + row + n, nv[j]);
   };
   if (kRing) {
 #pragma unroll
@@ -339,6 +350,11 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
       }
       ring_issue(n0 + ESTEP_DEPTH * stride, slot);  // refill the slot just consumed
       slot = slot + 1 == ESTEP_DEPTH ? 0 : slot + 1;
+    } else if (kStream) {
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+        __stcs(reinterpret_cast<float4*>(hatW + j * plane + row + n0),
+               make_float4((float)w[j][0], (float)w[j][1], (float)w[j][VEC - 2], (float)w[j][VEC - 1]));
     } else {
 #pragma unroll
       for (int j = 0; j < J; ++j) store_vec<T>(hatW + j * plane + row + n0, w[j]);
@@ -537,11 +553,11 @@ static int dispatch_wiener(int J, const void* X, const void* V, const double* co
 
 // Tuning variant of the float32 kernel: PYFASST_ESTEP_VARIANT = OPT bits (1: packed moment
 // accumulation, 2: hardware float->double conversion, 4: cp.async ring, 8: shared-memory-resident
-// I/O (15 only), 16: fewer conversions (19 only), 32: interleaved splits (35 only)).
+// I/O (15 only), 16: fewer conversions (19 only), 32: interleaved splits (35, 99), 64: streaming cache hints (99 only)).
 static int estep_variant() {
   const char* e = getenv("PYFASST_ESTEP_VARIANT");
   int v = e != nullptr ? atoi(e) : ESTEP_DEFAULT_VARIANT;
-  if (v < 0 || (v > 7 && v != 15 && v != 19 && v != 35)) v = ESTEP_DEFAULT_VARIANT;
+  if (v < 0 || (v > 7 && v != 15 && v != 19 && v != 35 && v != 99)) v = ESTEP_DEFAULT_VARIANT;
   return v;
 }
 
@@ -583,6 +599,7 @@ static int launch_estep(const void* X, const void* V, const double* coef, const 
     case 15: return launch_estep_opt<T, C, J, 15>(PF_ESTEP_ARGS);
     case 19: return launch_estep_opt<T, C, J, 19>(PF_ESTEP_ARGS);
     case 35: return launch_estep_opt<T, C, J, 35>(PF_ESTEP_ARGS);
+    case 99: return launch_estep_opt<T, C, J, 99>(PF_ESTEP_ARGS);
     default: return launch_estep_opt<T, C, J, 7>(PF_ESTEP_ARGS);
   }
 #undef PF_ESTEP_ARGS
