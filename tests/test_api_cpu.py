@@ -59,6 +59,40 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.pf_abi_version() == _lib.ABI_VERSION
 
 
+@pytest.mark.parametrize("J,F,N,dtype", [(4, 1025, 51682, 1), (3, 1025, 1122, 1), (4, 129, 51682, 1),
+                                         (4, 1025, 51682, 0), (1, 1, 1, 1), (6, 513, 2586, 1)])
+def test_estep_plan_covers_every_frame(J, F, N, dtype, monkeypatch):
+    """pf_estep_plan is host-only: the splits of a frequency row cover all its frames, the
+    workspace holds the partial moments of every (frequency, split) plus the per-frequency
+    coefficients, and enough CTAs are planned to fill a 148-SM part when the problem allows."""
+    from pyfasst_b200.build import build
+    lib = ctypes.CDLL(build())
+    i64, i32 = ctypes.c_int64, ctypes.c_int
+
+    def plan():
+        chunk, ns, nbytes = i64(), i32(), i64()
+        rc = lib.pf_estep_plan(i32(J), i64(N), i32(dtype), ctypes.byref(chunk), ctypes.byref(ns),
+                               ctypes.byref(nbytes), i32(F))
+        assert rc == 0
+        return chunk.value, ns.value, nbytes.value
+
+    monkeypatch.delenv("PYFASST_ESTEP_PASSES", raising=False)
+    monkeypatch.delenv("PYFASST_ESTEP_KERNEL", raising=False)
+    chunk, ns, nbytes = plan()
+    nacc = 4 * (J * (J + 1) // 2) + 9 * J + 1
+    ncoef = 4 * J + J * (J + 1) // 2
+    assert ns >= 1 and chunk * ns >= N and chunk * (ns - 1) < N
+    assert nbytes == F * ns * nacc * 8 + F * ncoef * 8
+    pass_bins = 128 * (2 if dtype == 1 else 4)  # PF_F64 = 1: double2 accesses
+    assert chunk % pass_bins == 0 and chunk // pass_bins <= 64
+    passes = -(-N // pass_bins)
+    assert F * ns >= min(148 * 8, F * passes)
+    # tuning knob: passes per CTA
+    monkeypatch.setenv("PYFASST_ESTEP_PASSES", "2")
+    chunk2, ns2, _ = plan()
+    assert chunk2 == min(chunk, 2 * pass_bins) and chunk2 * ns2 >= N
+
+
 def test_cuda_kernels_fail_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
