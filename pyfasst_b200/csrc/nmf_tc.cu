@@ -69,10 +69,20 @@ fb_contract_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fblk = blockIdx.y * FBT_ROWS;
   const int split = blockIdx.x;
-  const long begin = (long)split * chunk;
-  long end = begin + chunk;
-  if (end > N) end = N;
-  const int nsteps = (int)((end - begin + FBT_KN - 1) / FBT_KN);
+  // chunk < 0: the splits of a row block take the 32-frame steps in turn (split x works on steps
+  // x, x + nsplit, ...): together they read one contiguous region of every row at any moment
+  const bool interleave = chunk < 0;
+  const long step_stride = interleave ? (long)nsplit * FBT_KN : FBT_KN;
+  const long begin = interleave ? (long)split * FBT_KN : (long)split * chunk;
+  int nsteps;
+  if (interleave) {
+    const long total = (N + FBT_KN - 1) / FBT_KN;
+    nsteps = split < total ? (int)((total - split + nsplit - 1) / nsplit) : 0;
+  } else {
+    long end = begin + chunk;
+    if (end > N) end = N;
+    nsteps = (int)((end - begin + FBT_KN - 1) / FBT_KN);
+  }
 
   if (warp == 0) tc::tmem_alloc(&tmem_base, 32);
   if (tid == 0) {
@@ -104,7 +114,7 @@ fb_contract_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ 
 
   float4 hw_n[4], p_n[4], g_n;
   auto fetch = [&](int step) {
-    const long nb = begin + (long)step * FBT_KN;
+    const long nb = begin + (long)step * step_stride;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int f = fblk + prow[q];
@@ -209,10 +219,20 @@ spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fblk = blockIdx.y * 128;
   const long ntiles = (ldv + SPT_NT - 1) / SPT_NT;
-  const long t_begin = (long)blockIdx.x * tiles_per_cta;
-  long t_end = t_begin + tiles_per_cta;
-  if (t_end > ntiles) t_end = ntiles;
-  const int nt = (int)(t_end - t_begin);
+  // tiles_per_cta < 0: the CTAs of a row block take the frame tiles in turn (CTA x works on tiles
+  // x, x + gridDim.x, ...), so that together they write one contiguous region of every row at any
+  // moment; > 0: one contiguous run of tiles per CTA
+  const bool interleave = tiles_per_cta < 0;
+  const long t_step = interleave ? (long)gridDim.x : 1;
+  const long t_begin = interleave ? (long)blockIdx.x : (long)blockIdx.x * tiles_per_cta;
+  int nt;
+  if (interleave) {
+    nt = t_begin < ntiles ? (int)((ntiles - t_begin + t_step - 1) / t_step) : 0;
+  } else {
+    long t_end = t_begin + tiles_per_cta;
+    if (t_end > ntiles) t_end = ntiles;
+    nt = (int)(t_end - t_begin);
+  }
 
   if (warp == 0) tc::tmem_alloc(&tmem_base, 512);
   if (tid == 0) {
@@ -291,7 +311,7 @@ spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restri
       const int k = i >> 6, c = i & 63;
       st_split4(sm.b_hi[b], sm.b_lo[b], tc::mnmajor_off(k, c * 4, SPT_LBO, SPT_SBO), h_n[q]);
     }
-    if (t + 1 < nt) fetch(t_begin + t + 1);
+    if (t + 1 < nt) fetch(t_begin + (t + 1) * t_step);
     tc::fence_proxy_async();
     tc::fence_before_thread_sync();
     __syncthreads();
@@ -314,14 +334,14 @@ spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restri
     if (t > 0) {  // write tile t-1 while the tensor core works on tile t
       tc::mbar_wait(&mbar[b ^ 1], (uint32_t)(((t - 1) >> 1) & 1));
       tc::fence_after_thread_sync();
-      write_out(b ^ 1, t_begin + t - 1);
+      write_out(b ^ 1, t_begin + (t - 1) * t_step);
     }
   }
   if (nt > 0) {
     const int b = (nt - 1) & 1;
     tc::mbar_wait(&mbar[b], (uint32_t)(((nt - 1) >> 1) & 1));
     tc::fence_after_thread_sync();
-    write_out(b, t_begin + nt - 1);
+    write_out(b, t_begin + (nt - 1) * t_step);
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -839,9 +859,12 @@ int pf_fb_contract_tc(const float* hatW, const float* P, long ld, const float* G
     return PF_ERR_CUDA;
   }
   dim3 grid(nsplit, ceil_div(F, FBT_ROWS));
+  // PYFASST_FBT_INTERLEAVE=0: one contiguous run of frames per split (the older mapping)
+  const char* env = getenv("PYFASST_FBT_INTERLEAVE");
+  const bool interleave = env == nullptr || atoi(env) != 0;
   for (int k0 = 0; k0 < K; k0 += 32) {
-    fb_contract_tc_kernel<<<grid, FBT_THREADS, smem, st>>>(hatW, P, ld, G, ldg, k0, K, F, N, chunk,
-                                                         nsplit, num);
+    fb_contract_tc_kernel<<<grid, FBT_THREADS, smem, st>>>(hatW, P, ld, G, ldg, k0, K, F, N,
+                                                         interleave ? -chunk : chunk, nsplit, num);
     int rc = check_launch("fb_contract_tc_kernel");
     if (rc) return rc;
   }
@@ -866,7 +889,11 @@ int pf_spec_power_tc(const float* W, int ldw, const float* H, long ldh, float* V
   if (splits < 1) splits = 1;
   const int per = (int)((ntiles + splits - 1) / splits);
   dim3 grid(ceil_div(ntiles, per), fblocks);
-  spec_power_tc_kernel<<<grid, SPT_THREADS, smem, st>>>(W, ldw, H, ldh, V, ldv, F, K, N, per);
+  // PYFASST_SPT_INTERLEAVE=0: contiguous runs of tiles per CTA (the older mapping)
+  const char* env = getenv("PYFASST_SPT_INTERLEAVE");
+  const bool interleave = env == nullptr || atoi(env) != 0;
+  spec_power_tc_kernel<<<grid, SPT_THREADS, smem, st>>>(W, ldw, H, ldh, V, ldv, F, K, N,
+                                                        interleave ? -per : per);
   return check_launch("spec_power_tc_kernel");
 }
 
