@@ -114,7 +114,10 @@ int pf_wiener_stereo(const void* X, const void* V, const void* A, const int* src
                      int dtype, void* stream);
 
 /* ---- K2: fused E-step  (audioModel.py:580-764, tools/signalTools.py:132-196) --- */
-/* Workspace planning: bytes needed by pf_estep_stereo for this shape. */
+/* Workspace planning (host only, no device call): bytes needed by pf_estep_stereo for this
+ * shape.  *nsplit CTAs share one frequency row and *chunk is the number of frames each of them
+ * covers (chunk * nsplit >= N); the CTAs of a row take its passes in turn, so the frames of one
+ * CTA are not contiguous. */
 int pf_estep_plan(int J, int64_t N, int dtype, int64_t* chunk, int* nsplit,
                   int64_t* workspace_bytes, int F);
 /* X       : dtype planes [4][F][ld] (re0, im0, re1, im1): Cx = x x^H is rank one
