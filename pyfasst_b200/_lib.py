@@ -259,8 +259,6 @@ class CudaKernels(object):
         J, F, ld = V.shape
         R = A.shape[0]
         code = self.dtype_code(V)
-        if code == PF_F32 and os.environ.get("PYFASST_ESTEP_FLOAT_ALGEBRA") == "1":
-            code = 2  # measurement only: float32 per-bin algebra (inaccurate at high SNR)
         _check(self.lib.pf_estep_stereo(self._p(X), self._p(V), self._p(A), _iarr(src_of_sub), R,
                                         J, self._p(noise), F, N, ld, self._p(hatW), self._p(Rss),
                                         self._p(Rxs), self._p(ll_f), self._p(workspace),

@@ -193,7 +193,7 @@ class GemEngine(object):
             psd0 = np.asarray(lim1, dtype=np.float64)
         else:
             psd0 = np.asarray(psd, dtype=np.float64)
-        self.noise = self._f64(np.broadcast_to(psd0, (self.F_total,))[sl])
+        self.noise = self._f64(np.array(np.broadcast_to(psd0, (self.F_total,))[sl]))
 
     def set_model(self, spat_comps, spec_comps, nmfUpdateCoeff=1.0):
         """Validates the structure and uploads the parameters (host dicts -> HBM)."""

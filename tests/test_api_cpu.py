@@ -77,9 +77,8 @@ def test_estep_plan_covers_every_frame(J, F, N, dtype, monkeypatch):
         return chunk.value, ns.value, nbytes.value
 
     monkeypatch.delenv("PYFASST_ESTEP_PASSES", raising=False)
-    monkeypatch.delenv("PYFASST_ESTEP_KERNEL", raising=False)
     chunk, ns, nbytes = plan()
-    nacc = 4 * (J * (J + 1) // 2) + 9 * J + 1
+    nacc = 4 * (J * (J + 1) // 2) + 13 * J + 1  # S, Z, sv, clamp corrections, ll
     ncoef = 4 * J + J * (J + 1) // 2
     assert ns >= 1 and chunk * ns >= N and chunk * (ns - 1) < N
     assert nbytes == F * ns * nacc * 8 + F * ncoef * 8

@@ -95,36 +95,38 @@ def test_estep_stereo(ck, fk, dt, F, N, J, rank, consistent):
         k.estep_stereo(X.to(dev), V.to(dev), A.to(dev), src, noise.to(dev), N, hatW, Rss, Rxs, ll, ws)
         outs.append([t.cpu().numpy() for t in (hatW, Rss, Rxs, ll)])
     (hw0, rss0, rxs0, ll0), (hw1, rss1, rxs1, ll1) = outs
-    # storage may be float32 but the per-bin algebra is float64: only the final rounding differs
+    # storage may be float32 but the per-bin algebra AND the moment sums are float64: only the
+    # final rounding of hat_W differs
     assert rel(hw1[:, :, :N], hw0[:, :, :N]) < tol(dt, f32=1e-6)
     assert (hw1[:, :, N:] == 0).all(), "padding frames must stay zero"
-    # the moment sums are accumulated in the storage type: float32 rounding of the entries of
-    # M = y y^H - Sigma^-1 (~1/noise) is amplified by cond(Sigma) when contracted with the
-    # mixing vectors; the adversarial inputs square that (|y| ~ |x|/noise)
-    t = tol(dt, f32=1e-4 if consistent else 5e-3)
-    assert rel(rss1, rss0) < 20 * tol(dt) if dt == torch.float64 else rel(rss1, rss0) < t
-    assert rel(rxs1, rxs0) < 20 * tol(dt) if dt == torch.float64 else rel(rxs1, rxs0) < t
-    # per-frequency sums of N terms of either sign: absolute tolerance ~ N * eps32
+    # hat_Rxs comes from the identity x y^H = Sigma M + I (T_j = sv_j I + s2 Z_j + sum_l R_l S_lj),
+    # exact to 1e-16 cond(Sigma); the adversarial inputs (|y| ~ |x| / noise) stress that
+    t = 1e-9 if consistent else 1e-7
+    assert rel(rss1, rss0) < t
+    assert rel(rxs1, rxs0) < t
     assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-12, f32=1e-6),
                     atol=0.0 if dt == torch.float64 else 1e-6 * N)
     assert_allclose(rss1, np.conj(np.transpose(rss1, (0, 2, 1))), atol=1e-14 * np.abs(rss1).max())
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
-@pytest.mark.parametrize("F,N,J,rank", [(5, 77, 1, 1), (3, 1000, 3, 1), (4, 2600, 4, 2),
-                                        (2, 7001, 2, 3), (3, 4, 4, 1), (2, 20003, 4, 2)])
-def test_estep_stereo_warp_specialised(ck, fk, monkeypatch, cfg, F, N, J, rank):
-    """The warp-specialised float32 E-step (algebra warps + moment warps, records through shared
-    memory) against the kernel specification AND against the fused kernel: same per-bin algebra;
-    the moment sums only differ by the order of the float32 additions."""
-    dt = torch.float32
-    rng = np.random.default_rng(F * 1000 + N)
-    ld, R, src, X, V, A, noise = problem(rng, dt, F, N, J, rank, consistent=True)
+@pytest.mark.parametrize("dt", DTYPES)
+def test_estep_stereo_determinant_clamp(ck, fk, dt):
+    """Quiet rows: det Sigma < 1e-10 activates the reference's clamp (signalTools.py:183-188), where
+    Sigma_c^-1 is not the inverse of Sigma and the kernel's identity for x y^H needs its correction
+    term; rows 0-2 are clamped in every bin, rows 3-5 in some, the rest in none."""
+    rng = np.random.default_rng(77)
+    F, N, J, rank = 9, 1300, 3, 2
+    ld, R, src, X, V, A, noise = problem(rng, dt, F, N, J, rank)
+    scale = np.ones(F)
+    scale[:3], scale[3:6] = 1e-7, 3e-5
+    sc = torch.tensor(scale)
+    X = (X.to(torch.float64) * torch.sqrt(sc)[None, :, None]).to(dt)
+    V = (V.to(torch.float64) * sc[None, :, None]).to(dt)
+    V[:, 3:6, ::3] *= 1e-3
+    X[:, 3:6, ::3] *= 1e-2
+    noise = noise * sc
     outs = []
-    for k, dev, kern in ((fk, "cpu", None), (ck, "cuda", "fused"), (ck, "cuda", "ws")):
-        if kern is not None:
-            monkeypatch.setenv("PYFASST_ESTEP_KERNEL", kern)
-            monkeypatch.setenv("PYFASST_ESTEP_WSCFG", str(cfg))
+    for k, dev in ((fk, "cpu"), (ck, "cuda")):
         hatW = torch.zeros((J, F, ld), dtype=dt, device=dev)
         Rss = torch.zeros((F, R, R), dtype=torch.complex128, device=dev)
         Rxs = torch.zeros((F, 2, R), dtype=torch.complex128, device=dev)
@@ -133,14 +135,12 @@ def test_estep_stereo_warp_specialised(ck, fk, monkeypatch, cfg, F, N, J, rank):
                          dtype=torch.float64, device=dev)
         k.estep_stereo(X.to(dev), V.to(dev), A.to(dev), src, noise.to(dev), N, hatW, Rss, Rxs, ll, ws)
         outs.append([t.cpu().numpy() for t in (hatW, Rss, Rxs, ll)])
-    (hw0, rss0, rxs0, ll0), (hw1, rss1, rxs1, ll1), (hw2, rss2, rxs2, ll2) = outs
-    assert rel(hw2[:, :, :N], hw0[:, :, :N]) < 1e-6
-    assert (hw2[:, :, N:] == 0).all(), "padding frames must stay zero"
-    assert rel(hw2, hw1) < 1e-6, "same per-bin algebra as the fused kernel"
-    assert rel(rss2, rss0) < 1e-4 and rel(rxs2, rxs0) < 1e-4
-    assert rel(rss2, rss1) < 1e-4 and rel(rxs2, rxs1) < 1e-4
-    assert_allclose(ll2, ll0, rtol=1e-6, atol=1e-6 * N)
-    assert_allclose(rss2, np.conj(np.transpose(rss2, (0, 2, 1))), atol=1e-14 * np.abs(rss2).max())
+    (hw0, rss0, rxs0, ll0), (hw1, rss1, rxs1, ll1) = outs
+    for f in range(F):  # per row: the rows differ by many orders of magnitude
+        assert rel(hw1[:, f, :N], hw0[:, f, :N]) < tol(dt, f32=1e-6), f
+        assert rel(rss1[f], rss0[f]) < 1e-8, f
+        assert rel(rxs1[f], rxs0[f]) < 1e-8, f
+    assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-12, f32=1e-6), atol=0.0 if dt == torch.float64 else 1e-6 * N)
 
 
 @pytest.mark.parametrize("dt", DTYPES)
