@@ -82,7 +82,10 @@ class FASST(object):
         self.noise = {
             'PSD': np.zeros(self.sig_repr_params['fsize'] // 2 + 1),
             'sim_ann_opt': sim_ann_opt,
-            'ann_PSD_lim': ann_PSD_lim,
+            # (a copy: the reference stores the argument itself and fills it in place, so that
+            # its mutable default [None, None] leaks the limits of the first model of a process
+            # into every later one, audioModel.py:171,:236,:316-322 -- not reproduced)
+            'ann_PSD_lim': list(ann_PSD_lim),
         }
         self.spat_comps = {}
         self.spec_comps = {}

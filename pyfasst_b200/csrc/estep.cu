@@ -103,15 +103,21 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 
   const int f = blockIdx.y;
   const int split = blockIdx.x;
-  __shared__ double s_coef[4 * J];
+  __shared__ double s_coef[4 * J], s_coef2[4 * J];
   __shared__ double s_red[ESTEP_THREADS / 32][NA];
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  // [ESTEP_DEPTH][NPL][ESTEP_THREADS] 16-byte vectors, then the clamp-correction slots
-  // [8 J][ESTEP_THREADS] doubles
+  // [ESTEP_DEPTH][NPL][ESTEP_THREADS] 16-byte vectors (the ring), [J][ESTEP_THREADS] vectors
+  // (hat_W of the current pass), then the clamp-correction slots [8 J][ESTEP_THREADS] doubles
   typedef typename VecOf<T>::type VT;
   VT* s_ring = reinterpret_cast<VT*>(s_dyn);
-  double* s_corr = reinterpret_cast<double*>(s_dyn + (size_t)ESTEP_DEPTH * NPL * ESTEP_THREADS * 16);
-  if (threadIdx.x < 4 * J) s_coef[threadIdx.x] = coef[(size_t)f * NC + threadIdx.x];
+  VT* s_outv = s_ring + (size_t)ESTEP_DEPTH * NPL * ESTEP_THREADS;
+  double* s_corr = reinterpret_cast<double*>(s_outv + (size_t)J * ESTEP_THREADS);
+  T* so = reinterpret_cast<T*>(s_outv + threadIdx.x);
+  if (threadIdx.x < 4 * J) {
+    const double c = coef[(size_t)f * NC + threadIdx.x];
+    s_coef[threadIdx.x] = c;
+    s_coef2[threadIdx.x] = (threadIdx.x & 2) ? 2.0 * c : c;  // R00, R11, 2 Re R01, 2 Im R01
+  }
 #pragma unroll
   for (int i = 0; i < 8 * J; ++i) s_corr[i * ESTEP_THREADS + threadIdx.x] = 0.0;
   __syncthreads();
@@ -124,7 +130,45 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
 #pragma unroll
   for (int i = 0; i < NM; ++i) mom[i] = 0.0;
   double acc_ll = 0.0;
+  int ndead = 0;
   bool any_clamped = false;
+  auto ll_term = [&](double det) -> double {  // log(det * pi)
+    if (sizeof(T) == 8) return log(det) + kLogPi;
+    return (double)(__logf((float)det) + (float)kLogPi);
+  };
+  // one bin of the slow path (see above): recomputed from the inputs still in the ring slot
+  auto clamp_correction = [&](const T* sb, int es) {
+    const double a0r = (double)sb[0 * ESTEP_THREADS * VEC + es];
+    const double a0i = (double)sb[1 * ESTEP_THREADS * VEC + es];
+    const double a1r = (double)sb[2 * ESTEP_THREADS * VEC + es];
+    const double a1i = (double)sb[3 * ESTEP_THREADS * VEC + es];
+    double vj[J], s00 = s2, s11 = s2, s01r = 0.0, s01i = 0.0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      vj[j] = (double)sb[(4 + j) * ESTEP_THREADS * VEC + es];
+      s00 += vj[j] * s_coef[4 * j + 0];
+      s11 += vj[j] * s_coef[4 * j + 1];
+      s01r += vj[j] * s_coef[4 * j + 2];
+      s01i += vj[j] * s_coef[4 * j + 3];
+    }
+    const double det_raw = s00 * s11 - s01r * s01r - s01i * s01i;
+    const double idet = fast_rcp(kEps);
+    const double y0r = (s11 * a0r - s01r * a1r + s01i * a1i) * idet;
+    const double y0i = (s11 * a0i - s01r * a1i - s01i * a1r) * idet;
+    const double y1r = (s00 * a1r - s01r * a0r - s01i * a0i) * idet;
+    const double y1i = (s00 * a1i - s01r * a0i + s01i * a0r) * idet;
+    const double k1 = 1.0 - det_raw * idet;
+    const double u[8] = {a0r * y0r + a0i * y0i - 1.0, a0i * y0r - a0r * y0i,
+                         a0r * y1r + a0i * y1i,       a0i * y1r - a0r * y1i,
+                         a1r * y0r + a1i * y0i,       a1i * y0r - a1r * y0i,
+                         a1r * y1r + a1i * y1i - 1.0, a1i * y1r - a1r * y1i};
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const double c = k1 * vj[j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_corr[(8 * j + i) * ESTEP_THREADS + threadIdx.x] += c * u[i];
+    }
+  };
 
   const long plane = (long)F * ld;
   const long row = (long)f * ld;
@@ -158,12 +202,13 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         if (n0 + e >= end) {
 #pragma unroll
           for (int pl = 0; pl < NPL; ++pl) sb[pl * ESTEP_THREADS * VEC + e] = (T)0;
+          ++ndead;
         }
     }
+    unsigned cmask = 0;  // steps whose bin has the determinant clamp active
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const int es = (e + rot) & (VEC - 1);  // the bin of the vector this step works on
-      const bool live = n0 + es < end;
       const double a0r = (double)sb[0 * ESTEP_THREADS * VEC + es];
       const double a0i = (double)sb[1 * ESTEP_THREADS * VEC + es];
       const double a1r = (double)sb[2 * ESTEP_THREADS * VEC + es];
@@ -188,30 +233,34 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
       // |det| < eps, sign(det + eps) max(|det|, eps) = +eps)
       const double det_raw = s00 * s11 - s01r * s01r - s01i * s01i;
       const bool clamped = fabs(det_raw) < kEps;
+      cmask |= clamped ? (1u << e) : 0u;
       const double det = clamped ? kEps : det_raw;
       const double idet = fast_rcp(det);
-      // y' = adj(Sigma) x, y = y' / det
-      const double y0r = (s11 * a0r - s01r * a1r + s01i * a1i) * idet;
-      const double y0i = (s11 * a0i - s01r * a1i - s01i * a1r) * idet;
-      const double y1r = (s00 * a1r - s01r * a0r - s01i * a0i) * idet;
-      const double y1i = (s00 * a1i - s01r * a0i + s01i * a0r) * idet;
-      // log-likelihood integrand log(det*pi) + x^H Sigma^-1 x (audioModel.py:660-664)
-      const double quad = a0r * y0r + a0i * y0i + a1r * y1r + a1i * y1i;
-      if (sizeof(T) == 8)
-        acc_ll += live ? log(det) + kLogPi + quad : 0.0;
-      else
-        acc_ll += live ? (double)(__logf((float)det) + (float)kLogPi) + quad : 0.0;
-      // M = y y^H - Sigma^-1
-      const double m00 = y0r * y0r + y0i * y0i - s11 * idet;
-      const double m11 = y1r * y1r + y1i * y1i - s00 * idet;
-      const double m01r = y0r * y1r + y0i * y1i + s01r * idet;
-      const double m01i = y0i * y1r - y0r * y1i + s01i * idet;
+      // y' = adj(Sigma) x (y = y' / det) and P = y' y'^H do not wait for the 1/det chain
+      const double y0r = s11 * a0r - s01r * a1r + s01i * a1i;
+      const double y0i = s11 * a0i - s01r * a1i - s01i * a1r;
+      const double y1r = s00 * a1r - s01r * a0r - s01i * a0i;
+      const double y1i = s00 * a1i - s01r * a0i + s01i * a0r;
+      const double p00 = y0r * y0r + y0i * y0i;
+      const double p11 = y1r * y1r + y1i * y1i;
+      const double p01r = y0r * y1r + y0i * y1i;
+      const double p01i = y0i * y1r - y0r * y1i;
+      // log-likelihood integrand log(det*pi) + x^H Sigma^-1 x (audioModel.py:660-664).  Frames
+      // beyond the end of the row have x = 0, v = 0: their term log(det0 pi) is counted in
+      // `ndead` and taken out after the loop -- no branch in the unrolled body
+      const double quad = (a0r * y0r + a0i * y0i + a1r * y1r + a1i * y1i) * idet;
+      acc_ll += ll_term(det) + quad;
+      // M = y y^H - Sigma^-1 = (P / det - adj(Sigma)) / det
+      const double m00 = fma(idet, p00, -s11) * idet;
+      const double m11 = fma(idet, p11, -s00) * idet;
+      const double m01r = fma(idet, p01r, s01r) * idet;
+      const double m01i = fma(idet, p01i, s01i) * idet;
       // posterior source power (audioModel.py:727-729, :408-414)
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const T q = (T)(s_coef[4 * j + 0] * m00 + s_coef[4 * j + 1] * m11 +
-                        2.0 * (s_coef[4 * j + 2] * m01r + s_coef[4 * j + 3] * m01i));
-        sb[(4 + j) * ESTEP_THREADS * VEC + es] = pf_abs(vt[j] + vt[j] * vt[j] * (q * invrank[j]));
+        const T q = (T)(s_coef2[4 * j + 0] * m00 + s_coef2[4 * j + 1] * m11 +
+                        s_coef2[4 * j + 2] * m01r + s_coef2[4 * j + 3] * m01i);
+        so[j * ESTEP_THREADS * VEC + es] = pf_abs(vt[j] + vt[j] * vt[j] * (q * invrank[j]));
       }
       // S_jk += v_j v_k M ; Z_j += v_j M ; sv_j += v_j
       {
@@ -236,29 +285,24 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
           mom[4 * NP + 4 * J + j] += vj[j];
         }
       }
-      if (clamped) {  // rare: (1 - kappa) v_j (x y^H - I) into this thread's own slots
-        any_clamped = true;
-        const double k1 = 1.0 - det_raw * idet;
-        const double u[8] = {a0r * y0r + a0i * y0i - 1.0, a0i * y0r - a0r * y0i,
-                             a0r * y1r + a0i * y1i,       a0i * y1r - a0r * y1i,
-                             a1r * y0r + a1i * y0i,       a1i * y0r - a1r * y0i,
-                             a1r * y1r + a1i * y1i - 1.0, a1i * y1r - a1r * y1i};
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const double c = k1 * vj[j];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s_corr[(8 * j + i) * ESTEP_THREADS + threadIdx.x] += c * u[i];
-        }
-      }
     }
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      *reinterpret_cast<VT*>(hatW + j * plane + row + n0) =
-          *reinterpret_cast<const VT*>(sb + (4 + j) * ESTEP_THREADS * VEC);
+      *reinterpret_cast<VT*>(hatW + j * plane + row + n0) = s_outv[j * ESTEP_THREADS + threadIdx.x];
+    if (cmask != 0) {  // rare slow path, kept out of the unrolled body (no scheduling barrier there)
+      any_clamped = true;
+#pragma unroll 1
+      for (int e = 0; e < VEC; ++e)
+        if ((cmask >> e) & 1u) clamp_correction(sb, (e + rot) & (VEC - 1));
+    }
     ring_issue(n0 + ESTEP_DEPTH * stride, slot);  // refill the slot just consumed
     slot = slot + 1 == ESTEP_DEPTH ? 0 : slot + 1;
   }
   cp_async_wait<0>();
+  {  // the padding frames' log(det0 pi), formed exactly as in the loop (x = 0, v = 0)
+    const double det0 = s2 * s2;
+    acc_ll -= (double)ndead * ll_term(fabs(det0) < kEps ? kEps : det0);
+  }
 
   // fixed-order block reduction in double (H8: deterministic, no atomics)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -492,7 +536,7 @@ static int dispatch_wiener(int J, const void* X, const void* V, const double* co
 }
 
 static size_t estep_smem_bytes(int J) {
-  return (size_t)ESTEP_DEPTH * (4 + J) * ESTEP_THREADS * 16 + (size_t)8 * J * ESTEP_THREADS * 8;
+  return (size_t)(ESTEP_DEPTH * (4 + J) + J) * ESTEP_THREADS * 16 + (size_t)8 * J * ESTEP_THREADS * 8;
 }
 
 template <typename T, int J>
