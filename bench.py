@@ -292,7 +292,7 @@ def run_ours(args, rank, world):
     logliks = torch.ones(total_iters, dtype=torch.float64, device=eng.dev)
     eng.iter_dev.zero_()
     eng.flags.zero_()
-    eng.totals.fill_(1.0)
+    eng.totals.zero_()
     for _ in range(args.warmup):
         eng.gem_iteration(total_iters, logliks)
     events = []

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 9
+#define PF_ABI_VERSION 10
 
 #define PF_OK 0
 #define PF_ERR_ARG (-1)         /* invalid argument (ValueError on the Python side) */
@@ -101,6 +101,12 @@ int pf_overlap_norm(const double* prod, int wlen, int hop, int64_t N, double* no
 int pf_istft(const void* Y, int nsig, int F, int64_t N, int64_t ld, const double* synth,
              const double* norm, int wlen, int hop, int nfft, double* out, int64_t Lout,
              int16_t* pcm, double maxdata, int64_t drop, int pcm_round, int dtype, void* stream);
+
+/* Y[c1] = sum_c2 W[c1][c2] X[c2] per bin: the filtering step of filter_stft
+ * (tftransforms/stft.py:181-193).  X, Y planes [2 nc][F][ld]; W complex128 [nc][nc][F] (wn = 0)
+ * or [nc][nc][F][wn] with wn >= N frames */
+int pf_apply_filter(const void* X, const void* W, void* Y, int nc, int F, int64_t N, int64_t ld,
+                    int64_t wn, int dtype, void* stream);
 
 /* ---- K6: Wiener filter  (audioModel.py:1088-1236, :1327-1467) ----------------- */
 /* For every bin: Sigma = sum_j v_j R_j + s2 I, Y_g = (sum_{j in g} v_j R_j) Sigma^-1 x for
@@ -216,8 +222,18 @@ int pf_mult_update_splits(void* theta, int64_t ldt, const double* num_partial,
  * with pf_gemm_tf32x3(_splitk). */
 /* out [F][2 ld] = ( hatW / max(P,eps)^2 * max(O,eps) | max(O,eps) / max(P,eps) ), eps = 1e-10,
  * zero in the padding columns n >= N */
+/* Ptot / Pminus (NULL: none): the correlation penalty lambdaCorr of audioModel.py:1484-1703,
+ * c = lambda Pminus / max(Ptot^2, eps): den = O (1/P + c), num = (hatW / P^2 + 2 c P / Ptot) O */
 int pf_gem_ratio_planes(const void* hatW, const void* P, const void* O, void* out, int F,
-                        int64_t N, int64_t ld, int dtype, void* stream);
+                        int64_t N, int64_t ld, const void* Ptot, const void* Pminus, double lambda,
+                        int dtype, void* stream);
+/* Ptot = max(sum_j V_j, eps), Pminus = Ptot - max(V_own, eps) (clamped at eps when `clamp`), V planes
+ * [J][F][ld] (audioModel.py:1484-1508) */
+int pf_corr_planes(const void* V, int J, int own, void* Ptot, void* Pminus, int F, int64_t N,
+                   int64_t ld, int clamp, int dtype, void* stream);
+/* out[r] = sum_c M[r][c] in float64 (the row means of the time blobs, audioModel.py:2026-2030) */
+int pf_row_sums(const void* M, int64_t ldm, int rows, int64_t cols, double* out, int dtype,
+                void* stream);
 /* out (=, +=) a * b elementwise on [F][ld] planes (b = NULL: a); zero in the padding */
 int pf_mul_planes(const void* a, const void* b, void* out, int F, int64_t N, int64_t ld,
                   int accumulate, int dtype, void* stream);
@@ -248,7 +264,8 @@ int pf_scale_matrix(void* M, int64_t ldm, int rows, int64_t cols, const double* 
                     int divide, double* total, int dtype, void* stream);
 
 /* totals[s] < eps  ->  *flags |= PF_FLAG_TW_RESTART ; totals are reset to zero */
-int pf_check_totals(double* totals, int count, double eps, int* flags, void* stream);
+int pf_check_totals(double* totals, int count, double eps, int* flags, const int* iter_dev,
+                    int* first_iter, void* stream);
 
 /* ---- dense float32 GEMM on the tensor cores (SIMM: every np.dot of SIMM.py:303-393, :613-941) */
 /* C[M x N] = op(A) op(B), row-major float32, tcgen05 kind::tf32 with the 3xTF32 split

@@ -114,6 +114,24 @@ PATCHES = {
          "    # normalising the liutkus way:\n"
          "    data = data / normalisationSeq"),
         ("self.freqbins = self.ftlen / 2 + 1", "self.freqbins = self.ftlen // 2 + 1"),
+        # filter_stft (stft.py:133-227): float sizes / slice bounds that old numpy truncated
+        ("    numberFrames = np.ceil(lengthData / np.double(hopsize))\n    # to ensure that the data array s big enough,\n"
+         "    # assuming the first frame is centered on first sample:\n"
+         "    newLengthData = (numberFrames-1) * hopsize + lengthWindow\n    \n"
+         "    # !!! adding zeros to the beginning of data, such that the first window is\n"
+         "    # centered on the first sample of data\n"
+         "    data = np.concatenate((np.zeros([lengthWindow/2.0, nc]), data))",
+         "    numberFrames = int(np.ceil(lengthData / np.double(hopsize)))\n"
+         "    newLengthData = int((numberFrames-1) * hopsize + lengthWindow)\n"
+         "    data = np.concatenate((np.zeros([int(lengthWindow/2.0), nc]), data))"),
+        ("    numberFrequencies = nfft / 2 + 1\n    if numberFrequencies != W.shape[2]:",
+         "    numberFrequencies = int(nfft) // 2 + 1\n    if numberFrequencies != W.shape[2]:"),
+        ("    for n in np.arange(numberFrames):\n        beginFrame = n * hopsize\n"
+         "        endFrame = beginFrame + lengthWindow\n        \n        # Compute Fourier transforms",
+         "    for n in np.arange(numberFrames):\n        beginFrame = int(n * hopsize)\n"
+         "        endFrame = beginFrame + lengthWindow\n        \n        # Compute Fourier transforms"),
+        ("    ndata = ndata[(lengthWindow/2.0):]\n    normalisationSeq = normalisationSeq[(lengthWindow/2.0):]",
+         "    ndata = ndata[int(lengthWindow/2.0):]\n    normalisationSeq = normalisationSeq[int(lengthWindow/2.0):]"),
     ],
     "tools/utils.py": [
         # scipy moved the window functions to scipy.signal.windows (same function)

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("PYFASST_B200_LIB") or os.path.join(HERE, "libpyfasst_
 
 PF_F32, PF_F64 = 0, 1
 PF_FLAG_SINGULAR, PF_FLAG_TW_RESTART = 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 c_ip = ctypes.POINTER(ctypes.c_int)
@@ -66,7 +66,7 @@ SIGNATURES = {
     "pf_fb_scale_colmax": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp],
     "pf_fw_renorm": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "pf_scale_matrix": [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_vp],
-    "pf_check_totals": [c_vp, c_int, c_dbl, c_vp, c_vp],
+    "pf_check_totals": [c_vp, c_int, c_dbl, c_vp, c_vp, c_vp, c_vp],
     "pf_gemm_tf32x3": [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int,
                        c_vp],
     "pf_gemm_splitk_plan": [c_int, c_int, c_int, c_ip, ctypes.POINTER(c_i64)],
@@ -101,7 +101,11 @@ SIGNATURES = {
     "pf_simm_wm_scaled": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp],
     "pf_viterbi_workspace_bytes": [c_int, c_i64],
     "pf_viterbi": [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp],
-    "pf_gem_ratio_planes": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp],
+    "pf_gem_ratio_planes": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_dbl, c_int,
+                            c_vp],
+    "pf_corr_planes": [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_vp],
+    "pf_row_sums": [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_vp],
+    "pf_apply_filter": [c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_i64, c_int, c_vp],
     "pf_mul_planes": [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_vp],
     "pf_mult_update_same": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
     "pf_sparsity_reweigh": [c_vp, c_i64, c_int, c_i64, c_int, c_dbl, c_dbl, c_vp, c_vp, c_int, c_vp],
@@ -563,10 +567,27 @@ class CudaKernels(object):
                                         self.dtype_code(M), self._stream()), self.lib)
 
     # -- general factor structures -----------------------------------------------------------------
-    def gem_ratio_planes(self, hatW, P, O, out, N):
+    def gem_ratio_planes(self, hatW, P, O, out, N, Ptot=None, Pminus=None, lam=0.0):
         F, ld = hatW.shape
         _check(self.lib.pf_gem_ratio_planes(self._p(hatW), self._p(P), self._p(O), self._p(out), F,
-                                            N, ld, self.dtype_code(hatW), self._stream()), self.lib)
+                                            N, ld, self._p(Ptot), self._p(Pminus), float(lam),
+                                            self.dtype_code(hatW), self._stream()), self.lib)
+
+    def corr_planes(self, V, own, Ptot, Pminus, N, clamp=True):
+        J, F, ld = V.shape
+        _check(self.lib.pf_corr_planes(self._p(V), J, own, self._p(Ptot), self._p(Pminus), F, N, ld,
+                                       int(clamp), self.dtype_code(V), self._stream()), self.lib)
+
+    def row_sums(self, M, rows, cols, out):
+        _check(self.lib.pf_row_sums(self._p(M), M.stride(0), rows, cols, self._p(out),
+                                    self.dtype_code(M), self._stream()), self.lib)
+
+    def apply_filter(self, X, W, Y, N):
+        """Y[c1] = sum_c2 W[c1, c2] X[c2] per bin; W complex128 [nc, nc, F] or [nc, nc, F, >= N]."""
+        nc, F, ld = X.shape[0] // 2, X.shape[1], X.shape[2]
+        wn = W.shape[3] if W.dim() == 4 else 0
+        _check(self.lib.pf_apply_filter(self._p(X), self._p(W), self._p(Y), nc, F, N, ld, wn,
+                                        self.dtype_code(X), self._stream()), self.lib)
 
     def mul_planes(self, a, b, out, N, accumulate=False):
         F, ld = a.shape
@@ -585,11 +606,12 @@ class CudaKernels(object):
                                             self._p(work), self.dtype_code(TW), self._stream()),
                self.lib)
 
-    def check_totals(self, totals, eps, flags):
+    def check_totals(self, totals, eps, flags, iter_dev=None, first_iter=None):
+        """flags |= 2 where totals < eps (and first_iter = min(first_iter, *iter_dev)); totals = 0."""
         _check(self.lib.pf_check_totals(self._p(totals), totals.numel(), float(eps),
-                                        self._p(flags), self._stream()), self.lib)
+                                        self._p(flags), self._p(iter_dev), self._p(first_iter),
+                                        self._stream()), self.lib)
 
-    # -- glue ---------------------------------------------------------------------------
     def noise_anneal(self, sqrt0, sqrt1, iter_dev, n_iter, noise):
         _check(self.lib.pf_noise_anneal(self._p(sqrt0), self._p(sqrt1), self._p(iter_dev), n_iter,
                                         noise.numel(), self._p(noise), self._stream()), self.lib)

@@ -59,9 +59,6 @@ class FASST(object):
         if self.sig_repr_params['transf'] not in self.implemented_transf \
                 or self.sig_repr_params['transf'] not in tftransforms:
             raise NotImplementedError(self.sig_repr_params['transf'] + " not yet implemented.")
-        if lambdaCorr != 0:
-            raise NotImplementedError("lambdaCorr > 0 (correlation penalty, audioModel.py:"
-                                      "1534-1552) is not on the device path yet")
         if compute_dtype not in ('float32', 'float64'):
             raise ValueError("compute_dtype must be 'float32' or 'float64'")
         self.compute_dtype = compute_dtype
@@ -112,23 +109,32 @@ class FASST(object):
         lim = self.noise['ann_PSD_lim']
         opt = self.noise['sim_ann_opt'] if psd_mode is None else psd_mode
         eng.set_noise(opt, lim[0], lim[1], self.noise['PSD'])
-        eng.set_model(self.spat_comps, self.spec_comps, self.nmfUpdateCoeff)
+        eng.set_model(self.spat_comps, self.spec_comps, self.nmfUpdateCoeff, self.lambdaCorr)
         # (the sparsity re-weighting belongs to estim_param_a_post_model, not to GEM_iteration)
         eng.sparsity_enabled = psd_mode is None
         return eng
 
     def _general_structure(self):
         """True when the spectral structure is not the single-factor NMF of the standard models
-        (several factors, free FW, several spectral components per source, shared or large
-        dictionaries): GeneralGemEngine (engine_general.py) runs those."""
-        owners = []
+        (several factors, free FW, time blobs, several spectral components per source, parameter
+        arrays shared between components, large dictionaries, lambdaCorr > 0): GeneralGemEngine
+        (engine_general.py) runs those."""
+        if self.lambdaCorr > 0:
+            return True
+        owners, seen = [], set()
         for spec in self.spec_comps.values():
             owners.append(spec['spat_comp_ind'])
             if len(spec['factor']) != 1:
                 return True
             fac = list(spec['factor'].values())[0]
-            if fac['FW_frdm_prior'] == 'free' or np.shape(fac['FW'])[0] > 64:
+            if fac['FW_frdm_prior'] == 'free' or np.shape(fac['FW'])[0] > 64 or len(fac['TB']):
                 return True
+            for name in ('FB', 'FW', 'TW'):
+                # arrays shared between components stay ONE device buffer on GeneralGemEngine
+                # (the reference rescales the shared object once per component, quirk Q11)
+                if id(fac[name]) in seen:
+                    return True
+                seen.add(id(fac[name]))
         return sorted(owners) != list(range(len(self.spat_comps)))
 
     # ------------------------------------------------------------------ K1
@@ -217,15 +223,19 @@ class FASST(object):
 
     @property
     def Cx(self):
-        """Upper triangle of the empirical covariance, [3, F, N] complex128 (host copy)."""
+        """Upper triangle of the empirical covariance Cx[n1, n2] = X[n1] conj(X[n2]), n1 <= n2, as
+        [nc (nc + 1) / 2, F, N] complex128 in the reference's order (audioModel.py:293-302): a host
+        copy built on demand, the kernels read X."""
         if self._Cx is None:
             if self._X is None:
                 self.comp_transf_Cx()
             if self._comm is not None and self._comm.world > 1:
-                raise NotImplementedError("Cx is not gathered under frequency sharding")
+                raise NotImplementedError("Cx is not gathered when the model is sharded over GPUs")
             X = self._X[:, :, :self.nbFramesSigRepr].cpu().numpy().astype(np.float64)
-            x0, x1 = X[0] + 1j * X[1], X[2] + 1j * X[3]
-            self._Cx = np.array([x0 * np.conj(x0), x0 * np.conj(x1), x1 * np.conj(x1)])
+            nc = X.shape[0] // 2
+            x = [X[2 * c] + 1j * X[2 * c + 1] for c in range(nc)]
+            self._Cx = np.array([x[n1] * np.conj(x[n2]) for n1 in range(nc)
+                                 for n2 in range(n1, nc)])
         return self._Cx
 
     # ------------------------------------------------------------------ GEM
@@ -241,6 +251,14 @@ class FASST(object):
         eng = self._engine()
         t1 = time.perf_counter()
         logliks = eng.run(self.iter_num, use_graph=self._use_cuda_graph)
+        first = eng.vanished_iteration()
+        if first is not None:
+            # a TW vanished (sum < eps) at iteration `first`: the reference re-draws it with
+            # np.random inside renormalize_parameters (:2023-2025).  The device loop never waits
+            # for the host, so the run is replayed from the unchanged host parameters (the kernels
+            # are deterministic) and synchronises with the host from that iteration on.
+            eng = self._engine()
+            logliks = eng.run(self.iter_num, careful_from=first)
         t2 = time.perf_counter()
         eng.read_model(self.spat_comps, self.spec_comps)
         self.noise['PSD'] = eng.noise_psd()
@@ -253,7 +271,7 @@ class FASST(object):
     def GEM_iteration(self):
         """One GEM iteration with the current noise PSD (ref: audioModel.py:384-428)."""
         eng = self._engine(psd_mode='fixed')
-        ll = eng.run(1)
+        ll = eng.run(1, careful_from=0)
         eng.read_model(self.spat_comps, self.spec_comps)
         return float(ll[0])
 
@@ -339,13 +357,64 @@ class FASST(object):
                 hatW[:, :, :N].cpu().numpy().astype(np.float64), loglik)
 
     def renormalize_parameters(self):
-        """Energy normalisation across A, FB, FW, TW (ref: audioModel.py:1980-2040)."""
+        """Energy normalisation across A, FB, FW, TW(, TB) (ref: audioModel.py:1980-2040).  A TW
+        whose sum fell below eps is re-drawn with np.random like the reference (:2023-2025)."""
         eng = self._engine(psd_mode='fixed')
         eng.flags.zero_()
-        eng.totals.fill_(1.0)
+        eng.totals.zero_()
+        eng.sync_redraw = True
         eng.renormalize()
         eng.check_flags()
         eng.read_model(self.spat_comps, self.spec_comps)
+
+    # ------------------------------------------------------------------ M-step, by hand
+    def update_mix_matrix(self, hat_Rxs, hat_Rss, mix_matrix, rank_part_ind):
+        """Spatial M-step from given statistics (ref: audioModel.py:766-889): `mix_matrix`
+        [Rtot, nc, F] is updated IN PLACE and the 'params' of the free spatial components are
+        replaced, like the reference does.  (hat_Rxs is left untouched; the reference modifies it
+        in place when some instantaneous components are fixed, :810-818.)"""
+        import torch
+        eng = self._engine(psd_mode='fixed')
+        mix_matrix_in = mix_matrix
+        mix = np.asarray(mix_matrix)
+        if mix.shape != (eng.R, eng.I, self.nbFreqsSigRepr):
+            raise ValueError("mix_matrix must be [Rtot, nchannels, F]")
+        for j, idx in rank_part_ind.items():
+            if list(np.atleast_1d(idx)) != eng.ranks[j]:
+                raise NotImplementedError("rank_part_ind differs from retrieve_subsrc_params()")
+        eng.A = eng._upload(mix.astype(np.complex128))
+        eng.Rss.copy_(eng._upload(np.asarray(hat_Rss, dtype=np.complex128)))
+        eng.Rxs.copy_(eng._upload(np.asarray(hat_Rxs, dtype=np.complex128)))
+        eng.flags.zero_()
+        eng.update_mix()
+        eng.check_flags()
+        A = eng.A.cpu().numpy()
+        if isinstance(mix_matrix_in, np.ndarray) and mix_matrix_in.flags.writeable:
+            mix_matrix_in[...] = A if np.iscomplexobj(mix_matrix_in) else A.real
+        for j, sc in self.spat_comps.items():
+            if sc['frdm_prior'] == 'free':
+                if sc['mix_type'] == 'inst':
+                    sc['params'] = np.mean(A[eng.ranks[j]], axis=2).T
+                else:
+                    sc['params'] = np.ascontiguousarray(A[eng.ranks[j]])
+
+    def update_spectral_components(self, hat_W):
+        """Spectral M-step for given posterior powers hat_W [nb_spat_comps, F, N]
+        (ref: audioModel.py:1469-1978); the factors of `spec_comps` are updated."""
+        eng = self._engine(psd_mode='fixed')
+        hw = np.asarray(hat_W, dtype=np.float64)
+        if hw.shape != (eng.J, self.nbFreqsSigRepr, self.nbFramesSigRepr):
+            raise ValueError("hat_W must be [nb_spat_comps, F, N]")
+        if eng._sharded():
+            raise NotImplementedError("update_spectral_components of a sharded model: use "
+                                      "estim_param_a_post_model")
+        eng.hatW[:, :, :eng.N] = eng._upload(hw, eng.tdtype)
+        eng.compute_powers()
+        eng.update_spectral()
+        spat_before = {j: sc['params'] for j, sc in self.spat_comps.items()}
+        eng.read_model(self.spat_comps, self.spec_comps)
+        for j, p in spat_before.items():  # (only the spectral parameters change)
+            self.spat_comps[j]['params'] = p
 
     # ------------------------------------------------------------------ NMF initialisation
     def _mono_power(self):
@@ -450,6 +519,43 @@ class FASST(object):
             out.samplerate = self.audioObject.samplerate
             out._write()
 
+    def _wiener_groups(self, eng, spec_comp_ind, nbSources):
+        """Wiener-filtered STFT planes of the output groups.  Like the reference
+        (audioModel.py:1141-1166, :1327-1390): the covariance of group n is the sum, over the
+        spatial components its spectral components belong to, of R_spat times the power of THOSE
+        spectral components; the mixture covariance is the sum over the REQUESTED groups plus the
+        noise -- spectral components that are in no group do not enter it."""
+        # "virtual sources": one per (group, spatial component) pair
+        pairs = []
+        for n in range(nbSources):
+            for j in sorted(set(self.spec_comps[s]['spat_comp_ind'] for s in spec_comp_ind[n])):
+                pairs.append((n, j, [s for s in spec_comp_ind[n]
+                                     if self.spec_comps[s]['spat_comp_ind'] == j]))
+        full_cover = sorted(s for n in range(nbSources) for s in spec_comp_ind[n]) == \
+            sorted(self.spec_comps.keys()) and len(set(j for _, j, _ in pairs)) == len(pairs)
+        if full_cover:
+            # every spectral component in exactly one group, every spatial component in one group
+            group_of_src = [-1] * eng.J
+            for n, j, _ in pairs:
+                group_of_src[j] = n
+            return eng.wiener(group_of_src, nbSources)
+        Rv = sum(len(eng.ranks[j]) for _, j, _ in pairs)
+        if len(pairs) > 6 or Rv > 16:
+            raise NotImplementedError("separate_comps: more than 6 (group, spatial component) "
+                                      "pairs or 16 sub-sources in one call")
+        eng.compute_powers(with_G=False)
+        torch = eng.torch
+        Vv = eng._zeros([len(pairs), eng.F, eng.ld])
+        rows, src_of_sub, group_of_src = [], [], []
+        for v, (n, j, specs) in enumerate(pairs):
+            for s in specs:  # power of the selected spectral components of this spatial component
+                Vv[v] += eng.component_power(s)
+            rows.extend(eng.ranks[j])
+            src_of_sub.extend([v] * len(eng.ranks[j]))
+            group_of_src.append(n)
+        Av = eng.A[torch.tensor(rows, device=eng.dev)].contiguous()
+        return eng.wiener_custom(Vv, Av, src_of_sub, group_of_src, nbSources)
+
     def separate_comps_pcm(self, spec_comp_ind=None):
         """int16 [nbSources, L, 2]: the separated signals of `separate_comps` before they are
         written (device: Wiener filter K6 + inverse STFT with overlap-add)."""
@@ -461,15 +567,7 @@ class FASST(object):
             spec_comp_ind = {s: [s] for s in range(len(self.spec_comps))}
         nbSources = len(spec_comp_ind)
         eng = self._engine(psd_mode='fixed')
-        # group of each spatial component (one spectral component per spatial component)
-        group_of_src = [-1] * eng.J
-        for n in range(nbSources):
-            for s in spec_comp_ind[n]:
-                j = self.spec_comps[s]['spat_comp_ind']
-                if group_of_src[j] not in (-1, n):
-                    raise NotImplementedError("a spatial component in two output groups")
-                group_of_src[j] = n
-        Y = eng.wiener(group_of_src, nbSources)
+        Y = self._wiener_groups(eng, spec_comp_ind, nbSources)
         if eng._sharded():
             # the inverse STFT needs every frequency of every frame: gather the shards (every
             # rank then inverts the whole signal; separation is a one-off, not the GEM loop)

@@ -34,7 +34,7 @@ def estimate_batch(models, use_cuda_graph=True):
             ll = torch.ones([max(n_iter, 1)], dtype=torch.float64, device=dev)
             eng.iter_dev.zero_()
             eng.flags.zero_()
-            eng.totals.fill_(1.0)
+            eng.totals.zero_()
         engines.append(eng)
         logliks.append(ll)
     if use_cuda_graph and n_iter > 1:

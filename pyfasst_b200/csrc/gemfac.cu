@@ -16,11 +16,14 @@ constexpr int GF_THREADS = 256;
 constexpr double GF_EPS = 1e-10;  // audioModel.py:72
 
 // out[f][0:ld] = hatW / max(P,eps)^2 * max(O,eps), out[f][ld:2ld] = max(O,eps) / max(P,eps);
-// zero in the padding columns n >= N (the planes are contracted over n with padded lengths)
+// zero in the padding columns n >= N (the planes are contracted over n with padded lengths).
+// With lambdaCorr > 0 (Ptot != NULL): the correlation penalty of audioModel.py:1484-1703,
+//     c = lambda * Pminus / max(Ptot^2, eps),  den = O (1/P + c),  num = (hatW / P^2 + 2 c P / Ptot) O
 template <typename T>
 __global__ void __launch_bounds__(GF_THREADS)
 gem_ratio_planes_kernel(const T* __restrict__ hatW, const T* __restrict__ P,
-                        const T* __restrict__ O, T* __restrict__ out, int F, long N, long ld) {
+                        const T* __restrict__ O, T* __restrict__ out, int F, long N, long ld,
+                        const T* __restrict__ Ptot, const T* __restrict__ Pminus, double lambda) {
   const long n = (long)blockIdx.x * GF_THREADS + threadIdx.x;
   const int f = blockIdx.y;
   if (n >= ld) return;
@@ -30,11 +33,57 @@ gem_ratio_planes_kernel(const T* __restrict__ hatW, const T* __restrict__ P,
     const T p = pf_max(P[i], (T)GF_EPS);
     const T o = pf_max(O[i], (T)GF_EPS);
     const T ip = (T)1 / p;
-    den = o * ip;
-    num = hatW[i] * ip * ip * o;
+    if (Ptot == nullptr) {
+      den = o * ip;
+      num = hatW[i] * ip * ip * o;
+    } else {
+      const T pt = Ptot[i];
+      const T c = (T)lambda * Pminus[i] / pf_max(pt * pt, (T)GF_EPS);
+      den = o * (ip + c);
+      num = (hatW[i] * ip * ip + c * ((T)2 * (p / pt))) * o;
+    }
   }
   out[(size_t)f * 2 * ld + n] = num;
   out[(size_t)f * 2 * ld + ld + n] = den;
+}
+
+// Ptot = max(sum_j V_j, eps), Pminus = Ptot - max(V_own, eps) (clamped at eps when `clamp`):
+// the powers the correlation penalty is built from (audioModel.py:1484-1508)
+template <typename T>
+__global__ void __launch_bounds__(GF_THREADS)
+corr_planes_kernel(const T* __restrict__ V, int J, int own, T* __restrict__ Ptot,
+                   T* __restrict__ Pminus, int F, long N, long ld, int clamp) {
+  const long n = (long)blockIdx.x * GF_THREADS + threadIdx.x;
+  const int f = blockIdx.y;
+  if (n >= ld) return;
+  const size_t i = (size_t)f * ld + n;
+  T pt = (T)0, pm = (T)0;
+  if (n < N) {
+    for (int j = 0; j < J; ++j) pt += V[(size_t)j * F * ld + i];
+    pt = pf_max(pt, (T)GF_EPS);
+    pm = pt - pf_max(V[(size_t)own * F * ld + i], (T)GF_EPS);
+    if (clamp) pm = pf_max(pm, (T)GF_EPS);
+  }
+  Ptot[i] = pt;
+  Pminus[i] = pm;
+}
+
+// out[r] = sum_c M[r][c] (float64, fixed order): one CTA per row
+template <typename T>
+__global__ void __launch_bounds__(GF_THREADS)
+row_sums_kernel(const T* __restrict__ M, long ldm, long cols, double* __restrict__ out) {
+  __shared__ double s_red[GF_THREADS / 32];
+  const int r = blockIdx.x;
+  double acc = 0.0;
+  for (long c = threadIdx.x; c < cols; c += GF_THREADS) acc += (double)M[(size_t)r * ldm + c];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int w = 0; w < GF_THREADS / 32; ++w) d += s_red[w];
+    out[r] = d;
+  }
 }
 
 // out (=, +=) a * b  (b == NULL: a), zero in the padding
@@ -180,18 +229,49 @@ extern "C" int pf_sparsity_reweigh(void* TW, int64_t ldt, int K, int64_t N, int 
 }
 
 extern "C" int pf_gem_ratio_planes(const void* hatW, const void* P, const void* O, void* out, int F,
-                                   int64_t N, int64_t ld, int dtype, void* stream) {
+                                   int64_t N, int64_t ld, const void* Ptot, const void* Pminus,
+                                   double lambda, int dtype, void* stream) {
   PF_REQUIRE(F > 0 && N > 0 && ld >= N, "pf_gem_ratio_planes: F=%d N=%ld ld=%ld", F, (long)N,
              (long)ld);
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_gem_ratio_planes: bad dtype %d", dtype);
+  PF_REQUIRE((Ptot == nullptr) == (Pminus == nullptr), "pf_gem_ratio_planes: Ptot and Pminus go together");
   dim3 grid(ceil_div(ld, GF_THREADS), F);
   if (dtype == PF_F32)
     gem_ratio_planes_kernel<float><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
-        (const float*)hatW, (const float*)P, (const float*)O, (float*)out, F, N, ld);
+        (const float*)hatW, (const float*)P, (const float*)O, (float*)out, F, N, ld,
+        (const float*)Ptot, (const float*)Pminus, lambda);
   else
     gem_ratio_planes_kernel<double><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
-        (const double*)hatW, (const double*)P, (const double*)O, (double*)out, F, N, ld);
+        (const double*)hatW, (const double*)P, (const double*)O, (double*)out, F, N, ld,
+        (const double*)Ptot, (const double*)Pminus, lambda);
   return check_launch("gem_ratio_planes_kernel");
+}
+
+extern "C" int pf_corr_planes(const void* V, int J, int own, void* Ptot, void* Pminus, int F,
+                              int64_t N, int64_t ld, int clamp, int dtype, void* stream) {
+  PF_REQUIRE(F > 0 && N > 0 && ld >= N && J > 0 && own >= 0 && own < J,
+             "pf_corr_planes: F=%d N=%ld ld=%ld J=%d own=%d", F, (long)N, (long)ld, J, own);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_corr_planes: bad dtype %d", dtype);
+  dim3 grid(ceil_div(ld, GF_THREADS), F);
+  if (dtype == PF_F32)
+    corr_planes_kernel<float><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (const float*)V, J, own, (float*)Ptot, (float*)Pminus, F, N, ld, clamp);
+  else
+    corr_planes_kernel<double><<<grid, GF_THREADS, 0, as_stream(stream)>>>(
+        (const double*)V, J, own, (double*)Ptot, (double*)Pminus, F, N, ld, clamp);
+  return check_launch("corr_planes_kernel");
+}
+
+extern "C" int pf_row_sums(const void* M, int64_t ldm, int rows, int64_t cols, double* out,
+                           int dtype, void* stream) {
+  PF_REQUIRE(rows > 0 && cols > 0 && ldm >= cols, "pf_row_sums: rows=%d cols=%ld ldm=%ld", rows,
+             (long)cols, (long)ldm);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_row_sums: bad dtype %d", dtype);
+  if (dtype == PF_F32)
+    row_sums_kernel<float><<<rows, GF_THREADS, 0, as_stream(stream)>>>((const float*)M, ldm, cols, out);
+  else
+    row_sums_kernel<double><<<rows, GF_THREADS, 0, as_stream(stream)>>>((const double*)M, ldm, cols, out);
+  return check_launch("row_sums_kernel");
 }
 
 extern "C" int pf_mul_planes(const void* a, const void* b, void* out, int F, int64_t N, int64_t ld,

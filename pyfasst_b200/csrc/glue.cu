@@ -56,17 +56,66 @@ __global__ void small_matmul_kernel(const T* __restrict__ A, int lda, const T* _
   C[(size_t)m * ldc + n] = (T)acc;
 }
 
+// sum(TW) < eps after the renormalisation: the reference re-draws that TW at random
+// (audioModel.py:2023-2025).  The loop itself never synchronises with the host: the flag and the
+// first iteration at which it happened are recorded, and the host replays from there.
 __global__ void check_totals_kernel(double* __restrict__ totals, int count, double eps,
-                                    int* __restrict__ flags) {
+                                    int* __restrict__ flags, const int* __restrict__ iter_dev,
+                                    int* __restrict__ first_iter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  if (totals[i] < eps) atomicOr(flags, PF_FLAG_TW_RESTART);
+  if (totals[i] < eps) {
+    atomicOr(flags, PF_FLAG_TW_RESTART);
+    if (first_iter != nullptr) atomicMin(first_iter, iter_dev != nullptr ? *iter_dev : 0);
+  }
   totals[i] = 0.0;
+}
+
+// Y[c1] = sum_c2 W[c1][c2] X[c2] per time-frequency bin (tftransforms/stft.py:181-193): X, Y planes
+// [2 nc][F][ld] (re, im per channel), W complex128 [nc][nc][F] (wn = 0) or [nc][nc][F][wn]
+template <typename T>
+__global__ void apply_filter_kernel(const T* __restrict__ X, const double2* __restrict__ W,
+                                    T* __restrict__ Y, int nc, int F, long N, long ld, long wn) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (n >= ld) return;
+  const size_t plane = (size_t)F * ld, i = (size_t)f * ld + n;
+  for (int c1 = 0; c1 < nc; ++c1) {
+    double yr = 0.0, yi = 0.0;
+    if (n < N) {
+      for (int c2 = 0; c2 < nc; ++c2) {
+        const size_t wi = ((size_t)c1 * nc + c2) * F + f;
+        const double2 w = wn > 0 ? W[wi * wn + n] : W[wi];
+        const double xr = (double)X[(size_t)(2 * c2) * plane + i];
+        const double xi = (double)X[(size_t)(2 * c2 + 1) * plane + i];
+        yr += w.x * xr - w.y * xi;
+        yi += w.x * xi + w.y * xr;
+      }
+    }
+    Y[(size_t)(2 * c1) * plane + i] = (T)yr;
+    Y[(size_t)(2 * c1 + 1) * plane + i] = (T)yi;
+  }
 }
 
 }  // namespace pf
 
 using namespace pf;
+
+extern "C" int pf_apply_filter(const void* X, const void* W, void* Y, int nc, int F, int64_t N,
+                               int64_t ld, int64_t wn, int dtype, void* stream) {
+  PF_REQUIRE(nc >= 1 && nc <= 8 && F > 0 && N > 0 && ld >= N, "pf_apply_filter: nc=%d F=%d N=%ld ld=%ld",
+             nc, F, (long)N, (long)ld);
+  PF_REQUIRE(wn == 0 || wn >= N, "pf_apply_filter: W has %ld frames, X has %ld", (long)wn, (long)N);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_apply_filter: bad dtype %d", dtype);
+  dim3 grid(ceil_div(ld, 256), F);
+  if (dtype == PF_F32)
+    apply_filter_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+        (const float*)X, (const double2*)W, (float*)Y, nc, F, N, ld, wn);
+  else
+    apply_filter_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
+        (const double*)X, (const double2*)W, (double*)Y, nc, F, N, ld, wn);
+  return check_launch("apply_filter_kernel");
+}
 
 extern "C" int pf_set_device(int device) {
   cudaError_t e = cudaSetDevice(device);
@@ -77,9 +126,11 @@ extern "C" int pf_set_device(int device) {
   return PF_OK;
 }
 
-extern "C" int pf_check_totals(double* totals, int count, double eps, int* flags, void* stream) {
+extern "C" int pf_check_totals(double* totals, int count, double eps, int* flags,
+                               const int* iter_dev, int* first_iter, void* stream) {
   PF_REQUIRE(count > 0, "pf_check_totals: count=%d", count);
-  check_totals_kernel<<<ceil_div(count, 64), 64, 0, as_stream(stream)>>>(totals, count, eps, flags);
+  check_totals_kernel<<<ceil_div(count, 64), 64, 0, as_stream(stream)>>>(totals, count, eps, flags,
+                                                                        iter_dev, first_iter);
   return check_launch("check_totals_kernel");
 }
 

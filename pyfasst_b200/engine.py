@@ -195,9 +195,10 @@ class GemEngine(object):
             psd0 = np.asarray(psd, dtype=np.float64)
         self.noise = self._f64(np.array(np.broadcast_to(psd0, (self.F_total,))[sl]))
 
-    def set_model(self, spat_comps, spec_comps, nmfUpdateCoeff=1.0):
+    def set_model(self, spat_comps, spec_comps, nmfUpdateCoeff=1.0, lambdaCorr=0.0):
         """Validates the structure and uploads the parameters (host dicts -> HBM)."""
         torch = self.torch
+        self.lambdaCorr = float(lambdaCorr)
         J = len(spat_comps)
         if sorted(spat_comps.keys()) != list(range(J)):
             raise ValueError("spat_comps keys must be 0..J-1")
@@ -247,6 +248,8 @@ class GemEngine(object):
         fixed FW (the structures of MultiChanNMFInst_FASST / MultiChanNMFConv,
         audioModel.py:2355-2391).  Anything else: GeneralGemEngine (engine_general.py)."""
         J = self.J
+        if self.lambdaCorr > 0:
+            raise NotImplementedError("lambdaCorr > 0 runs on GeneralGemEngine")
         # spectral components: one per spatial component, single NMF factor
         S = len(spec_comps)
         if sorted(spec_comps.keys()) != list(range(S)):
@@ -263,7 +266,7 @@ class GemEngine(object):
                                           "models) are not on the device path yet")
             fac = facs[list(facs.keys())[0]]
             if len(fac["TB"]):
-                raise NotImplementedError("time-blob factors (TB) are not on the device path yet")
+                raise NotImplementedError("time-blob factors (TB) run on GeneralGemEngine")
             if fac.get("TW_constr", "NMF") != "NMF":
                 raise NotImplementedError("discrete-state TW constraints (GMM/HMM)")
             if fac["FW_frdm_prior"] == "free":
@@ -319,6 +322,10 @@ class GemEngine(object):
         self.ll_sum = self._zeros([1], f64)
         self.flags = self._zeros([1], torch.int32)
         self.iter_dev = self._zeros([1], torch.int32)
+        # first iteration (iter_dev at that time) at which a TW vanished, see redraw_vanished_TW
+        self.first_vanish = torch.full([1], 2 ** 30, dtype=torch.int32, device=self.dev)
+        self.sync_redraw = False
+        self.redrawn = 0
         code = k.dtype_code(self.V)
         # the stereo kernels for I = 2 (PYFASST_FORCE_MULTI=1: the general-I ones, for tests)
         self.multi = I != 2 or os.environ.get("PYFASST_FORCE_MULTI") == "1"
@@ -487,7 +494,23 @@ class GemEngine(object):
             self._for_each(self.spec, lambda s, e: (colmax(s, e), rescale(s, e)))
         if self._tshard():
             self.comm.allreduce_sum(self.totals)
-        k.check_totals(self.totals, EPS, self.flags)
+        if self.sync_redraw:
+            self.redraw_vanished_TW()
+        k.check_totals(self.totals, EPS, self.flags, self.iter_dev, self.first_vanish)
+
+    def redraw_vanished_TW(self):
+        """Host-synchronous part of the renormalisation: a TW whose sum fell below eps is re-drawn
+        with np.random (randn(K, N)^2 * 1e3 eps), like the reference (audioModel.py:2023-2025).
+        For the single-factor components of this engine nothing of the renormalisation depends on
+        TW afterwards, so doing it after the device kernels is exact.  Under frame sharding every
+        rank draws the whole matrix (same np.random state assumed) and keeps its frames."""
+        tot = self.totals.cpu().numpy()
+        for s, e in enumerate(self.spec):
+            if tot[s] < EPS:
+                Z = np.random.randn(e["Kw"], self.N_total) ** 2 * (1e3 * EPS)
+                e["TW"][:, :self.N] = self._upload(Z[:, self.n_lo:self.n_hi], self.tdtype)
+                self.totals[s] = float(Z.sum())
+                self.redrawn += 1
 
     def gem_iteration(self, n_iter_total, logliks, mark=None):
         """One GEM iteration (audioModel.py:364-376, :384-428), fully stream-ordered.
@@ -514,21 +537,35 @@ class GemEngine(object):
         mark("renorm")
 
     # ------------------------------------------------------------------ drivers
-    def run(self, n_iter, use_graph=False):
-        """estim_param_a_post_model: n_iter GEM iterations; returns logliks (host)."""
+    def run(self, n_iter, use_graph=False, careful_from=None):
+        """estim_param_a_post_model: n_iter GEM iterations; returns logliks (host).  The loop is
+        enqueued without a single host synchronisation.  `careful_from` = i: from iteration i on
+        the renormalisation synchronises with the host so that a vanished TW is re-drawn with
+        np.random exactly where the reference would (see vanished_iteration)."""
         torch = self.torch
         logliks = torch.ones([max(n_iter, 1)], dtype=torch.float64, device=self.dev)
         self.iter_dev.zero_()
         self.flags.zero_()
-        self.totals.fill_(1.0)
-        if use_graph and n_iter > 1 and self.dev.type == "cuda":
+        self.totals.zero_()
+        self.first_vanish.fill_(2 ** 30)
+        if use_graph and n_iter > 1 and self.dev.type == "cuda" and careful_from is None:
             self._run_graph(n_iter, logliks)
         else:
-            for _ in range(n_iter):
+            for it in range(n_iter):
+                self.sync_redraw = careful_from is not None and it >= careful_from
                 self.gem_iteration(n_iter, logliks)
+            self.sync_redraw = False
         self.n_iter_done = n_iter
         self.check_flags()
         return logliks[:n_iter].cpu().numpy()
+
+    def vanished_iteration(self):
+        """Index of the first iteration of the last run() whose renormalisation found a TW with
+        sum < eps and did NOT re-draw it (None: none).  The caller replays the run from the same
+        initial parameters with careful_from = that index: the kernels are deterministic, so the
+        replay reproduces the iterations before it bit for bit."""
+        first = int(self.first_vanish.cpu().item())
+        return None if first >= 2 ** 30 else max(first - 1, 0)
 
     def _run_graph(self, n_iter, logliks):
         torch = self.torch
@@ -547,10 +584,7 @@ class GemEngine(object):
         flags = int(self.flags.cpu().item())
         if flags & 1:
             raise np.linalg.LinAlgError("Singular Matrix")
-        if flags & 2:
-            import warnings
-            warnings.warn("sum(TW) fell below eps for a component: the reference would "
-                          "re-draw TW at random here (audioModel.py:2023-2025)")
+        # (flags & 2: a TW vanished and was not re-drawn on the spot -- see vanished_iteration)
 
     def suff_stat(self):
         """One E-step on the current parameters; returns host arrays shaped like the
@@ -635,6 +669,18 @@ class GemEngine(object):
 
     def noise_psd(self):
         return self._gather_f(self.noise, 0)
+
+    def component_power(self, s):
+        """Power plane [F, ld] of spectral component s (after compute_powers)."""
+        return self.V[self.spec[s]["j"]]
+
+    def wiener_custom(self, V, A, src_of_sub, group_of_src, ngroups):
+        """Wiener filter for an explicit list of sources: powers V [Jv, F, ld], mixing vectors
+        A [Rv, I, F] of their sub-sources, output group of each source."""
+        Y = self._zeros([ngroups * 2 * self.I, self.F, self.ld])
+        wiener = self.k.wiener_multi if self.multi else self.k.wiener_stereo
+        wiener(self.X, V, A, src_of_sub, self.noise, group_of_src, ngroups, self.N, Y, self.ws)
+        return Y
 
     def wiener(self, group_of_src, ngroups):
         """Wiener-filtered STFTs Y[g] = Sigma_g Sigma_x^-1 x as planes [ngroups * 2 I, F, ld]

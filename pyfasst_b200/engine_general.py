@@ -17,7 +17,9 @@ FASST.update_spectral_components (pyfasst/audioModel.py:1469-1727), comp_spat_co
 Every contraction with an F x N operand is one launch of the tensor-core GEMM
 (csrc/gemm_tc.cu, float32 3xTF32); the planes hat_W / P^2 * O and O / P are formed once per
 updated matrix by csrc/gemfac.cu.  float32 planes only on the GPU; one GPU (no sharding);
-time-blob factors (TB) and discrete-state TW constraints raise NotImplementedError.
+discrete-state TW constraints raise NotImplementedError.  Also here: time-blob factors
+(H = TW TB, the TB update :1931-1978 and its renormalisation :2026-2030) and the correlation
+penalty `lambdaCorr` (:1484-1703).
 
 The order of operations is the reference's Gauss-Seidel order: components in key order, factors
 in key order, FB -> FW -> TW inside a factor; the power P is recomputed from the current
@@ -60,31 +62,40 @@ class GeneralGemEngine(GemEngine):
             keys = sorted(spec_comps[s]["factor"].keys())
             for fi in keys:
                 fac = spec_comps[s]["factor"][fi]
-                if len(fac["TB"]):
-                    raise NotImplementedError("time-blob factors (TB) are not on the device path")
                 if fac.get("TW_constr", "NMF") != "NMF":
                     raise NotImplementedError("discrete-state TW constraints (GMM/HMM)")
                 FB, FW, TW = (np.asarray(fac[m]) for m in ("FB", "FW", "TW"))
-                if FB.shape[0] != self.F_total or TW.shape[1] != self.N_total or \
-                        FW.shape != (FB.shape[1], TW.shape[0]):
-                    raise ValueError("inconsistent factor shapes FB%s FW%s TW%s"
-                                     % (FB.shape, FW.shape, TW.shape))
+                has_tb = len(fac["TB"]) > 0
+                TB = np.asarray(fac["TB"]) if has_tb else None
+                # with time blobs the activations are H = TW TB: TW [Kw, L], TB [L, N] (:473-476)
+                L = TB.shape[0] if has_tb else self.N_total
+                if FB.shape[0] != self.F_total or TW.shape[1] != L or \
+                        FW.shape != (FB.shape[1], TW.shape[0]) or \
+                        (has_tb and TB.shape[1] != self.N_total):
+                    raise ValueError("inconsistent factor shapes FB%s FW%s TW%s TB%s"
+                                     % (FB.shape, FW.shape, TW.shape, np.shape(fac["TB"])))
                 Kb, Kw = FW.shape
-                Kb4, Kw4 = _round_up(Kb, 4), _round_up(Kw, 4)
+                Kb4, Kw4, L4 = _round_up(Kb, 4), _round_up(Kw, 4), _round_up(L, 4)
                 ent = {"key": fi, "Kb": Kb, "Kw": Kw, "Kb4": Kb4, "Kw4": Kw4,
+                       "has_tb": has_tb, "L": L, "L4": L4,
                        "FB_free": fac["FB_frdm_prior"] == "free",
                        "FW_free": fac["FW_frdm_prior"] == "free",
-                       "TW_free": fac["TW_frdm_prior"] == "free"}
-                for name, arr, rows, cols in (("FB", fac["FB"], self.F, Kb4),
-                                              ("FW", fac["FW"], Kb4, Kw4),
-                                              ("TW", fac["TW"], Kw4, self.ld)):
+                       "TW_free": fac["TW_frdm_prior"] == "free",
+                       "TB_free": has_tb and fac["TB_frdm_prior"] == "free"}
+                mats = [("FB", fac["FB"], self.F, Kb4), ("FW", fac["FW"], Kb4, Kw4),
+                        ("TW", fac["TW"], Kw4, L4 if has_tb else self.ld)]
+                if has_tb:
+                    mats.append(("TB", fac["TB"], L4, self.ld))
+                for name, arr, rows, cols in mats:
                     key = id(arr)
                     if key not in shared:
                         shared[key] = self._padded(arr, rows, cols)
                     ent[name] = shared[key]
                     ent[name + "_host"] = arr
                 ent["W"] = self._zeros([self.F, Kw4])    # FB FW
-                ent["G"] = self._zeros([Kb4, self.ld])   # FW TW (FB update)
+                # the activations H [Kw, N]: TW itself, or TW TB with time blobs
+                ent["H"] = self._zeros([Kw4, self.ld]) if has_tb else ent["TW"]
+                ent["G"] = self._zeros([Kb4, self.ld])   # FW H (FB update)
                 ent["P"] = self._zeros([self.F, self.ld])  # power of the factor
                 facs.append(ent)
             self.spec.append({"j": j, "fac": facs, "sparsity": spec_comps[s].get("sparsity"),
@@ -106,14 +117,24 @@ class GeneralGemEngine(GemEngine):
         self.tnd = self._zeros([2 * F * max(Kb4, Kw4)])   # planes contracted over the frames
         self.knd = self._zeros([Kw4, 2 * ld])            # planes contracted over the frequencies
         self.fwnd = self._zeros([2, Kb4, Kw4])
-        nb = self.k.gemm_splitk_workspace_bytes(2 * F, max(Kb4, Kw4), ld)
+        L4 = max([fc["L4"] for fc in facs if fc["has_tb"]] or [4])
+        if any(fc["has_tb"] for fc in facs):
+            self.tbnd = self._zeros([2 * F * L4])                 # planes TB^T (TW update)
+            self.twnd = self._zeros([2, Kw4, L4])
+            self.wl = self._zeros([F, L4])                        # FB FW TW (TB update)
+            self.lnd = self._zeros([L4, 2 * ld])
+            self.lvec = self._zeros([L4], f64)
+        if self.lambdaCorr > 0:
+            self.ptot = self._zeros([F, ld])
+            self.pminus = self._zeros([F, ld])
+        nb = self.k.gemm_splitk_workspace_bytes(2 * F, max(Kb4, Kw4, max([fc["L4"] for fc in facs if fc["has_tb"]] or [4])), ld)
         self.gemm_ws = self._zeros([(nb + 3) // 4], torch.float32)
         n = len(facs)
         self.colmax = self._zeros([n, Kb4], f64)
         self.wcol = self._zeros([n, Kb4], f64)
         self.w2 = self._zeros([n, Kw4], f64)
         self.totals = self._zeros([n], f64)      # sum of every TW after its rescaling
-        self.gcount = self._f64(np.array([fc["Kw"] * self.N_total for fc in facs], dtype=np.float64))
+        self.gcount = self._f64(np.array([fc["Kw"] * fc["L"] for fc in facs], dtype=np.float64))
         self.gvec = self._zeros([Kw4], f64)
         self.sparse_work = self._zeros([2 * self.N], f64)
         # sparsity re-weighting runs inside estim_param_a_post_model only (audioModel.py:2933-2979)
@@ -130,10 +151,12 @@ class GeneralGemEngine(GemEngine):
             self.k.small_matmul(fc["FB"], fc["FW"], fc["W"])
         else:  # the weights of a large dictionary: tensor-core GEMM
             self._gemm(fc["FB"], fc["FW"], fc["W"], self.F, fc["Kw4"], fc["Kb4"])
+        if fc["has_tb"]:  # H = TW TB
+            self._gemm(fc["TW"], fc["TB"], fc["H"], fc["Kw4"], self.ld, fc["L4"])
         if fc["Kw"] <= 32:
-            self.k.spec_power(fc["W"][:, :fc["Kw"]], fc["TW"][:fc["Kw"]], fc["P"], self.N, False)
+            self.k.spec_power(fc["W"][:, :fc["Kw"]], fc["H"][:fc["Kw"]], fc["P"], self.N, False)
         else:
-            self._gemm(fc["W"], fc["TW"], fc["P"], self.F, self.ld, fc["Kw4"])
+            self._gemm(fc["W"], fc["H"], fc["P"], self.F, self.ld, fc["Kw4"])
 
     def _refresh_comp(self, sp):
         """Power of one spectral component: product over its factors (audioModel.py:486-494)."""
@@ -159,6 +182,9 @@ class GeneralGemEngine(GemEngine):
         for j in range(self.J):
             self._refresh_src(j)
 
+    def component_power(self, s):
+        return self.spec[s]["C"]
+
     # ------------------------------------------------------------------ spectral M-step
     def _other(self, sp, fi):
         """other_fact_power, computed once per factor (audioModel.py:1511-1516).  Q1: for a
@@ -173,12 +199,26 @@ class GeneralGemEngine(GemEngine):
         for fc in rest[2:]:
             self.k.mul_planes(self.other, fc["P"], self.other, self.N)
 
+    def _ratio_planes(self, hatW, P):
+        if self.lambdaCorr > 0:
+            self.k.gem_ratio_planes(hatW, P, self.other, self.planes, self.N, self.ptot,
+                                    self.pminus, self.lambdaCorr)
+        else:
+            self.k.gem_ratio_planes(hatW, P, self.other, self.planes, self.N)
+
     def update_spectral(self):
         k, F, N, ld = self.k, self.F, self.N, self.ld
         for sp in self.spec:
             j = sp["j"]
+            if self.lambdaCorr > 0:
+                # the powers the correlation penalty is built from, once per spectral component
+                # with the parameters as they are now (audioModel.py:1484-1508).  The reference
+                # clamps Pminus at eps only when ALL its entries are >= 0 (:1502-1508, a debug
+                # leftover): Ptot >= max(V_j, eps) always holds here, so the clamp applies.
+                self.compute_powers()
+                k.corr_planes(self.V, j, self.ptot, self.pminus, N, True)
             for fi, fc in enumerate(sp["fac"]):
-                if not (fc["FB_free"] or fc["FW_free"] or fc["TW_free"]):
+                if not (fc["FB_free"] or fc["FW_free"] or fc["TW_free"] or fc["TB_free"]):
                     continue
                 Kb, Kw, Kb4, Kw4 = fc["Kb"], fc["Kw"], fc["Kb4"], fc["Kw4"]
                 # a dictionary shared with a component updated earlier may have changed
@@ -188,11 +228,11 @@ class GeneralGemEngine(GemEngine):
                 if fc["FB_free"]:
                     # Q3: the power of ALL the spectral components of the source (:1521-1523)
                     self._refresh_src(j)
-                    k.gem_ratio_planes(self.hatW[j], self.V[j], self.other, self.planes, N)
-                    if Kb4 * Kw4 <= 4096:                                # (FW TW), :1531-1540
-                        k.small_matmul(fc["FW"], fc["TW"], fc["G"])
+                    self._ratio_planes(self.hatW[j], self.V[j])
+                    if Kb4 * Kw4 <= 4096:                                # (FW H), :1531-1540
+                        k.small_matmul(fc["FW"], fc["H"], fc["G"])
                     else:
-                        self._gemm(fc["FW"], fc["TW"], fc["G"], Kb4, ld, Kw4)
+                        self._gemm(fc["FW"], fc["H"], fc["G"], Kb4, ld, Kw4)
                     T = self.tnd[:2 * F * Kb4].view(2 * F, Kb4)
                     self._gemm(self.planes.view(2 * F, ld), fc["G"], T, 2 * F, Kb4, ld,
                                transB=True, splitk=True)
@@ -201,10 +241,10 @@ class GeneralGemEngine(GemEngine):
                     self._refresh_factor(fc)
                     self._refresh_comp(sp)
                 if fc["FW_free"]:
-                    # FB^T [(planes) TW^T]  (:1577-1631)
-                    k.gem_ratio_planes(self.hatW[j], sp["C"], self.other, self.planes, N)
+                    # FB^T [(planes) H^T]  (:1577-1631)
+                    self._ratio_planes(self.hatW[j], sp["C"])
                     T = self.tnd[:2 * F * Kw4].view(2 * F, Kw4)
-                    self._gemm(self.planes.view(2 * F, ld), fc["TW"], T, 2 * F, Kw4, ld,
+                    self._gemm(self.planes.view(2 * F, ld), fc["H"], T, 2 * F, Kw4, ld,
                                transB=True, splitk=True)
                     Tv = T.view(F, 2 * Kw4)
                     for h in range(2):
@@ -215,11 +255,34 @@ class GeneralGemEngine(GemEngine):
                     self._refresh_factor(fc)
                     self._refresh_comp(sp)
                 if fc["TW_free"]:
-                    # (FB FW)^T (planes)  (:1634-1727)
-                    k.gem_ratio_planes(self.hatW[j], sp["C"], self.other, self.planes, N)
-                    C = self.knd[:Kw4]
-                    self._gemm(fc["W"], self.planes, C, Kw4, 2 * ld, F, transA=True)
-                    k.mult_update_same(fc["TW"], C[:, :ld], C[:, ld:], Kw, N, self.omega)
+                    self._ratio_planes(self.hatW[j], sp["C"])
+                    if fc["has_tb"]:
+                        # (FB FW)^T [(planes) TB^T]  (:1668-1689)
+                        L, L4 = fc["L"], fc["L4"]
+                        T = self.tbnd[:2 * F * L4].view(2 * F, L4)
+                        self._gemm(self.planes.view(2 * F, ld), fc["TB"], T, 2 * F, L4, ld,
+                                   transB=True, splitk=True)
+                        Tv = T.view(F, 2 * L4)
+                        for h in range(2):
+                            self._gemm(fc["W"], Tv[:, h * L4:(h + 1) * L4],
+                                       self.twnd[h, :Kw4, :L4], Kw4, L4, F, transA=True)
+                        k.mult_update_same(fc["TW"], self.twnd[0, :Kw4, :L4], self.twnd[1, :Kw4, :L4],
+                                           Kw, L, self.omega)
+                    else:
+                        # (FB FW)^T (planes)  (:1690-1727)
+                        C = self.knd[:Kw4]
+                        self._gemm(fc["W"], self.planes, C, Kw4, 2 * ld, F, transA=True)
+                        k.mult_update_same(fc["TW"], C[:, :ld], C[:, ld:], Kw, N, self.omega)
+                    self._refresh_factor(fc)
+                    self._refresh_comp(sp)
+                if fc["TB_free"]:
+                    # (FB FW TW)^T (planes)  (:1931-1978)
+                    L, L4 = fc["L"], fc["L4"]
+                    self._ratio_planes(self.hatW[j], sp["C"])
+                    self._gemm(fc["W"], fc["TW"], self.wl[:, :L4], F, L4, Kw4)
+                    C = self.lnd[:L4]
+                    self._gemm(self.wl[:, :L4], self.planes, C, L4, 2 * ld, F, transA=True)
+                    k.mult_update_same(fc["TB"], C[:, :ld], C[:, ld:], L, N, self.omega)
                     self._refresh_factor(fc)
                     self._refresh_comp(sp)
 
@@ -238,6 +301,8 @@ class GeneralGemEngine(GemEngine):
             for fi, fc in enumerate(sp["fac"]):
                 Kb, Kw = fc["Kb"], fc["Kw"]
                 FB, FW, TW = fc["FB"][:, :Kb], fc["FW"][:Kb, :Kw], fc["TW"][:Kw]
+                if fc["has_tb"]:
+                    TW = fc["TW"][:Kw, :fc["L"]]
                 if fi == 0:
                     k.fb_scale_colmax(FB, self.sums, self.counts, sp["j"], self.colmax[i])
                 else:  # global_energy = mean of the previous factor's TW (:2031)
@@ -246,19 +311,48 @@ class GeneralGemEngine(GemEngine):
                 k.fw_renorm(FW, self.colmax[i], self.wcol[i], self.w2[i])
                 k.scale_matrix(FB, self.F, Kb, self.wcol[i], False, True)
                 self.totals[i:i + 1].zero_()
-                k.scale_matrix(TW, Kw, self.N, self.w2[i], True, False, self.totals[i:i + 1])
+                ncol = fc["L"] if fc["has_tb"] else self.N
+                k.scale_matrix(TW, Kw, ncol, self.w2[i], True, False, self.totals[i:i + 1])
+                self._redraw_hook(i, fc)
+                if fc["has_tb"]:
+                    # TB /= its row means, TW *= them (:2026-2030); sum(TW) is taken again
+                    L = fc["L"]
+                    TB = fc["TB"][:L]
+                    k.row_sums(TB, L, self.N, self.lvec)
+                    lv = self.lvec[:L]
+                    lv.div_(float(self.N_total))
+                    lv[lv == 0] = 1.0
+                    k.scale_matrix(TB, L, self.N, self.lvec, True, True)
+                    self.totals[i:i + 1].zero_()
+                    k.scale_matrix(TW, Kw, L, self.lvec, False, False, self.totals[i:i + 1])
                 if fi < nfac - 1:  # TW /= its mean (:2032-2033); the sum itself is kept for
                     # the next factor and the restart check
                     torch.div(self.totals[i:i + 1], self.gcount[i:i + 1], out=self.gvec[:1])
                     self.gvec[:Kw] = self.gvec[:1].expand(Kw).clone()
-                    k.scale_matrix(TW, Kw, self.N, self.gvec, True, True)
+                    k.scale_matrix(TW, Kw, ncol, self.gvec, True, True)
                 i += 1
         # a TW that vanished would be re-drawn at random by the reference (:2023-2025)
         self._check_totals()
 
     def _check_totals(self):
         tot = self.totals.clone()
-        self.k.check_totals(tot, EPS, self.flags)
+        self.k.check_totals(tot, EPS, self.flags, self.iter_dev, self.first_vanish)
+
+    def redraw_vanished_TW(self):
+        pass  # (done inside the factor loop of renormalize, see _redraw_hook)
+
+    def _redraw_hook(self, i, fc):
+        """Host-synchronous renormalisation (renormalize_parameters() called by hand): a TW whose
+        sum fell below eps is re-drawn at random right here, like the reference (:2023-2025)."""
+        if not getattr(self, "sync_redraw", False):
+            return
+        if float(self.totals[i].cpu().item()) < EPS:
+            Kw = fc["Kw"]
+            ncol = fc["L"] if fc["has_tb"] else self.N
+            Z = np.random.randn(Kw, ncol) ** 2 * (1e3 * EPS)
+            fc["TW"][:Kw, :ncol] = self._upload(Z, self.tdtype)
+            self.totals[i] = float(Z.sum())
+            self.redrawn = getattr(self, "redrawn", 0) + 1
 
     # ------------------------------------------------------------------ sparsity
     def gem_iteration(self, n_iter_total, logliks, mark=None):
@@ -287,8 +381,11 @@ class GeneralGemEngine(GemEngine):
         for s, sp in enumerate(self.spec):
             for fc in sp["fac"]:
                 fac = spec_comps[s]["factor"][fc["key"]]
-                for name, r, c in (("FB", self.F, fc["Kb"]), ("FW", fc["Kb"], fc["Kw"]),
-                                   ("TW", fc["Kw"], self.N)):
+                mats = [("FB", self.F, fc["Kb"]), ("FW", fc["Kb"], fc["Kw"]),
+                        ("TW", fc["Kw"], fc["L"] if fc["has_tb"] else self.N)]
+                if fc["has_tb"]:
+                    mats.append(("TB", fc["L"], self.N))
+                for name, r, c in mats:
                     host = fc[name + "_host"]
                     if id(host) not in done:
                         done[id(host)] = fc[name][:r, :c].to(f64).cpu().numpy()

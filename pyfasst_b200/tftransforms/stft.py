@@ -123,6 +123,40 @@ def istft(X, window=sinebell(2048), analysisWindow=None, hopsize=256.0, nfft=204
     return out[0].cpu().numpy()
 
 
+def filter_stft(data, W, analysisWindow=None, synthWindow=sinebell(2048), hopsize=256.0,
+                nfft=2048.0, fs=44100.0, kernels=None):
+    """ndata = filter_stft(data, W, ...)   (ref: stft.py:133-227): STFT of every channel of
+    `data` [T, M], multiplication by the M x M x F (x N) filter W in every bin, inverse STFT with
+    overlap-add.  `ceil(T / hop)` frames, the first one centred on the first sample; the result
+    has (frames - 1) * hop + window / 2 samples, like the reference's."""
+    import torch
+    k = kernels or default_kernels()
+    data = np.asarray(data, dtype=np.float64)
+    W = np.asarray(W)
+    ns, nc = data.shape
+    if nc != W.shape[0]:
+        raise AttributeError("W does not have the right number of channels")
+    synthWindow = np.asarray(synthWindow, dtype=np.float64)
+    if analysisWindow is None or len(analysisWindow) != len(synthWindow):
+        analysisWindow = synthWindow
+    analysisWindow = np.asarray(analysisWindow, dtype=np.float64)
+    hopsize, nfft = int(hopsize), int(nfft)
+    N = int(np.ceil(ns / np.double(hopsize)))
+    if nfft // 2 + 1 != W.shape[2]:
+        raise AttributeError("W not the right size")
+    if W.ndim not in (3, 4):
+        raise NotImplementedError("For W.ndim== 3 or 4" + str(W.ndim))
+    if W.ndim == 4 and W.shape[3] < N:
+        raise IndexError("W holds %d frames, the signal has %d" % (W.shape[3], N))
+    pcm = torch.tensor(np.ascontiguousarray(data.T)).to(k.device)
+    X, _ = stft_planes(k, pcm, analysisWindow, hopsize, nfft, "float64", frames=(0, N))
+    Wd = torch.tensor(np.ascontiguousarray(W.astype(np.complex128))).to(k.device)
+    Y = torch.zeros_like(X)
+    k.apply_filter(X, Wd, Y, N)
+    out, _ = istft_planes(k, Y, N, synthWindow, analysisWindow, hopsize, nfft)
+    return np.ascontiguousarray(out.cpu().numpy().T)
+
+
 class STFT(object):
     """ref: stft.py:339-394 (same constructor, attributes and methods)."""
     transformname = 'stft'

@@ -438,15 +438,50 @@ class FakeKernels(object):
             _np(total)[0] += m[:rows, :cols].astype(np.float64).sum()
 
     # ---- general factor structures (csrc/gemfac.cu) ---------------------------------------
-    def gem_ratio_planes(self, hatW, P, O, out, N):
+    def gem_ratio_planes(self, hatW, P, O, out, N, Ptot=None, Pminus=None, lam=0.0):
         self.launches += 1
         F, ld = hatW.shape
         p = np.maximum(_np(P)[:, :N].astype(np.float64), EPS)
         o = np.maximum(_np(O)[:, :N].astype(np.float64), EPS)
         on = _np(out)
         on[:] = 0
-        on[:, :N] = _np(hatW)[:, :N] / p ** 2 * o
-        on[:, ld:ld + N] = o / p
+        if Ptot is None:
+            on[:, :N] = _np(hatW)[:, :N] / p ** 2 * o
+            on[:, ld:ld + N] = o / p
+        else:  # correlation penalty (audioModel.py:1544-1567)
+            pt = _np(Ptot)[:, :N].astype(np.float64)
+            c = lam * _np(Pminus)[:, :N] / np.maximum(pt ** 2, EPS)
+            on[:, ld:ld + N] = o * (1. / p + c)
+            on[:, :N] = (_np(hatW)[:, :N] / p ** 2 + c * 2 * (p / pt)) * o
+
+    def corr_planes(self, V, own, Ptot, Pminus, N, clamp=True):
+        self.launches += 1
+        v = _np(V)[:, :, :N].astype(np.float64)
+        pt = np.maximum(v.sum(axis=0), EPS)
+        pm = pt - np.maximum(v[own], EPS)
+        if clamp:
+            pm = np.maximum(pm, EPS)
+        for t, a in ((Ptot, pt), (Pminus, pm)):
+            tn = _np(t)
+            tn[:] = 0
+            tn[:, :N] = a
+
+    def row_sums(self, M, rows, cols, out):
+        self.launches += 1
+        _np(out)[:rows] = _np(M)[:rows, :cols].astype(np.float64).sum(axis=1)
+
+    def apply_filter(self, X, W, Y, N):
+        self.launches += 1
+        Xn, Wn, Yn = _np(X), _np(W), _np(Y)
+        nc = Xn.shape[0] // 2
+        Yn[:] = 0
+        Xc = [Xn[2 * c, :, :N].astype(np.float64) + 1j * Xn[2 * c + 1, :, :N] for c in range(nc)]
+        for c1 in range(nc):
+            acc = 0
+            for c2 in range(nc):
+                w = Wn[c1, c2][:, :N] if Wn.ndim == 4 else Wn[c1, c2][:, None]
+                acc = acc + w * Xc[c2]
+            Yn[2 * c1, :, :N], Yn[2 * c1 + 1, :, :N] = acc.real, acc.imag
 
     def mul_planes(self, a, b, out, N, accumulate=False):
         self.launches += 1
@@ -486,11 +521,14 @@ class FakeKernels(object):
         mask[:, pos] /= mask[-1][pos]
         tw[:K, :N] = v * mask
 
-    def check_totals(self, totals, eps, flags):
+    def check_totals(self, totals, eps, flags, iter_dev=None, first_iter=None):
         self.launches += 1
         tt = _np(totals)
         if (tt < eps).any():
             _np(flags)[0] |= 2
+            if first_iter is not None:
+                it = int(_np(iter_dev)[0]) if iter_dev is not None else 0
+                _np(first_iter)[0] = min(int(_np(first_iter)[0]), it)
         tt[:] = 0
 
     # ---- glue ---------------------------------------------------------------------------
