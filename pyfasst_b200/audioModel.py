@@ -209,7 +209,11 @@ class FASST(object):
         elif multi:
             from .engine import shard_bounds
             lo, hi = shard_bounds(F, self._comm.world)[self._comm.rank]
-            X = X[:, lo:hi].contiguous()
+            # (the engine's rows are a multiple of 32 * world frames long under frequency sharding)
+            ldp = -(-N // (32 * self._comm.world)) * (32 * self._comm.world)
+            Xs = torch.zeros([X.shape[0], hi - lo, ldp], dtype=X.dtype, device=X.device)
+            Xs[:, :, :X.shape[2]] = X[:, lo:hi]
+            X = Xs
         self._X = X
         lim = self.noise['ann_PSD_lim']
         if lim[0] is None or lim[1] is None:
@@ -260,13 +264,38 @@ class FASST(object):
             eng = self._engine()
             logliks = eng.run(self.iter_num, careful_from=first)
         t2 = time.perf_counter()
-        eng.read_model(self.spat_comps, self.spec_comps)
+        # (sharded over GPUs: every rank writes back its own rows / frames of the sharded factor;
+        # gather_parameters() completes the model on every rank)
+        eng.read_model(self.spat_comps, self.spec_comps, gather=False)
         self.noise['PSD'] = eng.noise_psd()
         t3 = time.perf_counter()
         # host-side wall times of the three stages (pack to HBM, GEM loop, unpack to NumPy)
         self._last_engine_stats = {'launches': self._k().launch_count(), 'pack_s': t1 - t0,
                                    'gem_s': t2 - t1, 'unpack_s': t3 - t2}
         return logliks
+
+    def gather_parameters(self):
+        """Model sharded over several GPUs (`comm`): after estim_param_a_post_model every rank holds
+        its own rows (frequency sharding: FB) or frames (frame sharding: TW) of the sharded
+        factor.  This collective call completes the parameter dicts on every rank."""
+        if self._comm is None or self._comm.world == 1:
+            return
+        import torch
+        from .engine import shard_bounds
+        dev = self._k().device
+        for sp in self.spec_comps.values():
+            for fac in sp['factor'].values():
+                name, axis = ('TW', 1) if self._shard == 'time' else ('FB', 0)
+                arr = np.ascontiguousarray(np.asarray(fac[name], dtype=np.float64))
+                bounds = shard_bounds(arr.shape[axis], self._comm.world)
+                lo, hi = bounds[self._comm.rank]
+                smax = max(b[1] - b[0] for b in bounds)
+                mine = np.moveaxis(arr, axis, 0)[lo:hi]
+                pad = torch.zeros((smax,) + mine.shape[1:], dtype=torch.float64, device=dev)
+                pad[:hi - lo] = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
+                parts = self._comm.allgather(pad)
+                full = torch.cat([p[:b[1] - b[0]] for p, b in zip(parts, bounds)], dim=0)
+                fac[name] = np.ascontiguousarray(np.moveaxis(full.cpu().numpy(), 0, axis))
 
     def GEM_iteration(self):
         """One GEM iteration with the current noise PSD (ref: audioModel.py:384-428)."""

@@ -57,6 +57,23 @@ class Comm(object):
         self.dist.all_gather(out, t.contiguous(), group=self.group)
         return out
 
+    def reduce_scatter_sum(self, out, inp):
+        """out = this rank's chunk of the sum over ranks of inp ([world, *out.shape], contiguous)."""
+        if self.dist.get_backend(self.group) == "gloo":  # (CPU tests: gloo has no reduce-scatter)
+            tmp = inp.clone()
+            self.dist.all_reduce(tmp, op=self.dist.ReduceOp.SUM, group=self.group)
+            out.copy_(tmp[self.rank])
+        else:
+            self.dist.reduce_scatter_tensor(out, inp, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def allgather_into(self, out, inp):
+        """out [world, *inp.shape] = the ranks' inp, in rank order."""
+        if self.dist.get_backend(self.group) == "gloo":
+            parts = [out[r] for r in range(self.world)]
+            self.dist.all_gather(parts, inp.contiguous(), group=self.group)
+        else:
+            self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
 
 def shard_bounds(F, world):
     """Contiguous frequency shards, sizes differing by at most one (1025 = 129 + 7*128)."""
@@ -94,7 +111,10 @@ class GemEngine(object):
         self.n_lo, self.n_hi = n_range
         self.F = self.f_hi - self.f_lo
         self.N = self.n_hi - self.n_lo   # local frames
-        self.ld = _round_up(self.N, 32)
+        # padded row length: every row starts on a 128-byte boundary; under frequency sharding
+        # the frames of the TW numerators / denominators are reduce-scattered over the ranks in
+        # equal chunks of whole 128-byte lines
+        self.ld = _round_up(self.N, 32 * comm.world if (multi and shard == "freq") else 32)
         if self.F <= 0 or self.N <= 0:
             raise ValueError("empty shard f=%r n=%r" % (f_range, n_range))
         self.X = None
@@ -129,6 +149,11 @@ class GemEngine(object):
                 fn(i, it)
         for i in range(len(items)):
             cur.wait_stream(self._side[i])
+
+    def _comm_stream(self):
+        if getattr(self, "_cstream", None) is None:
+            self._cstream = self.torch.cuda.Stream(device=self.dev)
+        return self._cstream
 
     # ------------------------------------------------------------------ allocation
     def _zeros(self, shape, dtype=None):
@@ -347,7 +372,9 @@ class GemEngine(object):
         self.colmax = self._zeros([S, Kmax], f64)
         self.wcol = self._zeros([S, Kmax], f64)
         self.w2 = self._zeros([S, Kmax], f64)
-        self.totals = self._zeros([S], f64)
+        self._totals2 = self._zeros([2, S], f64)
+        self._tot_parity = 0
+        self.totals = self._totals2[0]
         # FB update partial sums (one buffer, reused per component)
         self.fb_plan, fb_size = {}, 0
         for e in self.spec:
@@ -366,7 +393,19 @@ class GemEngine(object):
         self.tw_part = self._zeros([S, 2, tw_size], f64)
         # work planes for P' = W'H of the tensor-core TW path (float32 planes only)
         self.scratch = self._zeros([S, F, ld]) if self.tdtype == torch.float32 else None
-        self.tw_nd = self._zeros([S, 2, Kmax, ld], f64)
+        if self._fshard():
+            # reduce-scatter over the frames (plane type, fixed order) -> shard-local update ->
+            # all-gather of TW, per component on its side stream: 2.7x less NVLink
+            # traffic than the float64 all-reduce of num and den, and it overlaps the contraction
+            # of the next component
+            world = self.comm.world
+            c = ld // world
+            self.tw_rs_in = self._zeros([S, world, 2, Kmax, c])
+            self.tw_rs_out = self._zeros([S, 2, Kmax, c])
+            self.tw_ag = self._zeros([S, world, Kmax, c])
+            self.tw_nd = self._zeros([S, 2, Kmax, ld], f64)
+        else:
+            self.tw_nd = None
 
     # ------------------------------------------------------------------ pieces
     def compute_powers(self, with_G=True):
@@ -386,7 +425,10 @@ class GemEngine(object):
         estep = self.k.estep_multi if self.multi else self.k.estep_stereo
         estep(self.X, self.V, self.A, self.src_of_sub, self.noise, self.N, self.hatW, self.Rss,
               self.Rxs, self.ll_f, self.ws, self.N_total)
-        if self._tshard():  # means over all frames: sum the ranks' partial statistics
+
+    def reduce_estat(self):
+        """Frame sharding: the statistics are means over all frames -- sum the ranks' parts."""
+        if self._tshard():
             self.comm.allreduce_sum(self.estat)
 
     def update_mix(self):
@@ -459,22 +501,30 @@ class GemEngine(object):
             k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit,
                           None if self.scratch is None else self.scratch[s])
             if self._fshard():
-                k.sum_splits(pn, self.tw_nd[s, 0, :e["Kw"]])
-                k.sum_splits(pd, self.tw_nd[s, 1, :e["Kw"]])
+                Kw, world, rank = e["Kw"], self.comm.world, self.comm.rank
+                c = self.ld // world
+                k.sum_splits(pn, self.tw_nd[s, 0, :Kw])
+                k.sum_splits(pd, self.tw_nd[s, 1, :Kw])
+                # chunk-major copy in the plane type: [2, Kw, world, c] -> [world, 2, Kw, c]
+                self.tw_rs_in[s, :, :, :Kw].copy_(
+                    self.tw_nd[s, :, :Kw].view(2, Kw, world, c).permute(2, 0, 1, 3))
+                self.comm.reduce_scatter_sum(self.tw_rs_out[s], self.tw_rs_in[s])
+                # this rank's frames of TW (padding frames: 0 * (0 / eps) = 0)
+                chunk = e["TW"][:, rank * c:(rank + 1) * c]
+                k.mult_update_same(chunk, self.tw_rs_out[s, 0, :Kw], self.tw_rs_out[s, 1, :Kw],
+                                   Kw, c, self.omega)
+                self.tw_ag[s, rank, :Kw].copy_(chunk)
+                self.comm.allgather_into(self.tw_ag[s], self.tw_ag[s, rank])
+                e["TW"].view(Kw, world, c).copy_(self.tw_ag[s, :, :Kw].permute(1, 0, 2))
             else:  # reduce the frequency splits inside the update kernel
                 k.mult_update_splits(e["TW"], pn, pd, e["Kw"], N, self.omega)
-
-        def tw_apply(_, se):
-            s, e = se
-            k.mult_update(e["TW"], self.tw_nd[s, 0], self.tw_nd[s, 1], e["Kw"], N, self.omega)
         self._for_each(tw, tw_sums)
-        if tw and self._fshard():
-            self.comm.allreduce_sum(self.tw_nd)
-            self._for_each(tw, tw_apply)
 
     def renormalize(self):
         """renormalize_parameters (audioModel.py:1980-2040)."""
         k = self.k
+        if self._tshard() and self._use_streams:  # (the check issued one iteration ago: long done)
+            self.torch.cuda.current_stream(self.dev).wait_stream(self._comm_stream())
         k.spat_energy(self.A, self.src_of_sub, self.J, self.sums)
         if self._fshard():
             self.comm.allreduce_sum(self.sums)
@@ -492,6 +542,20 @@ class GemEngine(object):
             self._for_each(self.spec, rescale)
         else:
             self._for_each(self.spec, lambda s, e: (colmax(s, e), rescale(s, e)))
+        if self._tshard() and self._use_streams and not self.sync_redraw:
+            # the sum over the ranks only feeds the vanished-TW check: reduce and check it on
+            # the side stream, off the critical path (the next renormalisation accumulates into
+            # the other buffer and waits for this check before it comes back to this one)
+            torch = self.torch
+            cur, side = torch.cuda.current_stream(self.dev), self._comm_stream()
+            tot = self.totals
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.comm.allreduce_sum(tot)
+                k.check_totals(tot, EPS, self.flags, self.iter_dev, self.first_vanish)
+            self._tot_parity ^= 1
+            self.totals = self._totals2[self._tot_parity]
+            return
         if self._tshard():
             self.comm.allreduce_sum(self.totals)
         if self.sync_redraw:
@@ -525,13 +589,31 @@ class GemEngine(object):
         mark("powers")
         self.estep()
         mark("estep")
-        k.ll_reduce(self.ll_f, self.ll_sum)
-        if self._fshard():
-            self.comm.allreduce_sum(self.ll_sum)
-        k.ll_store(self.ll_sum, float(self.F_total) * self.N_total, logliks, self.iter_dev, True)
-        self.update_mix()
-        mark("mix")
-        self.update_spectral()
+
+        def stats_and_mix():
+            self.reduce_estat()
+            k.ll_reduce(self.ll_f, self.ll_sum)
+            if self._fshard():
+                self.comm.allreduce_sum(self.ll_sum)
+            k.ll_store(self.ll_sum, float(self.F_total) * self.N_total, logliks, self.iter_dev, True)
+            self.update_mix()
+        if self._tshard() and self._use_streams:
+            # only the mixing update needs the all-reduced statistics: it runs, with its
+            # all-reduce, on a side stream while the spectral M-step (which reads hat_W, V and
+            # the factors, never A) starts on this one
+            torch = self.torch
+            cur = torch.cuda.current_stream(self.dev)
+            side = self._comm_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                stats_and_mix()
+            mark("mix")
+            self.update_spectral()
+            cur.wait_stream(side)
+        else:
+            stats_and_mix()
+            mark("mix")
+            self.update_spectral()
         mark("spectral")
         self.renormalize()
         mark("renorm")
@@ -546,7 +628,7 @@ class GemEngine(object):
         logliks = torch.ones([max(n_iter, 1)], dtype=torch.float64, device=self.dev)
         self.iter_dev.zero_()
         self.flags.zero_()
-        self.totals.zero_()
+        self._totals2.zero_()
         self.first_vanish.fill_(2 ** 30)
         if use_graph and n_iter > 1 and self.dev.type == "cuda" and careful_from is None:
             self._run_graph(n_iter, logliks)
@@ -591,6 +673,7 @@ class GemEngine(object):
         reference's compute_suff_stat outputs (local frequency rows)."""
         self.compute_powers(with_G=False)
         self.estep()
+        self.reduce_estat()
         self.k.ll_reduce(self.ll_f, self.ll_sum)
         if self._fshard():
             self.comm.allreduce_sum(self.ll_sum)
@@ -622,8 +705,12 @@ class GemEngine(object):
         """`t` holds the local frames (without padding) along `axis`."""
         return self._gather(t, axis, self.N_total, "time")
 
-    def read_model(self, spat_comps, spec_comps):
-        """Writes the device parameters back into the user-visible dicts."""
+    def read_model(self, spat_comps, spec_comps, gather=True):
+        """Writes the device parameters back into the user-visible dicts.  Sharded models:
+        `gather` = True all-gathers the sharded factor (TW under frame sharding, FB under frequency
+        sharding) so that every rank holds the whole model; False writes only this rank's rows /
+        frames into the host arrays (a copy whose size does not grow with the number of ranks --
+        what estim_param_a_post_model does; FASST.gather_parameters() completes them)."""
         A = self._gather_f(self.A, 2)
         for j in range(self.J):
             if self.mix_type == "inst":
@@ -635,11 +722,33 @@ class GemEngine(object):
             fac = spec_comps[s]["factor"]
             fac = fac[list(fac.keys())[0]]
             f64 = self.torch.float64
-            fac["FB"] = self._to_host(self._gather_dev(e["FB"].to(f64), 0, self.F_total, "freq"),
-                                      fac["FB"])
+            if gather or not self._sharded():
+                fac["FB"] = self._to_host(
+                    self._gather_dev(e["FB"].to(f64), 0, self.F_total, "freq"), fac["FB"])
+                fac["TW"] = self._to_host(
+                    self._gather_dev(e["TW"][:, :self.N].to(f64), 1, self.N_total, "time"),
+                    fac["TW"])
+            else:
+                fac["FB"] = self._to_host_part(e["FB"].to(f64), fac["FB"], 0, self.f_lo, self.f_hi,
+                                               (self.F_total, e["Kb"]))
+                fac["TW"] = self._to_host_part(e["TW"][:, :self.N].to(f64), fac["TW"], 1,
+                                               self.n_lo, self.n_hi, (e["Kw"], self.N_total))
             fac["FW"] = e["FW"].to(f64).cpu().numpy()
-            fac["TW"] = self._to_host(
-                self._gather_dev(e["TW"][:, :self.N].to(f64), 1, self.N_total, "time"), fac["TW"])
+
+    def _to_host_part(self, t, old, axis, lo, hi, full_shape):
+        """Device tensor holding the slice [lo, hi) along `axis` of a host array of `full_shape`:
+        written in place into `old` when that is a writable float64 array of that shape (else into
+        a copy of it / a zero array)."""
+        if not (isinstance(old, np.ndarray) and old.dtype == np.float64 and old.flags.writeable
+                and old.shape == tuple(full_shape)):
+            old = np.array(old, dtype=np.float64) if np.shape(old) == tuple(full_shape) \
+                else np.zeros(full_shape)
+        view = old[lo:hi] if axis == 0 else old[:, lo:hi]
+        if t.is_cuda:
+            self.torch.from_numpy(view).copy_(t)
+        else:
+            view[...] = t.numpy()
+        return old
 
     def _to_host(self, t, old):
         """Device tensor -> host array.  When the user-visible array it replaces has the same

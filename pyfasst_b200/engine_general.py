@@ -133,7 +133,8 @@ class GeneralGemEngine(GemEngine):
         self.colmax = self._zeros([n, Kb4], f64)
         self.wcol = self._zeros([n, Kb4], f64)
         self.w2 = self._zeros([n, Kw4], f64)
-        self.totals = self._zeros([n], f64)      # sum of every TW after its rescaling
+        self._totals2 = self._zeros([1, n], f64)
+        self.totals = self._totals2[0]           # sum of every TW after its rescaling
         self.gcount = self._f64(np.array([fc["Kw"] * fc["L"] for fc in facs], dtype=np.float64))
         self.gvec = self._zeros([Kw4], f64)
         self.sparse_work = self._zeros([2 * self.N], f64)
@@ -369,7 +370,7 @@ class GeneralGemEngine(GemEngine):
                                         slope, self.iter_dev, self.sparse_work)
 
     # ------------------------------------------------------------------ results
-    def read_model(self, spat_comps, spec_comps):
+    def read_model(self, spat_comps, spec_comps, gather=True):
         A = self.A.cpu().numpy()
         for j in range(self.J):
             if self.mix_type == "inst":

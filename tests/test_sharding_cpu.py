@@ -138,7 +138,8 @@ def _worker_api(rank, world, port, shard, out_dir):
                                     shard=shard)
         model.makeItConvolutive()
         lls = model.estim_param_a_post_model()
-        pcm = model.separate_comps_pcm({j: [j] for j in range(2)})
+        pcm = model.separate_comps_pcm({j: [j] for j in range(2)})  # (on the rank-local shards)
+        model.gather_parameters()
         if rank == 0:
             np.savez(os.path.join(out_dir, "api.npz"), lls=lls, pcm=pcm,
                      FB0=model.spec_comps[0]["factor"][0]["FB"],
