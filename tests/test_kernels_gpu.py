@@ -80,7 +80,8 @@ def problem(rng, dt, F, N, J, rank, conv=True, consistent=True):
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("consistent", [True, False])
 @pytest.mark.parametrize("F,N,J,rank", [(5, 77, 1, 1), (33, 1000, 3, 1), (17, 2600, 4, 2),
-                                        (9, 515, 2, 3), (3, 4, 6, 1)])
+                                        (9, 515, 2, 3), (3, 4, 6, 1), (6, 1531, 4, 1),
+                                        (3, 5, 4, 2)])
 def test_estep_stereo(ck, fk, dt, F, N, J, rank, consistent):
     rng = np.random.default_rng(F * 1000 + N)
     ld, R, src, X, V, A, noise = problem(rng, dt, F, N, J, rank, consistent=consistent)
@@ -110,12 +111,13 @@ def test_estep_stereo(ck, fk, dt, F, N, J, rank, consistent):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-def test_estep_stereo_determinant_clamp(ck, fk, dt):
+@pytest.mark.parametrize("J", [3, 4])  # J = 4: the lane-pair kernel
+def test_estep_stereo_determinant_clamp(ck, fk, dt, J):
     """Quiet rows: det Sigma < 1e-10 activates the reference's clamp (signalTools.py:183-188), where
     Sigma_c^-1 is not the inverse of Sigma and the kernel's identity for x y^H needs its correction
     term; rows 0-2 are clamped in every bin, rows 3-5 in some, the rest in none."""
     rng = np.random.default_rng(77)
-    F, N, J, rank = 9, 1300, 3, 2
+    F, N, rank = 9, 1300, 2
     ld, R, src, X, V, A, noise = problem(rng, dt, F, N, J, rank)
     scale = np.ones(F)
     scale[:3], scale[3:6] = 1e-7, 3e-5
