@@ -73,6 +73,23 @@ __device__ __forceinline__ double pf_abs(double a) { return fabs(a); }
 __device__ __forceinline__ float pf_sqrt(float a) { return sqrtf(a); }
 __device__ __forceinline__ double pf_sqrt(double a) { return sqrt(a); }
 
+// 1/x: MUFU.RCP seed plus one (float) or two (double) Newton steps instead of the IEEE
+// division with its range check and slow-path call; relative error ~1e-7 / < 1e-14.  The
+// arguments here are clamped away from zero.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)x));
+  double r = (double)r0;
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  return r;
+}
+
 // ---- warp / block reductions (fixed order => deterministic) -------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

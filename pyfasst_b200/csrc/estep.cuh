@@ -23,23 +23,6 @@ struct SubMap {
   double invrank[MAXJ];
 };
 
-// 1/x: MUFU.RCP seed plus one (float) or two (double) Newton steps instead of the IEEE
-// division with its range check and slow-path call; relative error ~1e-7 / < 1e-14.  The
-// arguments here are clamped away from zero.
-__device__ __forceinline__ float fast_rcp(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
-__device__ __forceinline__ double fast_rcp(double x) {
-  float r0;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)x));
-  double r = (double)r0;
-  r = r * (2.0 - x * r);
-  r = r * (2.0 - x * r);
-  return r;
-}
-
 // Per-bin algebra of the Wiener filter.
 // Sigma = s2 I + sum_j v_j R_j ; returns Sigma^-1 (i00, i11, i01) in the compute type C and
 // det Sigma / the pair products v_j v_k in the type D.  The determinant is expanded into

@@ -24,7 +24,7 @@ namespace pf {
 
 constexpr int EM_THREADS = 128;
 #ifndef EM_MINB
-#define EM_MINB 2
+#define EM_MINB 3
 #endif
 constexpr int EM_MAXJ = 6;
 constexpr int EM_MAXR = 24;
@@ -41,9 +41,10 @@ struct MultiGroups {
 // lower-triangle index of (i, k), i > k
 __host__ __device__ constexpr int tri(int i, int k) { return i * (i - 1) / 2 + k; }
 __host__ __device__ constexpr int em_npairs(int J) { return J * (J + 1) / 2; }
-// per-frequency accumulators: S (I^2 per pair), T (2 I^2 per source), sv (J), ll (1)
+// per-frequency accumulators: S (I^2 per pair), Z (I^2 per source), sv (J), clamp correction
+// (2 I^2 per source), ll (1)
 __host__ __device__ constexpr int em_nacc(int I, int J) {
-  return em_npairs(J) * I * I + J * 2 * I * I + J + 1;
+  return em_npairs(J) * I * I + J * I * I + J + J * 2 * I * I + 1;
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -200,27 +201,174 @@ __device__ __forceinline__ void sigma_inverse_multi(const double (&v)[J], const 
   }
 }
 
-// ---- record of one bin in shared memory (float64 whatever the plane type) ----------------------------
-// The moment factors are kept and accumulated in float64: with R < I sub-sources, or in the
-// regime of the determinant clamp, M = y y^H - Sigma^-1 has entries ~ |x|^2 / s2^2 that cancel by
-// many orders of magnitude once contracted with the mixing vectors, and at ~500 FP64 operations
-// of per-bin algebra the 292 extra DFMAs per bin (spread over 32 lanes) do not show.
-//   [ pr (NP, padded to a multiple of 4) | M (I^2: diag, lower (re, im)) | v (J padded to 4) |
-//     U = x y^H (2 I^2: [a][b](re, im)) | 1 ]
+// ---- LDL^H variant of the per-bin algebra (E-step) ---------------------------------------------
+// Sigma = L D L^H (L unit lower), Li = L^-1, Sigma^-1 = Li^H D^-1 Li, y = Li^H D^-1 Li x.  No
+// square roots, 4 reciprocals; ~230 FP64 operations at I = 4 without the formation of Sigma.
+// Out: y and Sigma^-1 (diag + lower triangle), both scaled by sc = det / max(det, eps) (Q5 clamp on
+// the generic determinant), the clamped determinant, x^H Sigma^-1 x and sc.
 template <int I, int J>
-struct Rec {
+__device__ __forceinline__ void sigma_inverse_ldl(const double (&v)[J], const double2 (&x)[I],
+                                                  const double* __restrict__ coef, double s2,
+                                                  double2 (&y)[I], double (&sid)[I],
+                                                  double2 (&sio)[I * (I - 1) / 2 + 1],
+                                                  double& detc, double& quad, double& sc) {
+  constexpr int NM = I * I, NT = I * (I - 1) / 2;
+  double sd[I];
+  double2 w[NT + 1];  // lower triangle of Sigma, then the unnormalised columns of L
+#pragma unroll
+  for (int i = 0; i < I; ++i) sd[i] = s2;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) w[t] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const double* c = coef + j * NM;
+#pragma unroll
+    for (int i = 0; i < I; ++i) sd[i] += v[j] * c[i];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      w[t].x += v[j] * c[I + 2 * t];
+      w[t].y += v[j] * c[I + 2 * t + 1];
+    }
+  }
+  double r[I];
+  double2 L[NT + 1];
+  double det = 1.0;
+#pragma unroll
+  for (int j = 0; j < I; ++j) {
+    double d = sd[j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= w[tri(j, k)].x * L[tri(j, k)].x + w[tri(j, k)].y * L[tri(j, k)].y;
+    d = fmax(d, 1e-30);  // Sigma is positive definite (s2 > 0); guards rounding only
+    det *= d;
+    r[j] = fast_rcp(d);
+#pragma unroll
+    for (int i = j + 1; i < I; ++i) {
+      double2 a = w[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) {
+        const double2 p = cmulc(w[tri(i, k)], L[tri(j, k)]);
+        a.x -= p.x;
+        a.y -= p.y;
+      }
+      w[tri(i, j)] = a;
+      L[tri(i, j)] = make_double2(a.x * r[j], a.y * r[j]);
+    }
+  }
+  // Li = L^-1 (unit lower), G = D^-1 Li (strictly lower part)
+  double2 Li[NT + 1], G[NT + 1];
+#pragma unroll
+  for (int j = 0; j < I; ++j) {
+#pragma unroll
+    for (int i = j + 1; i < I; ++i) {
+      double2 a = L[tri(i, j)];
+#pragma unroll
+      for (int k = j + 1; k < i; ++k) {
+        const double2 p = cmul(L[tri(i, k)], Li[tri(k, j)]);
+        a.x += p.x;
+        a.y += p.y;
+      }
+      Li[tri(i, j)] = make_double2(-a.x, -a.y);
+      G[tri(i, j)] = make_double2(-a.x * r[i], -a.y * r[i]);
+    }
+  }
+  // Sigma^-1[i][j] = sum_{k >= i} conj(Li[k][i]) G[k][j], Li[k][k] = 1
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    double d = r[i];
+#pragma unroll
+    for (int k = i + 1; k < I; ++k) d += Li[tri(k, i)].x * G[tri(k, i)].x + Li[tri(k, i)].y * G[tri(k, i)].y;
+    sid[i] = d;
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      double2 a = G[tri(i, j)];
+#pragma unroll
+      for (int k = i + 1; k < I; ++k) {
+        const double2 p = cconjmul(Li[tri(k, i)], G[tri(k, j)]);
+        a.x += p.x;
+        a.y += p.y;
+      }
+      sio[tri(i, j)] = a;
+    }
+  }
+  // z = Li x, t = D^-1 z, quad = z^H t, y = Li^H t
+  double2 tt[I];
+  quad = 0.0;
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    double2 a = x[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      const double2 p = cmul(Li[tri(i, k)], x[k]);
+      a.x += p.x;
+      a.y += p.y;
+    }
+    tt[i] = make_double2(a.x * r[i], a.y * r[i]);
+    quad += a.x * tt[i].x + a.y * tt[i].y;
+  }
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    double2 a = tt[i];
+#pragma unroll
+    for (int k = i + 1; k < I; ++k) {
+      const double2 p = cconjmul(Li[tri(k, i)], tt[k]);
+      a.x += p.x;
+      a.y += p.y;
+    }
+    y[i] = a;
+  }
+  detc = det;
+  sc = 1.0;
+  if (det < 1e-10) {  // sign(det + eps) max(|det|, eps) with det > 0: Sigma^-1 := adj(Sigma) / eps
+    detc = 1e-10;
+    sc = det * 1e10;
+    quad *= sc;
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      sid[i] *= sc;
+      y[i].x *= sc;
+      y[i].y *= sc;
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      sio[t].x *= sc;
+      sio[t].y *= sc;
+    }
+  }
+}
+
+// D(8x8) += A(8x4) B(4x8) in float64 on the tensor-core path (DMMA).  Lane l holds A[l>>2][l&3],
+// B[l&3][l>>2] and D[l>>2][2 (l&3) + {0, 1}].  DMMA shares the FP64 pipe with DFMA
+// (profiles/r02/micro_dmma.txt: same 16 FMA per clock and scheduler), so it buys no arithmetic
+// throughput -- it replaces 8 DFMA + their operand loads per lane by one instruction and two loads.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// ---- the moments as a small GEMM over the bins --------------------------------------------------
+// Per frequency:  out[w][c] = sum_n W[w][n] Mc[c][n]  with the WR = NP + J weights
+// W = (v_j v_k for j <= k, then v_j) and the I^2 components of M (diag, then lower (re, im)):
+// rows 0..NP-1 are S_jk, rows NP..NP+J-1 are Z_j = sum_n v_j M.  The cross moments follow from
+// x y^H = Sigma M + I:   T_j = sv_j I + s2 Z_j + sum_l R_l S_lj   (as in the stereo kernel), plus,
+// where the determinant clamp is active (Sigma_c^-1 = sc Sigma^-1 is not the inverse of Sigma),
+// the correction  sum_n v_j (1 - sc) (x y_c^H - I),  accumulated by a second small GEMM only in
+// the passes of a warp that contain a clamped bin.
+// Every thread owns one bin per pass: it writes its weights and M components to a
+// component-major tile of shared memory ([component][bin], component stride 36 doubles: the
+// stores of a warp and the fragment loads below are both bank-conflict free), then the warp
+// contracts the 32 bins with DMMA m8n8k4 (8 steps of 4 bins).
+template <int I, int J>
+struct Mom {
   static constexpr int NP = em_npairs(J);
   static constexpr int NM = I * I, NU = 2 * I * I;
-  static constexpr int PR0 = 0;
-  static constexpr int M0 = (NP + 3) / 4 * 4;
-  static constexpr int V0 = M0 + NM;
-  static constexpr int U0 = V0 + (J + 3) / 4 * 4;
-  static constexpr int ONE = U0 + NU;
-  static constexpr int USED = ONE + 1;
-  // stride = 5 (mod 16) doubles: the 64-bit accesses of a half warp hit disjoint banks
-  static constexpr int STRIDE = (USED + 15) / 16 * 16 + 5;
-  static constexpr int NOUT = NP * NM + J * NU + J;  // accumulators (without ll)
-  static constexpr int PER_LANE = (NOUT + 31) / 32;
+  static constexpr int WR = NP + J;            // weight rows
+  static constexpr int MT = (WR + 7) / 8;      // 8-row tiles of weights
+  static constexpr int NT = (NM + 7) / 8;      // 8-column tiles of M components
+  static constexpr int NT2 = (NU + 7) / 8;     // 8-column tiles of the clamp correction
+  static constexpr int CS = 36;                // doubles per component (32 bins + 4: banks)
+  static constexpr int NCOMP = (MT + NT) * 8 > (1 + NT2) * 8 ? (MT + NT) * 8 : (1 + NT2) * 8;
+  static constexpr int NA = em_nacc(I, J);
 };
 
 template <typename T, int I, int J>
@@ -229,43 +377,38 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
                    const double* __restrict__ coef, const double* __restrict__ noise, MultiMap map,
                    T* __restrict__ hatW, double* __restrict__ partial, int F, long N, long ld,
                    long chunk, int nsplit) {
-  typedef Rec<I, J> RC;
-  constexpr int NM = I * I, NT = I * (I - 1) / 2, NA = em_nacc(I, J);
+  typedef Mom<I, J> MM;
+  constexpr int NM = I * I, NT = I * (I - 1) / 2, NA = MM::NA, CS = MM::CS;
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char em_smem[];
-  double* s_coef = reinterpret_cast<double*>(em_smem);                  // [J][NM]
-  double* s_red = s_coef + J * NM;                                      // [warps][NA]
-  double* s_rec = s_red + (EM_THREADS / 32) * NA;                       // [warps][32][STRIDE]
+  double* s_coef = reinterpret_cast<double*>(em_smem);   // [J][NM]
+  double* s_coef2 = s_coef + J * NM;                     // the same, off-diagonal entries doubled
+  double* s_rec = s_coef2 + J * NM;                      // [warps][NCOMP][CS]; [warps][NA] at the end
   const int f = blockIdx.y, split = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < J * NM; i += EM_THREADS) s_coef[i] = coef[(size_t)f * J * NM + i];
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int i = threadIdx.x; i < J * NM; i += EM_THREADS) {
+    const double c = coef[(size_t)f * J * NM + i];
+    s_coef[i] = c;
+    s_coef2[i] = (i % NM) >= I ? 2.0 * c : c;
+  }
+  double* wrec = s_rec + (size_t)warp * MM::NCOMP * CS;
+  for (int i = lane; i < MM::NCOMP * CS; i += 32) wrec[i] = 0.0;  // padding rows stay zero
   __syncthreads();
   const double s2 = noise[f];
-  double* rec = s_rec + ((size_t)warp * 32 + lane) * RC::STRIDE;  // this thread's record
-  const double* wrec = s_rec + (size_t)warp * 32 * RC::STRIDE;    // the warp's 32 records
-
-  // the accumulators this lane owns: o = lane + 32 m  ->  (offset of factor a, offset of factor b)
-  // of the record; recomputed for every pass (a few integer operations per 32 bins) so that they
-  // do not occupy registers during the per-bin algebra
-  auto offsets = [&](int m, int& oa, int& ob) {
-    const int o = lane + 32 * m;
-    if (o < RC::NP * NM) {
-      oa = RC::PR0 + o / NM;
-      ob = RC::M0 + o % NM;
-    } else if (o < RC::NP * NM + J * RC::NU) {
-      const int q = o - RC::NP * NM;
-      oa = RC::V0 + q / RC::NU;
-      ob = RC::U0 + q % RC::NU;
-    } else if (o < RC::NOUT) {
-      oa = RC::V0 + (o - RC::NP * NM - J * RC::NU);
-      ob = RC::ONE;
-    } else {  // beyond the last accumulator: 1 * 1, never stored
-      oa = RC::ONE;
-      ob = RC::ONE;
-    }
-  };
-  double acc[RC::PER_LANE];
+  T invrank[J];
 #pragma unroll
-  for (int m = 0; m < RC::PER_LANE; ++m) acc[m] = 0.0;
+  for (int j = 0; j < J; ++j) invrank[j] = (T)map.invrank[j];
+
+  double acc[MM::MT][MM::NT][2], cacc[MM::NT2][2], sv[J];
+#pragma unroll
+  for (int a = 0; a < MM::MT; ++a)
+#pragma unroll
+    for (int b = 0; b < MM::NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll
+  for (int b = 0; b < MM::NT2; ++b) cacc[b][0] = cacc[b][1] = 0.0;
+#pragma unroll
+  for (int j = 0; j < J; ++j) sv[j] = 0.0;
   double acc_ll = 0.0;
 
   const long plane = (long)F * ld, row = (long)f * ld;
@@ -275,20 +418,24 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
   for (long n0 = begin + warp * 32; n0 < end; n0 += EM_THREADS) {  // warp-uniform trip count
     const long n = n0 + lane;
     const bool live = n < end;
+    T vt[J];
     double v[J];
     double2 x[I];
 #pragma unroll
-    for (int j = 0; j < J; ++j) v[j] = live ? (double)V[j * plane + row + n] : 0.0;
+    for (int j = 0; j < J; ++j) {
+      vt[j] = live ? V[j * plane + row + n] : (T)0;
+      v[j] = (double)vt[j];
+    }
 #pragma unroll
     for (int i = 0; i < I; ++i)
       x[i] = live ? make_double2((double)X[(2 * i) * plane + row + n],
                                  (double)X[(2 * i + 1) * plane + row + n])
                   : make_double2(0.0, 0.0);
     double2 y[I], sio[NT + 1];
-    double sid[I], detc, quad;
-    sigma_inverse_multi<I, J>(v, x, s_coef, s2, y, sid, sio, detc, quad);
+    double sid[I], detc, quad, sc;
+    sigma_inverse_ldl<I, J>(v, x, s_coef, s2, y, sid, sio, detc, quad, sc);
     if (live) acc_ll += log(detc) + 1.1447298858494002 + quad;  // Q4: log(det * pi)
-    // M = y y^H - Sigma^-1 (diag + lower triangle)
+    // M = y y^H - Sigma^-1 (diag + lower triangle), straight into the warp's tile
     double md[I];
     double2 mo[NT + 1];
 #pragma unroll
@@ -300,84 +447,144 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
         mo[tri(i, k)] = make_double2(p.x - sio[tri(i, k)].x, p.y - sio[tri(i, k)].y);
       }
     }
-    // posterior source powers: tr(M R_j) = sum_i M_ii R_ii + 2 sum_{i>k} Re(M_ik conj(R_ik))
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const double* c = s_coef + j * NM;
-      double q = 0.0;
-#pragma unroll
-      for (int i = 0; i < I; ++i) q += md[i] * c[i];
-      double q2 = 0.0;
-#pragma unroll
-      for (int t = 0; t < NT; ++t) q2 += mo[t].x * c[I + 2 * t] + mo[t].y * c[I + 2 * t + 1];
-      q += 2.0 * q2;
-      const double w = fabs(v[j] + v[j] * v[j] * q * map.invrank[j]);
-      if (live) hatW[j * plane + row + n] = (T)w;
-    }
-    // the bin's record: v_j v_k, M, v_j, U = x y^H, 1
     {
+      double* mr = wrec + MM::MT * 8 * CS + lane;
+#pragma unroll
+      for (int i = 0; i < I; ++i) mr[i * CS] = md[i];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        mr[(I + 2 * t) * CS] = mo[t].x;
+        mr[(I + 2 * t + 1) * CS] = mo[t].y;
+      }
+      double* wr = wrec + lane;
       int p = 0;
 #pragma unroll
       for (int j = 0; j < J; ++j)
 #pragma unroll
-        for (int k = j; k < J; ++k) rec[RC::PR0 + p++] = v[j] * v[k];
+        for (int k = j; k < J; ++k) wr[(p++) * CS] = v[j] * v[k];
 #pragma unroll
-      for (int i = 0; i < I; ++i) rec[RC::M0 + i] = md[i];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        rec[RC::M0 + I + 2 * t] = mo[t].x;
-        rec[RC::M0 + I + 2 * t + 1] = mo[t].y;
+      for (int j = 0; j < J; ++j) {
+        wr[(MM::NP + j) * CS] = v[j];
+        sv[j] += v[j];
       }
+    }
+    // posterior source powers: tr(M R_j) = sum_i M_ii R_ii + 2 sum_{i>k} Re(M_ik conj(R_ik))
 #pragma unroll
-      for (int j = 0; j < J; ++j) rec[RC::V0 + j] = v[j];
+    for (int j = 0; j < J; ++j) {
+      const double* c = s_coef2 + j * NM;
+      double q = 0.0, q2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < I; ++i) q += md[i] * c[i];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) q2 += mo[t].x * c[I + 2 * t] + mo[t].y * c[I + 2 * t + 1];
+      const T qf = (T)(q + q2);
+      if (live) hatW[j * plane + row + n] = pf_abs(vt[j] + vt[j] * vt[j] * (qf * invrank[j]));
+    }
+    __syncwarp();
+    // contraction of the warp's 32 bins
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      double a[MM::MT], b[MM::NT];
+#pragma unroll
+      for (int mt = 0; mt < MM::MT; ++mt) a[mt] = wrec[(8 * mt + g) * CS + 4 * s + t4];
+#pragma unroll
+      for (int nt = 0; nt < MM::NT; ++nt) b[nt] = wrec[((MM::MT + nt) * 8 + g) * CS + 4 * s + t4];
+#pragma unroll
+      for (int mt = 0; mt < MM::MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < MM::NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+    const bool clamped = live && sc != 1.0;
+    if (__any_sync(FULL, clamped)) {
+      // slow path: rows 0..J-1 = v_j (1 - sc) (zero for the bins without clamp), columns
+      // 8.. = U - I with U = x y_c^H ([a][b] (re, im)); same tile, repaired afterwards
+      __syncwarp();
+      const double k1 = clamped ? 1.0 - sc : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wrec[j * CS + lane] = j < J ? k1 * v[j < J ? j : 0] : 0.0;
 #pragma unroll
       for (int a = 0; a < I; ++a)
 #pragma unroll
         for (int b = 0; b < I; ++b) {
           const double2 u = cmulc(x[a], y[b]);
-          rec[RC::U0 + 2 * (a * I + b)] = u.x;
-          rec[RC::U0 + 2 * (a * I + b) + 1] = u.y;
+          wrec[(8 + 2 * (a * I + b)) * CS + lane] = a == b ? u.x - 1.0 : u.x;
+          wrec[(8 + 2 * (a * I + b) + 1) * CS + lane] = u.y;
         }
-      rec[RC::ONE] = 1.0;
-    }
-    __syncwarp();
-    // cooperative accumulation of the warp's 32 records
-    {
-      int offa[RC::PER_LANE], offb[RC::PER_LANE];
 #pragma unroll
-      for (int m = 0; m < RC::PER_LANE; ++m) offsets(m, offa[m], offb[m]);
-#pragma unroll 4
-      for (int b = 0; b < 32; ++b) {
-        const double* rb = wrec + (size_t)b * RC::STRIDE;
+      for (int c = MM::NU; c < MM::NT2 * 8; ++c) wrec[(8 + c) * CS + lane] = 0.0;
+      __syncwarp();
 #pragma unroll
-        for (int m = 0; m < RC::PER_LANE; ++m) acc[m] += rb[offa[m]] * rb[offb[m]];
+      for (int s = 0; s < 8; ++s) {
+        const double a = wrec[g * CS + 4 * s + t4];
+#pragma unroll
+        for (int nt = 0; nt < MM::NT2; ++nt)
+          dmma884(cacc[nt][0], cacc[nt][1], a, wrec[((1 + nt) * 8 + g) * CS + 4 * s + t4]);
       }
+      __syncwarp();
+      // the padding rows / columns of the main tile that the slow path overwrote
+#pragma unroll
+      for (int c = MM::WR; c < MM::MT * 8; ++c) wrec[c * CS + lane] = 0.0;
+#pragma unroll
+      for (int c = MM::NM; c < MM::NT * 8; ++c) wrec[((MM::MT * 8) + c) * CS + lane] = 0.0;
+#pragma unroll
+      for (int c = (MM::MT + MM::NT) * 8; c < MM::NCOMP; ++c) wrec[c * CS + lane] = 0.0;
     }
     __syncwarp();
   }
-  // block reduction in a fixed order (deterministic): lanes own disjoint accumulators
+  // block reduction in a fixed order (deterministic): the fragments go to the warp's own tile
+  // (re-used as [NA] sums), then the warps are added in order
+  double* red = wrec;
+  __syncwarp();
+  for (int i = lane; i < NA; i += 32) red[i] = 0.0;
+  __syncwarp();
 #pragma unroll
-  for (int m = 0; m < RC::PER_LANE; ++m) {
-    const int o = lane + 32 * m;
-    if (o < RC::NOUT) s_red[warp * NA + o] = acc[m];
+  for (int mt = 0; mt < MM::MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < MM::NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = 8 * mt + g, c = 8 * nt + 2 * t4 + i;
+        if (r < MM::WR && c < NM) red[r * NM + c] = acc[mt][nt][i];
+      }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const double d = warp_sum(sv[j]);
+    if (lane == 0) red[MM::WR * NM + j] = d;
   }
+#pragma unroll
+  for (int nt = 0; nt < MM::NT2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = 8 * nt + 2 * t4 + i;
+      if (g < J && c < MM::NU) red[MM::WR * NM + J + g * MM::NU + c] = cacc[nt][i];
+    }
   {
     const double d = warp_sum(acc_ll);
-    if (lane == 0) s_red[warp * NA + NA - 1] = d;
+    if (lane == 0) red[NA - 1] = d;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NA; i += EM_THREADS) {
     double d = 0.0;
 #pragma unroll
-    for (int w = 0; w < EM_THREADS / 32; ++w) d += s_red[w * NA + i];
+    for (int w = 0; w < EM_THREADS / 32; ++w) d += s_rec[(size_t)w * MM::NCOMP * CS + i];
     partial[((size_t)f * nsplit + split) * NA + i] = d;
   }
 }
 
 // ---- per-frequency contraction with the mixing vectors ------------------------------------------------
-// hat_Rss[r1, r2] = a_r1^H S_{j1 j2} a_r2 / N + delta sv_{j1} / N ;  hat_Rxs[:, r] = T_j a_r / N
+// hat_Rss[r1, r2] = a_r1^H S_{j1 j2} a_r2 / N + delta sv_{j1} / N ;  hat_Rxs[:, r] = T_j a_r / N with
+// T_j = sv_j I + s2 Z_j + sum_l R_l S_lj + (clamp correction)
+// partial: [F][nsplit][ S (I^2 per pair) | Z (I^2 per source) | sv (J) | corr (2 I^2 per source) | ll ]
+__device__ __forceinline__ double2 herm_at(const double* P, int I, int a, int c) {
+  if (a == c) return make_double2(P[a], 0.0);
+  if (a > c) return make_double2(P[I + 2 * tri(a, c)], P[I + 2 * tri(a, c) + 1]);
+  return make_double2(P[I + 2 * tri(c, a)], -P[I + 2 * tri(c, a) + 1]);
+}
+
 __global__ void estep_finalize_multi_kernel(const double* __restrict__ partial,
-                                            const double2* __restrict__ A, MultiMap map, int R,
+                                            const double2* __restrict__ A,
+                                            const double* __restrict__ coef,
+                                            const double* __restrict__ noise, MultiMap map, int R,
                                             int J, int I, int F, long N, int nsplit,
                                             double2* __restrict__ hat_Rss,
                                             double2* __restrict__ hat_Rxs,
@@ -385,8 +592,9 @@ __global__ void estep_finalize_multi_kernel(const double* __restrict__ partial,
   const int f = blockIdx.x;
   const int NM = I * I, NU = 2 * I * I, NP = em_npairs(J), NA = em_nacc(I, J);
   extern __shared__ __align__(16) unsigned char fm_smem[];
-  double* s_acc = reinterpret_cast<double*>(fm_smem);            // [NA]
-  double2* s_a = reinterpret_cast<double2*>(s_acc + NA + (NA & 1));  // [R][I]
+  double* s_acc = reinterpret_cast<double*>(fm_smem);                    // [NA]
+  double2* s_a = reinterpret_cast<double2*>(s_acc + NA + (NA & 1));      // [R][I]
+  double2* s_T = s_a + R * I;                                            // [J][I][I]
   for (int i = threadIdx.x; i < NA; i += blockDim.x) {
     double d = 0.0;
     for (int s = 0; s < nsplit; ++s) d += partial[((size_t)f * nsplit + s) * NA + i];
@@ -396,8 +604,27 @@ __global__ void estep_finalize_multi_kernel(const double* __restrict__ partial,
   __syncthreads();
   const double invN = 1.0 / (double)N;
   if (threadIdx.x == 0) ll_f[f] = s_acc[NA - 1];
-  const double* T0 = s_acc + NP * NM;
-  const double* sv = T0 + J * NU;
+  const double* Z0 = s_acc + NP * NM;
+  const double* sv = Z0 + J * NM;
+  const double* C0 = sv + J;
+  const double s2 = noise[f];
+  for (int idx = threadIdx.x; idx < J * NM; idx += blockDim.x) {
+    const int j = idx / NM, a = (idx % NM) / I, b = idx % I;
+    const double2 z = herm_at(Z0 + j * NM, I, a, b);
+    double tr_ = s2 * z.x + C0[j * NU + 2 * (a * I + b)] + (a == b ? sv[j] : 0.0);
+    double ti = s2 * z.y + C0[j * NU + 2 * (a * I + b) + 1];
+    for (int l = 0; l < J; ++l) {
+      const int j1 = l < j ? l : j, j2 = l < j ? j : l;
+      const double* S = s_acc + (j1 * J - j1 * (j1 - 1) / 2 + (j2 - j1)) * NM;
+      const double* Rl = coef + ((size_t)f * J + l) * NM;
+      for (int c = 0; c < I; ++c) {
+        const double2 r = herm_at(Rl, I, a, c), s = herm_at(S, I, c, b);
+        tr_ += r.x * s.x - r.y * s.y;
+        ti += r.x * s.y + r.y * s.x;
+      }
+    }
+    s_T[idx] = make_double2(tr_, ti);
+  }
   for (int idx = threadIdx.x; idx < R * R; idx += blockDim.x) {
     const int r1 = idx / R, r2 = idx % R;
     if (r1 > r2) continue;
@@ -430,14 +657,15 @@ __global__ void estep_finalize_multi_kernel(const double* __restrict__ partial,
     hat_Rss[((size_t)f * R + r1) * R + r2] = make_double2(hr, hi);
     hat_Rss[((size_t)f * R + r2) * R + r1] = make_double2(hr, -hi);
   }
+  __syncthreads();
   for (int idx = threadIdx.x; idx < I * R; idx += blockDim.x) {
     const int c = idx / R, r = idx % R;
-    const double* T = T0 + map.src_of_sub[r] * NU + 2 * c * I;  // T_j[c][b] (re, im)
+    const double2* T = s_T + (map.src_of_sub[r] * I + c) * I;  // T_j[c][b]
     const double2* b = s_a + r * I;
     double hr = 0.0, hi = 0.0;
     for (int k = 0; k < I; ++k) {
-      hr += T[2 * k] * b[k].x - T[2 * k + 1] * b[k].y;
-      hi += T[2 * k] * b[k].y + T[2 * k + 1] * b[k].x;
+      hr += T[k].x * b[k].x - T[k].y * b[k].y;
+      hi += T[k].x * b[k].y + T[k].y * b[k].x;
     }
     hat_Rxs[((size_t)f * I + c) * R + r] = make_double2(hr * invN, hi * invN);
   }
@@ -505,8 +733,9 @@ wiener_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
 
 template <typename T, int I, int J>
 static size_t em_smem_bytes() {
-  return sizeof(double) * (J * I * I + (EM_THREADS / 32) * em_nacc(I, J) +
-                           (size_t)EM_THREADS * Rec<I, J>::STRIDE);
+  static_assert(em_nacc(I, J) <= Mom<I, J>::NCOMP * Mom<I, J>::CS, "the sums re-use the tile");
+  return sizeof(double) * (2 * J * I * I +
+                           (size_t)(EM_THREADS / 32) * Mom<I, J>::NCOMP * Mom<I, J>::CS);
 }
 
 template <typename T, int I, int J>
@@ -652,9 +881,9 @@ extern "C" int pf_estep_multi(const void* X, const void* V, const void* A, const
                             nsplit, st);
   if (rc) return rc;
   const int NA = em_nacc(I, J);
-  const size_t smem = sizeof(double) * (NA + (NA & 1)) + sizeof(double2) * R * I;
-  estep_finalize_multi_kernel<<<F, 128, smem, st>>>(partial, (const double2*)A, map, R, J, I, F,
-                                                   N_norm > 0 ? N_norm : N, nsplit,
+  const size_t smem = sizeof(double) * (NA + (NA & 1)) + sizeof(double2) * (R * I + J * I * I);
+  estep_finalize_multi_kernel<<<F, 128, smem, st>>>(partial, (const double2*)A, coef, noise_psd, map,
+                                                   R, J, I, F, N_norm > 0 ? N_norm : N, nsplit,
                                                    (double2*)hat_Rss, (double2*)hat_Rxs, ll_f);
   return check_launch("estep_finalize_multi_kernel");
 }

@@ -69,6 +69,43 @@ def test_estep_multi(ck, dt, I, F, N, J, rank):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("I,J,rank", [(4, 4, 2), (3, 2, 3), (2, 3, 2)])
+def test_estep_multi_determinant_clamp(ck, dt, I, J, rank):
+    """Quiet rows: det Sigma < 1e-10 activates the determinant clamp (the generic form of
+    signalTools.py:183-188), where the scaled Sigma^-1 is not the inverse of Sigma and the kernel's
+    identity for x y^H needs its correction term; rows 0-2 are clamped in every bin, rows 3-5 in
+    some, the rest in none."""
+    rng = np.random.default_rng(177 + I)
+    F, N = 9, 1300
+    ld, R, src, X, V, A, noise = problem(rng, dt, I, F, N, J, rank)
+    scale = np.ones(F)
+    scale[:3], scale[3:6] = 10.0 ** (-14.0 / I), 10.0 ** (-9.0 / I)
+    sc = torch.tensor(scale)
+    X = (X.to(torch.float64) * torch.sqrt(sc)[None, :, None]).to(dt)
+    V = (V.to(torch.float64) * sc[None, :, None]).to(dt)
+    V[:, 3:6, ::3] *= 1e-3
+    X[:, 3:6, ::3] *= 1e-2
+    noise = noise * sc
+    outs = []
+    for k, dev in ((FakeKernels(), "cpu"), (ck, "cuda")):
+        hatW = torch.zeros((J, F, ld), dtype=dt, device=dev)
+        Rss = torch.zeros((F, R, R), dtype=torch.complex128, device=dev)
+        Rxs = torch.zeros((F, I, R), dtype=torch.complex128, device=dev)
+        ll = torch.zeros(F, dtype=torch.float64, device=dev)
+        ws = torch.zeros((k.estep_multi_workspace_bytes(I, J, F, N) + 7) // 8, dtype=torch.float64,
+                         device=dev)
+        k.estep_multi(X.to(dev), V.to(dev), A.to(dev), src, noise.to(dev), N, hatW, Rss, Rxs, ll, ws)
+        outs.append([t.cpu().numpy() for t in (hatW, Rss, Rxs, ll)])
+    (hw0, rss0, rxs0, ll0), (hw1, rss1, rxs1, ll1) = outs
+    assert np.isfinite(hw1).all() and np.isfinite(rss1).all() and np.isfinite(rxs1).all()
+    for f in range(F):  # per row: the rows differ by many orders of magnitude
+        assert rel(hw1[:, f, :N], hw0[:, f, :N]) < tol(dt, f64=1e-7, f32=1e-5), f
+        assert rel(rss1[f], rss0[f]) < 1e-7, f
+        assert rel(rxs1[f], rxs0[f]) < 1e-7, f
+    assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-10, f32=1e-6))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("I", [2, 3, 4])
 def test_wiener_multi(ck, dt, I):
     rng = np.random.default_rng(5 + I)
