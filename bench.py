@@ -132,7 +132,11 @@ class ClockSampler(object):
     def start(self):
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
-        time.sleep(0.02)
+        # NVML initialisation takes a few ms: do not let a short timed region end before the
+        # first sample is in
+        t0 = time.time()
+        while not self.samples and self.error is None and time.time() - t0 < 2.0:
+            time.sleep(0.005)
 
     def stop(self):
         self._stop.set()
@@ -148,6 +152,10 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- CPU arm
+CPU_CROP_S = 8.0   # crop of the synthetic mixture the CPU arms run on (both of them)
+CPU_ITERS, CPU_WARM = 5, 1  # in-line cpu_baseline; `--impl reference` takes --steps / --warmup
+
+
 def oracle_model(pcm, iters):
     from oracle import fasst_oracle as fo
     maxdata = np.maximum(1.1 * np.abs(pcm).max(), 1e-10)
@@ -409,11 +417,13 @@ def run_ours(args, rank, world):
     cpu = None
     if world == 1 and not args.no_cpu_baseline and args.channels == 2:
         cores = host_threads()
-        rate, cbins, cdt = cpu_gem_rate(args.cpu_crop_s, 1)
+        # the same sample as `--impl reference`: the same crop, warm iterations first
+        rate, cbins, cdt = cpu_gem_rate(args.cpu_crop_s, CPU_ITERS, CPU_WARM)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "1 GEM iteration of the oracle (NumPy float64 restatement of the "
-                         "reference) on a %.1f s crop (%d bins, %.1f s)" %
-                         (args.cpu_crop_s, cbins, cdt)}
+               "sample": "%d GEM iterations (after %d warm) of the oracle (NumPy float64 "
+                         "restatement of the reference) on a %.1f s crop (%d bins, %.1f s), "
+                         "BLAS threads = %d" %
+                         (CPU_ITERS, CPU_WARM, args.cpu_crop_s, cbins, cdt, cores)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -459,13 +469,11 @@ def main():
         args.warmup = 3
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.cpu_crop_s is None:
+        args.cpu_crop_s = CPU_CROP_S  # one crop for both CPU arms
     if args.impl == "reference":
-        if args.cpu_crop_s is None:
-            args.cpu_crop_s = 4.0
         run_reference(args, rank)
         return
-    if args.cpu_crop_s is None:
-        args.cpu_crop_s = 20.0
     if world != args.gpus:
         sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE\n"
                          % (args.gpus, world))

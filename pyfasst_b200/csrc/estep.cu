@@ -333,300 +333,6 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   }
 }
 
-// ---- J = 4: the two lanes of a pair share the moment sums ----------------------------------
-// The 61 float64 moment sums of estep_stereo_kernel cost 122 registers: 255 registers per thread,
-// 2 warps per scheduler, and the FP64 pipe (the real ceiling of this kernel: 143 FP64 operations
-// per bin at 64 per clock and SM, profiles/r02/micro_fp64_lat.txt) idles 43 % of the time behind
-// the dependent chains of the per-bin algebra (profiles/r02/ncu_estep_stereo_kernel.txt).  Here
-// lanes 2i and 2i+1 each do the algebra of their OWN bins, exchange M (shuffles) and the source
-// powers (the partner's ring slot), and each accumulates HALF of the moments for BOTH bins -- the
-// same FP64 work, 30 accumulators per lane instead of 61, 168 registers, 3 warps per scheduler.
-// Role r = lane & 1 works in the rotated source order vr_i = v_{(i + r) mod 4} (rotated
-// shared-memory addresses, no selects) and owns, in that order, the pairs
-//   (0,0) (2,2) (0,1) (2,3) (0,2)   and   Z, sv of vr_0, vr_2:
-// role 0 covers the pairs 00 22 01 23 02, role 1 the pairs 11 33 12 03 13 -- all ten.
-template <typename T>
-__global__ void __launch_bounds__(ESTEP_THREADS, 3)
-estep_stereo_pair_kernel(const T* __restrict__ X, const T* __restrict__ V,
-                         const double* __restrict__ coef, const double* __restrict__ noise,
-                         SubMap map, T* __restrict__ hatW, double* __restrict__ partial, int F,
-                         long N, long ld, int nsplit) {
-  constexpr int J = 4;
-  constexpr int VEC = VecOf<T>::N;
-  constexpr int NP = npairs(J);
-  constexpr int NA = nacc(J);
-  constexpr int NC = ncoef(J);
-  constexpr int NPL = 4 + J;
-  constexpr int NM = 4 * NP + 5 * J;
-  constexpr double kLogPi = 1.1447298858494002;
-  constexpr double kEps = 1e-10;
-  constexpr int PS = ESTEP_THREADS * VEC;  // scalars per plane of a ring slot
-
-  const int f = blockIdx.y;
-  const int split = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int role = lane & 1;
-  __shared__ double s_coef[4 * (J + 1)], s_coef2[4 * (J + 1)];  // source 0 repeated after source 3
-  __shared__ double s_red[ESTEP_THREADS / 32][NA];
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  typedef typename VecOf<T>::type VT;
-  VT* s_ring = reinterpret_cast<VT*>(s_dyn);  // [ESTEP_DEPTH][NPL][ESTEP_THREADS] vectors
-  VT* s_outv = s_ring + (size_t)ESTEP_DEPTH * NPL * ESTEP_THREADS;  // [J][ESTEP_THREADS] vectors
-  T* so = reinterpret_cast<T*>(s_outv + threadIdx.x);
-  if (threadIdx.x < 4 * (J + 1)) {
-    const double c = coef[(size_t)f * NC + (threadIdx.x & (4 * J - 1))];
-    s_coef[threadIdx.x] = c;
-    s_coef2[threadIdx.x] = (threadIdx.x & 2) ? 2.0 * c : c;
-  }
-  __syncthreads();
-  const double* cf = s_coef + 4 * role;    // R of vr_i at cf[4 i ..]
-  const double* cf2 = s_coef2 + 4 * role;
-  const double s2 = noise[f];
-  T invrank[J];
-  int pofs[J];  // plane of vr_i in a ring slot / in the output tile
-#pragma unroll
-  for (int i = 0; i < J; ++i) {
-    invrank[i] = (T)map.invrank[(i + role) & 3];
-    pofs[i] = ((i + role) & 3) * PS;
-  }
-  const int pshift = role ? -VEC : VEC;  // the partner's vector in a ring plane
-
-  double accS[5][4], accZ[2][4], accV[2];
-#pragma unroll
-  for (int p = 0; p < 5; ++p)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) accS[p][c] = 0.0;
-#pragma unroll
-  for (int p = 0; p < 2; ++p) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) accZ[p][c] = 0.0;
-    accV[p] = 0.0;
-  }
-  double acc_ll = 0.0;
-  int ndead = 0;
-  bool any_clamped = false;
-  double corr[8 * J];  // clamp corrections: thread-local memory, touched by the slow path only
-#pragma unroll 1
-  for (int i = 0; i < 8 * J; ++i) corr[i] = 0.0;
-  auto ll_term = [&](double det) -> double {
-    if (sizeof(T) == 8) return log(det) + kLogPi;
-    return (double)(__logf((float)det) + (float)kLogPi);
-  };
-  auto clamp_correction = [&](const T* sb, int es) {  // as in estep_stereo_kernel, natural order
-    const double a0r = (double)sb[0 * PS + es], a0i = (double)sb[1 * PS + es];
-    const double a1r = (double)sb[2 * PS + es], a1i = (double)sb[3 * PS + es];
-    double vj[J], s00 = s2, s11 = s2, s01r = 0.0, s01i = 0.0;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      vj[j] = (double)sb[(4 + j) * PS + es];
-      s00 += vj[j] * s_coef[4 * j + 0];
-      s11 += vj[j] * s_coef[4 * j + 1];
-      s01r += vj[j] * s_coef[4 * j + 2];
-      s01i += vj[j] * s_coef[4 * j + 3];
-    }
-    const double det_raw = s00 * s11 - s01r * s01r - s01i * s01i;
-    const double idet = fast_rcp(kEps);
-    const double y0r = (s11 * a0r - s01r * a1r + s01i * a1i) * idet;
-    const double y0i = (s11 * a0i - s01r * a1i - s01i * a1r) * idet;
-    const double y1r = (s00 * a1r - s01r * a0r - s01i * a0i) * idet;
-    const double y1i = (s00 * a1i - s01r * a0i + s01i * a0r) * idet;
-    const double k1 = 1.0 - det_raw * idet;
-    const double u[8] = {a0r * y0r + a0i * y0i - 1.0, a0i * y0r - a0r * y0i,
-                         a0r * y1r + a0i * y1i,       a0i * y1r - a0r * y1i,
-                         a1r * y0r + a1i * y0i,       a1i * y0r - a1r * y0i,
-                         a1r * y1r + a1i * y1i - 1.0, a1i * y1r - a1r * y1i};
-#pragma unroll 1
-    for (int j = 0; j < J; ++j) {
-      const double c = k1 * vj[j];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) corr[8 * j + i] += c * u[i];
-    }
-  };
-  // S += w_j w_k M, Z += w M, sv += w for the pairs / sources this role owns (w in role order)
-  auto moments = [&](const double (&w)[J], double m00, double m11, double m01r, double m01i) {
-    const double pr[5] = {w[0] * w[0], w[2] * w[2], w[0] * w[1], w[2] * w[3], w[0] * w[2]};
-#pragma unroll
-    for (int p = 0; p < 5; ++p) {
-      accS[p][0] += pr[p] * m00;
-      accS[p][1] += pr[p] * m11;
-      accS[p][2] += pr[p] * m01r;
-      accS[p][3] += pr[p] * m01i;
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      accZ[p][0] += w[2 * p] * m00;
-      accZ[p][1] += w[2 * p] * m11;
-      accZ[p][2] += w[2 * p] * m01r;
-      accZ[p][3] += w[2 * p] * m01i;
-      accV[p] += w[2 * p];
-    }
-  };
-
-  const long plane = (long)F * ld;
-  const long row = (long)f * ld;
-  const long stride = (long)PS * nsplit;
-  const long first = (long)split * PS + (long)threadIdx.x * VEC;
-  const long end = N;
-  auto ring_issue = [&](long n, int slot) {
-    if (n < end) {
-      VT* dst = s_ring + (size_t)slot * NPL * ESTEP_THREADS + threadIdx.x;
-#pragma unroll
-      for (int pl = 0; pl < 4; ++pl)
-        cp_async16(dst + pl * ESTEP_THREADS, X + pl * plane + row + n, 16);
-#pragma unroll
-      for (int j = 0; j < J; ++j)
-        cp_async16(dst + (4 + j) * ESTEP_THREADS, V + j * plane + row + n, 16);
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int d = 0; d < ESTEP_DEPTH; ++d) ring_issue(first + d * stride, d);
-  int slot = 0;
-  const int rot = (threadIdx.x >> 3) & (VEC - 1);
-  // warp-uniform trip count (the lanes of a pair work together): a lane whose frames lie beyond
-  // the end of the row runs on zero inputs and stores nothing
-  for (long n0 = first; n0 - (long)lane * VEC < end; n0 += stride) {
-    T* sb = reinterpret_cast<T*>(s_ring + (size_t)slot * NPL * ESTEP_THREADS + threadIdx.x);
-    cp_async_wait<ESTEP_DEPTH - 1>();
-    if (n0 + VEC > end) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e)
-        if (n0 + e >= end) {
-#pragma unroll
-          for (int pl = 0; pl < NPL; ++pl) sb[pl * PS + e] = (T)0;
-          ++ndead;
-        }
-    }
-    __syncwarp();  // the partner reads this thread's source powers from the slot
-    const T* sbv = sb + 4 * PS;
-    unsigned cmask = 0;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int es = (e + rot) & (VEC - 1);
-      const double a0r = (double)sb[0 * PS + es];
-      const double a0i = (double)sb[1 * PS + es];
-      const double a1r = (double)sb[2 * PS + es];
-      const double a1i = (double)sb[3 * PS + es];
-      T vt[J];
-      double vj[J], wj[J];
-#pragma unroll
-      for (int i = 0; i < J; ++i) {
-        vt[i] = sbv[pofs[i] + es];
-        vj[i] = (double)vt[i];
-        wj[i] = (double)sbv[pofs[i] + pshift + es];  // the partner's bin, in this role's order
-      }
-      double s00 = s2, s11 = s2, s01r = 0.0, s01i = 0.0;
-#pragma unroll
-      for (int i = 0; i < J; ++i) {
-        s00 += vj[i] * cf[4 * i + 0];
-        s11 += vj[i] * cf[4 * i + 1];
-        s01r += vj[i] * cf[4 * i + 2];
-        s01i += vj[i] * cf[4 * i + 3];
-      }
-      const double det_raw = s00 * s11 - s01r * s01r - s01i * s01i;
-      const bool clamped = fabs(det_raw) < kEps;
-      cmask |= clamped ? (1u << e) : 0u;
-      const double det = clamped ? kEps : det_raw;
-      const double idet = fast_rcp(det);
-      const double y0r = s11 * a0r - s01r * a1r + s01i * a1i;
-      const double y0i = s11 * a0i - s01r * a1i - s01i * a1r;
-      const double y1r = s00 * a1r - s01r * a0r - s01i * a0i;
-      const double y1i = s00 * a1i - s01r * a0i + s01i * a0r;
-      const double p00 = y0r * y0r + y0i * y0i;
-      const double p11 = y1r * y1r + y1i * y1i;
-      const double p01r = y0r * y1r + y0i * y1i;
-      const double p01i = y0i * y1r - y0r * y1i;
-      const double quad = (a0r * y0r + a0i * y0i + a1r * y1r + a1i * y1i) * idet;
-      acc_ll += ll_term(det) + quad;
-      const double m00 = fma(idet, p00, -s11) * idet;
-      const double m11 = fma(idet, p11, -s00) * idet;
-      const double m01r = fma(idet, p01r, s01r) * idet;
-      const double m01i = fma(idet, p01i, s01i) * idet;
-#pragma unroll
-      for (int i = 0; i < J; ++i) {
-        const T q = (T)(cf2[4 * i + 0] * m00 + cf2[4 * i + 1] * m11 + cf2[4 * i + 2] * m01r +
-                        cf2[4 * i + 3] * m01i);
-        so[pofs[i] + es] = pf_abs(vt[i] + vt[i] * vt[i] * (q * invrank[i]));
-      }
-      const double q00 = __shfl_xor_sync(0xffffffffu, m00, 1);
-      const double q11 = __shfl_xor_sync(0xffffffffu, m11, 1);
-      const double q01r = __shfl_xor_sync(0xffffffffu, m01r, 1);
-      const double q01i = __shfl_xor_sync(0xffffffffu, m01i, 1);
-      moments(vj, m00, m11, m01r, m01i);
-      moments(wj, q00, q11, q01r, q01i);
-    }
-    if (n0 < end) {
-#pragma unroll
-      for (int j = 0; j < J; ++j)
-        *reinterpret_cast<VT*>(hatW + j * plane + row + n0) = s_outv[j * ESTEP_THREADS + threadIdx.x];
-    }
-    if (cmask != 0) {
-      any_clamped = true;
-#pragma unroll 1
-      for (int e = 0; e < VEC; ++e)
-        if ((cmask >> e) & 1u) clamp_correction(sb, (e + rot) & (VEC - 1));
-    }
-    __syncwarp();  // the partner is done with this thread's slot
-    ring_issue(n0 + ESTEP_DEPTH * stride, slot);
-    slot = slot + 1 == ESTEP_DEPTH ? 0 : slot + 1;
-  }
-  cp_async_wait<0>();
-  {
-    const double det0 = s2 * s2;
-    acc_ll -= (double)ndead * ll_term(fabs(det0) < kEps ? kEps : det0);
-  }
-
-  // fixed-order reduction: lanes of equal role (xor 2, 4, 8, 16), then over the warps
-  auto role_sum = [&](double v) -> double {
-#pragma unroll
-    for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  };
-  {
-    // pair index (row-major upper triangle) of the role's pairs: role 0: 00 22 01 23 02,
-    // role 1: 11 33 12 03 13
-    const int pidx[5] = {role ? 4 : 0, role ? 9 : 7, role ? 5 : 1, role ? 3 : 8, role ? 6 : 2};
-#pragma unroll
-    for (int p = 0; p < 5; ++p)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double d = role_sum(accS[p][c]);
-        if (lane < 2) s_red[warp][4 * pidx[p] + c] = d;
-      }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double d = role_sum(accZ[p][c]);
-        if (lane < 2) s_red[warp][4 * NP + 4 * (2 * p + role) + c] = d;
-      }
-      const double d = role_sum(accV[p]);
-      if (lane < 2) s_red[warp][4 * NP + 4 * J + 2 * p + role] = d;
-    }
-  }
-  {
-    const double d = warp_sum(acc_ll);
-    if (lane == 0) s_red[warp][NA - 1] = d;
-  }
-  if (__syncthreads_or(any_clamped)) {
-#pragma unroll 1
-    for (int i = 0; i < 8 * J; ++i) {
-      const double d = warp_sum(corr[i]);
-      if (lane == 0) s_red[warp][NM + i] = d;
-    }
-  } else if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8 * J; ++i) s_red[warp][NM + i] = 0.0;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NA; i += ESTEP_THREADS) {
-    double d = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < ESTEP_THREADS / 32; ++w2) d += s_red[w2][i];
-    partial[((size_t)f * nsplit + split) * NA + i] = d;
-  }
-}
-
 // ---- per-frequency contraction with the mixing vectors -------------------------
 // hat_Rss: complex128 [F][R][R], hat_Rxs: complex128 [F][2][R], ll_f: [F]
 // partial: [F][nsplit][ S (4 per pair) | Z (4 per source) | sv (J) | clamp corr. (8 per source) | ll ]
@@ -851,38 +557,9 @@ static int launch_estep(const void* X, const void* V, const double* coef, const 
 }
 
 template <typename T>
-static int launch_estep_pair(const void* X, const void* V, const double* coef, const double* noise,
-                             const SubMap& map, void* hatW, double* partial, int F, long N, long ld,
-                             int nsplit, cudaStream_t st) {
-  dim3 grid(nsplit, F);
-  const size_t smem = (size_t)(ESTEP_DEPTH * (4 + 4) + 4) * ESTEP_THREADS * 16;
-  cudaError_t e = cudaFuncSetAttribute(estep_stereo_pair_kernel<T>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_error("estep_stereo_pair_kernel: %zu bytes of shared memory: %s", smem,
-              cudaGetErrorString(e));
-    return PF_ERR_CUDA;
-  }
-  estep_stereo_pair_kernel<T><<<grid, ESTEP_THREADS, smem, st>>>(
-      (const T*)X, (const T*)V, coef, noise, map, (T*)hatW, partial, F, N, ld, nsplit);
-  return check_launch("estep_stereo_pair_kernel");
-}
-
-// PYFASST_ESTEP_PAIR=0: the one-thread-per-bin kernel for J = 4 as well (A/B measurements)
-static bool estep_pair_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("PYFASST_ESTEP_PAIR");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  return on;
-}
-
-template <typename T>
 static int dispatch_estep(int J, const void* X, const void* V, const double* coef,
                           const double* noise, const SubMap& map, void* hatW, double* partial,
                           int F, long N, long ld, int nsplit, cudaStream_t st) {
-  if (J == 4 && estep_pair_enabled())
-    return launch_estep_pair<T>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
   switch (J) {
     case 1: return launch_estep<T, 1>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
     case 2: return launch_estep<T, 2>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);

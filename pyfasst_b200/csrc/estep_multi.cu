@@ -24,7 +24,7 @@ namespace pf {
 
 constexpr int EM_THREADS = 128;
 #ifndef EM_MINB
-#define EM_MINB 3
+#define EM_MINB 2
 #endif
 constexpr int EM_MAXJ = 6;
 constexpr int EM_MAXR = 24;
@@ -57,6 +57,23 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
 // conj(a) * b
 __device__ __forceinline__ double2 cconjmul(double2 a, double2 b) {
   return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+
+// fused accumulations (4 DFMA each; a separate product + add costs 6 FP64 operations)
+// acc += a * b
+__device__ __forceinline__ void cmac(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc -= a * conj(b)
+__device__ __forceinline__ void cmsubc(double2& acc, double2 a, double2 b) {
+  acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(-a.y, b.x, acc.y); acc.y = fma(a.x, b.y, acc.y);
+}
+// acc += conj(a) * b
+__device__ __forceinline__ void cconjmac(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
 }
 
 // ---- per-frequency coefficients: R_j = sum_{r in j} a_r a_r^H as (diag[I], lower triangle) ----
@@ -237,7 +254,10 @@ __device__ __forceinline__ void sigma_inverse_ldl(const double (&v)[J], const do
   for (int j = 0; j < I; ++j) {
     double d = sd[j];
 #pragma unroll
-    for (int k = 0; k < j; ++k) d -= w[tri(j, k)].x * L[tri(j, k)].x + w[tri(j, k)].y * L[tri(j, k)].y;
+    for (int k = 0; k < j; ++k) {
+      d = fma(-w[tri(j, k)].x, L[tri(j, k)].x, d);
+      d = fma(-w[tri(j, k)].y, L[tri(j, k)].y, d);
+    }
     d = fmax(d, 1e-30);  // Sigma is positive definite (s2 > 0); guards rounding only
     det *= d;
     r[j] = fast_rcp(d);
@@ -245,30 +265,25 @@ __device__ __forceinline__ void sigma_inverse_ldl(const double (&v)[J], const do
     for (int i = j + 1; i < I; ++i) {
       double2 a = w[tri(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; ++k) {
-        const double2 p = cmulc(w[tri(i, k)], L[tri(j, k)]);
-        a.x -= p.x;
-        a.y -= p.y;
-      }
+      for (int k = 0; k < j; ++k) cmsubc(a, w[tri(i, k)], L[tri(j, k)]);
       w[tri(i, j)] = a;
       L[tri(i, j)] = make_double2(a.x * r[j], a.y * r[j]);
     }
   }
-  // Li = L^-1 (unit lower), G = D^-1 Li (strictly lower part)
+  // nLi = -L^-1 (strictly lower part), G = D^-1 L^-1 (strictly lower part)
   double2 Li[NT + 1], G[NT + 1];
 #pragma unroll
   for (int j = 0; j < I; ++j) {
 #pragma unroll
     for (int i = j + 1; i < I; ++i) {
-      double2 a = L[tri(i, j)];
+      double2 a = make_double2(-L[tri(i, j)].x, -L[tri(i, j)].y);
 #pragma unroll
-      for (int k = j + 1; k < i; ++k) {
-        const double2 p = cmul(L[tri(i, k)], Li[tri(k, j)]);
-        a.x += p.x;
-        a.y += p.y;
+      for (int k = j + 1; k < i; ++k) {  // a -= L[i][k] Li[k][j]
+        a.x = fma(-L[tri(i, k)].x, Li[tri(k, j)].x, a.x); a.x = fma(L[tri(i, k)].y, Li[tri(k, j)].y, a.x);
+        a.y = fma(-L[tri(i, k)].x, Li[tri(k, j)].y, a.y); a.y = fma(-L[tri(i, k)].y, Li[tri(k, j)].x, a.y);
       }
-      Li[tri(i, j)] = make_double2(-a.x, -a.y);
-      G[tri(i, j)] = make_double2(-a.x * r[i], -a.y * r[i]);
+      Li[tri(i, j)] = a;
+      G[tri(i, j)] = make_double2(a.x * r[i], a.y * r[i]);
     }
   }
   // Sigma^-1[i][j] = sum_{k >= i} conj(Li[k][i]) G[k][j], Li[k][k] = 1
@@ -276,17 +291,16 @@ __device__ __forceinline__ void sigma_inverse_ldl(const double (&v)[J], const do
   for (int i = 0; i < I; ++i) {
     double d = r[i];
 #pragma unroll
-    for (int k = i + 1; k < I; ++k) d += Li[tri(k, i)].x * G[tri(k, i)].x + Li[tri(k, i)].y * G[tri(k, i)].y;
+    for (int k = i + 1; k < I; ++k) {
+      d = fma(Li[tri(k, i)].x, G[tri(k, i)].x, d);
+      d = fma(Li[tri(k, i)].y, G[tri(k, i)].y, d);
+    }
     sid[i] = d;
 #pragma unroll
     for (int j = 0; j < i; ++j) {
       double2 a = G[tri(i, j)];
 #pragma unroll
-      for (int k = i + 1; k < I; ++k) {
-        const double2 p = cconjmul(Li[tri(k, i)], G[tri(k, j)]);
-        a.x += p.x;
-        a.y += p.y;
-      }
+      for (int k = i + 1; k < I; ++k) cconjmac(a, Li[tri(k, i)], G[tri(k, j)]);
       sio[tri(i, j)] = a;
     }
   }
@@ -297,23 +311,16 @@ __device__ __forceinline__ void sigma_inverse_ldl(const double (&v)[J], const do
   for (int i = 0; i < I; ++i) {
     double2 a = x[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) {
-      const double2 p = cmul(Li[tri(i, k)], x[k]);
-      a.x += p.x;
-      a.y += p.y;
-    }
+    for (int k = 0; k < i; ++k) cmac(a, Li[tri(i, k)], x[k]);
     tt[i] = make_double2(a.x * r[i], a.y * r[i]);
-    quad += a.x * tt[i].x + a.y * tt[i].y;
+    quad = fma(a.x, tt[i].x, quad);
+    quad = fma(a.y, tt[i].y, quad);
   }
 #pragma unroll
   for (int i = 0; i < I; ++i) {
     double2 a = tt[i];
 #pragma unroll
-    for (int k = i + 1; k < I; ++k) {
-      const double2 p = cconjmul(Li[tri(k, i)], tt[k]);
-      a.x += p.x;
-      a.y += p.y;
-    }
+    for (int k = i + 1; k < I; ++k) cconjmac(a, Li[tri(k, i)], tt[k]);
     y[i] = a;
   }
   detc = det;
@@ -415,6 +422,17 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
   const long begin = (long)split * chunk;
   long end = begin + chunk;
   if (end > N) end = N;
+  // the inputs of the next pass are loaded before the algebra of the current one (the kernel is
+  // latency bound otherwise: 3 warps per scheduler, ~1500 cycles of dependent FP64 per pass)
+  T vt_n[J], xt_n[2 * I];
+  auto fetch = [&](long n) {
+    const bool ok = n < end;
+#pragma unroll
+    for (int j = 0; j < J; ++j) vt_n[j] = ok ? V[j * plane + row + n] : (T)0;
+#pragma unroll
+    for (int i = 0; i < 2 * I; ++i) xt_n[i] = ok ? X[i * plane + row + n] : (T)0;
+  };
+  fetch(begin + warp * 32 + lane);
   for (long n0 = begin + warp * 32; n0 < end; n0 += EM_THREADS) {  // warp-uniform trip count
     const long n = n0 + lane;
     const bool live = n < end;
@@ -423,28 +441,28 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
     double2 x[I];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      vt[j] = live ? V[j * plane + row + n] : (T)0;
+      vt[j] = vt_n[j];
       v[j] = (double)vt[j];
     }
 #pragma unroll
-    for (int i = 0; i < I; ++i)
-      x[i] = live ? make_double2((double)X[(2 * i) * plane + row + n],
-                                 (double)X[(2 * i + 1) * plane + row + n])
-                  : make_double2(0.0, 0.0);
+    for (int i = 0; i < I; ++i) x[i] = make_double2((double)xt_n[2 * i], (double)xt_n[2 * i + 1]);
+    fetch(n + EM_THREADS);
     double2 y[I], sio[NT + 1];
     double sid[I], detc, quad, sc;
     sigma_inverse_ldl<I, J>(v, x, s_coef, s2, y, sid, sio, detc, quad, sc);
-    if (live) acc_ll += log(detc) + 1.1447298858494002 + quad;  // Q4: log(det * pi)
+    // Q4: log(det * pi); float32 planes take the float logarithm as the stereo kernel does
+    if (live)
+      acc_ll += (sizeof(T) == 8 ? log(detc) : (double)__logf((float)detc)) + 1.1447298858494002 + quad;
     // M = y y^H - Sigma^-1 (diag + lower triangle), straight into the warp's tile
     double md[I];
     double2 mo[NT + 1];
 #pragma unroll
     for (int i = 0; i < I; ++i) {
-      md[i] = y[i].x * y[i].x + y[i].y * y[i].y - sid[i];
+      md[i] = fma(y[i].x, y[i].x, fma(y[i].y, y[i].y, -sid[i]));
 #pragma unroll
-      for (int k = 0; k < i; ++k) {
-        const double2 p = cmulc(y[i], y[k]);
-        mo[tri(i, k)] = make_double2(p.x - sio[tri(i, k)].x, p.y - sio[tri(i, k)].y);
+      for (int k = 0; k < i; ++k) {  // y_i conj(y_k) - Sigma^-1_ik
+        mo[tri(i, k)].x = fma(y[i].x, y[k].x, fma(y[i].y, y[k].y, -sio[tri(i, k)].x));
+        mo[tri(i, k)].y = fma(y[i].y, y[k].x, fma(-y[i].x, y[k].y, -sio[tri(i, k)].y));
       }
     }
     {
@@ -472,11 +490,14 @@ estep_multi_kernel(const T* __restrict__ X, const T* __restrict__ V,
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const double* c = s_coef2 + j * NM;
-      double q = 0.0, q2 = 0.0;
+      double q = 0.0, q2 = 0.0;  // two chains
 #pragma unroll
-      for (int i = 0; i < I; ++i) q += md[i] * c[i];
+      for (int i = 0; i < I; ++i) q = fma(md[i], c[i], q);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) q2 += mo[t].x * c[I + 2 * t] + mo[t].y * c[I + 2 * t + 1];
+      for (int t = 0; t < NT; ++t) {
+        q2 = fma(mo[t].x, c[I + 2 * t], q2);
+        q2 = fma(mo[t].y, c[I + 2 * t + 1], q2);
+      }
       const T qf = (T)(q + q2);
       if (live) hatW[j * plane + row + n] = pf_abs(vt[j] + vt[j] * vt[j] * (qf * invrank[j]));
     }

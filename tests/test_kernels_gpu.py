@@ -111,7 +111,7 @@ def test_estep_stereo(ck, fk, dt, F, N, J, rank, consistent):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("J", [3, 4])  # J = 4: the lane-pair kernel
+@pytest.mark.parametrize("J", [3, 4])
 def test_estep_stereo_determinant_clamp(ck, fk, dt, J):
     """Quiet rows: det Sigma < 1e-10 activates the reference's clamp (signalTools.py:183-188), where
     Sigma_c^-1 is not the inverse of Sigma and the kernel's identity for x y^H needs its correction

@@ -64,7 +64,9 @@ def test_estep_multi(ck, dt, I, F, N, J, rank):
     t = tol(dt, f64=1e-9, f32=1e-9)  # the moments are float64 whatever the plane type
     assert rel(rss1, rss0) < t
     assert rel(rxs1, rxs0) < t
-    assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-11, f32=1e-6))
+    # float32 planes take the float logarithm (as the stereo kernel): ~1e-6 absolute per bin
+    assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-11, f32=1e-6),
+                    atol=0.0 if dt == torch.float64 else 1e-6 * N)
     assert_allclose(rss1, np.conj(np.transpose(rss1, (0, 2, 1))), atol=1e-14 * np.abs(rss1).max())
 
 
@@ -102,7 +104,8 @@ def test_estep_multi_determinant_clamp(ck, dt, I, J, rank):
         assert rel(hw1[:, f, :N], hw0[:, f, :N]) < tol(dt, f64=1e-7, f32=1e-5), f
         assert rel(rss1[f], rss0[f]) < 1e-7, f
         assert rel(rxs1[f], rxs0[f]) < 1e-7, f
-    assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-10, f32=1e-6))
+    assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-10, f32=1e-6),
+                    atol=0.0 if dt == torch.float64 else 1e-6 * N)
 
 
 @pytest.mark.parametrize("dt", DTYPES)
