@@ -156,18 +156,20 @@ CPU_CROP_S = 8.0   # crop of the synthetic mixture the CPU arms run on (both of 
 CPU_ITERS, CPU_WARM = 5, 1  # in-line cpu_baseline; `--impl reference` takes --steps / --warmup
 
 
-def oracle_model(pcm, iters):
+def oracle_model(pcm, iters, nsrc=NSRC, nnmf=NNMF, rank=RANK):
     from oracle import fasst_oracle as fo
     maxdata = np.maximum(1.1 * np.abs(pcm).max(), 1e-10)
     np.random.seed(0)
-    return fo.OracleFASST((FS, pcm / maxdata, maxdata), nbComps=NSRC, nbNMFComps=NNMF,
-                          spatial_rank=RANK, wlen=WLEN, hopsize=HOP, iter_num=iters)
+    return fo.OracleFASST((FS, pcm / maxdata, maxdata), nbComps=nsrc, nbNMFComps=nnmf,
+                          spatial_rank=rank, wlen=WLEN, hopsize=HOP, iter_num=iters)
 
 
-def cpu_gem_rate(crop_s, iters, warm=0):
+def cpu_gem_rate(crop_s, iters, warm=0, workload="configs1"):
     """TF-bins*iters/s of the oracle (reference algorithm, NumPy float64) on a crop."""
-    pcm = synth_mix(crop_s)
-    m = oracle_model(pcm, iters + warm)
+    if workload == "tamy":  # configs[0] is the reference's own CPU-runnable case: the whole file
+        m = oracle_model(tamy_pcm(), iters + warm, 3, 4, 1)
+    else:
+        m = oracle_model(synth_mix(crop_s), iters + warm)
     bins = m.nbFreqsSigRepr * m.nbFramesSigRepr
     for _ in range(warm):
         m.GEM_iteration()
@@ -196,17 +198,17 @@ def run_reference(args, rank):
         return
     crop_s = args.cpu_crop_s
     cores = host_threads()
-    rate, bins, dt = cpu_gem_rate(crop_s, args.steps, args.warmup)
+    rate, bins, dt = cpu_gem_rate(crop_s, args.steps, args.warmup, args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": data_kind(args),
         "config": workload_config(args, note="CPU arm: the oracle (NumPy restatement of the "
-                                  "reference's GEM_iteration, float64) on a %.1f s crop of "
-                                  "the same synthetic mixture (%d TF bins per step); the "
-                                  "reference itself is Python 2 and cannot be run" %
-                                  (crop_s, bins)),
+                                  "reference's GEM_iteration, float64) on %s (%d TF bins per "
+                                  "step); the reference itself is Python 2 and cannot be run" %
+                                  ("the whole file" if args.workload == "tamy" else
+                                   "a %.1f s crop of the same synthetic mixture" % crop_s, bins)),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d GEM iterations on a %.1f s crop (%d bins), NumPy "
                                    "float64, BLAS threads = %d" % (args.steps, crop_s, bins, cores)},
@@ -217,6 +219,19 @@ def run_reference(args, rank):
 
 
 def workload_config(args, note=None):
+    if getattr(args, "workload", "configs1") == "tamy":
+        L = tamy_pcm().shape[0]
+        cfg = {"workload": "configs[0]: data/tamy.wav (the reference's fixture, %.1f s stereo 44.1 kHz), "
+                           "MultiChanNMFInst_FASST 3 sources x K=4, spatial rank 1, STFT %d/hop %d; "
+                           "one step = one GEM iteration" % (L / float(FS), WLEN, HOP),
+               "channels": 2, "F": WLEN // 2 + 1, "N": n_frames(L),
+               "tf_bins": (WLEN // 2 + 1) * n_frames(L), "sources": 3, "nmf_comps": 4,
+               "spatial_rank": 1, "sharding": "none (one GPU)",
+               "l2": "the whole problem (14 planes x 4.6 MB) is L2 resident: an iteration of this "
+                     "size is bound by its ~60 launches, not by HBM"}
+        if note:
+            cfg["note"] = note
+        return cfg
     blocks = getattr(args, "blocks", 1)
     L = int(round(args.duration_s * FS)) * args.gpus * blocks
     model = "MultiChanNMFConv (convolutive mixing)" if getattr(args, "model", "inst") == "conv" \
@@ -244,6 +259,19 @@ def workload_config(args, note=None):
     return cfg
 
 
+def data_kind(args):
+    return "tests/golden/tamy.wav (copy of the reference's data/tamy.wav)" \
+        if args.workload == "tamy" else "synthetic"
+
+
+def tamy_pcm():
+    """int16 PCM of the reference's own fixture (committed copy: tests/golden/tamy.wav)."""
+    from scipy.io import wavfile
+    fs, pcm = wavfile.read(os.path.join(ROOT, "tests", "golden", "tamy.wav"))
+    assert fs == FS and pcm.ndim == 2 and pcm.shape[1] == 2
+    return np.ascontiguousarray(pcm)
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, world):
     import torch
@@ -265,7 +293,9 @@ def run_ours(args, rank, world):
 
     # N = 1: the 10-min mixture of configs[1].  N > 1: weak scaling -- the mixture is N such
     # blocks back to back (one per GPU) and its frames are sharded over the ranks.
-    block = synth_mix(args.duration_s, channels=args.channels)
+    tamy = args.workload == "tamy"
+    nsrc, nnmf = (3, 4) if tamy else (NSRC, NNMF)
+    block = tamy_pcm() if tamy else synth_mix(args.duration_s, channels=args.channels)
     # (--blocks B: B such blocks per GPU, e.g. --duration-s 450 --blocks 8 on one GPU is the
     # same 1-hour mixture as --duration-s 450 on 8 GPUs: strong-scaling pairs)
     reps = world * args.blocks
@@ -285,7 +315,7 @@ def run_ours(args, rank, world):
     def make_model(iters, raw=None):
         np.random.seed(0)
         cls = am.MultiChanNMFConv if args.model == "conv" else am.MultiChanNMFInst_FASST
-        m = cls(audio=make_audio(pcm if raw is None else raw), nbComps=NSRC, nbNMFComps=NNMF,
+        m = cls(audio=make_audio(pcm if raw is None else raw), nbComps=nsrc, nbNMFComps=nnmf,
                 spatial_rank=args.rank, wlen=WLEN, hopsize=HOP, iter_num=iters,
                 ann_PSD_lim=[None, None], compute_dtype=dtype, comm=comm, shard=args.shard)
         if args.model == "conv":
@@ -397,7 +427,7 @@ def run_ours(args, rank, world):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     sz = 4 if args.dtype == "f32" else 8
     # 2 I reals of x (Cx = x x^H is rank one; = I^2 at I = 2) + V_j + hat_W_j
-    bytes_per_bin = sz * (2 * args.channels + 2 * NSRC)
+    bytes_per_bin = sz * (2 * args.channels + 2 * nsrc)
     local_bins = bins / float(world)  # frames are split evenly over the ranks
     achieved = bytes_per_bin * local_bins / (estep_ms * 1e-3) / 1e9
     traffic = args.traffic
@@ -418,7 +448,7 @@ def run_ours(args, rank, world):
     if world == 1 and not args.no_cpu_baseline and args.channels == 2:
         cores = host_threads()
         # the same sample as `--impl reference`: the same crop, warm iterations first
-        rate, cbins, cdt = cpu_gem_rate(args.cpu_crop_s, CPU_ITERS, CPU_WARM)
+        rate, cbins, cdt = cpu_gem_rate(args.cpu_crop_s, CPU_ITERS, CPU_WARM, args.workload)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d GEM iterations (after %d warm) of the oracle (NumPy float64 "
                          "restatement of the reference) on a %.1f s crop (%d bins, %.1f s), "
@@ -428,7 +458,7 @@ def run_ours(args, rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": data_kind(args),
         "config": workload_config(args), "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "phases_ms": phases, "loglik_last": float(final_ll[total_iters - 1]),
@@ -462,6 +492,11 @@ def main():
     ap.add_argument("--rank", type=int, default=RANK, help="spatial rank of every source")
     ap.add_argument("--shard", default="time", choices=["time", "freq"],
                     help="multi-GPU partition: frames (default) or frequency bins")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "tamy", "simm"],
+                    help="configs1 (default): BASELINE configs[1], the 10-min synthetic stereo "
+                         "mixture; tamy: configs[0], the reference's data/tamy.wav, 3 sources, "
+                         "rank 1 (one GPU); simm: configs[2], Stereo_SIMM with the 480-pitch "
+                         "dictionary (scripts/bench_simm.py, one GPU)")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per E-step launch from the committed ncu capture")
     args = ap.parse_args()
@@ -469,6 +504,21 @@ def main():
         args.warmup = 3
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.workload == "simm":  # configs[2]: its own script, the same JSON schema
+        if rank == 0:
+            sys.argv = [os.path.join(ROOT, "scripts", "bench_simm.py"), "--steps", str(args.steps),
+                        "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_simm
+            bench_simm.main()
+        return
+    if args.workload == "tamy":
+        args.rank = 1
+        if world != 1:
+            sys.stderr.write("bench.py: --workload tamy runs on one GPU (rank 0)\n")
+            if rank != 0:
+                return
+            world = args.gpus = 1
     if args.cpu_crop_s is None:
         args.cpu_crop_s = CPU_CROP_S  # one crop for both CPU arms
     if args.impl == "reference":

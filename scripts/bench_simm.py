@@ -86,7 +86,8 @@ def main():
     finite = all(np.isfinite(np.asarray(v)).all() for v in r.values())
     bins = F * N
     line = {"metric": "simm_tf_bins_iters_per_s", "value": bins / (ms * 1e-3),
-            "unit": "TF-bins*iters/s", "ms_per_step": ms, "steps": args.steps,
+            "unit": "TF-bins*iters/s", "n_gpus": 1, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "data": "synthetic", "ms_per_step": ms, "steps": args.steps,
             "warmup": args.warmup, "dtype": "f32 (3xTF32 tensor-core products)",
             "config": {"workload": "configs[2]: Stereo_SIMM, F=%d N=%d NF0=%d P=%d K=%d R=%d"
                                    % (F, N, NF0, P, K, R), "tf_bins": bins},
