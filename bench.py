@@ -283,7 +283,10 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(local_rank)
     comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # (NCCL's own stream at high priority: the collectives of the frequency partition overlap
+        # the contraction kernels of the next component, which fill the GPU)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
         comm = Comm()
 
     def barrier():

@@ -55,6 +55,12 @@ unsigned long long pf_launch_count(void);
  * with the device the tensors live on). */
 int pf_set_device(int device);
 
+/* Strided 2-D copy between host and device (direction inferred from the pointers): `height` rows of
+ * `width_bytes` bytes, pitches in bytes; complete on return.  Moves a rank's column range of a
+ * user-visible parameter matrix (audioModel.py:1573, :1725 update those arrays in place). */
+int pf_copy_2d(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
+               int64_t height, void* stream);
+
 /* ---- K1: STFT front end  (tftransforms/stft.py:3-69, audioModel.py:250-328) --- */
 /* Framing + window + real FFT of `nch` channels in one launch.
  * pcm     : the samples in the layout the host has them in (pcm_format):
@@ -203,6 +209,12 @@ int pf_nmf_tw_contract(const void* hatW, const void* O, int64_t ld, const void* 
                        const void* H, int64_t ldh, int F, int K, int64_t N, double* num_partial,
                        double* den_partial, int64_t ldo, int fchunk, int fsplit,
                        void* scratch_plane, int dtype, void* stream);
+/* Frequency-sharded TW update (the K x N numerators / denominators are the one large
+ * exchange of the frequency partition): out[w][q][k][i] = sum_s part_q[s][k][w c + i], c = ld / world,
+ * q = 0 num / 1 den, in the plane type -- the chunk-major input of the reduce-scatter over frames. */
+int pf_tw_pack_chunks(const double* num_partial, const double* den_partial, int nsplit,
+                      int64_t split_stride, int K, int64_t ld, int world, int Kmax, void* out,
+                      int dtype, void* stream);
 /* out[i] = sum_s in[s][i] in a fixed order */
 int pf_sum_splits(const double* in, int nsplit, int64_t count, double* out, void* stream);
 /* theta[r][c] *= (num[r][c] / max(den[r][c], 1e-10))^omega (audioModel.py:1573,:1725) */

@@ -24,6 +24,7 @@ c_ip = ctypes.POINTER(ctypes.c_int)
 # name -> argument ctypes (return type is int unless listed in _RESTYPE)
 SIGNATURES = {
     "pf_last_error": [],
+    "pf_copy_2d": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "pf_abi_version": [],
     "pf_launch_count": [],
     "pf_set_device": [c_int],
@@ -58,6 +59,7 @@ SIGNATURES = {
     "pf_nmf_tw_contract": [c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_i64, c_vp,
                            c_vp, c_i64, c_int, c_int, c_vp, c_int, c_vp],
     "pf_sum_splits": [c_vp, c_int, c_i64, c_vp, c_vp],
+    "pf_tw_pack_chunks": [c_vp, c_vp, c_int, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_int, c_vp],
     "pf_mult_update": [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_i64, c_dbl, c_int, c_vp],
     "pf_mult_update_splits": [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_i64, c_dbl,
                               c_int, c_vp],
@@ -183,6 +185,24 @@ class CudaKernels(object):
         _check(self.lib.pf_set_device(self.device.index), self.lib)
 
     # -- helpers ----------------------------------------------------------------
+    def copy_cols_to_device(self, host, lo, hi, dev_t):
+        """dev_t [rows, hi - lo] (contiguous, dtype of `host`) <- host[:, lo:hi] of a C-contiguous
+        2-D host array: one strided DMA, no host-side temporary."""
+        rows, isz = host.shape[0], host.itemsize
+        assert host.flags.c_contiguous and dev_t.is_contiguous() and dev_t.element_size() == isz
+        _check(self.lib.pf_copy_2d(dev_t.data_ptr(), (hi - lo) * isz,
+                                   host.ctypes.data + lo * isz, host.shape[1] * isz,
+                                   (hi - lo) * isz, rows, self._stream()), self.lib)
+
+    def copy_cols_to_host(self, dev_t, host, lo, hi):
+        """host[:, lo:hi] <- dev_t [rows, hi - lo] (contiguous, dtype of `host`)."""
+        rows, isz = host.shape[0], host.itemsize
+        assert host.flags.c_contiguous and host.flags.writeable and dev_t.is_contiguous() \
+            and dev_t.element_size() == isz
+        _check(self.lib.pf_copy_2d(host.ctypes.data + lo * isz, host.shape[1] * isz,
+                                   dev_t.data_ptr(), (hi - lo) * isz, (hi - lo) * isz, rows,
+                                   self._stream()), self.lib)
+
     def _p(self, t):
         if t is None:
             return None
@@ -357,6 +377,14 @@ class CudaKernels(object):
                                            num_partial.shape[-1], fchunk, fsplit,
                                            self._p(scratch), self.dtype_code(hatW),
                                            self._stream()), self.lib)
+
+    def tw_pack_chunks(self, num_partial, den_partial, out, world):
+        """out [world, 2, Kmax, c] (plane type) <- the split sums of num/den_partial [nsplit, K, ld]."""
+        nsplit, K, ld = num_partial.shape
+        _check(self.lib.pf_tw_pack_chunks(self._p(num_partial), self._p(den_partial), nsplit,
+                                          num_partial.stride(0), K, ld, world, out.shape[2],
+                                          self._p(out), self.dtype_code(out), self._stream()),
+               self.lib)
 
     def sum_splits(self, parts, out):
         nsplit = parts.shape[0]

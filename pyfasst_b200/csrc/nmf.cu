@@ -487,6 +487,28 @@ __global__ void sum_splits_kernel(const double* __restrict__ in, int nsplit, lon
   out[i] = d;
 }
 
+// Frequency sharding: the split partial sums of the TW numerators / denominators, reduced in a
+// fixed order, converted to the plane type and laid out chunk-major for the reduce-scatter over
+// the frames:  out[w][q][k][i] = sum_s part_q[s][k][w c + i]  (q = 0 num, 1 den; c = ld / world;
+// k < K of Kmax rows).  One launch instead of two sum_splits and a strided copy.
+template <typename T>
+__global__ void tw_pack_chunks_kernel(const double* __restrict__ num, const double* __restrict__ den,
+                                      int nsplit, long split_stride, int K, long ld, long c,
+                                      int Kmax, T* __restrict__ out) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (n >= ld) return;
+  double sn = 0.0, sd = 0.0;
+  for (int s = 0; s < nsplit; ++s) {
+    sn += num[(size_t)s * split_stride + (size_t)k * ld + n];
+    sd += den[(size_t)s * split_stride + (size_t)k * ld + n];
+  }
+  const long w = n / c, i = n - w * c;
+  T* o = out + ((size_t)w * 2 * Kmax + k) * c + i;
+  o[0] = (T)sn;
+  o[(size_t)Kmax * c] = (T)sd;
+}
+
 // theta[r][c] *= (num/max(den, eps))^omega over a rows x cols view (:1573, :1725)
 template <typename T>
 __global__ void mult_update_kernel(T* __restrict__ theta, long ldt, const double* __restrict__ num,
@@ -798,6 +820,23 @@ extern "C" int pf_nmf_tw_contract(const void* hatW, const void* O, int64_t ld, c
                               den_partial, ldo, st);
   return dispatch_tw<double>(hatW, O, ld, W, ldw, H, ldh, K, F, N, fchunk, fsplit, num_partial,
                              den_partial, ldo, st);
+}
+
+extern "C" int pf_tw_pack_chunks(const double* num_partial, const double* den_partial, int nsplit,
+                                 int64_t split_stride, int K, int64_t ld, int world, int Kmax,
+                                 void* out, int dtype, void* stream) {
+  PF_REQUIRE(nsplit >= 1 && K >= 1 && K <= Kmax && world >= 1 && ld > 0 && ld % world == 0,
+             "pf_tw_pack_chunks: nsplit=%d K=%d Kmax=%d ld=%ld world=%d", nsplit, K, Kmax, (long)ld,
+             world);
+  PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_tw_pack_chunks: bad dtype %d", dtype);
+  dim3 grid(ceil_div(ld, 256), K);
+  if (dtype == PF_F32)
+    tw_pack_chunks_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+        num_partial, den_partial, nsplit, split_stride, K, ld, ld / world, Kmax, (float*)out);
+  else
+    tw_pack_chunks_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
+        num_partial, den_partial, nsplit, split_stride, K, ld, ld / world, Kmax, (double*)out);
+  return check_launch("tw_pack_chunks_kernel");
 }
 
 extern "C" int pf_sum_splits(const double* in, int nsplit, int64_t count, double* out,

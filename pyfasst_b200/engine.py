@@ -174,6 +174,17 @@ class GemEngine(object):
             t = t.to(dtype)
         return t.contiguous()
 
+    def _upload_cols(self, arr, lo, hi, dtype):
+        """arr[:, lo:hi] of a 2-D host array -> new device tensor: a proper column range (the
+        frames of one rank) goes as ONE strided DMA instead of a host-side gather."""
+        if self.dev.type == "cuda" and (lo > 0 or hi < arr.shape[1]) and arr.flags.c_contiguous \
+                and hasattr(self.k, "copy_cols_to_device"):
+            t = self.torch.empty((arr.shape[0], hi - lo), device=self.dev,
+                                 dtype=self.torch.from_numpy(arr[:1, :1]).dtype)
+            self.k.copy_cols_to_device(arr, lo, hi, t)
+            return t if t.dtype == dtype else t.to(dtype)
+        return self._upload(arr[:, lo:hi], dtype)
+
     def _f64(self, arr):
         return self._upload(np.asarray(arr, dtype=np.float64))
 
@@ -305,7 +316,7 @@ class GemEngine(object):
                                  % (FB.shape, FW.shape, TW.shape))
             Kb, Kw = FW.shape
             TWd = self._zeros([Kw, self.ld])
-            TWd[:, :self.N] = self._upload(TW[:, self.n_lo:self.n_hi], self.tdtype)
+            TWd[:, :self.N] = self._upload_cols(TW, self.n_lo, self.n_hi, self.tdtype)
             ent = {
                 "j": owner[s], "Kb": Kb, "Kw": Kw,
                 "FB_free": fac["FB_frdm_prior"] == "free",
@@ -403,9 +414,6 @@ class GemEngine(object):
             self.tw_rs_in = self._zeros([S, world, 2, Kmax, c])
             self.tw_rs_out = self._zeros([S, 2, Kmax, c])
             self.tw_ag = self._zeros([S, world, Kmax, c])
-            self.tw_nd = self._zeros([S, 2, Kmax, ld], f64)
-        else:
-            self.tw_nd = None
 
     # ------------------------------------------------------------------ pieces
     def compute_powers(self, with_G=True):
@@ -501,24 +509,49 @@ class GemEngine(object):
             k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit,
                           None if self.scratch is None else self.scratch[s])
             if self._fshard():
-                Kw, world, rank = e["Kw"], self.comm.world, self.comm.rank
-                c = self.ld // world
-                k.sum_splits(pn, self.tw_nd[s, 0, :Kw])
-                k.sum_splits(pd, self.tw_nd[s, 1, :Kw])
-                # chunk-major copy in the plane type: [2, Kw, world, c] -> [world, 2, Kw, c]
-                self.tw_rs_in[s, :, :, :Kw].copy_(
-                    self.tw_nd[s, :, :Kw].view(2, Kw, world, c).permute(2, 0, 1, 3))
-                self.comm.reduce_scatter_sum(self.tw_rs_out[s], self.tw_rs_in[s])
-                # this rank's frames of TW (padding frames: 0 * (0 / eps) = 0)
-                chunk = e["TW"][:, rank * c:(rank + 1) * c]
-                k.mult_update_same(chunk, self.tw_rs_out[s, 0, :Kw], self.tw_rs_out[s, 1, :Kw],
-                                   Kw, c, self.omega)
-                self.tw_ag[s, rank, :Kw].copy_(chunk)
-                self.comm.allgather_into(self.tw_ag[s], self.tw_ag[s, rank])
-                e["TW"].view(Kw, world, c).copy_(self.tw_ag[s, :, :Kw].permute(1, 0, 2))
+                self._tw_exchange(s, e, pn, pd)
             else:  # reduce the frequency splits inside the update kernel
                 k.mult_update_splits(e["TW"], pn, pd, e["Kw"], N, self.omega)
         self._for_each(tw, tw_sums)
+        if tw and self._fshard() and self._use_streams:
+            self.torch.cuda.current_stream(self.dev).wait_stream(self._exchange_stream())
+
+    def _exchange_stream(self):
+        """High-priority stream of the frequency partition's TW exchange: the chain of component s
+        (pack, reduce-scatter, update, all-gather, unpack) starts as soon as its contraction is
+        done and its small kernels get SM slots ahead of the CTAs of the next component's
+        contraction, which fills the GPU."""
+        if getattr(self, "_xstream", None) is None:
+            self._xstream = self.torch.cuda.Stream(device=self.dev, priority=-1)
+        return self._xstream
+
+    def _tw_exchange(self, s, e, pn, pd):
+        """Frequency partition: sum over the ranks of the TW numerators / denominators as a
+        reduce-scatter over the FRAMES (plane type, fixed order), shard-local multiplicative
+        update, all-gather of the updated TW."""
+        k = self.k
+        Kw, world, rank = e["Kw"], self.comm.world, self.comm.rank
+        c = self.ld // world
+
+        def chain():
+            # split sums -> plane type, chunk-major [world, 2, Kmax, c]: one kernel
+            k.tw_pack_chunks(pn, pd, self.tw_rs_in[s], world)
+            self.comm.reduce_scatter_sum(self.tw_rs_out[s], self.tw_rs_in[s])
+            # this rank's frames of TW (padding frames: 0 * (0 / eps) = 0)
+            chunk = e["TW"][:, rank * c:(rank + 1) * c]
+            k.mult_update_same(chunk, self.tw_rs_out[s, 0, :Kw], self.tw_rs_out[s, 1, :Kw],
+                               Kw, c, self.omega)
+            self.tw_ag[s, rank, :Kw].copy_(chunk)
+            self.comm.allgather_into(self.tw_ag[s], self.tw_ag[s, rank])
+            e["TW"].view(Kw, world, c).copy_(self.tw_ag[s, :, :Kw].permute(1, 0, 2))
+        if not self._use_streams:
+            chain()
+            return
+        torch = self.torch
+        xs = self._exchange_stream()
+        xs.wait_stream(torch.cuda.current_stream(self.dev))  # (the component's side stream)
+        with torch.cuda.stream(xs):
+            chain()
 
     def renormalize(self):
         """renormalize_parameters (audioModel.py:1980-2040)."""
@@ -744,7 +777,10 @@ class GemEngine(object):
             old = np.array(old, dtype=np.float64) if np.shape(old) == tuple(full_shape) \
                 else np.zeros(full_shape)
         view = old[lo:hi] if axis == 0 else old[:, lo:hi]
-        if t.is_cuda:
+        if t.is_cuda and axis == 1 and old.ndim == 2 and old.flags.c_contiguous \
+                and t.dtype == self.torch.float64 and hasattr(self.k, "copy_cols_to_host"):
+            self.k.copy_cols_to_host(t.contiguous(), old, lo, hi)  # one strided DMA
+        elif t.is_cuda:
             self.torch.from_numpy(view).copy_(t)
         else:
             view[...] = t.numpy()

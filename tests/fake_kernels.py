@@ -372,6 +372,15 @@ class FakeKernels(object):
         _np(num_partial)[0, :, :N] = np.dot(Wn.T.astype(np.float64), e1.astype(np.float64))
         _np(den_partial)[0, :, :N] = np.dot(Wn.T.astype(np.float64), e2.astype(np.float64))
 
+    def tw_pack_chunks(self, num_partial, den_partial, out, world):
+        self.launches += 1
+        o = _np(out)
+        nsplit, K, ld = num_partial.shape
+        c = ld // world
+        for q, part in enumerate((num_partial, den_partial)):
+            tot = _np(part).sum(0)                                   # [K, ld]
+            o[:, q, :K] = tot.reshape(K, world, c).transpose(1, 0, 2)
+
     def sum_splits(self, parts, out):
         self.launches += 1
         p = _np(parts)

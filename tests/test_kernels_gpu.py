@@ -399,6 +399,23 @@ def test_stft_istft(ck, fk, dt, L, wlen, hop):
     assert (np.abs(q1.astype(int) - q0.astype(int)) <= 1).all()
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("world,nsplit,K,Kmax", [(2, 3, 5, 8), (8, 1, 32, 32), (4, 2, 7, 7)])
+def test_tw_pack_chunks(ck, fk, dt, world, nsplit, K, Kmax):
+    """Split sums of the TW numerators / denominators, chunk-major for the reduce-scatter over the
+    frames (frequency partition)."""
+    rng = np.random.default_rng(world * 10 + K)
+    ld = 32 * world * 3
+    pn, pd = torch.tensor(rng.standard_normal((nsplit, K, ld))), torch.tensor(rng.random((nsplit, K, ld)))
+    outs = []
+    for k, dev in ((fk, "cpu"), (ck, "cuda")):
+        out = torch.full((world, 2, Kmax, ld // world), 7.0, dtype=dt, device=dev)
+        k.tw_pack_chunks(pn.to(dev), pd.to(dev), out, world)
+        outs.append(out.cpu().numpy())
+    assert_allclose(outs[1][:, :, :K], outs[0][:, :, :K], rtol=0, atol=tol(dt, f64=1e-14, f32=1e-6))
+    assert (outs[1][:, :, K:] == 7.0).all(), "rows beyond K are not touched"
+
+
 def test_library_errors(ck):
     from pyfasst_b200 import _lib
     lib = _lib.load_library()
