@@ -25,7 +25,7 @@ def estimate_batch(models, use_cuda_graph=True):
     dev = models[0]._k().device
     main = torch.cuda.current_stream(dev)
     streams = [torch.cuda.Stream(device=dev) for _ in models]
-    engines, logliks, graphs = [], [], []
+    engines, logliks = [], []
     # pack: STFT (if not done) + parameters to HBM, each on its own stream
     for m, s in zip(models, streams):
         s.wait_stream(main)
@@ -38,17 +38,29 @@ def estimate_batch(models, use_cuda_graph=True):
         engines.append(eng)
         logliks.append(ll)
     if use_cuda_graph and n_iter > 1:
-        # iteration 0 doubles as the warm-up run CUDA graph capture needs; then one capture per
-        # clip (the iteration counter and the annealed noise PSD live in device memory, so the
-        # same graph serves every iteration)
+        # iteration 0 doubles as the warm-up run CUDA graph capture needs (the iteration counter
+        # and the annealed noise PSD live in device memory, so one graph serves every iteration)
         for eng, ll, s in zip(engines, logliks, streams):
             with torch.cuda.stream(s):
                 eng.gem_iteration(n_iter, ll)
         torch.cuda.synchronize(dev)
+        # one graph per clip, replayed round-robin on the clips' streams.  (capture_begin /
+        # capture_end directly: the `torch.cuda.graph` context manager synchronises, collects
+        # garbage and EMPTIES the caching allocator on every entry -- 25 ms per clip, and every
+        # later allocation of the batch, the separation's buffers included, then pays a
+        # cudaMalloc.  Every graph keeps its own memory pool: they are replayed concurrently.
+        # Measured alternatives, profiles/r02/batch_experiments.txt: ONE graph with a branch per
+        # clip is slower, 1.65 s against 1.26 s for 32 clips x 100 iterations; so are 32 hardware
+        # queues instead of the default 8 -- fewer clips in flight keep more of a clip L2 resident.)
+        graphs = []
         for eng, ll, s in zip(engines, logliks, streams):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=s):
-                eng.gem_iteration(n_iter, ll)
+            with torch.cuda.stream(s):
+                g.capture_begin()
+                try:
+                    eng.gem_iteration(n_iter, ll)
+                finally:
+                    g.capture_end()
             graphs.append(g)
         for _ in range(n_iter - 1):
             for g, s in zip(graphs, streams):

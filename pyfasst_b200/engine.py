@@ -690,8 +690,16 @@ class GemEngine(object):
             self.gem_iteration(n_iter, logliks)  # warm-up iteration, also iteration 0
         torch.cuda.current_stream(self.dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self.gem_iteration(n_iter, logliks)
+        # (not the `torch.cuda.graph` context manager: it empties the caching allocator on entry)
+        cap = torch.cuda.Stream(device=self.dev)
+        cap.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(cap):
+            graph.capture_begin()
+            try:
+                self.gem_iteration(n_iter, logliks)
+            finally:
+                graph.capture_end()
+        torch.cuda.current_stream(self.dev).wait_stream(cap)
         for _ in range(n_iter - 1):
             graph.replay()
 
