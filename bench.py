@@ -46,9 +46,9 @@ WLEN, HOP = 2048, 512
 NSRC, NNMF, RANK = 4, 32, 2
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused E-step kernel on the
 # default workload, from the committed `ncu --set full` capture
-# profiles/r01/ncu_estep_stereo_kernel.txt (1.697144 GB + 0.823602 GB); the algorithmic figure is
-# 48 B x 52,974,050 bins = 2.543 GB, i.e. no wasted re-reads.
-ESTEP_DRAM_BYTES_PER_LAUNCH = 2.520746e9
+# profiles/r02/ncu_estep_stereo_kernel_inst.txt (1.696543 GB + 0.821810 GB); the algorithmic figure
+# is 48 B x 52,974,050 bins = 2.543 GB, i.e. no wasted re-reads.
+ESTEP_DRAM_BYTES_PER_LAUNCH = 2.518353e9
 METRIC = "gem_tf_bins_iters_per_s"
 UNIT = "TF-bins*iters/s"
 
@@ -355,11 +355,15 @@ def run_ours(args, rank, world):
     launches0 = kern.launch_count()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
+    kern.estep_timing(True)  # an event pair around the per-bin E-step kernel alone, on its stream
     t_start.record()
     for _ in range(args.steps):
         eng.gem_iteration(total_iters, logliks, mark)
     t_end.record()
     barrier()
+    kern.estep_timing(False)
+    estep_kernel_ms, estep_launches = kern.estep_timing_read()
+    estep_kernel_ms /= max(estep_launches, 1)
     clocks = sampler.stop()
     launches = kern.launch_count() - launches0
     ms = t_start.elapsed_time(t_end)
@@ -370,7 +374,7 @@ def run_ours(args, rank, world):
             phases[l1] = phases.get(l1, 0.0) + e0.elapsed_time(e1)
     phases = {k: v / args.steps for k, v in phases.items()}
     ms_t = torch.tensor([ms], dtype=torch.float64, device=eng.dev)
-    est = torch.tensor([phases["estep"]], dtype=torch.float64, device=eng.dev)
+    est = torch.tensor([estep_kernel_ms], dtype=torch.float64, device=eng.dev)
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(est, op=dist.ReduceOp.MAX)
@@ -441,7 +445,8 @@ def run_ours(args, rank, world):
     achieved = bytes_per_bin * local_bins / (estep_ms * 1e-3) / 1e9
     traffic = args.traffic
     if traffic is None and world == 1 and args.dtype == "f32" and args.duration_s == 600.0 and args.blocks == 1 \
-            and args.channels == 2 and args.rank == RANK:
+            and args.channels == 2 and args.rank == RANK and args.model == "inst" \
+            and args.workload == "configs1":
         traffic = ESTEP_DRAM_BYTES_PER_LAUNCH  # same workload as the committed capture
     roofline = {"bound": "hbm",
                 "kernel": "estep_stereo_kernel" if args.channels == 2 else "estep_multi_kernel",
@@ -449,6 +454,9 @@ def run_ours(args, rank, world):
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "bytes_per_bin": bytes_per_bin, "ms_per_launch": estep_ms,
+                "how": "CUDA events recorded by the library on the launching stream right before and "
+                       "after the per-bin kernel, every launch of the timed region (average); "
+                       "phases_ms.estep also holds the two small per-frequency kernels around it",
                 "algorithmic_bytes_per_launch": bytes_per_bin * local_bins,
                 "traffic": traffic}
 

@@ -126,6 +126,11 @@ int pf_wiener_stereo(const void* X, const void* V, const void* A, const int* src
                      int dtype, void* stream);
 
 /* ---- K2: fused E-step  (audioModel.py:580-764, tools/signalTools.py:132-196) --- */
+/* Measurement aid (bench.py's roofline): pf_estep_timing(1) makes every following E-step call record
+ * a CUDA event pair on its stream right before and after the per-bin kernel alone;
+ * pf_estep_timing_read() waits for them and returns their summed elapsed time and their number. */
+int pf_estep_timing(int enable);
+int pf_estep_timing_read(double* total_ms, int* launches);
 /* Workspace planning (host only, no device call): bytes needed by pf_estep_stereo for this
  * shape.  *nsplit CTAs share one frequency row and *chunk is the number of frames each of them
  * covers (chunk * nsplit >= N); the CTAs of a row take its passes in turn, so the frames of one
@@ -146,6 +151,15 @@ int pf_estep_plan(int J, int64_t N, int dtype, int64_t* chunk, int* nsplit,
  * N_norm  : number of frames the means hat_Rss / hat_Rxs are taken over (0 = N); when the
  *           frames of a mixture are sharded over GPUs, pass the total and sum the results */
 int pf_estep_stereo(const void* X, const void* V, const void* A, const int* src_of_sub, int R,
+                    int J, const double* noise_psd, int F, int64_t N, int64_t ld, void* hatW,
+                    void* hat_Rss, void* hat_Rxs, double* ll_f, void* workspace,
+                    int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream);
+/* The same for REAL mixing vectors (Im A = 0: instantaneous mixing, audioModel.py:2349-2393) when
+ * the statistics only feed the instantaneous mixing update, which takes their real parts
+ * (np.real(np.mean(...)), audioModel.py:818-820): Sigma is real symmetric, Im M01 is neither
+ * needed for hatW nor accumulated (112 instead of 143 FP64 operations per bin).  hatW, ll_f and the
+ * real parts of hat_Rss / hat_Rxs are those of pf_estep_stereo; the imaginary parts are zero. */
+int pf_estep_stereo_inst(const void* X, const void* V, const void* A, const int* src_of_sub, int R,
                     int J, const double* noise_psd, int F, int64_t N, int64_t ld, void* hatW,
                     void* hat_Rss, void* hat_Rxs, double* ll_f, void* workspace,
                     int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream);

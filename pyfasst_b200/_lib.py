@@ -24,6 +24,8 @@ c_ip = ctypes.POINTER(ctypes.c_int)
 # name -> argument ctypes (return type is int unless listed in _RESTYPE)
 SIGNATURES = {
     "pf_last_error": [],
+    "pf_estep_timing": [c_int],
+    "pf_estep_timing_read": [ctypes.POINTER(ctypes.c_double), c_ip],
     "pf_copy_2d": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "pf_abi_version": [],
     "pf_launch_count": [],
@@ -38,6 +40,8 @@ SIGNATURES = {
     "pf_estep_plan": [c_int, c_i64, c_int, ctypes.POINTER(c_i64), c_ip, ctypes.POINTER(c_i64),
                       c_int],
     "pf_estep_stereo": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_int, c_i64, c_i64, c_vp,
+                        c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
+    "pf_estep_stereo_inst": [c_vp, c_vp, c_vp, c_ip, c_int, c_int, c_vp, c_int, c_i64, c_i64, c_vp,
                         c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
     "pf_estep_multi_plan": [c_int, c_int, c_int, c_i64, ctypes.POINTER(c_i64), c_ip,
                             ctypes.POINTER(c_i64)],
@@ -185,6 +189,15 @@ class CudaKernels(object):
         _check(self.lib.pf_set_device(self.device.index), self.lib)
 
     # -- helpers ----------------------------------------------------------------
+    def estep_timing(self, enable):
+        _check(self.lib.pf_estep_timing(1 if enable else 0), self.lib)
+
+    def estep_timing_read(self):
+        """(summed ms, launches) of the per-bin E-step kernels bracketed since estep_timing(True)."""
+        ms, n = ctypes.c_double(), c_int()
+        _check(self.lib.pf_estep_timing_read(ctypes.byref(ms), ctypes.byref(n)), self.lib)
+        return float(ms.value), int(n.value)
+
     def copy_cols_to_device(self, host, lo, hi, dev_t):
         """dev_t [rows, hi - lo] (contiguous, dtype of `host`) <- host[:, lo:hi] of a C-contiguous
         2-D host array: one strided DMA, no host-side temporary."""
@@ -288,6 +301,20 @@ class CudaKernels(object):
                                         self._p(Rxs), self._p(ll_f), self._p(workspace),
                                         workspace.numel() * workspace.element_size(),
                                         int(N_norm), code, self._stream()), self.lib)
+
+    def estep_stereo_inst(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace,
+                          N_norm=0):
+        """estep_stereo for REAL mixing vectors (instantaneous mixing): the imaginary parts of
+        hat_Rss / hat_Rxs are not formed (returned as zero)."""
+        J, F, ld = V.shape
+        R = A.shape[0]
+        code = self.dtype_code(V)
+        _check(self.lib.pf_estep_stereo_inst(self._p(X), self._p(V), self._p(A), _iarr(src_of_sub),
+                                             R, J, self._p(noise), F, N, ld, self._p(hatW),
+                                             self._p(Rss), self._p(Rxs), self._p(ll_f),
+                                             self._p(workspace),
+                                             workspace.numel() * workspace.element_size(),
+                                             int(N_norm), code, self._stream()), self.lib)
 
     # -- K2 / K6 for I = 2..4 channels (X: [2 I, F, ld], A: [R, I, F], Rxs: [F, I, R]) --------
     def estep_multi_workspace_bytes(self, I, J, F, N):

@@ -22,8 +22,14 @@
 // Layout: SoA planes, frames contiguous: X[4][F][ld] (re0, im0, re1, im1),
 // V[J][F][ld], hatW[J][F][ld]; one CTA owns one frequency and a run of frames,
 // a thread owns VEC consecutive frames (float4 / double2 accesses).
+#include <utility>
+#include <vector>
+
 #include "estep.cuh"
 
+#ifndef ESTEP_MINB_RR
+#define ESTEP_MINB_RR 2
+#endif
 namespace pf {
 
 // ---- per-frequency coefficients from the mixing matrix ----------------------
@@ -86,8 +92,14 @@ __global__ void spat_coef_kernel(const double2* __restrict__ A, SubMap map, int 
 // writes hat_W back over V, so that no input / output / prefetch vector is live across the
 // algebra.  Lane l visits the VEC bins of its vector rotated by l / 8: the scalar accesses at a
 // 16-byte stride are then bank-conflict free.
-template <typename T, int J>
-__global__ void __launch_bounds__(ESTEP_THREADS, 2)
+// RR (real R): every mixing vector is real (instantaneous mixing, audioModel.py:2349-2393), so
+// R_j and Sigma are real symmetric and the instantaneous mixing update only takes the REAL parts
+// of hat_Rss / hat_Rxs (np.real(np.mean(...)), audioModel.py:818-820): Im M01 is neither needed
+// for hat_W (tr(M R_j) with real R_j) nor accumulated -- 112 instead of 143 FP64 operations per
+// bin, 46 instead of 61 float64 sums.  The imaginary parts of the statistics come out as zero
+// (GEM loop of all-instantaneous models only; compute_suff_stat takes RR = false).
+template <typename T, int J, bool RR>
+__global__ void __launch_bounds__(ESTEP_THREADS, RR ? ESTEP_MINB_RR : 2)
 estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
                     const double* __restrict__ coef, const double* __restrict__ noise,
                     SubMap map, T* __restrict__ hatW, double* __restrict__ partial, int F,
@@ -100,6 +112,10 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
   constexpr int NM = 4 * NP + 5 * J;  // S, Z, sv: the register-resident sums
   constexpr double kLogPi = 1.1447298858494002;  // log(pi): Q4, log(det*pi)
   constexpr double kEps = 1e-10;                 // ref: audioModel.py:61, signalTools.py:11
+  // RR kernel, float32 planes: the reciprocal seed from MUFU.RCP64H and the float logarithms of
+  // a pass summed in float32 (0.640 -> 0.631 ms; the same two changes SLOW the general kernel,
+  // 0.764 -> 0.83 ms, profiles/r02/estep_inst_experiment.txt: it keeps its round-1 forms)
+  constexpr bool LLP = RR && sizeof(T) == 4;
 
   const int f = blockIdx.y;
   const int split = blockIdx.x;
@@ -206,6 +222,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         }
     }
     unsigned cmask = 0;  // steps whose bin has the determinant clamp active
+    float ll_pass = 0.f;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const int es = (e + rot) & (VEC - 1);  // the bin of the vector this step works on
@@ -227,39 +244,46 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
         s00 += vj[j] * s_coef[4 * j + 0];
         s11 += vj[j] * s_coef[4 * j + 1];
         s01r += vj[j] * s_coef[4 * j + 2];
-        s01i += vj[j] * s_coef[4 * j + 3];
+        if (!RR) s01i += vj[j] * s_coef[4 * j + 3];
       }
       // det as the reference forms it, with its clamp (signalTools.py:183-188: for
       // |det| < eps, sign(det + eps) max(|det|, eps) = +eps)
-      const double det_raw = s00 * s11 - s01r * s01r - s01i * s01i;
+      const double det_raw = RR ? s00 * s11 - s01r * s01r : s00 * s11 - s01r * s01r - s01i * s01i;
       const bool clamped = fabs(det_raw) < kEps;
       cmask |= clamped ? (1u << e) : 0u;
       const double det = clamped ? kEps : det_raw;
-      const double idet = fast_rcp(det);
+      const double idet = RR ? fast_rcp_h(det) : fast_rcp(det);
       // y' = adj(Sigma) x (y = y' / det) and P = y' y'^H do not wait for the 1/det chain
-      const double y0r = s11 * a0r - s01r * a1r + s01i * a1i;
-      const double y0i = s11 * a0i - s01r * a1i - s01i * a1r;
-      const double y1r = s00 * a1r - s01r * a0r - s01i * a0i;
-      const double y1i = s00 * a1i - s01r * a0i + s01i * a0r;
+      const double y0r = RR ? s11 * a0r - s01r * a1r : s11 * a0r - s01r * a1r + s01i * a1i;
+      const double y0i = RR ? s11 * a0i - s01r * a1i : s11 * a0i - s01r * a1i - s01i * a1r;
+      const double y1r = RR ? s00 * a1r - s01r * a0r : s00 * a1r - s01r * a0r - s01i * a0i;
+      const double y1i = RR ? s00 * a1i - s01r * a0i : s00 * a1i - s01r * a0i + s01i * a0r;
       const double p00 = y0r * y0r + y0i * y0i;
       const double p11 = y1r * y1r + y1i * y1i;
       const double p01r = y0r * y1r + y0i * y1i;
-      const double p01i = y0i * y1r - y0r * y1i;
+      const double p01i = RR ? 0.0 : y0i * y1r - y0r * y1i;
       // log-likelihood integrand log(det*pi) + x^H Sigma^-1 x (audioModel.py:660-664).  Frames
       // beyond the end of the row have x = 0, v = 0: their term log(det0 pi) is counted in
       // `ndead` and taken out after the loop -- no branch in the unrolled body
       const double quad = (a0r * y0r + a0i * y0i + a1r * y1r + a1i * y1i) * idet;
-      acc_ll += ll_term(det) + quad;
+      if (LLP) {  // the float logarithms of a pass are summed in float32
+        ll_pass += __logf((float)det);
+        acc_ll += quad;
+      } else {
+        acc_ll += ll_term(det) + quad;
+      }
       // M = y y^H - Sigma^-1 = (P / det - adj(Sigma)) / det
       const double m00 = fma(idet, p00, -s11) * idet;
       const double m11 = fma(idet, p11, -s00) * idet;
       const double m01r = fma(idet, p01r, s01r) * idet;
-      const double m01i = fma(idet, p01i, s01i) * idet;
+      const double m01i = RR ? 0.0 : fma(idet, p01i, s01i) * idet;
       // posterior source power (audioModel.py:727-729, :408-414)
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const T q = (T)(s_coef2[4 * j + 0] * m00 + s_coef2[4 * j + 1] * m11 +
-                        s_coef2[4 * j + 2] * m01r + s_coef2[4 * j + 3] * m01i);
+        const T q = RR ? (T)(s_coef2[4 * j + 0] * m00 + s_coef2[4 * j + 1] * m11 +
+                             s_coef2[4 * j + 2] * m01r)
+                       : (T)(s_coef2[4 * j + 0] * m00 + s_coef2[4 * j + 1] * m11 +
+                             s_coef2[4 * j + 2] * m01r + s_coef2[4 * j + 3] * m01i);
         so[j * ESTEP_THREADS * VEC + es] = pf_abs(vt[j] + vt[j] * vt[j] * (q * invrank[j]));
       }
       // S_jk += v_j v_k M ; Z_j += v_j M ; sv_j += v_j
@@ -273,7 +297,7 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
             mom[4 * p + 0] += pr * m00;
             mom[4 * p + 1] += pr * m11;
             mom[4 * p + 2] += pr * m01r;
-            mom[4 * p + 3] += pr * m01i;
+            if (!RR) mom[4 * p + 3] += pr * m01i;
             ++p;
           }
 #pragma unroll
@@ -281,11 +305,12 @@ estep_stereo_kernel(const T* __restrict__ X, const T* __restrict__ V,
           mom[4 * NP + 4 * j + 0] += vj[j] * m00;
           mom[4 * NP + 4 * j + 1] += vj[j] * m11;
           mom[4 * NP + 4 * j + 2] += vj[j] * m01r;
-          mom[4 * NP + 4 * j + 3] += vj[j] * m01i;
+          if (!RR) mom[4 * NP + 4 * j + 3] += vj[j] * m01i;
           mom[4 * NP + 4 * J + j] += vj[j];
         }
       }
     }
+    if (LLP) acc_ll += (double)(ll_pass + (float)VEC * (float)kLogPi);
 #pragma unroll
     for (int j = 0; j < J; ++j)
       *reinterpret_cast<VT*>(hatW + j * plane + row + n0) = s_outv[j * ESTEP_THREADS + threadIdx.x];
@@ -341,7 +366,8 @@ __global__ void estep_finalize_kernel(const double* __restrict__ partial,
                                       const double* __restrict__ coef,
                                       const double* __restrict__ noise, SubMap map, int R, int J,
                                       int F, long N, int nsplit, double2* __restrict__ hat_Rss,
-                                      double2* __restrict__ hat_Rxs, double* __restrict__ ll_f) {
+                                      double2* __restrict__ hat_Rxs, double* __restrict__ ll_f,
+                                      int real_only) {
   const int f = blockIdx.x;
   const int NA = nacc(J), NP = npairs(J), NC = ncoef(J);
   __shared__ double s_acc[nacc(MAXJ)];
@@ -410,6 +436,7 @@ __global__ void estep_finalize_kernel(const double* __restrict__ partial,
       hr += s_acc[4 * NP + 4 * J + map.src_of_sub[r1]] * invN;
       hi = 0.0;  // Hermitian symmetrisation (audioModel.py:733-740)
     }
+    if (real_only) hi = 0.0;  // (the imaginary moments were not accumulated)
     hat_Rss[((size_t)f * R + r1) * R + r2] = make_double2(hr, hi);
     hat_Rss[((size_t)f * R + r2) * R + r1] = make_double2(hr, -hi);
   }
@@ -420,7 +447,7 @@ __global__ void estep_finalize_kernel(const double* __restrict__ partial,
     const double2 b0 = s_a[r][0], b1 = s_a[r][1];
     const double hr = t[0] * b0.x - t[1] * b0.y + t[2] * b1.x - t[3] * b1.y;
     const double hi = t[0] * b0.y + t[1] * b0.x + t[2] * b1.y + t[3] * b1.x;
-    hat_Rxs[((size_t)f * 2 + c) * R + r] = make_double2(hr * invN, hi * invN);
+    hat_Rxs[((size_t)f * 2 + c) * R + r] = make_double2(hr * invN, real_only ? 0.0 : hi * invN);
   }
 }
 
@@ -539,34 +566,34 @@ static size_t estep_smem_bytes(int J) {
   return (size_t)(ESTEP_DEPTH * (4 + J) + J) * ESTEP_THREADS * 16 + (size_t)8 * J * ESTEP_THREADS * 8;
 }
 
-template <typename T, int J>
+template <typename T, int J, bool RR>
 static int launch_estep(const void* X, const void* V, const double* coef, const double* noise,
                         const SubMap& map, void* hatW, double* partial, int F, long N, long ld,
                         int nsplit, cudaStream_t st) {
   dim3 grid(nsplit, F);
   const size_t smem = estep_smem_bytes(J);
-  cudaError_t e = cudaFuncSetAttribute(estep_stereo_kernel<T, J>,
+  cudaError_t e = cudaFuncSetAttribute(estep_stereo_kernel<T, J, RR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("estep_stereo_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return PF_ERR_CUDA;
   }
-  estep_stereo_kernel<T, J><<<grid, ESTEP_THREADS, smem, st>>>(
+  estep_stereo_kernel<T, J, RR><<<grid, ESTEP_THREADS, smem, st>>>(
       (const T*)X, (const T*)V, coef, noise, map, (T*)hatW, partial, F, N, ld, nsplit);
   return check_launch("estep_stereo_kernel");
 }
 
-template <typename T>
+template <typename T, bool RR>
 static int dispatch_estep(int J, const void* X, const void* V, const double* coef,
                           const double* noise, const SubMap& map, void* hatW, double* partial,
                           int F, long N, long ld, int nsplit, cudaStream_t st) {
   switch (J) {
-    case 1: return launch_estep<T, 1>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
-    case 2: return launch_estep<T, 2>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
-    case 3: return launch_estep<T, 3>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
-    case 4: return launch_estep<T, 4>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
-    case 5: return launch_estep<T, 5>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
-    case 6: return launch_estep<T, 6>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
+    case 1: return launch_estep<T, 1, RR>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
+    case 2: return launch_estep<T, 2, RR>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
+    case 3: return launch_estep<T, 3, RR>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
+    case 4: return launch_estep<T, 4, RR>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
+    case 5: return launch_estep<T, 5, RR>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
+    case 6: return launch_estep<T, 6, RR>(X, V, coef, noise, map, hatW, partial, F, N, ld, nsplit, st);
   }
   set_error("pf_estep_stereo: J=%d spatial components not supported (1..%d)", J, MAXJ);
   return PF_ERR_UNSUPPORTED;
@@ -599,11 +626,57 @@ extern "C" int pf_estep_plan(int J, int64_t N, int dtype, int64_t* chunk, int* n
   return PF_OK;
 }
 
-extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
-                               const int* src_of_sub, int R, int J, const double* noise_psd,
-                               int F, int64_t N, int64_t ld, void* hatW, void* hat_Rss,
-                               void* hat_Rxs, double* ll_f, void* workspace,
-                               int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream) {
+// ---- optional CUDA-event bracket around the per-bin kernel alone (bench.py's roofline) -----------
+// pf_estep_timing(1) makes every following pf_estep_* call record an event pair on ITS stream right
+// before and after the per-bin kernel (not the two small per-frequency kernels around it);
+// pf_estep_timing_read() synchronises on them and returns the sum of the elapsed times.
+namespace pf {
+static bool g_estep_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_estep_events;
+void estep_timing_begin(cudaStream_t st) {
+  if (!g_estep_timing) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  g_estep_events.push_back(std::make_pair(a, b));
+}
+void estep_timing_end(cudaStream_t st) {
+  if (!g_estep_timing) return;
+  cudaEventRecord(g_estep_events.back().second, st);
+}
+}  // namespace pf
+
+extern "C" int pf_estep_timing(int enable) {
+  pf::g_estep_timing = enable != 0;
+  return PF_OK;
+}
+
+extern "C" int pf_estep_timing_read(double* total_ms, int* launches) {
+  double sum = 0.0;
+  int n = 0;
+  for (auto& ev : pf::g_estep_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+      sum += ms;
+      ++n;
+    }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  pf::g_estep_events.clear();
+  *total_ms = sum;
+  *launches = n;
+  return PF_OK;
+}
+
+static int estep_stereo_impl(const void* X, const void* V, const void* A,
+                             const int* src_of_sub, int R, int J, const double* noise_psd,
+                             int F, int64_t N, int64_t ld, void* hatW, void* hat_Rss,
+                             void* hat_Rxs, double* ll_f, void* workspace,
+                             int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream,
+                             bool real_mixing) {
   if (J > MAXJ || R > MAXR) {
     set_error("pf_estep_stereo: J=%d spatial components / R=%d sub-sources not supported "
               "(max %d / %d)", J, R, MAXJ, MAXR);
@@ -638,17 +711,42 @@ extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
   int rc = check_launch("spat_coef_kernel");
   if (rc) return rc;
   // the per-bin algebra and the moment sums run in float64 whatever the plane type
+  estep_timing_begin(st);
   if (dtype == PF_F32)
-    rc = dispatch_estep<float>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, nsplit, st);
+    rc = real_mixing
+             ? dispatch_estep<float, true>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, nsplit, st)
+             : dispatch_estep<float, false>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, nsplit, st);
   else
-    rc = dispatch_estep<double>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, nsplit, st);
+    rc = real_mixing
+             ? dispatch_estep<double, true>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, nsplit, st)
+             : dispatch_estep<double, false>(J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, nsplit, st);
+  estep_timing_end(st);
   if (rc) return rc;
   // hat_Rss / hat_Rxs are means over N_norm frames: the local N, or the length of the whole
   // mixture when the frames are sharded over several GPUs (the partial means are then summed)
   estep_finalize_kernel<<<F, 64, 0, st>>>(partial, (const double2*)A, coef, noise_psd, map, R, J,
                                           F, N_norm > 0 ? N_norm : N, nsplit, (double2*)hat_Rss,
-                                          (double2*)hat_Rxs, ll_f);
+                                          (double2*)hat_Rxs, ll_f, real_mixing ? 1 : 0);
   return check_launch("estep_finalize_kernel");
+}
+
+extern "C" int pf_estep_stereo(const void* X, const void* V, const void* A,
+                               const int* src_of_sub, int R, int J, const double* noise_psd,
+                               int F, int64_t N, int64_t ld, void* hatW, void* hat_Rss,
+                               void* hat_Rxs, double* ll_f, void* workspace,
+                               int64_t workspace_bytes, int64_t N_norm, int dtype, void* stream) {
+  return estep_stereo_impl(X, V, A, src_of_sub, R, J, noise_psd, F, N, ld, hatW, hat_Rss, hat_Rxs,
+                           ll_f, workspace, workspace_bytes, N_norm, dtype, stream, false);
+}
+
+extern "C" int pf_estep_stereo_inst(const void* X, const void* V, const void* A,
+                                    const int* src_of_sub, int R, int J, const double* noise_psd,
+                                    int F, int64_t N, int64_t ld, void* hatW, void* hat_Rss,
+                                    void* hat_Rxs, double* ll_f, void* workspace,
+                                    int64_t workspace_bytes, int64_t N_norm, int dtype,
+                                    void* stream) {
+  return estep_stereo_impl(X, V, A, src_of_sub, R, J, noise_psd, F, N, ld, hatW, hat_Rss, hat_Rxs,
+                           ll_f, workspace, workspace_bytes, N_norm, dtype, stream, true);
 }
 
 extern "C" int pf_wiener_stereo(const void* X, const void* V, const void* A,

@@ -21,6 +21,8 @@
 #include "common.cuh"
 
 namespace pf {
+void estep_timing_begin(cudaStream_t st);  // estep.cu
+void estep_timing_end(cudaStream_t st);
 
 constexpr int EM_THREADS = 128;
 #ifndef EM_MINB
@@ -898,8 +900,10 @@ extern "C" int pf_estep_multi(const void* X, const void* V, const void* A, const
   spat_coef_multi_kernel<<<ceil_div(F, 128), 128, 0, st>>>((const double2*)A, map, R, J, I, F, coef);
   rc = check_launch("spat_coef_multi_kernel");
   if (rc) return rc;
+  estep_timing_begin(st);
   rc = dispatch_estep_multi(dtype, I, J, X, V, coef, noise_psd, map, hatW, partial, F, N, ld, chunk,
                             nsplit, st);
+  estep_timing_end(st);
   if (rc) return rc;
   const int NA = em_nacc(I, J);
   const size_t smem = sizeof(double) * (NA + (NA & 1)) + sizeof(double2) * (R * I + J * I * I);

@@ -428,9 +428,18 @@ class GemEngine(object):
                 k.spec_power(e["FW"], e["TW"], e["G"], self.N, False)
         self._for_each(self.spec, powers)
 
-    def estep(self):
-        """compute_suff_stat (audioModel.py:580-764) on the current parameters."""
-        estep = self.k.estep_multi if self.multi else self.k.estep_stereo
+    def estep(self, for_update=False):
+        """compute_suff_stat (audioModel.py:580-764) on the current parameters.  for_update: the
+        statistics only feed this iteration's mixing update -- with instantaneous mixing (real
+        mixing vectors) that update takes their real parts (audioModel.py:818-820), and the stereo
+        kernel then skips the imaginary moments (pf_estep_stereo_inst)."""
+        if self.multi:
+            estep = self.k.estep_multi
+        elif for_update and self.mix_type == "inst" and hasattr(self.k, "estep_stereo_inst") \
+                and os.environ.get("PYFASST_ESTEP_INST", "1") != "0":
+            estep = self.k.estep_stereo_inst
+        else:
+            estep = self.k.estep_stereo
         estep(self.X, self.V, self.A, self.src_of_sub, self.noise, self.N, self.hatW, self.Rss,
               self.Rxs, self.ll_f, self.ws, self.N_total)
 
@@ -620,7 +629,7 @@ class GemEngine(object):
             k.noise_anneal(self.sqrt0, self.sqrt1, self.iter_dev, n_iter_total, self.noise)
         self.compute_powers()
         mark("powers")
-        self.estep()
+        self.estep(for_update=True)
         mark("estep")
 
         def stats_and_mix():

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--rank", type=int, default=2)
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--conv", action="store_true")
+    ap.add_argument("--for-update", action="store_true",
+                    help="the E-step as the GEM loop calls it (instantaneous mixing: pf_estep_stereo_inst)")
     args = ap.parse_args()
     k = CudaKernels()
     F, N, J, K, I = args.F, args.frames, args.J, args.K, args.I
@@ -51,12 +53,12 @@ def main():
     eng.set_model(spat, spec)
     eng.compute_powers()
     for _ in range(3):
-        eng.estep()
+        eng.estep(args.for_update)
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.reps):
-        eng.estep()
+        eng.estep(args.for_update)
     t1.record()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / args.reps

@@ -235,6 +235,14 @@ class FakeKernels(object):
     def estep_workspace_bytes(self, J, F, N, dtype_code):
         return 64
 
+    def estep_stereo_inst(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace,
+                          N_norm=0):
+        """Real mixing vectors: the real parts of the statistics, zero imaginary parts."""
+        assert float(np.abs(_np(A).imag).max()) == 0.0, "estep_stereo_inst needs real mixing vectors"
+        self.estep_stereo(X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace, N_norm)
+        _np(Rss).imag[...] = 0.0
+        _np(Rxs).imag[...] = 0.0
+
     def estep_stereo(self, X, V, A, src_of_sub, noise, N, hatW, Rss, Rxs, ll_f, workspace,
                      N_norm=0):
         self.launches += 3

@@ -111,6 +111,44 @@ def test_estep_stereo(ck, fk, dt, F, N, J, rank, consistent):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("F,N,J,rank,quiet", [(17, 2600, 4, 2, False), (9, 1300, 3, 1, True),
+                                              (5, 77, 1, 2, False), (4, 700, 6, 1, True)])
+def test_estep_stereo_inst(ck, fk, dt, F, N, J, rank, quiet):
+    """Real mixing vectors (instantaneous mixing): hat_W, the log-likelihood and the REAL parts of
+    the statistics equal those of the general kernel; the imaginary parts are returned as zero.
+    quiet: some rows inside the determinant clamp."""
+    rng = np.random.default_rng(F * 77 + N)
+    ld, R, src, X, V, A, noise = problem(rng, dt, F, N, J, rank)
+    A = torch.complex(A.real.contiguous(), torch.zeros_like(A.real))
+    if quiet:
+        scale = np.ones(F)
+        scale[:2], scale[2:4] = 1e-7, 3e-5
+        sc = torch.tensor(scale)
+        X = (X.to(torch.float64) * torch.sqrt(sc)[None, :, None]).to(dt)
+        V = (V.to(torch.float64) * sc[None, :, None]).to(dt)
+        noise = noise * sc
+    outs = []
+    for k, dev, fn in ((fk, "cpu", "estep_stereo"), (ck, "cuda", "estep_stereo_inst")):
+        hatW = torch.zeros((J, F, ld), dtype=dt, device=dev)
+        Rss = torch.zeros((F, R, R), dtype=torch.complex128, device=dev)
+        Rxs = torch.zeros((F, 2, R), dtype=torch.complex128, device=dev)
+        ll = torch.zeros(F, dtype=torch.float64, device=dev)
+        ws = torch.zeros((k.estep_workspace_bytes(J, F, N, k.dtype_code(V)) + 7) // 8,
+                         dtype=torch.float64, device=dev)
+        getattr(k, fn)(X.to(dev), V.to(dev), A.to(dev), src, noise.to(dev), N, hatW, Rss, Rxs, ll, ws)
+        outs.append([t.cpu().numpy() for t in (hatW, Rss, Rxs, ll)])
+    (hw0, rss0, rxs0, ll0), (hw1, rss1, rxs1, ll1) = outs
+    for f in range(F):
+        assert rel(hw1[:, f, :N], hw0[:, f, :N]) < tol(dt, f32=1e-6), f
+        assert rel(rss1[f].real, rss0[f].real) < 1e-8, f
+        assert rel(rxs1[f].real, rxs0[f].real) < 1e-8, f
+    assert (rss1.imag == 0).all() and (rxs1.imag == 0).all()
+    assert (hw1[:, :, N:] == 0).all()
+    assert_allclose(ll1, ll0, rtol=tol(dt, f64=1e-12, f32=1e-6),
+                    atol=0.0 if dt == torch.float64 else 1e-6 * N)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("J", [3, 4])
 def test_estep_stereo_determinant_clamp(ck, fk, dt, J):
     """Quiet rows: det Sigma < 1e-10 activates the reference's clamp (signalTools.py:183-188), where
