@@ -15,6 +15,8 @@
 // it and store the hi / lo tiles into shared memory in the canonical UMMA layouts of tc.cuh;
 // one elected thread issues the MMAs; completion is tracked with mbarriers (tcgen05.commit) so
 // that the next tile is produced while the tensor core consumes the previous one.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -205,12 +207,19 @@ struct SptSmem {
   unsigned char a_lo[128 * 32 * 4];
   unsigned char b_hi[2][32 * SPT_NT * 4];
   unsigned char b_lo[2][32 * SPT_NT * 4];
-  float tr[SPT_THREADS / 32][32 * 36];  // per-warp transpose tiles of the write-out
+  // per-warp 32 x 32 boxes of the write-out (128-byte rows in the TMA SWIZZLE_128B pattern)
+  float tr[SPT_THREADS / 32][2][32 * 32];  // two boxes per warp: one is filled while the TMA reads the other
 };
 
+// The write-out goes through the TMA: a warp reads 32 rows x 32 columns of the accumulator from
+// TMEM (thread = row), stores them as a swizzled 32 x 128-byte box (conflict-free 16-byte
+// stores) and ONE lane hands the box to cp.async.bulk.tensor.2d (UTMASTG) -- no global store
+// instructions, no bounds predicates (the tensor map clips rows >= F and columns >= ldv), and the
+// copy out of shared memory overlaps the next TMEM load.
 __global__ void __launch_bounds__(SPT_THREADS, 1)
 spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restrict__ H, long ldh,
-                     float* __restrict__ V, long ldv, int F, int K, long N, int tiles_per_cta) {
+                     const __grid_constant__ CUtensorMap tmapV, long ldv, int F, int K, long N,
+                     int tiles_per_cta) {
   extern __shared__ __align__(1024) unsigned char spt_smem[];
   __shared__ uint64_t mbar[2];
   __shared__ uint32_t tmem_base;
@@ -270,10 +279,8 @@ spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restri
       h_n[q] = (k < K && n + 4 <= ldh) ? ldg4(H + (long)k * ldh + n) : zero4;
     }
   };
-  // write-out of one accumulator: a warp reads 32 rows x 32 columns from TMEM (thread = row),
-  // transposes them through a padded shared-memory tile and stores 4 rows x 128 contiguous
-  // bytes per instruction (full 128-byte lines instead of 32 half-used sectors)
-  float* tr = reinterpret_cast<float*>(sm.tr[warp]);
+  // write-out of one accumulator (see above)
+  int box = 0;
   auto write_out = [&](int b, long tile) {
     // warps 0-3: columns [0,128); warps 4-7: columns [128,256) of accumulator b
     const int wq = warp & 3, half = warp >> 2;
@@ -283,21 +290,22 @@ spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restri
       uint32_t v[32];
       tc::tmem_ld_32x32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * SPT_NT + half * 128 + c0), v);
       tc::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(tr + lane * 36 + i) =
-            make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                        __uint_as_float(v[i + 3]));
+      float* tr = sm.tr[warp][box];
+      if (lane == 0) tc::tma_store_wait_read<1>();  // the box before the previous one has left shared memory
       __syncwarp();
-      const long n = nb + c0 + (lane & 7) * 4;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3);
-        const int f = fblk + wq * 32 + r;
-        const float4 x = *reinterpret_cast<const float4*>(tr + r * 36 + (lane & 7) * 4);
-        if (f < F && n + 4 <= ldv) *reinterpret_cast<float4*>(V + (long)f * ldv + n) = x;
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(tr) + lane * 128 +
+                                   ((c ^ (lane & 7)) << 4)) =
+            make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                        __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {  // (always a group, possibly empty: the wait above counts groups)
+        if (nb + c0 < ldv) tc::tma_store_2d(&tmapV, tc::smem_u32(tr), (int)(nb + c0), fblk + wq * 32);
+        tc::tma_store_commit();
       }
-      __syncwarp();
+      box ^= 1;
     }
   };
 
@@ -343,6 +351,7 @@ spec_power_tc_kernel(const float* __restrict__ W, int ldw, const float* __restri
     tc::fence_after_thread_sync();
     write_out(b, t_begin + (nt - 1) * t_step);
   }
+  if (lane == 0) tc::tma_store_wait<0>();  // this warp's boxes are written before the CTA retires
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
@@ -871,9 +880,46 @@ int pf_fb_contract_tc(const float* hatW, const float* P, long ld, const float* G
   return PF_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*pf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                       const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static pf_encode_tiled_fn tensor_map_encoder() {
+  static pf_encode_tiled_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (pf_encode_tiled_fn)p;
+  }();
+  return fn;
+}
+
 // V = W H for float32 planes, K <= 32 (called from pf_spec_power)
 int pf_spec_power_tc(const float* W, int ldw, const float* H, long ldh, float* V, long ldv, int F,
                      int K, long N, cudaStream_t st) {
+  // tensor map of the output plane [F rows][ldv columns] float32, boxes of 32 x 32, 128-byte swizzle
+  pf_encode_tiled_fn encode = tensor_map_encoder();
+  if (encode == nullptr) {
+    set_error("spec_power_tc_kernel: cuTensorMapEncodeTiled is not available from this driver");
+    return PF_ERR_CUDA;
+  }
+  CUtensorMap tmapV;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)ldv, (cuuint64_t)F};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldv * sizeof(float)};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    const CUresult r = encode(&tmapV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)V, dims, strides,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("spec_power_tc_kernel: cuTensorMapEncodeTiled failed (%d) for V=%p ldv=%ld F=%d",
+                (int)r, (void*)V, ldv, F);
+      return PF_ERR_CUDA;
+    }
+  }
   const size_t smem = sizeof(SptSmem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(spec_power_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -892,7 +938,7 @@ int pf_spec_power_tc(const float* W, int ldw, const float* H, long ldh, float* V
   // PYFASST_SPT_INTERLEAVE=0: contiguous runs of tiles per CTA (the older mapping)
   const char* env = getenv("PYFASST_SPT_INTERLEAVE");
   const bool interleave = env == nullptr || atoi(env) != 0;
-  spec_power_tc_kernel<<<grid, SPT_THREADS, smem, st>>>(W, ldw, H, ldh, V, ldv, F, K, N,
+  spec_power_tc_kernel<<<grid, SPT_THREADS, smem, st>>>(W, ldw, H, ldh, tmapV, ldv, F, K, N,
                                                         interleave ? -per : per);
   return check_launch("spec_power_tc_kernel");
 }

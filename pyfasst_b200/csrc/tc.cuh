@@ -162,6 +162,29 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- TMA (bulk tensor) stores: shared -> global through a CUtensorMap ------------------------
+// box written by cp.async.bulk.tensor.2d: `smem_addr` holds the box row-major in the tensor map's
+// swizzle (SWIZZLE_128B with 128-byte rows: 16-byte chunk c of row r sits at chunk c ^ (r & 7);
+// tile base 1024-byte aligned); coordinates (x = innermost = column, y = row); parts of the box
+// outside the tensor are not written.  Issued by ONE thread, which also commits / waits its groups.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_addr, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :: "l"(tmap), "r"(smem_addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all but the newest N groups of this thread have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+// ... have completed (their writes are done)
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+
 // ---- 3xTF32 split ----------------------------------------------------------------------------
 // x = hi + lo with hi = tf32-rounded x (round to nearest) and lo = x - hi (exact in fp32);
 // A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi has a relative error of ~2^-21 per product, i.e. fp32-class
