@@ -39,7 +39,8 @@ def build(conv, rank, dtype, iters=50, **kw):
 
 def sdr_db(ref, est):
     ref, est = ref.astype(np.float64), est.astype(np.float64)
-    return 10 * np.log10((ref ** 2).sum() / max(((ref - est) ** 2).sum(), 1e-300))
+    err = ((ref - est) ** 2).sum()
+    return float('inf') if err == 0 else 10 * np.log10((ref ** 2).sum() / err)
 
 
 def params_err(model, g, prefix):
