@@ -273,6 +273,9 @@ class GemEngine(object):
                 if p.shape[2] != self.F_total:
                     raise ValueError("convolutive params must be [rank, channels, F]")
                 A[self.ranks[j]] = p[:, :, self.f_lo:self.f_hi]
+        # (instantaneous parameters are real in the reference; a user-supplied complex array keeps
+        # the general E-step kernel)
+        self.real_mixing = self.mix_type == "inst" and not np.any(A.imag)
         self.J, self.R = J, R
         self.A = self._upload(A)
         self.omega = float(nmfUpdateCoeff)
@@ -435,7 +438,7 @@ class GemEngine(object):
         kernel then skips the imaginary moments (pf_estep_stereo_inst)."""
         if self.multi:
             estep = self.k.estep_multi
-        elif for_update and self.mix_type == "inst" and hasattr(self.k, "estep_stereo_inst") \
+        elif for_update and getattr(self, "real_mixing", False) and hasattr(self.k, "estep_stereo_inst") \
                 and os.environ.get("PYFASST_ESTEP_INST", "1") != "0":
             estep = self.k.estep_stereo_inst
         else:

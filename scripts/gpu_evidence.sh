@@ -12,7 +12,7 @@ done
 CMD="python scripts/bench_separation.py 600"
 timeout 600 $CMD > gpurun_out/${TAG}_separation.json 2> gpurun_out/${TAG}_separation.err || echo "separation failed"
 tail -1 gpurun_out/${TAG}_separation.json
-for kern in stft_kernel istft_kernel wiener_stereo_kernel; do
+for kern in "^stft_kernel" istft_kernel wiener_stereo_kernel; do
   timeout 900 $NCU -k regex:$kern -s 1 -o gpurun_out/${TAG}_prof_$kern $CMD > gpurun_out/${TAG}_ncu_$kern.log 2>&1; echo "ncu $kern $?"
 done
 CMD="python scripts/bench_viterbi.py"

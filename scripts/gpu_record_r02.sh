@@ -41,6 +41,6 @@ for kern in spec_power_tc_kernel; do
   echo "ncu $kern exit $?"
 done
 CMD3="python scripts/bench_separation.py 600"
-$CMD3 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:::stft_kernel -s 0 -c 1 \
+$CMD3 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k "regex:^stft_kernel" -s 0 -c 1 \
       -f -o gpurun_out/${TAG}_prof_stft_kernel $CMD3 > gpurun_out/${TAG}_ncu_stft.log 2>&1; echo "ncu stft exit $?"
 ls gpurun_out/${TAG}_*.ncu-rep
