@@ -835,6 +835,302 @@ tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restr
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// ---- the same kernel as two half-CTA pipelines (round 2) ------------------------------------------
+// The 16 rows of a step belong to two groups of 4 warps: group h forms and stores the operands of
+// rows 8h..8h+7, synchronises with a NAMED barrier over its 128 threads only, its first thread
+// issues the MMAs of its 8 rows (K = 8) into the group's OWN accumulators and commits to the
+// group's own completion barrier.  The groups drift apart, so the barrier / issue / MMA latency
+// of one overlaps the operand work of the other (per-line stall profile of the single-pipeline
+// kernel: 15.6 % block barrier, 13.4 % wait for the operand stage,
+// profiles/r02/ncu_tw_contract_fused_tc_kernel.txt).  Shared between the groups: the H tile, the
+// W' rows and the P' MMA of a 64-row block (staged by all threads, handed to thread 0 through an
+// mbarrier with 256 arrivals, which also proves that every thread has read the P' buffer that the
+// new block overwrites).  The two accumulator pairs are added in a fixed order in the write-out.
+// (original notes:) thread = one frame x 8 rows straight out of
+// TMEM (4-byte accesses) 229 us per launch; the same with fewer address instructions 240 us; with
+// an mbarrier hand-over to a dedicated MMA warp 293 us; this one -- P' transposed through
+// shared memory one step ahead so that the threads keep 16-byte accesses -- 220 us; that one
+// with the MMA issue moved to a ninth warp 322 us (9 warps of 112 registers: three of them land
+// on one scheduler's 16 K registers, so only ONE CTA fits per SM -- the same holds for every
+// 288-thread variant above).
+__global__ void __launch_bounds__(TWF_THREADS, 2)
+tw_contract_fused2_tc_kernel(const float* __restrict__ hatW, const float* __restrict__ Op, long ld,
+                            const float* __restrict__ W, int ldw, const float* __restrict__ H,
+                            long ldh, int K, int F, long N, int fchunk, int fsplit,
+                            double* __restrict__ num, double* __restrict__ den, long ldo) {
+  extern __shared__ __align__(1024) unsigned char twf_smem[];
+  __shared__ uint64_t s_desc[28];
+  __shared__ uint64_t mbar_free[2];  // per group: the MMAs of its previous step have read its tiles
+  __shared__ uint64_t mbar_p[2];
+  __shared__ uint64_t mbar_wp;       // 256 arrivals: the W' rows of the next P' block are staged
+  __shared__ uint64_t mbar_done;     // 2 arrivals: the last MMAs of both groups
+  __shared__ uint32_t tmem_base;
+  unsigned char* base = twf_smem + ((1024 - (tc::smem_u32(twf_smem) & 1023)) & 1023);
+  TwfSmem& sm = *reinterpret_cast<TwfSmem*>(base);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long nb = (long)blockIdx.x * TWF_NT;
+  const int split = blockIdx.y;
+  const int fb = split * fchunk;
+  int fe = fb + fchunk;
+  if (fe > F) fe = F;
+  const int nsteps = (fe - fb + TWF_FR - 1) / TWF_FR;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
+  if (tid == 0) {
+    tc::mbar_init(&mbar_free[0], 1);
+    tc::mbar_init(&mbar_free[1], 1);
+    tc::mbar_init(&mbar_p[0], 1);
+    tc::mbar_init(&mbar_p[1], 1);
+    tc::mbar_init(&mbar_wp, TWF_THREADS);
+    tc::mbar_init(&mbar_done, 2);
+    tc::fence_mbar_init();
+  }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // H tile 32 k x 128 n (zero beyond K and beyond the row): 4 float4 per thread
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + q * TWF_THREADS;  // 0 .. 1023
+    const int k = i >> 5, c = (i & 31) * 4;
+    const long n = nb + c;
+    const float4 h = (k < K && n + 4 <= ldh) ? ldg4(H + (long)k * ldh + n) : zero4;
+    st_split4(sm.h_hi, sm.h_lo, tc::mnmajor_off(k, c, TWF_HLBO, TWF_SBO), h);
+  }
+  // W rows: the first 64 threads of a group hold 4 consecutive k of one of its 8 rows of a step
+  const int grp = warp >> 2, gt = tid & 127;
+  const int wrow = 8 * grp + (gt >> 3), wk = (tid & 7) * 4;
+  const uint32_t woff = tc::mnmajor_off(wrow, wk, TWF_LBO, TWF_SBO);   // main B (f = K index)
+  auto load_w = [&](int step) {
+    float4 w = zero4;
+    if (gt < 64 && step < nsteps) {
+      const int f = fb + step * TWF_FR + wrow;
+      if (f < fe) {
+        const float* wr = W + (long)f * ldw;
+        w.x = (wk + 0 < K) ? __ldg(wr + wk + 0) : 0.f;
+        w.y = (wk + 1 < K) ? __ldg(wr + wk + 1) : 0.f;
+        w.z = (wk + 2 < K) ? __ldg(wr + wk + 2) : 0.f;
+        w.w = (wk + 3 < K) ? __ldg(wr + wk + 3) : 0.f;
+      }
+    }
+    return w;
+  };
+  // W' rows of one P' block (64 rows x 32 k = 512 float4: two per thread), K-major tile
+  auto stage_wp_block = [&](int blk) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * TWF_THREADS;  // 0 .. 511
+      const int r = i >> 3, kk = (i & 7) * 4;
+      const int f = fb + blk * TWF_PB + r;
+      float4 w = zero4;
+      if (f < fe) {
+        const float* wr = W + (long)f * ldw;
+        w.x = (kk + 0 < K) ? __ldg(wr + kk + 0) : 0.f;
+        w.y = (kk + 1 < K) ? __ldg(wr + kk + 1) : 0.f;
+        w.z = (kk + 2 < K) ? __ldg(wr + kk + 2) : 0.f;
+        w.w = (kk + 3 < K) ? __ldg(wr + kk + 3) : 0.f;
+      }
+      float4 hi, lo;
+      tc::split_tf32(w.x, hi.x, lo.x); tc::split_tf32(w.y, hi.y, lo.y);
+      tc::split_tf32(w.z, hi.z, lo.z); tc::split_tf32(w.w, hi.w, lo.w);
+      const uint32_t off = tc::kmajor_off(r, kk);
+      *reinterpret_cast<float4*>(sm.wp_hi + off) = hi;
+      *reinterpret_cast<float4*>(sm.wp_lo + off) = lo;
+    }
+  };
+  // plane elements of this thread: float4 (f, n4) of the 16 x 128 tiles, 2 per plane and step
+  int prow[2], pcol[2];
+  uint32_t poff[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {  // group h: rows 8h .. 8h+7, two per warp
+    prow[q] = 8 * grp + 2 * (warp & 3) + q;
+    pcol[q] = lane * 4;
+    poff[q] = tc::mnmajor_off(prow[q], pcol[q], TWF_LBO, TWF_SBO);
+  }
+  float4 hw_n[2], o_n[2];
+  auto fetch = [&](int step) {
+    const int f0 = fb + step * TWF_FR;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int f = f0 + prow[q];
+      const long n = nb + pcol[q];
+      const bool ok = (f < fe) && (n + 4 <= ld);
+      const long off = (long)f * ld + n;
+      hw_n[q] = ok ? ldg4(hatW + off) : zero4;
+      o_n[q] = ok ? ldg4(Op + off) : zero4;
+    }
+  };
+  // TMEM -> ptile: this thread's TMEM lane is frame nl, it moves rows fhalf * 8 .. + 7
+  const int nl = (warp & 3) * 32 + lane, fhalf = warp >> 2;
+  const uint32_t tmem_lane = (uint32_t)((warp & 3) * 32) << 16;
+
+  const int nblocks = (nsteps + 3) / 4;
+  float4 w_cur = load_w(0), w_n1 = load_w(1);
+  stage_wp_block(0);
+  tc::fence_proxy_async();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = tc::idesc_tf32(128, 32, 1, 1);
+  const uint32_t idesc_p = tc::idesc_tf32(128, TWF_PB, 1, 0);
+  // every shared-memory descriptor is loop invariant (one operand stage): thread 0 builds them
+  // once; issuing a step is then 28 shared loads + 36 MMAs instead of ~400 ALU instructions on
+  // the critical path of warp 0
+  if (tid == 0) {
+    const uint32_t hh = tc::smem_u32(sm.h_hi), hl = tc::smem_u32(sm.h_lo);
+    const uint32_t wh = tc::smem_u32(sm.wp_hi), wl = tc::smem_u32(sm.wp_lo);
+    for (int j = 0; j < 4; ++j) {
+      s_desc[j] = tc::smem_desc_mnmajor(hh + j * 1024, TWF_HLBO, TWF_SBO);
+      s_desc[4 + j] = tc::smem_desc_mnmajor(hl + j * 1024, TWF_HLBO, TWF_SBO);
+      s_desc[8 + j] = tc::smem_desc_kmajor(wh + j * 32);
+      s_desc[12 + j] = tc::smem_desc_kmajor(wl + j * 32);
+    }
+    const uint32_t a1h = tc::smem_u32(sm.a1_hi), a1l = tc::smem_u32(sm.a1_lo);
+    const uint32_t a2h = tc::smem_u32(sm.a2_hi), a2l = tc::smem_u32(sm.a2_lo);
+    const uint32_t bh = tc::smem_u32(sm.b_hi), bl = tc::smem_u32(sm.b_lo);
+    for (int j = 0; j < TWF_FR / 8; ++j) {
+      s_desc[16 + 6 * j + 0] = tc::smem_desc_mnmajor(bh + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 1] = tc::smem_desc_mnmajor(bl + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 2] = tc::smem_desc_mnmajor(a1h + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 3] = tc::smem_desc_mnmajor(a1l + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 4] = tc::smem_desc_mnmajor(a2h + j * 1024, TWF_LBO, TWF_SBO);
+      s_desc[16 + 6 * j + 5] = tc::smem_desc_mnmajor(a2l + j * 1024, TWF_LBO, TWF_SBO);
+    }
+  }
+  // P'(block) -> TMEM columns 64 + 64 (block & 1) .. + 63; W' rows are in wp_hi / wp_lo
+  auto issue_p = [&](int blk) {
+    const int step = blk;  // (mbarrier slot = block parity)
+    const uint32_t d = tmem + 64u + (uint32_t)TWF_PB * (uint32_t)(blk & 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t dah = s_desc[j], dal = s_desc[4 + j], dbh = s_desc[8 + j], dbl = s_desc[12 + j];
+      tc::mma_tf32(d, dah, dbh, idesc_p, j > 0 ? 1u : 0u);
+      tc::mma_tf32(d, dah, dbl, idesc_p, 1u);
+      tc::mma_tf32(d, dal, dbh, idesc_p, 1u);
+    }
+    tc::mma_commit(&mbar_p[step & 1]);
+  };
+  // P' of a step: wait for the MMA of its block, move this thread's 8 values from TMEM to
+  // ptile[step & 1]
+  auto p_to_smem = [&](int step) {
+    const int blk = step >> 2, bb = blk & 1;
+    tc::mbar_wait(&mbar_p[bb], (uint32_t)((blk >> 1) & 1));
+    tc::fence_after_thread_sync();
+    uint32_t pv[8];
+    tc::tmem_ld_32x8(tmem + tmem_lane + 64u + (uint32_t)TWF_PB * (uint32_t)bb +
+                         16u * (uint32_t)(step & 3) + 8u * (uint32_t)fhalf, pv);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sm.ptile[step & 1][fhalf * 8 + q][nl] = __uint_as_float(pv[q]);
+  };
+  __syncthreads();  // the descriptors built by thread 0 are read by both issuing threads
+  const bool issuer = gt == 0;           // threads 0 and 128
+  const uint32_t dacc = tmem + 192u * (uint32_t)grp;  // the group's accumulators: num, den (+32)
+  if (nsteps > 0) {
+    fetch(0);
+    if (tid == 0) issue_p(0);
+    p_to_smem(0);                       // (also: the P' MMA of block 0 has finished reading wp)
+    tc::fence_before_thread_sync();
+    tc::named_bar_sync(1 + grp, 128);   // the group's rows of ptile[0] are complete
+  }
+  for (int s = 0; s < nsteps; ++s) {
+    float4 hw[2], o[2], p[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { hw[q] = hw_n[q]; o[q] = o_n[q]; }
+    if (s + 1 < nsteps) fetch(s + 1);
+    const float4 w_n2 = load_w(s + 2);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      p[q] = *reinterpret_cast<const float4*>(&sm.ptile[s & 1][prow[q]][pcol[q]]);
+    float4 e1[2], e2[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      // rows beyond the shard (all-zero loads) contribute nothing: W is zero there as well
+      auto e12 = [&](float hwv, float ov, float pvv, float& a, float& c) {
+        const float oc = fmaxf(ov, kEpsF);
+        const float rp = fast_rcpf(fmaxf(pvv, kEpsF));
+        c = oc * rp;                // other / P'            (audioModel.py:1694-1701)
+        a = oc * (hwv * rp * rp);   // other * hat_W / P'^2  (audioModel.py:1714-1720)
+      };
+      e12(hw[q].x, o[q].x, p[q].x, e1[q].x, e2[q].x);
+      e12(hw[q].y, o[q].y, p[q].y, e1[q].y, e2[q].y);
+      e12(hw[q].z, o[q].z, p[q].z, e1[q].z, e2[q].z);
+      e12(hw[q].w, o[q].w, p[q].w, e1[q].w, e2[q].w);
+    }
+    // the group's MMAs of the previous step must have finished reading its operand rows
+    if (s >= 1) tc::mbar_wait(&mbar_free[grp], (uint32_t)((s - 1) & 1));
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      st_split4(sm.a1_hi, sm.a1_lo, poff[q], e1[q]);
+      st_split4(sm.a2_hi, sm.a2_lo, poff[q], e2[q]);
+    }
+    if (gt < 64) st_split4(sm.b_hi, sm.b_lo, woff, w_cur);
+    if (s + 1 < nsteps) p_to_smem(s + 1);  // its block's MMA was issued >= 2 steps ago
+    // second step of a block: stage the W' rows of the next block (wp is free: the MMA of the
+    // current block completed before its first rows were read); thread 0 issues its MMA once all
+    // 256 threads have arrived -- which also means that nobody reads the P' buffer it overwrites
+    const bool next_block = (s & 3) == 1 && (s >> 2) + 1 < nblocks;
+    if (next_block) stage_wp_block((s >> 2) + 1);
+    w_cur = w_n1;
+    w_n1 = w_n2;
+    tc::fence_proxy_async();
+    tc::fence_before_thread_sync();
+    if (next_block) tc::mbar_arrive(&mbar_wp);
+    tc::named_bar_sync(1 + grp, 128);
+    if (issuer) {
+      tc::fence_after_thread_sync();
+      if (grp == 0 && next_block) {
+        tc::mbar_wait(&mbar_wp, (uint32_t)((s >> 2) & 1));
+        tc::fence_after_thread_sync();
+        issue_p((s >> 2) + 1);
+      }
+      const uint64_t dbh = s_desc[16 + 6 * grp + 0], dbl = s_desc[16 + 6 * grp + 1];
+      const uint64_t d1h = s_desc[16 + 6 * grp + 2], d1l = s_desc[16 + 6 * grp + 3];
+      const uint64_t d2h = s_desc[16 + 6 * grp + 4], d2l = s_desc[16 + 6 * grp + 5];
+      const uint32_t acc = s > 0 ? 1u : 0u;
+      tc::mma_tf32(dacc, d1h, dbh, idesc, acc);
+      tc::mma_tf32(dacc, d1h, dbl, idesc, 1u);
+      tc::mma_tf32(dacc, d1l, dbh, idesc, 1u);
+      tc::mma_tf32(dacc + 32, d2h, dbh, idesc, acc);
+      tc::mma_tf32(dacc + 32, d2h, dbl, idesc, 1u);
+      tc::mma_tf32(dacc + 32, d2l, dbh, idesc, 1u);
+      tc::mma_commit(&mbar_free[grp]);
+      if (s == nsteps - 1) tc::mma_commit(&mbar_done);
+    }
+  }
+  if (nsteps > 0) tc::mbar_wait(&mbar_done, 0);
+  tc::fence_after_thread_sync();
+  if (warp < 4) {
+    const long no = nb + warp * 32 + lane;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      double* out = which ? den : num;
+#pragma unroll 1
+      for (int k0 = 0; k0 < 32; k0 += 8) {  // 8 columns of both accumulators at a time
+        uint32_t v[8], v2[8];
+        if (nsteps > 0) {
+          tc::tmem_ld_32x8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(which * 32 + k0), v);
+          tc::tmem_ld_32x8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(192 + which * 32 + k0), v2);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = v2[i] = 0u;
+        }
+        if (no < ldo) {
+          const bool live = no < N;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // rows 0-7 of every step, then rows 8-15: a fixed order
+            if (k0 + k < K)
+              out[((size_t)split * K + k0 + k) * ldo + no] =
+                  live ? (double)__uint_as_float(v[k]) + (double)__uint_as_float(v2[k]) : 0.0;
+        }
+      }
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace pf
 
 using namespace pf;
@@ -852,6 +1148,22 @@ int pf_tw_contract_fused_tc(const float* hatW, const float* O, long ld, const fl
     return PF_ERR_CUDA;
   }
   dim3 grid(ceil_div(N, TWF_NT), fsplit);
+  // PYFASST_TW_HALVES=0: the single-pipeline kernel (one block barrier per step)
+  static const bool halves = [] {
+    const char* e2 = getenv("PYFASST_TW_HALVES");
+    return e2 == nullptr || atoi(e2) != 0;
+  }();
+  if (halves) {
+    e = cudaFuncSetAttribute(tw_contract_fused2_tc_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("tw_contract_fused2_tc_kernel: %s", cudaGetErrorString(e));
+      return PF_ERR_CUDA;
+    }
+    tw_contract_fused2_tc_kernel<<<grid, TWF_THREADS, smem, st>>>(hatW, O, ld, W, ldw, H, ldh, K, F,
+                                                                N, fchunk, fsplit, num, den, ldo);
+    return check_launch("tw_contract_fused2_tc_kernel");
+  }
   tw_contract_fused_tc_kernel<<<grid, TWF_THREADS, smem, st>>>(hatW, O, ld, W, ldw, H, ldh, K, F, N,
                                                              fchunk, fsplit, num, den, ldo);
   return check_launch("tw_contract_fused_tc_kernel");
