@@ -846,6 +846,9 @@ tw_contract_fused_tc_kernel(const float* __restrict__ hatW, const float* __restr
 // W' rows and the P' MMA of a 64-row block (staged by all threads, handed to thread 0 through an
 // mbarrier with 256 arrivals, which also proves that every thread has read the P' buffer that the
 // new block overwrites).  The two accumulator pairs are added in a fixed order in the write-out.
+// 209 -> 191 us per launch (profiles/r02/ncu_tw_contract_fused2_tc_kernel.txt).  Not kept: warps
+// that own 8 rows x their own 32 frames, transpose P' through a private tile and hand over through
+// mbarriers only (no named barrier): 1.091 -> 1.114 ms for the spectral phase.
 // (original notes:) thread = one frame x 8 rows straight out of
 // TMEM (4-byte accesses) 229 us per launch; the same with fewer address instructions 240 us; with
 // an mbarrier hand-over to a dedicated MMA warp 293 us; this one -- P' transposed through
@@ -1065,10 +1068,11 @@ tw_contract_fused2_tc_kernel(const float* __restrict__ hatW, const float* __rest
     }
     if (gt < 64) st_split4(sm.b_hi, sm.b_lo, woff, w_cur);
     if (s + 1 < nsteps) p_to_smem(s + 1);  // its block's MMA was issued >= 2 steps ago
-    // second step of a block: stage the W' rows of the next block (wp is free: the MMA of the
-    // current block completed before its first rows were read); thread 0 issues its MMA once all
-    // 256 threads have arrived -- which also means that nobody reads the P' buffer it overwrites
-    const bool next_block = (s & 3) == 1 && (s >> 2) + 1 < nblocks;
+    // first step of a block: stage the W' rows of the next block (wp is free: the MMA of the
+    // current block completed before its first rows were read, one step ago); thread 0 issues its
+    // MMA once all 256 threads have arrived -- which also means that nobody reads the P' buffer it
+    // overwrites any more (last read two steps ago)
+    const bool next_block = (s & 3) == 0 && (s >> 2) + 1 < nblocks;
     if (next_block) stage_wp_block((s >> 2) + 1);
     w_cur = w_n1;
     w_n1 = w_n2;
