@@ -502,6 +502,18 @@ class GemEngine(object):
                           self.fb_nd[s, 1, :cnt].view(F, e["Kb"]), F, e["Kb"], self.omega)
             if not e["FW_identity"]:
                 k.small_matmul(e["FB"], e["FW"], e["W"])
+        if self._fshard() and self._use_streams and os.environ.get("PYFASST_FREQ_PIPELINE", "1") != "0":
+            # Frequency partition: one component after the other on this stream (FB_s, TW_s), the
+            # exchange of component s on the high-priority stream while component s + 1 is
+            # contracted -- only the last exchange is exposed.  Equivalent to the phase order
+            # below: FB_s reads its own component's TW only, which changes after FB_s.
+            for s, e in enumerate(self.spec):
+                if e["FB_free"]:
+                    fb_sums(0, (s, e))
+                if e["TW_free"]:
+                    self._tw_contract_and_exchange(s, e)
+            self.torch.cuda.current_stream(self.dev).wait_stream(self._exchange_stream())
+            return
         # NB every FB update reads G_s = FW_s TW_s of its own component only, and no TW changes
         # before all the FB updates are done (Gauss-Seidel order FB -> TW, Q2)
         self._for_each(fb, fb_sums)
@@ -511,22 +523,25 @@ class GemEngine(object):
         # TW: contraction over the (local) frequencies with the updated W
         tw = [(s, e) for s, e in enumerate(self.spec) if e["TW_free"]]
 
-        def tw_sums(_, se):
-            s, e = se
-            j = e["j"]
-            fchunk, fsplit = self.tw_plan[id(e)]
-            cnt = e["Kw"] * self.ld
-            pn = self.tw_part[s, 0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
-            pd = self.tw_part[s, 1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
-            k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], N, pn, pd, fchunk, fsplit,
-                          None if self.scratch is None else self.scratch[s])
-            if self._fshard():
-                self._tw_exchange(s, e, pn, pd)
-            else:  # reduce the frequency splits inside the update kernel
-                k.mult_update_splits(e["TW"], pn, pd, e["Kw"], N, self.omega)
-        self._for_each(tw, tw_sums)
+        self._for_each(tw, lambda _, se: self._tw_contract_and_exchange(*se))
         if tw and self._fshard() and self._use_streams:
             self.torch.cuda.current_stream(self.dev).wait_stream(self._exchange_stream())
+
+    def _tw_contract_and_exchange(self, s, e):
+        """TW update of one component: contraction over the (local) frequencies with the updated W,
+        then the multiplicative update (after the exchange under frequency sharding)."""
+        k = self.k
+        j = e["j"]
+        fchunk, fsplit = self.tw_plan[id(e)]
+        cnt = e["Kw"] * self.ld
+        pn = self.tw_part[s, 0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+        pd = self.tw_part[s, 1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+        k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], self.N, pn, pd, fchunk, fsplit,
+                      None if self.scratch is None else self.scratch[s])
+        if self._fshard():
+            self._tw_exchange(s, e, pn, pd)
+        else:  # reduce the frequency splits inside the update kernel
+            k.mult_update_splits(e["TW"], pn, pd, e["Kw"], self.N, self.omega)
 
     def _exchange_stream(self):
         """High-priority stream of the frequency partition's TW exchange: the chain of component s
