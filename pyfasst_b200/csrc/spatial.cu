@@ -373,18 +373,25 @@ __global__ void fw_col_means_kernel(const T* __restrict__ FW, int ldfw, int Kb,
 
 // M[r][c] *= (by_row ? s[r] : s[c]) or /= ; optional sum of the result (TW restart test,
 // audioModel.py:2023): one atomic per CTA after a block reduction
+constexpr int SCALE_EPT = 8;
 template <typename T>
 __global__ void scale_matrix_kernel(T* __restrict__ M, long ldm, int rows, long cols,
                                     const double* __restrict__ s, int by_row, int divide,
                                     double* __restrict__ total) {
-  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   double v = 0.0;
-  if (c < cols && r < rows) {
-    const double sc = by_row ? s[r] : s[c];
-    v = (double)M[(size_t)r * ldm + c];
-    v = divide ? v / sc : v * sc;
-    M[(size_t)r * ldm + c] = (T)v;
+  if (r < rows) {  // SCALE_EPT elements per thread, a block-wide stride apart (coalesced)
+#pragma unroll
+    for (int i = 0; i < SCALE_EPT; ++i) {
+      const long c = ((long)blockIdx.x * SCALE_EPT + i) * blockDim.x + threadIdx.x;
+      if (c < cols) {
+        const double sc = by_row ? s[r] : s[c];
+        double x = (double)M[(size_t)r * ldm + c];
+        x = divide ? x / sc : x * sc;
+        M[(size_t)r * ldm + c] = (T)x;
+        v += x;
+      }
+    }
   }
   if (total != nullptr) {
     __shared__ double s_red[32];
@@ -520,7 +527,7 @@ extern "C" int pf_scale_matrix(void* M, int64_t ldm, int rows, int64_t cols, con
                                int by_row, int divide, double* total, int dtype, void* stream) {
   PF_REQUIRE(dtype == PF_F32 || dtype == PF_F64, "pf_scale_matrix: bad dtype %d", dtype);
   PF_REQUIRE(rows > 0 && rows <= 65535 && cols > 0, "pf_scale_matrix: rows=%d", rows);
-  dim3 grid(ceil_div(cols, 256), rows);
+  dim3 grid(ceil_div(cols, 256L * SCALE_EPT), rows);
   if (dtype == PF_F32)
     scale_matrix_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)M, ldm, rows, cols, s,
                                                                    by_row, divide, total);
