@@ -657,9 +657,9 @@ class GemEngine(object):
                 self.comm.allreduce_sum(self.ll_sum)
             k.ll_store(self.ll_sum, float(self.F_total) * self.N_total, logliks, self.iter_dev, True)
             self.update_mix()
-        if self._tshard() and self._use_streams:
-            # only the mixing update needs the all-reduced statistics: it runs, with its
-            # all-reduce, on a side stream while the spectral M-step (which reads hat_W, V and
+        if self._use_streams:
+            # only the mixing update needs the (all-reduced) statistics: it runs, with its
+            # collectives, on a side stream while the spectral M-step (which reads hat_W, V and
             # the factors, never A) starts on this one
             torch = self.torch
             cur = torch.cuda.current_stream(self.dev)
