@@ -187,6 +187,8 @@ class CudaKernels(object):
         self.device = torch.device("cuda", torch.cuda.current_device()
                                    if device is None else device)
         _check(self.lib.pf_set_device(self.device.index), self.lib)
+        self._dev_index = self.device.index
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
     # -- helpers ----------------------------------------------------------------
     def estep_timing(self, enable):
@@ -225,6 +227,11 @@ class CudaKernels(object):
         return t.data_ptr()
 
     def _stream(self):
+        # (the raw handle of torch's current stream: ~0.3 us instead of ~4 us through
+        # torch.cuda.current_stream() -- called once per kernel launch, ~60 times per GEM iteration)
+        raw = self._raw_stream
+        if raw is not None:
+            return raw(self._dev_index)
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def dtype_code(self, t):
