@@ -31,11 +31,6 @@ import time
 
 import numpy as np
 
-# The M-step runs the components' kernel chains on side streams and the frequency partition's
-# exchange on a high-priority one: with the default 8 hardware queues, streams alias and the
-# exchange of component s waits behind the contraction of component s + 1 (measured:
-# profiles/r02/trace_n8_4ch_freq.txt).  Must be set before the CUDA context exists.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
