@@ -368,22 +368,61 @@ class FASST(object):
         eng = GemEngine(k, F, N, dtype=self.compute_dtype)
         eng.set_X_planes(self._X)
         eng.set_noise('fixed', self.noise['PSD'], self.noise['PSD'], self.noise['PSD'])
-        Vp = np.zeros([R, F, eng.ld])
-        Vp[:, :, :N] = powers
-        V = eng._upload(Vp, eng.tdtype)
         A = eng._upload(mix.astype(np.complex128))
-        src = list(range(R))
-        hatW = eng._zeros([R, F, eng.ld])
         Rss = eng._zeros([F, R, R], torch.complex128)
         Rxs = eng._zeros([F, 2, R], torch.complex128)
         ll_f = eng._zeros([F], torch.float64)
-        ws = eng._zeros([(k.estep_workspace_bytes(R, F, N, k.dtype_code(V)) + 7) // 8],
-                        torch.float64)
-        k.estep_stereo(eng.X, V, A, src, eng.noise, N, hatW, Rss, Rxs, ll_f, ws)
+        hat_Ws = np.zeros([R, F, N])
+        # The kernel takes up to MAX_COMPS spatial components.  Sub-sources with the SAME power
+        # (the rank columns of one source, as retrieve_subsrc_params returns them) may share a
+        # component -- Sigma only sees sum_r a_r a_r^H per power -- but hat_Ws is wanted per
+        # sub-source: each pass gives every sub-source of some groups its own component and merges
+        # the others; hat_Rss, hat_Rxs and the log-likelihood are the same in every pass.
+        groups = []
+        for r in range(R):
+            for g in groups:
+                if np.array_equal(powers[g[0]], powers[r]):
+                    g.append(r)
+                    break
+            else:
+                groups.append([r])
+        MAX_COMPS = 6
+        if len(groups) > MAX_COMPS:
+            raise NotImplementedError("compute_suff_stat: %d sub-sources with distinct powers "
+                                      "(the E-step kernel takes %d)" % (len(groups), MAX_COMPS))
+        pending = list(groups)
+        while pending:
+            chosen, ncomp = [], len(groups)
+            for g in list(pending):
+                if ncomp + len(g) - 1 <= MAX_COMPS:
+                    chosen.append(g)
+                    ncomp += len(g) - 1
+                    pending.remove(g)
+            src, comp_rows, own = [0] * R, [], {}
+            for g in groups:
+                if any(g is c for c in chosen):
+                    for r in g:
+                        src[r] = len(comp_rows)
+                        own[r] = len(comp_rows)
+                        comp_rows.append(r)
+                else:
+                    for r in g:
+                        src[r] = len(comp_rows)
+                    comp_rows.append(g[0])
+            J = len(comp_rows)
+            Vp = np.zeros([J, F, eng.ld])
+            Vp[:, :, :N] = powers[comp_rows]
+            V = eng._upload(Vp, eng.tdtype)
+            hatW = eng._zeros([J, F, eng.ld])
+            ws = eng._zeros([(k.estep_workspace_bytes(J, F, N, k.dtype_code(V)) + 7) // 8],
+                            torch.float64)
+            k.estep_stereo(eng.X, V, A, src, eng.noise, N, hatW, Rss, Rxs, ll_f, ws)
+            hw = hatW[:, :, :N].cpu().numpy().astype(np.float64)
+            for r, c in own.items():
+                hat_Ws[r] = hw[c]
         loglik = -float(ll_f.sum().cpu().item()) / (F * N)
         hat_Rxx = np.mean(self.Cx, axis=-1)
-        return (hat_Rxx, Rxs.cpu().numpy(), Rss.cpu().numpy(),
-                hatW[:, :, :N].cpu().numpy().astype(np.float64), loglik)
+        return (hat_Rxx, Rxs.cpu().numpy(), Rss.cpu().numpy(), hat_Ws, loglik)
 
     def renormalize_parameters(self):
         """Energy normalisation across A, FB, FW, TW(, TB) (ref: audioModel.py:1980-2040).  A TW

@@ -119,6 +119,32 @@ def build_model(wav, conv, rank, nbcomps, dtype="float64", iters=6):
     return model
 
 
+@pytest.mark.parametrize("nbcomps,rank,conv", [(4, 2, False), (3, 3, True), (5, 2, False)])
+def test_compute_suff_stat_more_than_six_subsources(nbcomps, rank, conv):
+    """8 / 9 / 10 sub-sources (e.g. the headline model: 4 sources at rank 2): the E-step kernel takes
+    6 spatial components, compute_suff_stat covers the sub-sources in several passes (sub-sources
+    of equal power merged); checked against the oracle (reference algorithm, any R)."""
+    from oracle import fasst_oracle as fo
+    wav = "mix_conv.wav" if conv else "mix_inst.wav"
+    model = build_model(wav, conv, rank, nbcomps)
+    np.random.seed(0)
+    ref = fo.OracleFASST(os.path.join(GOLDEN, wav), nbComps=nbcomps, nbNMFComps=4,
+                         spatial_rank=rank, wlen=256, hopsize=64, iter_num=1)
+    if conv:
+        ref.makeItConvolutive()
+    # the same parameters on both sides
+    ref.spat_comps, ref.spec_comps = model.spat_comps, model.spec_comps
+    ref.noise["PSD"] = model.noise["PSD"] = model.noise["ann_PSD_lim"][0]
+    powers, mix, ranks = model.retrieve_subsrc_params()
+    assert powers.shape[0] == nbcomps * rank > 6
+    _, hRxs, hRss, hWs, ll = model.compute_suff_stat(powers, mix)
+    _, rRxs, rRss, rWs, rll = ref.compute_suff_stat(powers, mix)
+    assert_allclose(hRxs, rRxs, rtol=1e-8, atol=1e-13)
+    assert_allclose(hRss, rRss, rtol=1e-8, atol=1e-13)
+    assert_allclose(hWs, rWs, rtol=1e-7, atol=1e-300)
+    assert_allclose(ll, np.real(rll), rtol=1e-11)
+
+
 def rel_err(a, b):
     return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
 
