@@ -27,6 +27,26 @@ def build_model(wav, conv, rank, nbcomps, dtype, iters=6, **kw):
     return model
 
 
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 2e-6)])
+def test_compute_suff_stat_more_than_six_subsources(dtype, tol):
+    """4 sources at rank 2 = 8 sub-sources (the headline model): several kernel passes; against the
+    oracle (the reference algorithm takes any number of sub-sources)."""
+    from oracle import fasst_oracle as fo
+    model = build_model("mix_inst.wav", False, 2, 4, dtype)
+    ref = fo.OracleFASST(os.path.join(GOLDEN, "mix_inst.wav"), nbComps=4, nbNMFComps=4,
+                         spatial_rank=2, wlen=256, hopsize=64, iter_num=1)
+    ref.spat_comps, ref.spec_comps = model.spat_comps, model.spec_comps
+    ref.noise["PSD"] = model.noise["PSD"] = model.noise["ann_PSD_lim"][0]
+    powers, mix, ranks = model.retrieve_subsrc_params()
+    assert powers.shape[0] == 8
+    _, hRxs, hRss, hWs, ll = model.compute_suff_stat(powers, mix)
+    _, rRxs, rRss, rWs, rll = ref.compute_suff_stat(powers, mix)
+    # (float32 planes: the statistics are float64 sums, the inputs are rounded to float32)
+    assert rel_err(hRxs, rRxs) < tol and rel_err(hRss, rRss) < tol
+    assert rel_err(hWs, rWs) < max(tol, 1e-6 if dtype == "float32" else 0)
+    assert_allclose(ll, np.real(rll), rtol=1e-10 if dtype == "float64" else 1e-6)
+
+
 def sdr_db(ref, est):
     ref, est = ref.astype(np.float64), est.astype(np.float64)
     err = ((ref - est) ** 2).sum()
