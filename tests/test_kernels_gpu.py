@@ -289,6 +289,78 @@ def test_tw_contract(ck, fk, dt, F, K, N, scratch):
     assert (res[1][0][:, N:] == 0).all() and (res[1][1][:, N:] == 0).all()
 
 
+def test_hot_kernels_are_deterministic(ck):
+    """Run-to-run bit identity of the kernels that synchronise by hand (cp.async ring without
+    barriers, mbarriers / named barriers around tcgen05 MMAs, TMA stores, DMMA tiles): a data race
+    shows up as a result that changes between launches.  (compute-sanitizer is refused on this
+    GPU pool, profiles/r02/sanitizer_closed_on_this_pool.log.)  Sizes: several CTAs per SM and
+    several waves."""
+    dt = torch.float32
+    rng = np.random.default_rng(2024)
+    F, N, K = 300, 40000, 32
+    ld = (N + 31) // 32 * 32
+    hatW = rnd(rng, (F, N), dt, positive=True, pad_to=ld).cuda()
+    O = rnd(rng, (F, N), dt, positive=True, pad_to=ld).cuda()
+    W = rnd(rng, (F, K), dt, positive=True).cuda()
+    H = rnd(rng, (K, N), dt, positive=True, pad_to=ld).cuda()
+
+    def tw():
+        fchunk, fsplit = ck.tw_plan(F, K, N, ck.dtype_code(hatW))
+        pn = torch.zeros((fsplit, K, ld), dtype=torch.float64, device="cuda")
+        pd = torch.zeros((fsplit, K, ld), dtype=torch.float64, device="cuda")
+        ck.tw_contract(hatW, O, W, H, N, pn, pd, fchunk, fsplit, torch.zeros((F, ld), dtype=dt, device="cuda"))
+        return pn, pd
+
+    def fb():
+        chunk, nsplit = ck.fb_plan(F, K, N, ck.dtype_code(hatW))
+        pn = torch.zeros((nsplit, F, K), dtype=torch.float64, device="cuda")
+        pd = torch.zeros((nsplit, F, K), dtype=torch.float64, device="cuda")
+        ck.fb_contract(hatW, O, O, H, N, pn, pd, chunk, nsplit)
+        return pn, pd
+
+    def power():
+        V = torch.zeros((F, ld), dtype=dt, device="cuda")
+        ck.spec_power(W, H, V, N, False)
+        return (V,)
+
+    def estep(which, J, rank, I):
+        if I == 2:
+            ldx, R, src, X, V, A, noise = problem(np.random.default_rng(5), dt, 40, 30000, J, rank)
+            if which == "estep_stereo_inst":
+                A = torch.complex(A.real.contiguous(), torch.zeros_like(A.real))
+        else:
+            from tests.test_multichannel_gpu import problem as problem_multi
+            ldx, R, src, X, V, A, noise = problem_multi(np.random.default_rng(5), dt, I, 40, 30000, J, rank)
+        X, V, A, noise = X.cuda(), V.cuda(), A.cuda(), noise.cuda()
+        Nn, Fn = 30000, 40
+
+        def run():
+            hw = torch.zeros((J, Fn, ldx), dtype=dt, device="cuda")
+            Rss = torch.zeros((Fn, R, R), dtype=torch.complex128, device="cuda")
+            Rxs = torch.zeros((Fn, I, R), dtype=torch.complex128, device="cuda")
+            ll = torch.zeros(Fn, dtype=torch.float64, device="cuda")
+            if I == 2:
+                ws = torch.zeros((ck.estep_workspace_bytes(J, Fn, Nn, ck.dtype_code(V)) + 7) // 8,
+                                 dtype=torch.float64, device="cuda")
+            else:
+                ws = torch.zeros((ck.estep_multi_workspace_bytes(I, J, Fn, Nn) + 7) // 8,
+                                 dtype=torch.float64, device="cuda")
+            getattr(ck, which)(X, V, A, src, noise, Nn, hw, Rss, Rxs, ll, ws)
+            return hw, torch.view_as_real(Rss), torch.view_as_real(Rxs), ll
+        return run
+
+    cases = {"tw_contract": tw, "fb_contract": fb, "spec_power": power,
+             "estep_stereo": estep("estep_stereo", 4, 2, 2),
+             "estep_stereo_inst": estep("estep_stereo_inst", 4, 2, 2),
+             "estep_multi": estep("estep_multi", 4, 2, 4)}
+    for name, fn in cases.items():
+        first = [t.clone() for t in fn()]
+        for _ in range(3):
+            again = fn()
+            for a, b in zip(first, again):
+                assert torch.equal(a, b), name
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 def test_mult_update_and_scaling(ck, fk, dt):
     rng = np.random.default_rng(3)
