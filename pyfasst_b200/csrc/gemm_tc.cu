@@ -338,8 +338,15 @@ extern "C" int pf_gemm_splitk_plan(int M, int N, int K, int* ksplit, int64_t* wo
   PF_REQUIRE(M > 0 && N > 0 && K > 0, "pf_gemm_splitk_plan: empty problem %d x %d x %d", M, N, K);
   const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
   const long tiles = (long)ceil_div(N, bn) * ceil_div(M, GT_BM);
-  // two waves of CTAs on a 148-SM part, but at least 8 K chunks per CTA
-  long want = (2L * 148 + tiles - 1) / tiles;
+  // ONE wave of co-resident CTAs (two per SM on a 148-SM part: 296 slots), never a CTA more --
+  // rounding the split count UP (33 splits x 9 row tiles = 297 CTAs for the F x R products of the
+  // SIMM model) left one CTA to run alone after the wave --, but at least 8 K chunks per CTA
+  long slots = 2L * 148;
+  if (const char* e = getenv("PYFASST_GEMM_SPLIT_SLOTS")) {  // tuning override
+    const long v = atol(e);
+    if (v > 0) slots = v;
+  }
+  long want = slots / tiles;
   const long most = (K + 8L * GT_BK - 1) / (8L * GT_BK);
   if (want > most) want = most;
   if (want < 1) want = 1;
