@@ -194,12 +194,16 @@ __device__ __forceinline__ void tma_store_wait() {
 }
 
 // ---- 3xTF32 split ----------------------------------------------------------------------------
-// x = hi + lo with hi = tf32-rounded x (round to nearest) and lo = x - hi (exact in fp32);
-// A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi has a relative error of ~2^-21 per product, i.e. fp32-class
+// x = hi + lo with hi = tf32-rounded x (round to nearest, ties away from zero) and lo = x - hi
+// (exact in fp32); A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi has a relative error of ~2^-21 per product,
+// i.e. fp32-class.  The rounding is done on the bit pattern -- add half an ulp of tf32 to the
+// magnitude, clear the 13 low mantissa bits: exactly `cvt.rna.tf32.f32` for every finite x --
+// because ptxas EMULATES that conversion on sm_100a (no CVT in the SASS: ~10 ISETP / FSETP / SEL /
+// LOP3 / VIADD per element for its NaN / infinity cases), which made the operand producers of
+// every tcgen05 kernel here instruction-bound (ncu of gemm_tf32x3_ws_kernel: 40 instructions per
+// float4, profiles/r02/ncu_gemm_tf32x3_ws_kernel_D_q.txt).  Two integer operations instead.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
 

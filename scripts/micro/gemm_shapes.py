@@ -52,6 +52,7 @@ def main():
     tn = torch.empty(F, ru4(K), device=dev)
     ws = torch.empty(max(k.gemm_splitk_workspace_bytes(F, K, ldn),
                          k.gemm_splitk_workspace_bytes(F, R, ldn), 16) // 4, device=dev)
+    plane = rnd(F, ldn)             # one contiguous plane (row stride ldn instead of 4 ldn)
     pl = F * ldn * 4  # bytes of one F x N plane
     # name, call, flops (2 m n k), compulsory bytes
     shapes = [
@@ -76,6 +77,12 @@ def main():
         ("tn = plane HPHI^T  [F x 4, K=N] split-K",
          lambda: k.gemm_view(work[:, :ldn], HPHI, tn, F, K, ldn, transB=True, workspace=ws),
          2.0 * F * K * ldn, pl + K * ldn * 4),
+        ("D_q compact plane  [F x 40, K=N] split-K",
+         lambda: k.gemm_view(plane, HM, D, F, R, ldn, transB=True, workspace=ws),
+         2.0 * F * R * ldn, pl + R * ldn * 4),
+        ("C_phi compact      [4 x N, K=F]",
+         lambda: k.gemm_view(WPHI, plane, C_phi[:, :ldn], K, ldn, F, transA=True),
+         2.0 * K * ldn * F, pl),
     ]
     only = [s for s in args.only.split(",") if s]
     print("PYFASST_GEMM_* =", {kk: v for kk, v in os.environ.items() if kk.startswith("PYFASST_GEMM")})

@@ -35,7 +35,8 @@ def test_tc_selftest(a_mn, b_mn, N, K, split3):
 @pytest.mark.parametrize("transA", [False, True])
 @pytest.mark.parametrize("transB", [False, True])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 32), (1025, 700, 480), (480, 1000, 1028),
-                                   (4, 515, 1025), (300, 40, 2048), (130, 5, 64)])
+                                   (4, 515, 1025), (300, 40, 2048), (130, 5, 64),
+                                   (40, 1300, 1025)])
 def test_gemm_tf32x3(transA, transB, M, N, K):
     """pf_gemm_tf32x3 against float64 NumPy for all operand layouts, ragged sizes included."""
     from pyfasst_b200._lib import CudaKernels
