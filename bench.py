@@ -93,13 +93,16 @@ def n_frames(L):
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
     """SM clock and throttle reasons DURING the timed region, polled through NVML
-    (nvidia-ml-py) every ~5 ms from a thread; nvidia-smi is the fallback."""
+    (nvidia-ml-py) every ~12 ms from a thread; nvidia-smi is the fallback."""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
                "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
+
+    PERIOD_S = 0.012
 
     def __init__(self, index):
         self.index = index
         self.samples = []
+        self.query_s = []
         self.reasons = set()
         self.sm_max = None
         self._stop = threading.Event()
@@ -121,12 +124,16 @@ class ClockSampler(object):
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             while not self._stop.is_set():
+                t0 = time.perf_counter()
                 self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                 mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.query_s.append(time.perf_counter() - t0)
                 for name, bit in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.005)
+                # (a 40-ms timed region gets 3-4 samples; polling faster buys nothing and every
+                # NVML query goes through the driver the launching thread is also calling into)
+                self._stop.wait(self.PERIOD_S)
         except Exception as exc:  # noqa: BLE001 -- reported in the JSON line
             self.error = repr(exc)
 
@@ -145,8 +152,9 @@ class ClockSampler(object):
             self.thread.join(timeout=5)
         out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
                "sm_max_mhz": self.sm_max, "samples": len(self.samples),
-               "reasons": sorted(self.reasons), "how": "NVML polled every 5 ms during the "
-                                                       "timed region"}
+               "reasons": sorted(self.reasons),
+               "nvml_query_ms": round(1e3 * float(np.median(self.query_s)), 3) if self.query_s else None,
+               "how": "NVML polled every %d ms during the timed region" % round(1e3 * self.PERIOD_S)}
         if self.error:
             out["error"] = self.error
         return out

@@ -405,8 +405,24 @@ class GemEngine(object):
             self.tw_plan[id(e)] = (fchunk, fsplit)
             tw_size = max(tw_size, fsplit * e["Kw"] * ld)
         self.tw_part = self._zeros([S, 2, tw_size], f64)
-        # work planes for P' = W'H of the tensor-core TW path (float32 planes only)
-        self.scratch = self._zeros([S, F, ld]) if self.tdtype == torch.float32 else None
+        # the views the contraction kernels write, made once (tensor indexing costs the host
+        # several microseconds per view, 16 views per iteration)
+        for s, e in enumerate(self.spec):
+            nsplit = self.fb_plan[id(e)][1]
+            cnt = F * e["Kb"]
+            e["fb_pn"] = self.fb_part[s, 0, :nsplit * cnt].view(nsplit, F, e["Kb"])
+            e["fb_pd"] = self.fb_part[s, 1, :nsplit * cnt].view(nsplit, F, e["Kb"])
+            fsplit = self.tw_plan[id(e)][1]
+            cnt = e["Kw"] * ld
+            e["tw_pn"] = self.tw_part[s, 0, :fsplit * cnt].view(fsplit, e["Kw"], ld)
+            e["tw_pd"] = self.tw_part[s, 1, :fsplit * cnt].view(fsplit, e["Kw"], ld)
+        # work planes for P' = W'H of the two-kernel tensor-core TW path (float32 planes only;
+        # PYFASST_TW_FUSED=0).  Not zeroed: that path writes a plane in full before it reads it,
+        # the default fused kernel never touches it (a 1.7 GB fill per model of configs[1]).
+        self.scratch = torch.empty([S, F, ld], dtype=self.tdtype, device=self.dev) \
+            if self.tdtype == torch.float32 else None
+        for s, e in enumerate(self.spec):
+            e["scratch"] = None if self.scratch is None else self.scratch[s]
         if self._fshard():
             # reduce-scatter over the frames (plane type, fixed order) -> shard-local update ->
             # all-gather of TW, per component on its side stream: 2.7x less NVLink
@@ -484,8 +500,7 @@ class GemEngine(object):
             j = e["j"]
             chunk, nsplit = self.fb_plan[id(e)]
             cnt = F * e["Kb"]
-            pn = self.fb_part[s, 0, :nsplit * cnt].view(nsplit, F, e["Kb"])
-            pd = self.fb_part[s, 1, :nsplit * cnt].view(nsplit, F, e["Kb"])
+            pn, pd = e["fb_pn"], e["fb_pd"]
             k.fb_contract(self.hatW[j], self.V[j], self.V[j], e["G"], N, pn, pd, chunk, nsplit)
             if self._tshard():
                 k.sum_splits(pn, self.fb_nd[s, 0, :cnt])
@@ -545,11 +560,9 @@ class GemEngine(object):
         k = self.k
         j = e["j"]
         fchunk, fsplit = self.tw_plan[id(e)]
-        cnt = e["Kw"] * self.ld
-        pn = self.tw_part[s, 0, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
-        pd = self.tw_part[s, 1, :fsplit * cnt].view(fsplit, e["Kw"], self.ld)
+        pn, pd = e["tw_pn"], e["tw_pd"]
         k.tw_contract(self.hatW[j], self.V[j], e["W"], e["TW"], self.N, pn, pd, fchunk, fsplit,
-                      None if self.scratch is None else self.scratch[s])
+                      e["scratch"])
         if self._fshard():
             self._tw_exchange(s, e, pn, pd)
         else:  # reduce the frequency splits inside the update kernel
