@@ -24,7 +24,10 @@
 
 namespace pf {
 
-constexpr int FFT_THREADS = 256;
+#ifndef PF_FFT_THREADS
+#define PF_FFT_THREADS 256
+#endif
+constexpr int FFT_THREADS = PF_FFT_THREADS;  // (-DPF_FFT_THREADS=...: CTA-shape experiments)
 
 __device__ __forceinline__ double2 cmul_d(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
