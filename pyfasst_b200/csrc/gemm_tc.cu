@@ -473,14 +473,6 @@ static int launch_gemm_stages(const float* A, long lda, const float* B, long ldb
   return check_launch("gemm_tf32x3_kernel");
 }
 
-// operand chunks in flight per thread: PYFASST_GEMM_PF = 1 (round 1), 2, 4 (BN = 64 only)
-static int gemm_prefetch_depth() {
-  static const int v = [] {
-    const char* e = getenv("PYFASST_GEMM_PF");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
-}
 // PYFASST_GEMM_WS=0: the barrier-per-chunk kernel for long contractions too (round 1)
 static bool gemm_use_ws() {
   static const bool v = [] {
@@ -507,39 +499,21 @@ static int launch_gemm_ws(const float* A, long lda, const float* B, long ldb, fl
   return check_launch("gemm_tf32x3_ws_kernel");
 }
 
-template <bool TA, bool TB, int BN, int STAGES>
-static int launch_gemm_pf(const float* A, long lda, const float* B, long ldb, float* C, long ldc,
-                          int M, int N, int K, int ksplit, int kper, long cstride, cudaStream_t st) {
-  const int pf = gemm_prefetch_depth();
-  if (pf == 1)
-    return launch_gemm_stages<TA, TB, BN, STAGES, 1>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper,
-                                                     cstride, st);
-  if constexpr (BN == 64) {
-    if (pf == 4)
-      return launch_gemm_stages<TA, TB, BN, STAGES, 4>(A, lda, B, ldb, C, ldc, M, N, K, ksplit,
-                                                       kper, cstride, st);
-  }
-  return launch_gemm_stages<TA, TB, BN, STAGES, 2>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper,
-                                                   cstride, st);
-}
-
 template <bool TA, bool TB, int BN>
 static int launch_gemm(const float* A, long lda, const float* B, long ldb, float* C, long ldc,
                        int M, int N, int K, int ksplit, int kper, long cstride, cudaStream_t st) {
   // short contractions (at most two K chunks per CTA: the K = R products of the SIMM
   // accompaniment model) take the one-stage ring and two CTAs per SM
   const long kspan = ksplit > 1 ? kper : K;
-  if (kspan <= 2 * GT_BK) {
-    if (gemm_prefetch_depth() == 0)  // (one register set: two CTAs per SM also at BN = 256)
-      return launch_gemm_stages<TA, TB, BN, 1, 1>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper,
-                                                  cstride, st);
-    return launch_gemm_pf<TA, TB, BN, 1>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
-  }
+  if (kspan <= 2 * GT_BK)  // (one register set: two CTAs per SM also at BN = 256)
+    return launch_gemm_stages<TA, TB, BN, 1, 1>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper,
+                                                cstride, st);
   // long contractions: dedicated MMA warp, one CTA per SM, 4 (BN = 64) / 2 chunks in flight
   if (gemm_use_ws())
     return launch_gemm_ws<TA, TB, BN, BN == 64 ? 4 : 2, false>(A, lda, B, ldb, C, ldc, M, N, K,
                                                                ksplit, kper, cstride, st);
-  return launch_gemm_pf<TA, TB, BN, 2>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper, cstride, st);
+  return launch_gemm_stages<TA, TB, BN, 2, 2>(A, lda, B, ldb, C, ldc, M, N, K, ksplit, kper,
+                                              cstride, st);
 }
 
 template <bool TA, bool TB>

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the PYFASST_GEMM_PF switch of this experiment existed at commit 39e18aa; the prefetch depth is now fixed per kernel)
 # ncu --set full of gemm_tf32x3_kernel on three SIMM shapes (tensor-bound, padded-M, skinny split-K)
 mkdir -p gpurun_out
 export PYFASST_GEMM_PF=${PF:-2}

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the PYFASST_GEMM_PF switch of this experiment existed at commit 39e18aa; the prefetch depth is now fixed per kernel)
 # prefetch depth A/B of gemm_tf32x3_kernel on the SIMM shapes + its parity tests at each depth
 mkdir -p gpurun_out
 for pf in 2 4 1; do
