@@ -9,11 +9,16 @@
 // not give.
 //
 // The hi / lo operand tiles cannot come from TMA (they are computed from the loaded values):
-// the 256 threads of a CTA load a K chunk of 32, split it and store it into shared memory in the
-// canonical UMMA layouts of tc.cuh -- K-major for an operand that is contiguous along K,
-// MN-major (SWIZZLE_128B_BASE32B) for one contiguous along M / N -- while one elected thread
-// issues the MMAs of the previous chunk; ring slots are recycled through mbarriers
-// (tcgen05.commit).  One CTA owns a 128 x BN tile of C.
+// threads load a K chunk of 32, split it and store it into shared memory in the canonical UMMA
+// layouts of tc.cuh -- K-major for an operand that is contiguous along K, MN-major
+// (SWIZZLE_128B_BASE32B) for one contiguous along M / N; ring slots are recycled through mbarriers
+// (tcgen05.commit).  One CTA owns a 128 x BN tile of C.  Two kernels:
+//   gemm_tf32x3_ws_kernel  long contractions (more than two K chunks per CTA): 16 producer warps
+//                          and a dedicated MMA warp, full / free mbarriers per ring slot, no
+//                          CTA-wide barrier in the loop, one CTA per SM
+//   gemm_tf32x3_kernel     short contractions (the K = R products): 8 warps, a barrier per chunk,
+//                          one elected thread issues the MMAs; two CTAs per SM so that one CTA's
+//                          write-out overlaps the other's loads (also the PYFASST_GEMM_WS=0 path)
 #include "common.cuh"
 #include "tc.cuh"
 
